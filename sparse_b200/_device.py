@@ -1,0 +1,138 @@
+"""Device-memory plumbing: torch owns HBM allocations and streams, nothing else.
+
+Containers keep their arrays as ``torch`` CUDA tensors (moved to HBM once) and
+hand raw device pointers to the C ABI.  NumPy mirrors are materialised lazily
+when a caller reads ``.coords`` / ``.data`` / ``.indices`` / ``.indptr``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+
+        _torch = _t
+    return _torch
+
+
+_NP2T = None
+
+
+def _np2t():
+    global _NP2T
+    if _NP2T is None:
+        t = torch()
+        _NP2T = {
+            np.dtype("float32"): t.float32,
+            np.dtype("float64"): t.float64,
+            np.dtype("int32"): t.int32,
+            np.dtype("int64"): t.int64,
+            np.dtype("int16"): t.int16,
+            np.dtype("int8"): t.int8,
+            np.dtype("uint8"): t.uint8,
+            np.dtype("bool"): t.bool,
+        }
+    return _NP2T
+
+
+_CODES = {
+    np.dtype("float32"): _lib.F32,
+    np.dtype("float64"): _lib.F64,
+    np.dtype("int32"): _lib.I32,
+    np.dtype("int64"): _lib.I64,
+    np.dtype("bool"): _lib.BOOL,
+}
+
+
+def dtype_code(dt) -> int:
+    dt = np.dtype(dt)
+    if dt not in _CODES:
+        raise TypeError(f"sparse_b200: dtype {dt} is outside the supported CUDA dtype matrix "
+                        f"({', '.join(str(k) for k in _CODES)})")
+    return _CODES[dt]
+
+
+def torch_dtype(dt):
+    dt = np.dtype(dt)
+    m = _np2t()
+    if dt not in m:
+        raise TypeError(f"sparse_b200: dtype {dt} has no device representation")
+    return m[dt]
+
+
+def np_dtype(t) -> np.dtype:
+    for k, v in _np2t().items():
+        if v == t.dtype:
+            return k
+    raise TypeError(f"unsupported torch dtype {t.dtype}")
+
+
+def have_device() -> bool:
+    try:
+        return bool(torch().cuda.is_available())
+    except Exception:  # pragma: no cover
+        return False
+
+
+def require_device():
+    if not have_device():
+        raise RuntimeError(
+            "sparse_b200: no CUDA device available. The hot path runs only on a B200 (sm_100a); "
+            "there is no CPU fallback."
+        )
+    _lib.load()
+
+
+def device():
+    t = torch()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return int(torch().cuda.current_stream().cuda_stream)
+
+
+def is_device_tensor(x) -> bool:
+    t = _torch
+    return t is not None and isinstance(x, t.Tensor) and x.is_cuda
+
+
+def upload(arr, dtype=None):
+    """Host ndarray -> contiguous CUDA tensor (one H2D copy; async if `arr` is pinned)."""
+    require_device()
+    t = torch()
+    a = np.asarray(arr)
+    if dtype is not None and a.dtype != np.dtype(dtype):
+        a = a.astype(dtype)
+    if a.dtype.kind == "u" and a.dtype.itemsize > 1:  # uintp coords etc.
+        a = a.astype(np.int64)
+    torch_dtype(a.dtype)
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()
+    return t.from_numpy(a).to(device(), non_blocking=True)
+
+
+def download(x) -> np.ndarray:
+    return x.detach().cpu().numpy()
+
+
+def empty(shape, dtype):
+    require_device()
+    return torch().empty(shape, dtype=torch_dtype(dtype), device=device())
+
+
+def zeros(shape, dtype):
+    require_device()
+    return torch().zeros(shape, dtype=torch_dtype(dtype), device=device())
+
+
+def ptr(x) -> int:
+    return int(x.data_ptr())
