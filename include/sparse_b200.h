@@ -96,6 +96,136 @@ int b2s_spmm_csr_dense_host(int dtype, int64_t M, int64_t K, int64_t N, int64_t 
  * 2 = 1-D bulk-TMA (cp.async.bulk) gather through a shared-memory ring. */
 int b2s_spmm_set_variant(int variant, int unroll);
 
+
+/* ---- streaming primitives (prims.cu): COO canonicalisation / format conversion ------------ */
+/* linear_loc (_coo/common.py:56-64) with an arbitrary axis permutation folded into `strides_host`:
+ * keys[i] = sum_d coords[d][i] * strides_host[d]. coords is [ndim, nnz] with row stride `row_stride` elements. */
+int b2s_coo_linearize(int idx_bytes, int ndim, int64_t nnz, const void *coords_dev, int64_t row_stride,
+                      const int64_t *strides_host, int64_t *keys_out_dev, void *stream);
+/* inverse of linear_loc for C-order `shape_host`; writes coords [ndim, nnz] of width idx_bytes. */
+int b2s_coo_unravel(int idx_bytes, int ndim, int64_t nnz, const int64_t *keys_dev, const int64_t *shape_host,
+                    void *coords_out_dev, int64_t row_stride, void *stream);
+/* COO._sort_indices' test `(np.diff(linear) >= 0).all()` and _sum_duplicates' uniqueness test
+ * (_coo/core.py:1310-1313, 1340-1343). Synchronises the stream. */
+int b2s_keys_flags(const int64_t *keys_dev, int64_t n, int *unsorted_host, int *has_dups_host, void *stream);
+/* stable argsort of non-negative int64 keys over their low `key_bits` bits (np.argsort(kind="mergesort"),
+ * _coo/core.py:1315): keys_out = sorted keys, perm_out = source positions. */
+int b2s_sort_keys(const int64_t *keys_in_dev, int64_t n, int key_bits, int64_t *keys_out_dev, int64_t *perm_out_dev,
+                  void *stream);
+int b2s_gather(int elem_bytes, const void *in_dev, const int64_t *perm_dev, int64_t n, void *out_dev, void *stream);
+int b2s_flag_heads(const int64_t *keys_dev, int64_t n, uint8_t *flags_out_dev, void *stream);
+/* keep-flags of COO._prune / GCXS._prune: bits(data[i]) != bits(fill) (`equivalent`, _utils.py:448-452). */
+int b2s_flag_not_fill(int elem_bytes, const void *data_dev, int64_t n, const void *fill_host, uint8_t *flags_out_dev,
+                      void *stream);
+/* exclusive scan of 0/1 flags; returns the number of set flags on the host (synchronises). */
+int b2s_scan_flags(const uint8_t *flags_dev, int64_t n, int64_t *pos_out_dev, int64_t *total_host, void *stream);
+int b2s_exclusive_scan_i64(const int64_t *in_dev, int64_t n, int64_t *out_dev, void *stream);
+int b2s_compact(int elem_bytes, const void *in_dev, const uint8_t *flags_dev, const int64_t *pos_dev, int64_t n,
+                void *out_dev, void *stream);
+int b2s_compact_rows(int elem_bytes, int nrows, const void *in_dev, int64_t in_stride, const uint8_t *flags_dev,
+                     const int64_t *pos_dev, int64_t n, void *out_dev, int64_t out_stride, void *stream);
+/* COO._sum_duplicates (np.add.reduceat over runs, _coo/core.py:1350): out[pos[i]] = sum of the run headed at i. */
+int b2s_segment_sum(int dtype, const void *data_dev, const uint8_t *heads_dev, const int64_t *pos_dev, int64_t n,
+                    void *out_dev, void *stream);
+/* bincount + cumsum of _from_coo (_compressed/compressed.py:72-74) and of _dot's COO branch (_common.py:452-458). */
+int b2s_indptr_from_sorted(int in_idx_bytes, const void *rows_dev, int64_t n, int64_t nrows, int out_idx_bytes,
+                           void *indptr_out_dev, void *stream);
+/* sorted 2-D linear keys -> (rows?, indices, indptr?) of the compressed (nrows x ncols) view (_from_coo :66-75). */
+int b2s_csr_from_keys(const int64_t *keys_dev, int64_t n, int64_t nrows, int64_t ncols, int out_idx_bytes,
+                      void *rows_out_dev_or_null, void *indices_out_dev, void *indptr_out_dev, void *stream);
+/* uncompress_dimension (_compressed/convert.py:81-87). */
+int b2s_rows_from_indptr(int in_idx_bytes, const void *indptr_dev, int64_t nrows, int out_idx_bytes,
+                         void *rows_out_dev, void *stream);
+/* todense (COO.todense, _coo/core.py): out[keys[i]] = data[i] over a buffer pre-filled with the fill value. */
+int b2s_scatter(int elem_bytes, const void *data_dev, const int64_t *keys_dev, int64_t n, void *out_dev, void *stream);
+int b2s_fill(int elem_bytes, void *out_dev, int64_t n, const void *value_host, void *stream);
+int b2s_cast(int src_dtype, int dst_dtype, const void *in_dev, int64_t n, void *out_dev, void *stream);
+int b2s_transpose_dense(int elem_bytes, const void *in_dev, int64_t rows, int64_t cols, int64_t ld_in, void *out_dev,
+                        int64_t ld_out, void *stream);
+/* nan_check (_common.py:51-69), used for matmul's RuntimeWarning. Synchronises. */
+int b2s_any_nan(int dtype, const void *data_dev, int64_t n, int *result_host, void *stream);
+
+/* ---- CSR x CSR -> CSR / COO x COO -> COO (K4, spgemm.cu) ---------------------------------- */
+/*
+ * Replaces _dot_csr_csr_type(dt1,dt2)(out_shape, a_data, b_data, a_indices, b_indices, a_indptr, b_indptr)
+ * (_common.py:639-717, called at :359-373) and _dot_coo_coo (:907-976, called at :459-461).
+ * begin(): runs the whole numeric product into an upper-bound layout and returns the structural nnz and the
+ * nnz after dropping sums bitwise equal to +0.  finish(): writes caller-allocated outputs
+ * (indptr[M+1] or NULL, indices[nnz], rows[nnz] or NULL, data[nnz]) and frees the plan.
+ * sorted_order = 0: reverse-first-touch column order per row, bit-identical to the reference's linked list
+ * (incl. the all-dense row flip); 1: ascending columns (canonical COO order).
+ * wide_accumulate = 1: float64 accumulator and "skip if sum == 0" of _dot_csc_ndarray_sparse (:835, :852).
+ */
+int b2s_spgemm_begin(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t n_col, const void *a_indptr_dev,
+                     const void *a_indices_dev, const void *a_data_dev, const void *b_indptr_dev,
+                     const void *b_indices_dev, const void *b_data_dev, int sorted_order, int wide_accumulate,
+                     void **plan_out, int64_t *nnz_struct_out, int64_t *nnz_pruned_out, void *stream);
+int b2s_spgemm_finish(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev,
+                      int64_t *rows_out_dev, void *data_out_dev);
+int b2s_spgemm_abort(void *plan);
+int b2s_spgemm_set_thresholds(int64_t t0, int64_t t1); /* test hook: row-binning thresholds on products/row */
+
+/* ---- sparse-output sparse x dense (K3, spmm_sparse.cu) ------------------------------------ */
+/* _dot_csr_ndarray_sparse arithmetic (_common.py:758-804): product rounded to dtype, running sum in the type
+ * numba unifies `val = 0` with (f64 for floats, i64 for ints); flags[i,j] = structural test of
+ * _csr_ndarray_count_nnz (:573-600).  out and flags are dense (M x N, contiguous). */
+int b2s_spmm_csr_dense_flagged(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, const void *a_data_dev,
+                               const void *a_indices_dev, const void *a_indptr_dev, const void *b_dev, int64_t ldb,
+                               void *out_dev, uint8_t *flags_out_dev, void *stream);
+/* dense (M x N) -> CSR/COO entries.  flags_or_null: externally computed keep flags; else mode 0: x != 0
+ * (`if data_curr != 0`, _common.py:1062,1149), mode 1: bits(x) != bits(+0) (prune). */
+int b2s_dense_to_csr_begin(int dtype, int64_t M, int64_t N, const void *x_dev, const uint8_t *flags_or_null_dev,
+                           int mode, void **plan_out, int64_t *nnz_out, void *stream);
+int b2s_dense_to_csr_finish(void *plan, int64_t *rows_out_or_null_dev, int64_t *cols_out_dev, void *data_out_dev,
+                            int64_t *indptr_out_or_null_dev);
+/* GCXS._prune's indptr rebuild (_compressed/compressed.py:836-842): new_indptr[r] = pos[old_indptr[r]]. */
+int b2s_indptr_remap(int idx_bytes, const void *old_indptr_dev, int64_t nrows, const int64_t *pos_dev, int64_t n,
+                     int64_t total, void *new_indptr_dev, void *stream);
+
+/* ---- broadcasting element-wise coiteration (K5, elemwise.cu) ------------------------------ */
+/* Operator codes: binary 0..13 value ops (add sub mul div maximum minimum fmax fmin pow floordiv mod band bor bxor),
+ * 32..40 predicates (gt ge lt le eq ne land lor lxor); unary 0..31 value ops, 64..68 predicates (see elemwise.cu). */
+/* Replaces _Elemwise._match_coo + _match_arrays + _get_func_coords_data (_umath.py:656-751, 53-92, 576-654) for two
+ * COO operands: merge-path union of two sorted key streams, each optionally expanded virtually by a trailing
+ * broadcast factor R.  Outputs have na*Ra + nb*Rb slots; flags mark the entries to keep. */
+int b2s_ew_merge(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
+                 const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb, const void *fill_a_host,
+                 const void *fill_b_host, const void *out_fill_host, int64_t *out_keys_dev, void *out_vals_dev,
+                 uint8_t *out_flags_dev, void *stream);
+/* COO (x) scalar (mode 0: f(x,s), 1: f(s,x)) and unary maps (mode 2). */
+int b2s_ew_map(int dtype, int op, int mode, const void *x_dev, int64_t n, const void *scalar_host,
+               const void *out_fill_host, void *out_vals_dev, uint8_t *out_flags_dev, void *stream);
+/* COO (x) dense ndarray: the mask (True, None) branch, np.broadcast_to(arg, shape)[coords] (_umath.py:606-608). */
+int b2s_ew_dense(int dtype, int op, int swap, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na,
+                 int64_t Ra, const void *dense_dev, int ndim, const int64_t *shape_host,
+                 const int64_t *dense_strides_host, const void *out_fill_host, int64_t *out_keys_dev,
+                 void *out_vals_dev, uint8_t *out_flags_dev, void *stream);
+/* _get_expanded_coords_data (_umath.py:220-277) for arbitrary broadcast axes: n*R (key, source index) pairs. */
+int b2s_ew_expand(int idx_bytes, const void *coords_dev, int64_t row_stride, int64_t n, int ndim,
+                  const int64_t *result_shape_host, const int32_t *is_bcast_host, const int32_t *src_row_host,
+                  int64_t *out_keys_dev, int64_t *out_src_dev, void *stream);
+
+/* ---- grouped reductions (K7, reduce.cu) ---------------------------------------------------- */
+/* Operator codes: 0 add, 1 multiply, 2 maximum, 3 minimum, 4 logical_and, 5 logical_or, 6..8 bitwise and/or/xor. */
+int b2s_group_ids(const int64_t *keys_dev, int64_t n, int64_t ncols, int64_t *gid_out_dev, void *stream);
+/* _grouped_reduce = _calc_counts_invidx + ufunc.reduceat (_coo/core.py:1601-1661). Outputs sized n. */
+int b2s_reduce_by_key(int dtype, int op, const int64_t *gid_dev, const void *vals_dev, int64_t n,
+                      int64_t *groups_out_dev, void *vals_out_dev, int64_t *counts_out_dev, int64_t *n_groups_host,
+                      void *stream);
+/* fill-value contribution of SparseArray.reduce (_sparse_array.py:405-422), in place. */
+int b2s_reduce_fill_fix(int dtype, int op, void *vals_dev, const int64_t *counts_dev, int64_t n_groups, int64_t ncols,
+                        const void *fill_host, void *stream);
+
+/* ---- fused example paths (K8 / K9, fused.cu) ---------------------------------------------- */
+/* examples/sddmm_example.py:51-52  s * (a @ b): out_vals[p] = s_vals[p] * dot(A[i_p,:], Bt[j_p,:]). */
+int b2s_sddmm(int dtype, int idx_bytes, int64_t M, int64_t N, int64_t K, const void *indptr_dev,
+              const void *cols_dev, const void *s_vals_dev, const void *a_dev, int64_t lda, const void *bt_dev,
+              int64_t ldbt, void *out_vals_dev, void *stream);
+/* examples/mttkrp_example.py:51-52: out[i,j] = sum_{k,l} B[i,k,l] * D[l,j] * C[k,j]. */
+int b2s_mttkrp(int dtype, int idx_bytes, int64_t I_, int64_t J, const void *indptr_dev, const void *k_dev,
+               const void *l_dev, const void *vals_dev, const void *d_dev, int64_t ldd, const void *c_dev, int64_t ldc,
+               void *out_dev, int64_t ldo, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

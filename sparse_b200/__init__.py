@@ -1,0 +1,56 @@
+"""sparse_b200 -- a B200-native (sm_100a) implementation of pydata/sparse's data-parallel hot path.
+
+Drop-in names for that path: ``COO``, ``GCXS`` (``CSR``/``CSC``), ``tensordot``, ``matmul``, ``dot``,
+``elemwise``, reductions (``sum``/``max``/``min``/``prod``/``mean``/``any``/``all``) and the NumPy protocols
+(``__array_ufunc__``, ``__array_function__``, ``@``), plus the fused ``sddmm`` and ``mttkrp`` example paths.
+Host code is Python; every data-path step is a hand-written CUDA kernel in ``libsparse_b200.so`` reached through a
+thin C ABI (``include/sparse_b200.h``) via ctypes.  There is no CPU fallback: without the library or a CUDA device
+operations raise.
+"""
+from ._coo import COO, as_coo
+from ._dot import dot, matmul, stack, tensordot
+from ._elemwise import broadcast_to, elemwise
+from ._fused import mttkrp, sddmm
+from ._gcxs import CSC, CSR, GCXS
+from ._random import random
+from ._sparse_array import SparseArray
+
+__version__ = "0.1.0"
+
+
+def asarray(x, /, *, format="coo", **kwargs):
+    if isinstance(x, SparseArray):
+        return x.asformat(format, **kwargs)
+    return as_coo(x).asformat(format, **kwargs)
+
+
+def sum(x, /, *, axis=None, dtype=None, keepdims=False):
+    return x.sum(axis=axis, keepdims=keepdims, dtype=dtype)
+
+
+def max(x, /, *, axis=None, keepdims=False):
+    return x.max(axis=axis, keepdims=keepdims)
+
+
+def min(x, /, *, axis=None, keepdims=False):
+    return x.min(axis=axis, keepdims=keepdims)
+
+
+def prod(x, /, *, axis=None, dtype=None, keepdims=False):
+    return x.prod(axis=axis, keepdims=keepdims, dtype=dtype)
+
+
+def mean(x, /, *, axis=None, keepdims=False, dtype=None):
+    return x.mean(axis=axis, keepdims=keepdims, dtype=dtype)
+
+
+def any(x, /, *, axis=None, keepdims=False):
+    return x.any(axis=axis, keepdims=keepdims)
+
+
+def all(x, /, *, axis=None, keepdims=False):
+    return x.all(axis=axis, keepdims=keepdims)
+
+
+__all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
+           "elemwise", "broadcast_to", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all"]

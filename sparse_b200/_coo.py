@@ -1,0 +1,449 @@
+"""COO container with device-resident coordinates and data.
+
+Mirrors sparse/numba_backend/_coo/core.py: constructor normalisation (sort / sum duplicates / prune,
+:198-291, :1294-1371), transpose (:725-807), reshape (:1034-1111), linear_loc, todense, asformat.
+The arrays live in HBM as torch CUDA tensors (moved there once); `.coords` / `.data` materialise NumPy
+mirrors lazily.  Every data-path step runs in libsparse_b200 kernels -- there is no CPU fallback: a COO
+whose construction needs work (unsorted input, duplicates, pruning) requires a CUDA device.
+"""
+from __future__ import annotations
+
+from collections.abc import Iterable
+
+import numpy as np
+
+from . import _device as D
+from . import _kernels as Kn
+from ._sparse_array import SparseArray
+from ._utils import _zero_of_dtype, c_strides, can_store, check_linear_range, key_bits, prod
+
+
+def _is_scipy_sparse(x):
+    mod = type(x).__module__
+    return mod.startswith("scipy.sparse") and hasattr(x, "tocoo")
+
+
+class COO(SparseArray):
+    """N-D sparse array in coordinate format: ``coords[ndim, nnz]`` + ``data[nnz]``."""
+
+    def __init__(self, coords, data=None, shape=None, has_duplicates=True, sorted=False, prune=False, cache=False,
+                 fill_value=None, idx_dtype=None):
+        self._coords_np = None
+        self._data_np = None
+        self._coords = None  # device [ndim, nnz]
+        self._data = None    # device [nnz]
+        self._keys = None    # device sorted linear keys (cache)
+
+        if isinstance(coords, COO):
+            if data is not None or shape is not None:
+                raise ValueError("If `coords` is `COO`, then no other arguments should be provided.")
+            self._copy_from(coords)
+            if fill_value is not None:
+                self.fill_value = self.dtype.type(fill_value)
+            return
+
+        if data is None:
+            arr = as_coo(coords, shape=shape, fill_value=fill_value, idx_dtype=idx_dtype)
+            self._copy_from(arr)
+            return
+
+        dev_in = D.is_device_tensor(coords) or D.is_device_tensor(data)
+        if dev_in:
+            t = D.torch()
+            if not D.is_device_tensor(coords):
+                coords = D.upload(np.asarray(coords))
+            if not D.is_device_tensor(data):
+                data = D.upload(np.asarray(data))
+            if coords.dim() == 1:
+                coords = coords[None, :]
+            if data.dim() == 0:
+                data = data.expand(coords.shape[1]).contiguous()
+            self._coords, self._data = coords, data
+            nnz, ndim_c = int(coords.shape[1]), int(coords.shape[0])
+            self._dtype = D.np_dtype(data)
+            if data.dim() != 1:
+                raise ValueError("`data` must be a scalar or 1-dimensional.")
+        else:
+            data = np.asarray(data)
+            coords = np.asarray(coords)
+            if coords.ndim == 1:
+                if coords.size == 0 and shape is not None:
+                    coords = coords.reshape((len(shape) if isinstance(shape, Iterable) else 1, len(data)))
+                else:
+                    coords = coords[None, :]
+            if data.ndim == 0:
+                data = np.broadcast_to(data, coords.shape[1])
+            if data.ndim != 1:
+                raise ValueError("`data` must be a scalar or 1-dimensional.")
+            self._coords_np, self._data_np = coords, data
+            nnz, ndim_c = int(coords.shape[1]), int(coords.shape[0])
+            self._dtype = data.dtype
+
+        if shape is None:
+            raise ValueError("`shape` was not provided.")
+        if not isinstance(shape, Iterable):
+            shape = (shape,)
+        shape = tuple(int(s) for s in shape)
+        if shape and nnz == 0 and not dev_in:
+            self._coords_np = np.zeros((len(shape), 0), dtype=np.intp)
+            ndim_c = len(shape)
+        super().__init__(shape, fill_value=None)
+        if fill_value is None:
+            fill_value = _zero_of_dtype(self._dtype)
+        self.fill_value = self._dtype.type(fill_value)
+
+        if idx_dtype:
+            if not can_store(idx_dtype, max(shape) if shape else 0):
+                raise ValueError(f"cannot cast array with shape {shape} to dtype {idx_dtype}.")
+            if self._coords_np is not None:
+                self._coords_np = self._coords_np.astype(idx_dtype)
+            else:
+                self._coords = Kn.cast(self._coords, idx_dtype)
+        if self.shape:
+            dlen = int(self._data.shape[0]) if self._data is not None else len(self._data_np)
+            if dlen != nnz:
+                raise ValueError("The data length does not match the coordinates given.\n"
+                                 f"len(data) = {dlen}, but {nnz} coords specified.")
+            if len(self.shape) != ndim_c:
+                raise ValueError("Shape specified by `shape` doesn't match the shape of `coords`; "
+                                 f"len(shape)={len(shape)} != coords.shape[0]={ndim_c}")
+        check_linear_range(self.shape)
+        if (not sorted) or has_duplicates or prune:
+            self._canonicalise(check_sort=not sorted, sum_dups=has_duplicates, prune=prune)
+
+    # ---- construction helpers ------------------------------------------------------------------------
+    def _copy_from(self, other):
+        SparseArray.__init__(self, other.shape, fill_value=None)
+        self._coords_np, self._data_np = other._coords_np, other._data_np
+        self._coords, self._data, self._keys = other._coords, other._data, other._keys
+        self._dtype = other._dtype
+        self.fill_value = other.fill_value
+
+    @classmethod
+    def _from_device(cls, coords, data, shape, fill_value=None, keys=None):
+        """Wrap canonical device arrays without any checks."""
+        self = cls.__new__(cls)
+        SparseArray.__init__(self, tuple(int(s) for s in shape), fill_value=None)
+        self._coords_np = self._data_np = None
+        self._coords, self._data, self._keys = coords, data, keys
+        self._dtype = D.np_dtype(data)
+        self.fill_value = self._dtype.type(0 if fill_value is None else fill_value)
+        return self
+
+    @classmethod
+    def from_numpy(cls, x, fill_value=None, idx_dtype=None):
+        """Dense ndarray -> COO (_coo/core.py:from_numpy): entries bitwise different from the fill value."""
+        x = np.asanyarray(x).view(type=np.ndarray)
+        if fill_value is None:
+            # 0-D: the element itself becomes the fill value (nnz = 0), _coo/core.py:371-372
+            fill_value = _zero_of_dtype(x.dtype) if x.shape else x[()]
+        fill_value = x.dtype.type(fill_value)
+        if x.ndim == 0:
+            from ._utils import equivalent
+
+            keep = 0 if bool(equivalent(x, fill_value)) else 1
+            return cls(np.empty((0, keep), dtype=np.intp), x.reshape(-1)[:keep], shape=(), has_duplicates=False,
+                       sorted=True, fill_value=fill_value)
+        D.require_device()
+        xd = D.upload(np.ascontiguousarray(x))
+        return cls._from_dense_device(xd, x.shape, fill_value, idx_dtype)
+
+    @classmethod
+    def _from_dense_device(cls, xd, shape, fill_value, idx_dtype=None):
+        n = prod(shape)
+        flat = xd.reshape(1, n)
+        if np.dtype(D.np_dtype(xd)).type(fill_value).tobytes() == b"\0" * xd.element_size():
+            _, keys, data, _ = Kn.dense_to_csr(flat, mode=1, want_indptr=False)
+        else:
+            flags = Kn.flag_not_fill(flat.reshape(-1), fill_value)
+            _, keys, data, _ = Kn.dense_to_csr(flat, flags=flags.reshape(1, n), want_indptr=False)
+        coords = Kn.unravel(keys, shape, idx_dtype or np.int64)
+        return cls._from_device(coords, data, shape, fill_value, keys=keys)
+
+    @classmethod
+    def from_scipy_sparse(cls, x):
+        x = x.tocoo()
+        coords = np.stack([x.row, x.col])
+        return cls(coords, x.data, shape=x.shape, has_duplicates=not getattr(x, "has_canonical_format", False),
+                   sorted=False)
+
+    # ---- device / host mirrors -----------------------------------------------------------------------
+    def _dev(self):
+        """Ensure the device copies exist (one H2D, then resident)."""
+        if self._data is None:
+            D.require_device()
+            self._coords = D.upload(self._coords_np)
+            self._data = D.upload(self._data_np)
+        return self._coords, self._data
+
+    @property
+    def coords(self):
+        if self._coords_np is None:
+            self._coords_np = D.download(self._coords)
+        return self._coords_np
+
+    @property
+    def data(self):
+        if self._data_np is None:
+            self._data_np = D.download(self._data)
+        return self._data_np
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def nnz(self):
+        if self._data is not None:
+            return int(self._data.shape[0])
+        return int(self._coords_np.shape[1])
+
+    @property
+    def nbytes(self):
+        c_item = self._coords.element_size() if self._coords is not None else self._coords_np.itemsize
+        return self.nnz * (self._dtype.itemsize + self.ndim * c_item)
+
+    @property
+    def format(self):
+        return "coo"
+
+    # ---- canonicalisation (COO.__init__ tail, _coo/core.py:283-291) -----------------------------------
+    def sorted_keys(self):
+        """Device linear keys (C order over self.shape) of the canonical entries; cached."""
+        if self._keys is None:
+            coords, _ = self._dev()
+            self._keys = Kn.linearize(coords, c_strides(self.shape))
+        return self._keys
+
+    def _canonicalise(self, check_sort=True, sum_dups=True, prune=False):
+        coords, data = self._dev()
+        nnz = int(data.shape[0])
+        if nnz == 0:
+            self._keys = None
+            return
+        keys = Kn.linearize(coords, c_strides(self.shape))
+        changed = False
+        unsorted, dups = Kn.keys_flags(keys)
+        if check_sort and unsorted:
+            keys, perm = Kn.sort_keys(keys, key_bits(self.size))
+            data = Kn.gather(data, perm)
+            changed = True
+            _, dups = Kn.keys_flags(keys)
+        if sum_dups and dups:
+            heads = Kn.flag_heads(keys)
+            pos, total = Kn.scan_flags(heads)
+            data = Kn.segment_sum(data, heads, pos, total)
+            keys = Kn.compact(keys, heads, pos, total)
+            changed = True
+        if prune:
+            flags = Kn.flag_not_fill(data, self.fill_value)
+            pos, total = Kn.scan_flags(flags)
+            if total != int(data.shape[0]):
+                data = Kn.compact(data, flags, pos, total)
+                keys = Kn.compact(keys, flags, pos, total)
+                changed = True
+        if changed:
+            idt = D.np_dtype(coords)
+            self._coords = Kn.unravel(keys, self.shape, idt)
+            self._data = data
+            self._coords_np = self._data_np = None
+        if not (unsorted and not check_sort):
+            self._keys = keys  # keys are sorted (or the caller vouched for the order)
+
+    # ---- conversions ----------------------------------------------------------------------------------
+    def todense(self):
+        """Dense NumPy array (device scatter into a fill-initialised buffer, then one D2H)."""
+        return D.download(self.todense_device())
+
+    def todense_device(self):
+        coords, data = self._dev()
+        out = Kn.full(max(self.size, 1) if self.ndim == 0 else self.size, self.fill_value, self._dtype)
+        if self.ndim == 0:
+            if self.nnz:
+                out[:1] = data[:1]
+            return out[:1].reshape(())
+        if self.nnz:
+            Kn.scatter(data, self.sorted_keys(), out)
+        return out.reshape(self.shape)
+
+    def tocoo(self):
+        return self
+
+    def copy(self, deep=True):
+        return COO(self)
+
+    def asformat(self, format, **kwargs):
+        from ._gcxs import GCXS
+
+        if format in ("coo", COO) or (isinstance(format, type) and issubclass(format, COO)):
+            return self
+        if format in ("gcxs", GCXS) or (isinstance(format, type) and issubclass(format, GCXS)):
+            return GCXS.from_coo(self, **kwargs)
+        if format in (np.ndarray, "dense"):
+            return self.todense()
+        raise NotImplementedError(f"The given format is not supported: {format}")
+
+    def tocsr(self):
+        return self.asformat("gcxs", compressed_axes=(0,))
+
+    def astype(self, dtype, casting="unsafe", copy=True):
+        dtype = np.dtype(dtype)
+        if self.dtype == dtype and not copy:
+            return self
+        coords, data = self._dev()
+        out = COO._from_device(coords, Kn.cast(data, dtype) if self.dtype != dtype else data.clone(), self.shape,
+                               dtype.type(self.fill_value), keys=self._keys)
+        return out
+
+    def linear_loc(self):
+        return D.download(self.sorted_keys())
+
+    # ---- transpose / reshape (reference: :725-807, :1034-1111) -----------------------------------------
+    def transpose(self, axes=None):
+        if axes is None:
+            axes = tuple(reversed(range(self.ndim)))
+        axes = tuple(int(a) + self.ndim if int(a) < 0 else int(a) for a in axes)
+        if len(np.unique(axes)) < len(axes):
+            raise ValueError("repeated axis in transpose")
+        if not len(axes) == self.ndim:
+            raise ValueError("axes don't match array")
+        if axes == tuple(range(self.ndim)):
+            return self
+        return self._permute_reshape(axes, tuple(self.shape[a] for a in axes))
+
+    @property
+    def T(self):
+        return self.transpose(tuple(range(self.ndim))[::-1])
+
+    @property
+    def mT(self):
+        if self.ndim < 2:
+            raise ValueError("Cannot compute matrix transpose if `ndim < 2`.")
+        axes = list(range(self.ndim))
+        axes[-1], axes[-2] = axes[-2], axes[-1]
+        return self.transpose(axes)
+
+    def reshape(self, shape, order="C"):
+        shape = tuple(shape) if isinstance(shape, Iterable) else (shape,)
+        if order not in {"C", None}:
+            raise NotImplementedError("The `order` parameter is not supported")
+        shape = tuple(int(s) for s in shape)
+        if any(d == -1 for d in shape):
+            extra = int(self.size / np.prod([d for d in shape if d != -1]))
+            shape = tuple(d if d != -1 else extra for d in shape)
+        if self.size != prod(shape):
+            raise ValueError(f"cannot reshape array of size {self.size} into shape {shape}")
+        if self.shape == shape:
+            return self
+        check_linear_range(shape)
+        # linear index is invariant under a C-order reshape: only the coordinates are re-derived
+        if self.nnz == 0 and self._data is None:
+            return COO(np.zeros((len(shape), 0), dtype=np.intp), self._data_np[:0], shape=shape, has_duplicates=False,
+                       sorted=True, fill_value=self.fill_value)
+        coords, data = self._dev()
+        keys = self.sorted_keys()
+        new_coords = Kn.unravel(keys, shape, D.np_dtype(coords) if self.ndim else np.int64)
+        return COO._from_device(new_coords, data, shape, self.fill_value, keys=keys)
+
+    def _permute_reshape(self, axes, new_shape):
+        """transpose(axes) followed by reshape(new_shape) in one pass: linearise with permuted strides,
+        stable sort, unravel (COO rebuild + mergesort of the reference, _coo/core.py:796-803)."""
+        coords, data = self._dev()
+        perm_shape = tuple(self.shape[a] for a in axes)
+        st_perm = c_strides(perm_shape)
+        strides = [0] * self.ndim
+        for pos, a in enumerate(axes):
+            strides[a] = st_perm[pos]
+        idt = D.np_dtype(coords) if self.ndim else np.int64
+        if self.nnz == 0:
+            t = D.torch()
+            return COO._from_device(t.zeros((len(new_shape), 0), dtype=coords.dtype, device=coords.device), data,
+                                    new_shape, self.fill_value)
+        keys = Kn.linearize(coords, strides)
+        unsorted, _ = Kn.keys_flags(keys)
+        if unsorted:
+            keys, perm = Kn.sort_keys(keys, key_bits(self.size))
+            data = Kn.gather(data, perm)
+        new_coords = Kn.unravel(keys, new_shape, idt)
+        return COO._from_device(new_coords, data, new_shape, self.fill_value, keys=keys)
+
+    def broadcast_to(self, shape):
+        from ._elemwise import broadcast_to
+
+        return broadcast_to(self, shape)
+
+    # ---- indexing: only what the hot path's callers need ------------------------------------------------
+    def __getitem__(self, index):
+        """Supports `None` insertion, full slices and Ellipsis (`x[:, :, None]`, used by the MTTKRP expression
+        and by `outer`), plus an integer on the leading axis (batched matmul, _common.py:278-282)."""
+        if not isinstance(index, tuple):
+            index = (index,)
+        if any(i is Ellipsis for i in index):
+            n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
+            e = index.index(Ellipsis)
+            index = index[:e] + (slice(None),) * (self.ndim - n_real) + index[e + 1:]
+        if all(i is None or (isinstance(i, slice) and i == slice(None)) for i in index):
+            n_real = sum(1 for i in index if i is not None)
+            index = index + (slice(None),) * (self.ndim - n_real)
+            new_shape, d = [], 0
+            for i in index:
+                if i is None:
+                    new_shape.append(1)
+                else:
+                    new_shape.append(self.shape[d])
+                    d += 1
+            return self.reshape(tuple(new_shape))
+        if isinstance(index[0], (int, np.integer)) and all(
+                isinstance(i, slice) and i == slice(None) for i in index[1:]):
+            return self._take_leading(int(index[0]))
+        raise NotImplementedError("sparse_b200.COO supports only None/full-slice indexing and x[i] on the leading axis")
+
+    def _take_leading(self, i):
+        if i < 0:
+            i += self.shape[0]
+        if not 0 <= i < self.shape[0]:
+            raise IndexError("index out of range")
+        coords, data = self._dev()
+        self.sorted_keys()  # validates / caches the canonical order
+        lead = coords[0] if coords[0].is_contiguous() else coords[0].contiguous()
+        ip = D.download(Kn.indptr_from_sorted(lead, self.shape[0]))
+        lo, hi = int(ip[i]), int(ip[i + 1])
+        sub_coords = coords[1:, lo:hi].contiguous()
+        return COO._from_device(sub_coords, data[lo:hi].contiguous(), self.shape[1:], self.fill_value)
+
+    # ---- products ---------------------------------------------------------------------------------------
+    def dot(self, other):
+        from ._dot import dot
+
+        return dot(self, other)
+
+    def __matmul__(self, other):
+        from ._dot import matmul
+
+        try:
+            return matmul(self, other)
+        except NotImplementedError:
+            return NotImplemented
+
+    def __rmatmul__(self, other):
+        from ._dot import matmul
+
+        try:
+            return matmul(other, self)
+        except NotImplementedError:
+            return NotImplemented
+
+
+def as_coo(x, shape=None, fill_value=None, idx_dtype=None):
+    """_coo/common.py:as_coo."""
+    from ._gcxs import GCXS
+
+    if isinstance(x, COO):
+        return x
+    if isinstance(x, GCXS):
+        return x.tocoo()
+    if _is_scipy_sparse(x):
+        return COO.from_scipy_sparse(x)
+    if isinstance(x, np.ndarray) or np.isscalar(x):
+        return COO.from_numpy(np.asarray(x), fill_value=fill_value, idx_dtype=idx_dtype)
+    raise NotImplementedError(f"Format not supported for conversion: {type(x)}")

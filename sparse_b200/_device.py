@@ -11,6 +11,10 @@ import numpy as np
 from . import _lib
 
 _torch = None
+# Test hook ONLY (tests/_mock_kernels.py): lets the host-side logic be exercised on a box without a GPU by
+# pairing CPU torch tensors with a NumPy mock of `_kernels`.  Never set by the product; with it False (always,
+# outside the test-suite) every operation requires a CUDA device.
+_TEST_CPU = False
 
 
 def torch():
@@ -75,6 +79,8 @@ def np_dtype(t) -> np.dtype:
 
 
 def have_device() -> bool:
+    if _TEST_CPU:
+        return True
     try:
         return bool(torch().cuda.is_available())
     except Exception:  # pragma: no cover
@@ -87,21 +93,26 @@ def require_device():
             "sparse_b200: no CUDA device available. The hot path runs only on a B200 (sm_100a); "
             "there is no CPU fallback."
         )
-    _lib.load()
+    if not _TEST_CPU:
+        _lib.load()
 
 
 def device():
     t = torch()
+    if _TEST_CPU:
+        return t.device("cpu")
     return t.device("cuda", t.cuda.current_device())
 
 
 def stream_ptr() -> int:
+    if _TEST_CPU:
+        return 0
     return int(torch().cuda.current_stream().cuda_stream)
 
 
 def is_device_tensor(x) -> bool:
     t = _torch
-    return t is not None and isinstance(x, t.Tensor) and x.is_cuda
+    return t is not None and isinstance(x, t.Tensor) and (x.is_cuda or _TEST_CPU)
 
 
 def upload(arr, dtype=None):

@@ -1,0 +1,358 @@
+"""Broadcasting element-wise operations (`elemwise`, `__array_ufunc__` target).
+
+Host-side mirror of sparse/numba_backend/_umath.py: operand normalisation and output type selection
+(`_Elemwise.__init__`, :393-455), broadcast shape rules (:95-176), fill-value computation (:505-555).  The
+reference's mask enumeration + sort-merge joins (:457-503, :576-751) are replaced by one merge-path
+coiteration on the device (csrc/elemwise.cu); results are identical canonical COO arrays.
+
+Only an enumerated set of NumPy ufuncs runs on the CUDA path (see _BINARY / _UNARY); anything else raises
+TypeError -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from itertools import zip_longest
+
+import numpy as np
+
+from . import _device as D
+from . import _kernels as Kn
+from ._coo import COO, _is_scipy_sparse
+from ._sparse_array import SparseArray
+from ._utils import c_strides, isscalar, key_bits, prod
+
+# ufunc -> device op code (csrc/elemwise.cu)
+_BINARY = {
+    np.add: 0, np.subtract: 1, np.multiply: 2, np.true_divide: 3, np.maximum: 4, np.minimum: 5, np.fmax: 6,
+    np.fmin: 7, np.power: 8, np.floor_divide: 9, np.remainder: 10, np.bitwise_and: 11, np.bitwise_or: 12,
+    np.bitwise_xor: 13, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
+    np.not_equal: 37, np.logical_and: 38, np.logical_or: 39, np.logical_xor: 40,
+}
+_UNARY = {
+    np.negative: 0, np.absolute: 1, np.fabs: 1, np.sqrt: 2, np.square: 3, np.sign: 4, np.exp: 5, np.expm1: 6,
+    np.log: 7, np.log1p: 8, np.sin: 9, np.cos: 10, np.tan: 11, np.tanh: 12, np.sinh: 13, np.cosh: 14, np.arcsin: 15,
+    np.arctan: 16, np.floor: 17, np.ceil: 18, np.trunc: 19, np.rint: 20, np.reciprocal: 21, np.positive: 22,
+    np.invert: 23, np.arcsinh: 24, np.arctanh: 25, np.deg2rad: 26, np.rad2deg: 27, np.exp2: 28, np.log2: 29,
+    np.log10: 30, np.cbrt: 31, np.isnan: 64, np.isinf: 65, np.isfinite: 66, np.logical_not: 67, np.signbit: 68,
+}
+_BOOL_BITWISE = {np.bitwise_and: np.logical_and, np.bitwise_or: np.logical_or, np.bitwise_xor: np.logical_xor}
+_COMPUTE_DTYPES = (np.dtype("float32"), np.dtype("float64"), np.dtype("int32"), np.dtype("int64"))
+
+
+def _get_broadcast_shape(shape1, shape2, is_result=False):
+    """_umath.py:123-154."""
+    if not all((l1 == l2) or (l1 == 1) or ((l2 == 1) and not is_result)
+               for l1, l2 in zip(shape1[::-1], shape2[::-1], strict=False)):
+        raise ValueError(f"operands could not be broadcast together with shapes {shape1}, {shape2}")
+    return tuple(l1 if l1 != 1 else l2 for l1, l2 in zip_longest(shape1[::-1], shape2[::-1], fillvalue=1))[::-1]
+
+
+def _get_nary_broadcast_shape(*shapes):
+    """_umath.py:95-121."""
+    result_shape = ()
+    for shape in shapes:
+        try:
+            result_shape = _get_broadcast_shape(shape, result_shape)
+        except ValueError as e:
+            shapes_str = ", ".join(str(shape) for shape in shapes)
+            raise ValueError(f"operands could not be broadcast together with shapes {shapes_str}") from e
+    return result_shape
+
+
+def _op_code(func, table, what):
+    try:
+        return table[func]
+    except (KeyError, TypeError):
+        name = getattr(func, "__name__", repr(func))
+        raise TypeError(
+            f"sparse_b200: {what} function {name!r} is not in the CUDA op set "
+            f"({', '.join(sorted(f.__name__ for f in table))}); there is no CPU fallback."
+        ) from None
+
+
+def _check_compute_dtype(dt, func):
+    if np.dtype(dt) not in _COMPUTE_DTYPES:
+        raise TypeError(f"sparse_b200: {getattr(func, '__name__', func)} on dtype {dt} is outside the CUDA dtype matrix "
+                        "(float32, float64, int32, int64; bool for logical ops)")
+
+
+def _resolve(func, a_like, b_like=None):
+    """(out_dtype, compute_dtype) using NumPy's own type resolution on zero-size stand-ins."""
+    with np.errstate(all="ignore"):
+        res = func(a_like) if b_like is None else func(a_like, b_like)
+    out_dt = res.dtype
+    code_table = _UNARY if b_like is None else _BINARY
+    pred = code_table[func] >= (64 if b_like is None else 32)
+    if pred:
+        ins = [a_like] if b_like is None else [a_like, b_like]
+        T = np.result_type(*ins)
+        if T == np.bool_:
+            T = np.dtype("int32")
+    else:
+        T = out_dt
+    return out_dt, np.dtype(T)
+
+
+def _stand_in(x):
+    if isinstance(x, SparseArray):
+        return np.empty(0, dtype=x.dtype)
+    if isinstance(x, np.ndarray) and x.ndim > 0:
+        return np.empty(0, dtype=x.dtype)
+    if D.is_device_tensor(x):
+        return np.empty(0, dtype=D.np_dtype(x))
+    return x  # python / numpy scalar: keeps NEP-50 weak typing
+
+
+def _finish(keys, vals, flags, shape, fill, idx_dtype=np.int64):
+    """Stage B shared by every elemwise form: compact the kept candidates and derive coordinates."""
+    pos, total = Kn.scan_flags(flags)
+    if total != int(flags.shape[0]):
+        keys = Kn.compact(keys, flags, pos, total)
+        vals = Kn.compact(vals, flags, pos, total)
+    coords = Kn.unravel(keys, shape, idx_dtype)
+    return COO._from_device(coords, vals, shape, fill, keys=keys)
+
+
+def _stream(x, shape):
+    """Sorted key stream of COO `x` broadcast to `shape`: (keys, data, R).
+
+    Trailing broadcast axes are expanded virtually (R > 1); any other broadcast pattern is materialised with the
+    expansion kernel (+ a stable sort when the expansion is not already in key order)."""
+    coords, data = x._dev()
+    nd, xn = len(shape), x.ndim
+    off = nd - xn
+    # result axis d is a broadcast axis of x iff the result is wider there than x (x lacks it or has extent 1)
+    bcast = [shape[d] > 1 and (d < off or x.shape[d - off] != shape[d]) for d in range(nd)]
+    if not any(bcast):
+        if tuple(x.shape) == tuple(shape):
+            return x.sorted_keys(), data, 1
+        st = c_strides(shape)
+        return Kn.linearize(coords, [st[d + off] for d in range(xn)]), data, 1
+    first_b = bcast.index(True)
+    trailing = all(bcast[d] or shape[d] == 1 for d in range(first_b, nd))
+    if trailing:
+        R = prod(shape[first_b:])
+        st = c_strides(shape)
+        strides = [(st[d + off] // R if (d + off) < first_b else 0) for d in range(xn)]
+        return Kn.linearize(coords, strides), data, R
+    src_row = [(d - off if (d >= off and not bcast[d]) else -1) for d in range(nd)]
+    # axes that x lacks but have extent 1 contribute coordinate 0: treat as broadcast of extent 1
+    is_b = [1 if (bcast[d] or src_row[d] < 0) else 0 for d in range(nd)]
+    keys, src = Kn.ew_expand(coords, shape, is_b, src_row)
+    unsorted, _ = Kn.keys_flags(keys)
+    if unsorted:
+        keys, perm = Kn.sort_keys(keys, key_bits(prod(shape)))
+        src = Kn.gather(src, perm)
+    return keys, Kn.gather(data, src), 1
+
+
+def _dense_strides_over(shape, dshape):
+    """Element strides of a C-contiguous dense operand of `dshape` broadcast to `shape` (0 on broadcast axes)."""
+    nd, dn = len(shape), len(dshape)
+    st = c_strides(dshape)
+    out = [0] * nd
+    for d in range(dn):
+        rd = d + (nd - dn)
+        out[rd] = 0 if dshape[d] == 1 and shape[rd] != 1 else st[d]
+    return out
+
+
+class _Elemwise:
+    def __init__(self, func, *args, **kwargs):
+        from ._gcxs import GCXS
+
+        processed = []
+        sparse_args = [arg for arg in args if isinstance(arg, SparseArray)]
+        if len(sparse_args) == 0:
+            raise ValueError(f"None of the args is sparse: {args}")
+        out_kwargs = {}
+        if all(isinstance(arg, GCXS) for arg in sparse_args):
+            out_type = GCXS
+            if len({arg.compressed_axes for arg in sparse_args}) == 1:
+                out_kwargs["compressed_axes"] = sparse_args[0].compressed_axes
+        else:
+            out_type = COO
+        self.args = None
+        for arg in args:
+            if _is_scipy_sparse(arg):
+                processed.append(COO.from_scipy_sparse(arg))
+            elif isscalar(arg) or isinstance(arg, np.ndarray) or D.is_device_tensor(arg):
+                processed.append(arg)
+            elif isinstance(arg, SparseArray):
+                if not isinstance(arg, COO):
+                    arg = arg.asformat(COO)
+                if arg.ndim == 0:
+                    arg = arg.todense()
+                processed.append(arg)
+            else:
+                return
+        self.out_type, self.out_kwargs = out_type, out_kwargs
+        self.args = tuple(processed)
+        self.func = func
+        self.dtype = kwargs.pop("dtype", None)
+        kwargs.pop("casting", None)
+        kwargs.pop("where", None) if kwargs.get("where", True) is True else None
+        if kwargs:
+            raise TypeError(f"sparse_b200.elemwise: unsupported keyword arguments {sorted(kwargs)}")
+        self.shape = _get_nary_broadcast_shape(*tuple(tuple(a.shape) if hasattr(a, "shape") else np.shape(a)
+                                                      for a in self.args))
+
+    def get_result(self):
+        if self.args is None:
+            return NotImplemented
+        n = len(self.args)
+        if not any(isinstance(a, COO) for a in self.args):
+            # every sparse operand was 0-D and became a scalar (_umath.py:438-439): the result is the 0-D array
+            # whose fill value is func(scalars) -- host scalar arithmetic, no data path involved
+            host = [D.download(a) if D.is_device_tensor(a) else np.asarray(a) for a in self.args]
+            with np.errstate(all="ignore"):
+                res = np.asarray(self.func(*host))
+            if self.dtype is not None:
+                res = res.astype(self.dtype)
+            return COO.from_numpy(res) if res.ndim == 0 else res
+        if n == 1:
+            out = self._unary()
+        elif n == 2:
+            out = self._binary()
+        else:
+            raise NotImplementedError("sparse_b200.elemwise: only unary and binary functions run on the CUDA path")
+        if isinstance(out, COO):
+            if self.dtype is not None and np.dtype(self.dtype) != out.dtype:
+                out = out.astype(self.dtype)
+            return out.asformat(self.out_type, **self.out_kwargs)
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    def _unary(self):
+        (a,) = self.args
+        func = self.func
+        op = _op_code(func, _UNARY, "unary")
+        out_dt, T = _resolve(func, _stand_in(a))
+        _check_compute_dtype(T, func)
+        with np.errstate(all="ignore"):
+            fill = np.asarray(func(a.fill_value)).astype(out_dt)[()]
+        coords, data = a._dev()
+        if any(s == 0 for s in self.shape):
+            return COO(np.empty((len(self.shape), 0), dtype=np.intp), np.empty(0, dtype=out_dt), shape=self.shape,
+                       has_duplicates=False, sorted=True, fill_value=fill)
+        vals, flags = Kn.ew_map(op, 2, Kn.cast(data, T), None, fill, out_dt)
+        return self._keep(a, vals, flags, fill)
+
+    def _keep(self, a, vals, flags, fill):
+        coords, _ = a._dev()
+        pos, total = Kn.scan_flags(flags)
+        keys = a._keys
+        if total != a.nnz:
+            coords = Kn.compact_rows(coords, flags, pos, total)
+            vals = Kn.compact(vals, flags, pos, total)
+            keys = Kn.compact(keys, flags, pos, total) if keys is not None else None
+        return COO._from_device(coords, vals, a.shape, fill, keys=keys)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _binary(self):
+        a, b = self.args
+        func = self.func
+        a_sp, b_sp = isinstance(a, COO), isinstance(b, COO)
+        a_dn = (isinstance(a, np.ndarray) and a.ndim > 0) or D.is_device_tensor(a)
+        b_dn = (isinstance(b, np.ndarray) and b.ndim > 0) or D.is_device_tensor(b)
+        # bool bitwise ops are the logical ops
+        la, lb = _stand_in(a), _stand_in(b)
+        if func in _BOOL_BITWISE and all(getattr(x, "dtype", np.dtype(type(x))) == np.bool_ for x in (la, lb)):
+            func = _BOOL_BITWISE[func]
+        op = _op_code(func, _BINARY, "binary")
+        out_dt, T = _resolve(func, la, lb)
+        _check_compute_dtype(T, func)
+        if op < 32 and out_dt == np.bool_:
+            raise TypeError(f"sparse_b200: {func.__name__} with boolean output is outside the CUDA dtype matrix")
+        shape = self.shape
+        empty = any(s == 0 for s in shape)
+
+        def fv(x):
+            return x.fill_value if isinstance(x, COO) else x
+
+        if a_sp and b_sp:
+            with np.errstate(all="ignore"):
+                fill = np.asarray(func(a.fill_value, b.fill_value)).astype(out_dt)[()]
+            if empty:
+                return self._empty(out_dt, fill)
+            ka, da, Ra = _stream(a, shape)
+            kb, db, Rb = _stream(b, shape)
+            keys, vals, flags = Kn.ew_merge(op, ka, Kn.cast(da, T), Ra, kb, Kn.cast(db, T), Rb,
+                                            T.type(a.fill_value), T.type(b.fill_value), fill, out_dt)
+            return _finish(keys, vals, flags, shape, fill)
+
+        if (a_sp and not b_dn) or (b_sp and not a_dn):  # sparse (x) scalar
+            sp, sc, mode = (a, b, 0) if a_sp else (b, a, 1)
+            sc = np.asarray(sc)[()]
+            with np.errstate(all="ignore"):
+                fill = np.asarray(func(a.fill_value, sc) if a_sp else func(sc, b.fill_value)).astype(out_dt)[()]
+            if empty:
+                return self._empty(out_dt, fill)
+            _, data = sp._dev()
+            vals, flags = Kn.ew_map(op, mode, Kn.cast(data, T), T.type(sc), fill, out_dt)
+            return self._keep(sp, vals, flags, fill)
+
+        # sparse (x) dense ndarray: mask (True, None) of the reference
+        sp, dn, swap = (a, b, False) if a_sp else (b, a, True)
+        dense = D.upload(np.ascontiguousarray(dn)) if isinstance(dn, np.ndarray) else dn.contiguous()
+        dense = Kn.cast(dense, T)
+        dshape = tuple(dense.shape)
+        flat = dense.reshape(-1)
+        # _get_fill_value (:505-555): func(fill, ndarray) must be constant, else the result is dense
+        g, _ = Kn.ew_map(op, 1 if not swap else 0, flat, T.type(sp.fill_value), 0, out_dt)
+        if flat.shape[0] == 0:
+            return self._empty(out_dt, out_dt.type(0))
+        fill = D.download(g[:1])[0]
+        if fill != fill:
+            _, nflags = Kn.ew_map(_UNARY[np.isnan], 2, Kn.cast(g, T) if out_dt != T else g, None, True, np.bool_)
+        else:
+            _, nflags = Kn.ew_map(_BINARY[np.not_equal], 0, Kn.cast(g, T) if out_dt != T else g, T.type(fill), False,
+                                  np.bool_)
+        _, n_diff = Kn.scan_flags(nflags)
+        if n_diff != 0:
+            if tuple(shape) != dshape:
+                raise ValueError("Performing a mixed sparse-dense operation that would result in a dense array. "
+                                 "Please make sure that func(sparse_fill_values, ndarrays) is a constant array.")
+            return self._dense_result(sp, dense, swap, op, T, out_dt)
+        if empty:
+            return self._empty(out_dt, fill)
+        ks, ds, Rs = _stream(sp, shape)
+        keys, vals, flags = Kn.ew_dense(op, swap, ks, Kn.cast(ds, T), Rs, dense, shape,
+                                        _dense_strides_over(shape, dshape), fill, out_dt)
+        return _finish(keys, vals, flags, shape, fill)
+
+    def _dense_result(self, sp, dense, swap, op, T, out_dt):
+        """func(sparse.todense(), ndarray) when the fill value is not constant (_umath.py:463-465)."""
+        full = Kn.cast(sp.todense_device().reshape(-1), T)
+        keys = Kn.iota(int(full.shape[0]))
+        _, vals, _ = Kn.ew_dense(op, swap, keys, full, 1, dense, self.shape,
+                                 _dense_strides_over(self.shape, tuple(dense.shape)), 0, out_dt)
+        return D.download(vals.reshape(self.shape))
+
+    def _empty(self, out_dt, fill):
+        return COO(np.empty((len(self.shape), 0), dtype=np.intp), np.empty(0, dtype=out_dt), shape=self.shape,
+                   has_duplicates=False, sorted=True, fill_value=fill)
+
+
+def elemwise(func, *args, **kwargs):
+    """Apply a function to any number of arguments (reference: _umath.py:13-50)."""
+    return _Elemwise(func, *args, **kwargs).get_result()
+
+
+def broadcast_to(x, shape):
+    """numpy.broadcast_to for COO (reference: _umath.py:344-389); returns a new canonical COO."""
+    shape = tuple(int(s) for s in shape)
+    if shape == x.shape:
+        return x
+    result_shape = _get_broadcast_shape(x.shape, shape, is_result=True)
+    keys, data, R = _stream(x, result_shape)
+    if R > 1:
+        # materialise the virtual trailing expansion: key = k*R + r
+        coords, _ = x._dev()
+        nd, off = len(result_shape), len(result_shape) - x.ndim
+        bc = [not (d >= off and x.shape[d - off] == result_shape[d]) and result_shape[d] > 1 for d in range(nd)]
+        src_row = [(d - off if (d >= off and not bc[d]) else -1) for d in range(nd)]
+        is_b = [1 if (bc[d] or src_row[d] < 0) else 0 for d in range(nd)]
+        keys, src = Kn.ew_expand(coords, result_shape, is_b, src_row)
+        data = Kn.gather(data, src)
+    coords = Kn.unravel(keys, result_shape, np.int64)
+    return COO._from_device(coords, data, result_shape, x.fill_value, keys=keys)

@@ -1,0 +1,77 @@
+"""Fused SDDMM and MTTKRP: the reference's two example paths as single device kernels.
+
+* sddmm(s, a, b)   == s * (a @ b)                       (examples/sddmm_example.py:51-52)
+* mttkrp(B, D, C)  == sparse.sum(B[:, :, :, None] * D[None, None, :, :] * C[None, :, None, :], axis=(1, 2))
+                                                        (examples/mttkrp_example.py:51-52)
+The unfused expressions also run (through elemwise + reduce); these entry points avoid the dense (a @ b)
+intermediate and the nnz x J broadcast products.  Floating-point association differs from the reference's
+BLAS / reduceat order, so parity is tolerance-based (rtol 1e-5 f32, 1e-12 f64 in the tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _device as D
+from . import _kernels as Kn
+from ._coo import COO
+from ._dot import _coo_as_csr, _dense_dev, _narrow_idx
+from ._sparse_array import SparseArray
+from ._utils import check_zero_fill_value
+
+
+def _dense_dt(x):
+    return x.dtype if isinstance(x, np.ndarray) else D.np_dtype(x)
+
+
+def sddmm(s, a, b):
+    """Sampled dense-dense matrix product: ``s * (a @ b)`` for sparse 2-D ``s`` and dense ``a`` (M,K), ``b`` (K,N)."""
+    from ._gcxs import GCXS
+
+    if not isinstance(s, SparseArray) or s.ndim != 2:
+        raise TypeError("sddmm: `s` must be a 2-D sparse_b200 array")
+    check_zero_fill_value(s)
+    M, N = s.shape
+    if a.ndim != 2 or b.ndim != 2 or a.shape[0] != M or b.shape[1] != N or a.shape[1] != b.shape[0]:
+        raise ValueError(f"sddmm: shape mismatch s{s.shape}, a{tuple(a.shape)}, b{tuple(b.shape)}")
+    K = int(a.shape[1])
+    T = np.result_type(s.dtype, _dense_dt(a), _dense_dt(b))
+    if T not in (np.dtype("float32"), np.dtype("float64")):
+        raise TypeError(f"sddmm: dtype {T} is outside the CUDA dtype matrix (float32, float64)")
+    was_gcxs = isinstance(s, GCXS)
+    c = s.tocoo() if was_gcxs else s
+    vals, cols, indptr = _coo_as_csr(c, T)
+    ad = _dense_dev(a, T)
+    bt = Kn.transpose_dense(_dense_dev(b, T))  # (N, K): gathered vectors become contiguous
+    out = Kn.sddmm(indptr, cols, vals, ad, bt, M, N, K)
+    coords, _ = c._dev()
+    res = COO._from_device(coords, out, s.shape, T.type(0), keys=c._keys)
+    res._canonicalise(check_sort=False, sum_dups=False, prune=True)  # s * dense drops exact zeros (_umath.py:627-633)
+    return res.asformat("gcxs", compressed_axes=s.compressed_axes) if was_gcxs else res
+
+
+def mttkrp(B, Dm, Cm):
+    """Matricised tensor times Khatri-Rao product: out[i, j] = sum_{k,l} B[i,k,l] * D[l,j] * C[k,j]."""
+    from ._gcxs import GCXS
+
+    if not isinstance(B, SparseArray) or B.ndim != 3:
+        raise TypeError("mttkrp: `B` must be a 3-D sparse_b200 array")
+    check_zero_fill_value(B)
+    I_, K_, L_ = B.shape
+    if Dm.ndim != 2 or Cm.ndim != 2 or Dm.shape[0] != L_ or Cm.shape[0] != K_ or Dm.shape[1] != Cm.shape[1]:
+        raise ValueError(f"mttkrp: shape mismatch B{B.shape}, D{tuple(Dm.shape)}, C{tuple(Cm.shape)}")
+    J = int(Dm.shape[1])
+    T = np.result_type(B.dtype, _dense_dt(Dm), _dense_dt(Cm))
+    if T not in (np.dtype("float32"), np.dtype("float64")):
+        raise TypeError(f"mttkrp: dtype {T} is outside the CUDA dtype matrix (float32, float64)")
+    was_gcxs = isinstance(B, GCXS)
+    c = B.tocoo() if was_gcxs else B
+    coords, data = c._dev()
+    c.sorted_keys()
+    lead = coords[0].contiguous()
+    indptr = Kn.indptr_from_sorted(lead, I_, D.np_dtype(coords))
+    kk, ll, indptr = _narrow_idx(coords[1].contiguous(), coords[2].contiguous(), indptr, limit=max(K_, L_, c.nnz))
+    out = Kn.mttkrp(indptr, kk, ll, Kn.cast(data, T), _dense_dev(Dm, T), _dense_dev(Cm, T), I_, J)
+    rows, cols, vals, _ = Kn.dense_to_csr(out, mode=1, want_rows=True, want_indptr=False)
+    t = D.torch()
+    res = COO._from_device(t.stack([rows, cols]), vals, (I_, J), T.type(0))
+    return GCXS.from_coo(res) if was_gcxs else res

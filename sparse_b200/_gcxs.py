@@ -1,0 +1,399 @@
+"""GCXS container (generalised CSR/CSC) with device-resident data / indices / indptr.
+
+Mirrors sparse/numba_backend/_compressed/compressed.py: `_from_coo` (:25-77), constructor (:135-187),
+`tocoo` (:425-460), `change_compressed_axes` (:388-423), O(1) 2-D transpose (:743-768), `_prune` (:816-842).
+An N-D array is stored as the 2-D CSR of its (compressed axes ; remaining axes) flattening.
+"""
+from __future__ import annotations
+
+from collections.abc import Iterable
+
+import numpy as np
+
+from . import _device as D
+from . import _kernels as Kn
+from ._coo import COO, _is_scipy_sparse
+from ._sparse_array import SparseArray
+from ._utils import _zero_of_dtype, c_strides, check_compressed_axes, check_linear_range, key_bits, normalize_axis, prod
+
+
+class GCXS(SparseArray):
+    def __init__(self, arg, shape=None, compressed_axes=None, prune=False, fill_value=None, idx_dtype=None):
+        self._data_np = self._indices_np = self._indptr_np = None
+        self._data = self._indices = self._indptr = None
+        if _is_scipy_sparse(arg):
+            arg = GCXS.from_scipy_sparse(arg)
+        if isinstance(arg, np.ndarray):
+            arg = GCXS.from_coo(COO.from_numpy(arg, fill_value=fill_value), compressed_axes)
+        elif isinstance(arg, COO):
+            arg = GCXS.from_coo(arg, compressed_axes, idx_dtype)
+        if isinstance(arg, GCXS):
+            if compressed_axes is not None and arg.compressed_axes != tuple(compressed_axes):
+                arg = arg.change_compressed_axes(compressed_axes)
+            self._adopt(arg)
+            if fill_value is not None:
+                self.fill_value = self._dtype.type(fill_value)
+            if prune:
+                self._prune()
+            return
+        if shape is None:
+            raise ValueError("missing `shape` argument")
+        shape = tuple(int(s) for s in shape) if isinstance(shape, Iterable) else (int(shape),)
+        check_compressed_axes(len(shape), compressed_axes)
+        if len(shape) == 1:
+            compressed_axes = None
+        data, indices, indptr = arg
+        dev_in = D.is_device_tensor(data)
+        if dev_in:
+            self._data, self._indices = data, indices
+            self._indptr = indptr if D.is_device_tensor(indptr) else None
+            if self._indptr is None:
+                self._indptr_np = np.asarray(indptr)
+            self._dtype = D.np_dtype(data)
+            if data.dim() != 1:
+                raise ValueError("data must be a scalar or 1-dimensional.")
+        else:
+            self._data_np = np.asarray(data)
+            self._indices_np = np.asarray(indices)
+            self._indptr_np = np.asarray(indptr)
+            if self._data_np.ndim != 1:
+                raise ValueError("data must be a scalar or 1-dimensional.")
+            self._dtype = self._data_np.dtype
+        SparseArray.__init__(self, shape, fill_value=None)
+        if fill_value is None:
+            fill_value = _zero_of_dtype(self._dtype)
+        self._compressed_axes = tuple(int(a) for a in compressed_axes) if isinstance(compressed_axes, Iterable) else None
+        self.fill_value = self._dtype.type(fill_value)
+        if prune:
+            self._prune()
+
+    def _adopt(self, o):
+        SparseArray.__init__(self, o.shape, fill_value=None)
+        self._data_np, self._indices_np, self._indptr_np = o._data_np, o._indices_np, o._indptr_np
+        self._data, self._indices, self._indptr = o._data, o._indices, o._indptr
+        self._dtype = o._dtype
+        self._compressed_axes = o._compressed_axes
+        self.fill_value = o.fill_value
+
+    @classmethod
+    def _from_device(cls, data, indices, indptr, shape, compressed_axes, fill_value=None):
+        self = cls.__new__(cls)
+        SparseArray.__init__(self, tuple(int(s) for s in shape), fill_value=None)
+        self._data_np = self._indices_np = self._indptr_np = None
+        self._data, self._indices, self._indptr = data, indices, indptr
+        self._dtype = D.np_dtype(data)
+        self._compressed_axes = tuple(int(a) for a in compressed_axes) if compressed_axes is not None else None
+        self.fill_value = self._dtype.type(0 if fill_value is None else fill_value)
+        return self
+
+    # ---- layout metadata (compressed.py:221-262) -----------------------------------------------------------
+    @property
+    def compressed_axes(self):
+        return self._compressed_axes
+
+    @property
+    def _axis_order(self):
+        axis_order = list(self.compressed_axes)
+        axis_order.extend(a for a in range(self.ndim) if a not in set(self.compressed_axes))
+        return axis_order
+
+    @property
+    def _axisptr(self):
+        return len(self.compressed_axes)
+
+    @property
+    def _reordered_shape(self):
+        return tuple(self.shape[i] for i in self._axis_order)
+
+    @property
+    def _compressed_shape(self):
+        rs = self._reordered_shape
+        return (prod(rs[: self._axisptr]), prod(rs[self._axisptr:]))
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def nnz(self):
+        return int(self._data.shape[0]) if self._data is not None else int(self._data_np.shape[0])
+
+    @property
+    def format(self):
+        return "gcxs"
+
+    @property
+    def nbytes(self):
+        isz = self._indices.element_size() if self._indices is not None else self._indices_np.itemsize
+        nptr = (self._indptr.shape[0] if self._indptr is not None else len(self._indptr_np))
+        return self.nnz * (self._dtype.itemsize + isz) + nptr * isz
+
+    # ---- mirrors ---------------------------------------------------------------------------------------------
+    def _dev(self):
+        if self._data is None:
+            D.require_device()
+            self._data = D.upload(self._data_np)
+            self._indices = D.upload(self._indices_np)
+        if self._indptr is None:
+            ip = np.asarray(self._indptr_np)
+            if ip.size == 0:
+                ip = np.zeros(0, dtype=np.int64)
+            self._indptr = D.upload(ip.astype(D.np_dtype(self._indices)) if ip.dtype != D.np_dtype(self._indices) else ip)
+        if self._indptr.dtype != self._indices.dtype:
+            self._indptr = Kn.cast(self._indptr, D.np_dtype(self._indices))
+        return self._data, self._indices, self._indptr
+
+    @property
+    def data(self):
+        if self._data_np is None:
+            self._data_np = D.download(self._data)
+        return self._data_np
+
+    @property
+    def indices(self):
+        if self._indices_np is None:
+            self._indices_np = D.download(self._indices)
+        return self._indices_np
+
+    @property
+    def indptr(self):
+        if self._indptr_np is None:
+            self._indptr_np = D.download(self._indptr)
+        return self._indptr_np
+
+    # ---- COO <-> GCXS ----------------------------------------------------------------------------------------
+    @classmethod
+    def from_coo(cls, x, compressed_axes=None, idx_dtype=None):
+        """_from_coo (compressed.py:25-77) on the device."""
+        if x.ndim == 0:
+            if compressed_axes is not None:
+                raise ValueError("no axes to compress for 0d array")
+            _, data = x._dev()
+            return cls._from_device(data, x._coords, D.torch().zeros(0, dtype=x._coords.dtype, device=data.device),
+                                    x.shape, None, x.fill_value)
+        if x.ndim == 1:
+            if compressed_axes is not None:
+                raise ValueError("no axes to compress for 1d array")
+            coords, data = x._dev()
+            return cls._from_device(data, coords[0].contiguous(),
+                                    D.torch().zeros(0, dtype=coords.dtype, device=data.device), x.shape, None,
+                                    x.fill_value)
+        compressed_axes = normalize_axis(compressed_axes, x.ndim)
+        if compressed_axes is None:
+            compressed_axes = (int(np.argmin(x.shape)),)
+        if isinstance(compressed_axes, int):
+            compressed_axes = (compressed_axes,)
+        check_compressed_axes(x.shape, compressed_axes)
+        axis_order = list(compressed_axes)
+        axisptr = len(compressed_axes)
+        axis_order.extend(a for a in range(x.ndim) if a not in set(compressed_axes))
+        reordered_shape = tuple(x.shape[i] for i in axis_order)
+        row_size, col_size = prod(reordered_shape[:axisptr]), prod(reordered_shape[axisptr:])
+        check_linear_range(x.shape)
+        coords, data = x._dev()
+        idt = idx_dtype or D.np_dtype(coords)
+        if axis_order == list(range(x.ndim)):
+            keys = x.sorted_keys()
+        else:
+            st = c_strides(reordered_shape)
+            strides = [0] * x.ndim
+            for pos, a in enumerate(axis_order):
+                strides[a] = st[pos]
+            keys = Kn.linearize(coords, strides)
+            unsorted, _ = Kn.keys_flags(keys)
+            if unsorted:
+                keys, perm = Kn.sort_keys(keys, key_bits(x.size))
+                data = Kn.gather(data, perm)
+        _, indices, indptr = Kn.csr_from_keys(keys, row_size, col_size, idt)
+        return cls._from_device(data, indices, indptr, x.shape, compressed_axes, x.fill_value)
+
+    def tocoo(self):
+        """compressed.py:425-460: rows from indptr, then undo the axis reordering (COO rebuild + sort)."""
+        data, indices, indptr = self._dev()
+        if self.ndim == 0:
+            return COO._from_device(indices.reshape(0, -1), data, self.shape, self.fill_value)
+        if self.ndim == 1:
+            return COO(indices[None, :], data, shape=self.shape, fill_value=self.fill_value)
+        nrows, ncols = self._compressed_shape
+        idt = D.np_dtype(indices)
+        rows = Kn.rows_from_indptr(indptr, self.nnz, idt)
+        t = D.torch()
+        coords2 = t.stack([rows, indices])
+        keys2 = Kn.linearize(coords2, [ncols, 1])
+        axis_order = self._axis_order
+        if axis_order == list(range(self.ndim)):
+            keys = keys2
+        else:
+            # key over the reordered shape -> key over the original shape
+            re_coords = Kn.unravel(keys2, self._reordered_shape, np.int64)
+            st = c_strides(self.shape)
+            keys = Kn.linearize(re_coords, [st[a] for a in axis_order])
+        unsorted, _ = Kn.keys_flags(keys)
+        if unsorted:
+            keys, perm = Kn.sort_keys(keys, key_bits(self.size))
+            data = Kn.gather(data, perm)
+        coords = Kn.unravel(keys, self.shape, idt)
+        return COO._from_device(coords, data, self.shape, self.fill_value, keys=keys)
+
+    @classmethod
+    def from_numpy(cls, x, compressed_axes=None, fill_value=None, idx_dtype=None):
+        return cls.from_coo(COO.from_numpy(x, fill_value=fill_value, idx_dtype=idx_dtype), compressed_axes)
+
+    @classmethod
+    def from_scipy_sparse(cls, x):
+        if x.format == "csc":
+            x.sort_indices() if not x.has_sorted_indices else None
+            return cls((x.data, x.indices, x.indptr), shape=x.shape, compressed_axes=(1,))
+        x = x.asformat("csr")
+        if not x.has_sorted_indices:
+            x.sort_indices()
+        return cls((x.data, x.indices, x.indptr), shape=x.shape, compressed_axes=(0,))
+
+    def todense(self):
+        return self.tocoo().todense()
+
+    def todense_device(self):
+        return self.tocoo().todense_device()
+
+    def copy(self, deep=True):
+        return GCXS(self)
+
+    def asformat(self, format, **kwargs):
+        if format in ("gcxs", GCXS) or (isinstance(format, type) and issubclass(format, GCXS)):
+            ca = kwargs.pop("compressed_axes", None)
+            if ca is None:
+                return self
+            return self.change_compressed_axes(ca)
+        if format in ("coo", COO) or (isinstance(format, type) and issubclass(format, COO)):
+            return self.tocoo()
+        if format in (np.ndarray, "dense"):
+            return self.todense()
+        raise NotImplementedError(f"The given format is not supported: {format}")
+
+    def astype(self, dtype, casting="unsafe", copy=True):
+        dtype = np.dtype(dtype)
+        if self.dtype == dtype and not copy:
+            return self
+        data, indices, indptr = self._dev()
+        return GCXS._from_device(Kn.cast(data, dtype) if dtype != self.dtype else data.clone(), indices, indptr,
+                                 self.shape, self.compressed_axes, dtype.type(self.fill_value))
+
+    def change_compressed_axes(self, new_compressed_axes):
+        """compressed.py:388-423."""
+        if new_compressed_axes is not None:
+            new_compressed_axes = tuple(normalize_axis(a, self.ndim) for a in new_compressed_axes)
+        if new_compressed_axes == self.compressed_axes:
+            return self
+        if self.ndim == 1:
+            raise NotImplementedError("no axes to compress for 1d array")
+        if len(new_compressed_axes) >= len(self.shape):
+            raise ValueError("cannot compress all axes")
+        if len(set(new_compressed_axes)) != len(new_compressed_axes):
+            raise ValueError("repeated axis in compressed_axes")
+        return GCXS.from_coo(self.tocoo(), new_compressed_axes)
+
+    # ---- transpose ---------------------------------------------------------------------------------------------
+    def _2d_transpose(self):
+        """O(1): CSR of (m, n) is CSC of (n, m) (compressed.py:743-768)."""
+        ca = [(self.compressed_axes[0] + 1) % 2]
+        data, indices, indptr = self._dev()
+        return GCXS._from_device(data, indices, indptr, self.shape[::-1], ca, self.fill_value)
+
+    def transpose(self, axes=None, compressed_axes=None):
+        if axes is None:
+            axes = tuple(reversed(range(self.ndim)))
+        axes = tuple(int(a) + self.ndim if int(a) < 0 else int(a) for a in axes)
+        if self.ndim == 2 and axes == (1, 0) and compressed_axes is None:
+            return self._2d_transpose()
+        if axes == tuple(range(self.ndim)):
+            return self
+        if self.ndim == 1:
+            return self
+        out = self.tocoo().transpose(axes)
+        return GCXS.from_coo(out, compressed_axes)
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    def reshape(self, shape, order="C", compressed_axes=None):
+        """compressed.py:622-682."""
+        shape = tuple(shape) if isinstance(shape, Iterable) else (shape,)
+        if order not in {"C", None}:
+            raise NotImplementedError("The 'order' parameter is not supported")
+        shape = tuple(int(s) for s in shape)
+        if any(d == -1 for d in shape):
+            extra = int(self.size / np.prod([d for d in shape if d != -1]))
+            shape = tuple(d if d != -1 else extra for d in shape)
+        if self.shape == shape:
+            return self
+        if self.size != prod(shape):
+            raise ValueError(f"cannot reshape array of size {self.size} into shape {shape}")
+        if len(shape) == 0:
+            return GCXS.from_coo(self.tocoo().reshape(shape))
+        if compressed_axes is None:
+            if len(shape) == self.ndim:
+                compressed_axes = self.compressed_axes
+            elif len(shape) == 1:
+                compressed_axes = None
+            else:
+                compressed_axes = (int(np.argmin(shape)),)
+        return GCXS.from_coo(self.tocoo().reshape(shape), compressed_axes)
+
+    def flatten(self, order="C"):
+        return self.reshape(-1)
+
+    def __getitem__(self, index):
+        """`None` insertion / full slices only (the MTTKRP expression, examples/mttkrp_example.py:51)."""
+        return GCXS.from_coo(self.tocoo()[index])
+
+    # ---- prune (compressed.py:816-842) ---------------------------------------------------------------------------
+    def _prune(self):
+        data, indices, indptr = self._dev()
+        if self.nnz == 0:
+            return
+        flags = Kn.flag_not_fill(data, self.fill_value)
+        pos, total = Kn.scan_flags(flags)
+        if total == self.nnz:
+            return
+        self._data = Kn.compact(data, flags, pos, total)
+        self._indices = Kn.compact(indices, flags, pos, total)
+        if self.ndim > 1:
+            self._indptr = Kn.indptr_remap(indptr, pos, int(flags.shape[0]), total)
+        self._data_np = self._indices_np = self._indptr_np = None
+
+    # ---- products ---------------------------------------------------------------------------------------------------
+    def dot(self, other):
+        from ._dot import dot
+
+        return dot(self, other)
+
+    def __matmul__(self, other):
+        from ._dot import matmul
+
+        try:
+            return matmul(self, other)
+        except NotImplementedError:
+            return NotImplemented
+
+    def __rmatmul__(self, other):
+        from ._dot import matmul
+
+        try:
+            return matmul(other, self)
+        except NotImplementedError:
+            return NotImplemented
+
+
+class CSR(GCXS):
+    """2-D GCXS with compressed_axes=(0,)."""
+
+    def __init__(self, arg, shape=None, prune=False, fill_value=None):
+        super().__init__(arg, shape=shape, compressed_axes=(0,), prune=prune, fill_value=fill_value)
+
+
+class CSC(GCXS):
+    """2-D GCXS with compressed_axes=(1,)."""
+
+    def __init__(self, arg, shape=None, prune=False, fill_value=None):
+        super().__init__(arg, shape=shape, compressed_axes=(1,), prune=prune, fill_value=fill_value)

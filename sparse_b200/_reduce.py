@@ -1,0 +1,93 @@
+"""Reductions (`x.sum(axis)`, `np.max(x, axis)`, `x.reduce(ufunc, axis)`).
+
+Host-side mirror of SparseArray.reduce (sparse/numba_backend/_sparse_array.py:372-437),
+COO._reduce_calc/_reduce_return (_coo/core.py:693-723) and GCXS._reduce_calc/_reduce_return
+(_compressed/compressed.py:354-386).  The grouped reduction itself (transpose -> 2-D -> reduceat over runs) runs on
+the device: permuted linearisation + stable sort (only when the reduced axes are not trailing), then one
+segmented reduce-by-key pass and the fill-value correction kernel (csrc/reduce.cu).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _device as D
+from . import _kernels as Kn
+from ._coo import COO
+from ._sparse_array import _reduce_super_ufunc
+from ._utils import equivalent, normalize_axis, prod
+
+_RED = {np.add: 0, np.multiply: 1, np.maximum: 2, np.minimum: 3, np.logical_and: 4, np.logical_or: 5,
+        np.bitwise_and: 6, np.bitwise_or: 7, np.bitwise_xor: 8}
+_RED_DTYPES = (np.dtype("float32"), np.dtype("float64"), np.dtype("int32"), np.dtype("int64"), np.dtype("bool"))
+
+
+def reduce_impl(x, method, axis=(0,), keepdims=False, **kwargs):
+    from ._gcxs import GCXS
+
+    if method not in _RED:
+        raise TypeError(f"sparse_b200: reduction with {getattr(method, '__name__', method)!r} is not in the CUDA op set "
+                        f"({', '.join(sorted(m.__name__ for m in _RED))}); there is no CPU fallback.")
+    axis = normalize_axis(axis, x.ndim)
+    red_kwargs = {k: v for k, v in kwargs.items() if v is not None}
+    with np.errstate(all="ignore"):
+        zero_reduce_result = method.reduce([x.fill_value, x.fill_value], **red_kwargs)
+    super_ufunc = _reduce_super_ufunc.get(method)
+    if not equivalent(zero_reduce_result, x.fill_value) and super_ufunc is None:
+        raise ValueError(f"Performing this reduction operation would produce a dense result: {method!s}")
+    if not isinstance(axis, tuple):
+        axis = (axis,)
+    if axis == (None,):
+        axis = tuple(range(x.ndim))
+    was_gcxs = isinstance(x, GCXS)
+    c = x.tocoo() if was_gcxs else x
+
+    out = _reduce_coo(c, method, axis, super_ufunc, red_kwargs)
+    if keepdims:
+        shape = list(x.shape)
+        for ax in axis:
+            shape[ax] = 1
+        out = out.reshape(tuple(shape))
+    if out.ndim == 0:
+        # 0-D result per the Array API: the element becomes the fill value (nnz = 0)
+        return COO.from_numpy(out.todense()) if not was_gcxs or True else out
+    if was_gcxs:
+        return GCXS.from_coo(out, None if out.ndim == 1 else (int(np.argmin(out.shape)),))
+    return out
+
+
+def _reduce_coo(x, method, axis, super_ufunc, kwargs):
+    op = _RED[method]
+    neg_axis = tuple(ax for ax in range(x.ndim) if ax not in set(axis))
+    nrows = prod(x.shape[d] for d in neg_axis)
+    ncols = prod(x.shape[d] for d in axis)
+    # result dtype by NumPy's own rules (e.g. add.reduce(int32) -> int64; logical_* -> bool)
+    with np.errstate(all="ignore"):
+        res_dt = method.reduce(np.zeros(1, dtype=x.dtype), **kwargs).dtype
+    if res_dt not in _RED_DTYPES:
+        raise TypeError(f"sparse_b200: reduction dtype {res_dt} is outside the CUDA dtype matrix")
+    work_dt = res_dt
+    a = x._permute_reshape(neg_axis + tuple(axis), (nrows, ncols)) if (neg_axis + tuple(axis)) != tuple(
+        range(x.ndim)) else x.reshape((nrows, ncols))
+    _, data = a._dev()
+    fill_in = x.fill_value
+    if op in (4, 5):  # logical reductions work on truth values
+        data = Kn.cast(Kn.cast(data, np.bool_) if x.dtype != np.bool_ else data, np.bool_)
+        fill_w = np.bool_(bool(fill_in))
+    else:
+        data = Kn.cast(data, work_dt)
+        fill_w = work_dt.type(fill_in)
+    result_fill = fill_w
+    if super_ufunc is not None:
+        with np.errstate(all="ignore"):
+            result_fill = np.asarray(super_ufunc(fill_w, ncols)).astype(work_dt)[()]
+    if a.nnz == 0:
+        return COO(np.zeros((len(neg_axis), 0), dtype=np.intp), np.empty(0, dtype=work_dt),
+                   shape=tuple(x.shape[d] for d in neg_axis), has_duplicates=False, sorted=True,
+                   fill_value=result_fill)
+    gid = Kn.group_ids(a.sorted_keys(), ncols)
+    groups, vals, counts = Kn.reduce_by_key(op, gid, data)
+    Kn.reduce_fill_fix(op, vals, counts, ncols, fill_w)
+    # _reduce_return: COO(coords=groups, data, sorted=True, prune=True).reshape(kept dims)
+    out = COO(groups[None, :], vals, shape=(nrows,), has_duplicates=False, sorted=True, prune=True,
+              fill_value=result_fill)
+    return out.reshape(tuple(x.shape[d] for d in neg_axis))

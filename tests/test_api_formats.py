@@ -1,0 +1,48 @@
+"""COO canonicalisation, COO <-> GCXS, transpose, reshape vs golden outputs of the reference
+(_coo/core.py:198-291, 725-807, 1034-1111; _compressed/compressed.py:25-77, 425-460)."""
+import numpy as np
+import pytest
+
+from _api import check_result, dec, sp  # noqa: F401
+from _golden import load
+
+CASES = load("formats_api")
+
+
+def _id(c):
+    return f"{c['op']}-{c.get('dtype','')}-{c.get('shape','')}-{c.get('ca','')}-{c.get('axes','')}".replace(" ", "")
+
+
+@pytest.mark.parametrize("c", CASES, ids=[f"{i}-{_id(c)}" for i, c in enumerate(CASES)])
+def test_formats(sp, c):
+    op = c["op"]
+    if op in ("coo_ctor", "coo_ctor_noprune"):
+        got = sp.COO(np.array(c.arr["coords"]), np.array(c.arr["data"]), shape=tuple(c["shape"]),
+                     prune=(op == "coo_ctor"))
+        # duplicates are summed with np.add.reduceat upstream; the test data are small integers / halves -> exact
+        check_result(sp, got, c)
+        return
+    x = dec(sp, c, "a_")
+    if op == "from_coo":
+        got = sp.GCXS(x, compressed_axes=None if c["ca"] is None else tuple(c["ca"]))
+    elif op == "tocoo":
+        got = sp.GCXS(x, compressed_axes=None if c["ca"] is None else tuple(c["ca"])).tocoo()
+    elif op == "transpose":
+        got = x.transpose(tuple(c["axes"]))
+    elif op == "reshape":
+        got = x.reshape(tuple(c["shape"]))
+    else:
+        raise AssertionError(op)
+    check_result(sp, got, c)
+
+
+def test_todense_roundtrip(sp):
+    rng = np.random.default_rng(3)
+    d = rng.random((5, 6, 7))
+    d[d < 0.7] = 0
+    x = sp.COO.from_numpy(d)
+    assert x.nnz == np.count_nonzero(d)
+    assert np.array_equal(x.todense(), d)
+    g = sp.GCXS.from_numpy(d, compressed_axes=(1,))
+    assert np.array_equal(g.todense(), d)
+    assert np.array_equal(g.T.todense() if g.ndim == 2 else g.tocoo().transpose().todense(), d.T)
