@@ -48,10 +48,11 @@ __device__ __forceinline__ T bin_apply(int op, T a, T b) {
             case OP_SUB: return add_rn(a, -b);
             case OP_MUL: return mul_rn(a, b);
             case OP_DIV: return a / b;
-            case OP_MAXIMUM: return (is_nan(a) || is_nan(b)) ? (is_nan(a) ? a : b) : (a >= b ? a : b);  // NaN propagates
-            case OP_MINIMUM: return (is_nan(a) || is_nan(b)) ? (is_nan(a) ? a : b) : (a <= b ? a : b);
-            case OP_FMAX: return is_nan(a) ? b : (is_nan(b) ? a : (a >= b ? a : b));
-            case OP_FMIN: return is_nan(a) ? b : (is_nan(b) ? a : (a <= b ? a : b));
+            // NaN propagates; ties (+0 vs -0) return the SECOND operand, like NumPy's x86 SIMD loops (maxpd/minpd)
+            case OP_MAXIMUM: return (is_nan(a) || is_nan(b)) ? (is_nan(a) ? a : b) : (a > b ? a : b);
+            case OP_MINIMUM: return (is_nan(a) || is_nan(b)) ? (is_nan(a) ? a : b) : (a < b ? a : b);
+            case OP_FMAX: return is_nan(a) ? b : (is_nan(b) ? a : (a > b ? a : b));
+            case OP_FMIN: return is_nan(a) ? b : (is_nan(b) ? a : (a < b ? a : b));
             case OP_POW: return pow(a, b);
             case OP_FLOORDIV: {
                 if (b == T(0)) return a / b;

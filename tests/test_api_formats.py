@@ -46,3 +46,19 @@ def test_todense_roundtrip(sp):
     g = sp.GCXS.from_numpy(d, compressed_axes=(1,))
     assert np.array_equal(g.todense(), d)
     assert np.array_equal(g.T.todense() if g.ndim == 2 else g.tocoo().transpose().todense(), d.T)
+
+
+@pytest.mark.gpu
+def test_cuda_backend_really_launches_kernels():
+    """Guards against a silent fallback: the public API must launch kernels from libsparse_b200.so."""
+    import _mock_kernels
+    import sparse_b200
+    from sparse_b200 import _lib
+
+    _mock_kernels.uninstall()
+    n0 = _lib.launch_count()
+    rng = np.random.default_rng(0)
+    x = sparse_b200.random((50, 60), density=0.1, random_state=rng)
+    y = sparse_b200.random((60, 40), density=0.1, random_state=rng)
+    (x @ y).todense(); (x + x).todense(); x.sum(axis=0).todense()
+    assert _lib.launch_count() - n0 >= 10
