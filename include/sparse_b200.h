@@ -82,15 +82,15 @@ int b2s_spmm_csr_dense(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N
                        void *out_dev, int64_t ldc, void *stream);
 
 /*
- * Same product through HOST buffers (the reference-facing call: numpy arrays in,
- * numpy array out).  Uploads A and B, runs K1, downloads out; synchronous.
- * Host buffers should be pinned (b2s_host_register) for full link rate.
- * a_indices/a_indptr are int64 on the host (np.intp, as the reference holds
- * them); they are narrowed to int32 on the device when M, K and nnz allow.
+ * Same product through HOST buffers (the reference-facing call: numpy arrays in, numpy array out).
+ * A three-stream pipeline overlaps the uploads of A (in nnz-balanced row chunks), K1 on the rows that have landed
+ * and the download of finished rows of C; synchronous on return.  Host buffers should be pinned
+ * (b2s_host_register) for full link rate.  a_indices/a_indptr have idx_bytes (8 = np.intp as the reference holds
+ * them, narrowed to int32 on the device when K and nnz allow; 4 = int32, e.g. arrays that came from SciPy).
  */
-int b2s_spmm_csr_dense_host(int dtype, int64_t M, int64_t K, int64_t N, int64_t nnz, const void *a_data_host,
-                            const int64_t *a_indices_host, const int64_t *a_indptr_host, const void *b_host,
-                            void *out_host);
+int b2s_spmm_csr_dense_host(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, int64_t nnz,
+                            const void *a_data_host, const void *a_indices_host, const void *a_indptr_host,
+                            const void *b_host, void *out_host);
 
 /* Tuning knob for K1 (0 = default).  variant: 1 = register-staged LDG gather,
  * 2 = 1-D bulk-TMA (cp.async.bulk) gather through a shared-memory ring. */

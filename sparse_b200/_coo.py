@@ -168,6 +168,11 @@ class COO(SparseArray):
                    sorted=False)
 
     # ---- device / host mirrors -----------------------------------------------------------------------
+    def to_device(self):
+        """Move the arrays to HBM now (they stay resident); returns self."""
+        self._dev()
+        return self
+
     def _dev(self):
         """Ensure the device copies exist (one H2D, then resident)."""
         if self._data is None:

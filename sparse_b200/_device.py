@@ -131,8 +131,29 @@ def upload(arr, dtype=None):
     return t.from_numpy(a).to(device(), non_blocking=True)
 
 
+_PIN_MIN_BYTES = 1 << 20
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """NumPy array backed by page-locked host memory (torch's caching host allocator keeps the pages mapped,
+    so repeated results of the same size do not pay cudaHostAlloc again).  The array keeps the allocation alive."""
+    t = torch()
+    if _TEST_CPU or not t.cuda.is_available():
+        return np.empty(shape, dtype=dtype)
+    return t.empty(shape, dtype=torch_dtype(dtype), pin_memory=True).numpy()
+
+
 def download(x) -> np.ndarray:
-    return x.detach().cpu().numpy()
+    """Device tensor -> NumPy (one D2H; large results land in pinned memory so the copy runs at link rate)."""
+    x = x.detach()
+    if _TEST_CPU or not x.is_cuda:
+        return x.cpu().numpy()
+    if x.numel() * x.element_size() >= _PIN_MIN_BYTES:
+        t = torch()
+        host = t.empty(x.shape, dtype=x.dtype, pin_memory=True)
+        host.copy_(x, non_blocking=False)
+        return host.numpy()
+    return x.cpu().numpy()
 
 
 def empty(shape, dtype):

@@ -23,15 +23,20 @@ def _dense_dt(x):
     return x.dtype if isinstance(x, np.ndarray) else D.np_dtype(x)
 
 
-def sddmm(s, a, b):
-    """Sampled dense-dense matrix product: ``s * (a @ b)`` for sparse 2-D ``s`` and dense ``a`` (M,K), ``b`` (K,N)."""
+def sddmm(s, a, b, *, b_transposed=False):
+    """Sampled dense-dense matrix product: ``s * (a @ b)`` for sparse 2-D ``s`` and dense ``a`` (M,K), ``b`` (K,N).
+    With ``b_transposed=True`` `b` is given as b^T (N,K), the layout the kernel gathers from."""
     from ._gcxs import GCXS
 
     if not isinstance(s, SparseArray) or s.ndim != 2:
         raise TypeError("sddmm: `s` must be a 2-D sparse_b200 array")
     check_zero_fill_value(s)
     M, N = s.shape
-    if a.ndim != 2 or b.ndim != 2 or a.shape[0] != M or b.shape[1] != N or a.shape[1] != b.shape[0]:
+    if b_transposed:
+        bN, bK = int(b.shape[0]), int(b.shape[1])
+    else:
+        bK, bN = int(b.shape[0]), int(b.shape[1])
+    if a.ndim != 2 or b.ndim != 2 or a.shape[0] != M or bN != N or a.shape[1] != bK:
         raise ValueError(f"sddmm: shape mismatch s{s.shape}, a{tuple(a.shape)}, b{tuple(b.shape)}")
     K = int(a.shape[1])
     T = np.result_type(s.dtype, _dense_dt(a), _dense_dt(b))
@@ -41,7 +46,7 @@ def sddmm(s, a, b):
     c = s.tocoo() if was_gcxs else s
     vals, cols, indptr = _coo_as_csr(c, T)
     ad = _dense_dev(a, T)
-    bt = Kn.transpose_dense(_dense_dev(b, T))  # (N, K): gathered vectors become contiguous
+    bt = _dense_dev(b, T) if b_transposed else Kn.transpose_dense(_dense_dev(b, T))  # (N, K): contiguous gathers
     out = Kn.sddmm(indptr, cols, vals, ad, bt, M, N, K)
     coords, _ = c._dev()
     res = COO._from_device(coords, out, s.shape, T.type(0), keys=c._keys)

@@ -129,6 +129,11 @@ class GCXS(SparseArray):
         return self.nnz * (self._dtype.itemsize + isz) + nptr * isz
 
     # ---- mirrors ---------------------------------------------------------------------------------------------
+    def to_device(self):
+        """Move the arrays to HBM now (they stay resident); returns self."""
+        self._dev()
+        return self
+
     def _dev(self):
         if self._data is None:
             D.require_device()

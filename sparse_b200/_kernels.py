@@ -94,14 +94,16 @@ def spmm_csr_dense_host(a_data: np.ndarray, a_indices: np.ndarray, a_indptr: np.
     assert b.dtype == dt
     M = len(a_indptr) - 1
     K, N = b.shape
-    a_indices = np.ascontiguousarray(a_indices, dtype=np.int64)
-    a_indptr = np.ascontiguousarray(a_indptr, dtype=np.int64)
+    idt = np.int32 if (a_indices.dtype == np.int32 and a_indptr.dtype == np.int32) else np.int64
+    a_indices = np.ascontiguousarray(a_indices, dtype=idt)
+    a_indptr = np.ascontiguousarray(a_indptr, dtype=idt)
     b = np.ascontiguousarray(b)
     if out is None:
         out = np.empty((M, N), dtype=dt)
     rc = lib.b2s_spmm_csr_dense_host(
-        i32(D.dtype_code(dt)), i64(M), i64(K), i64(N), i64(len(a_data)), vp(a_data.ctypes.data),
-        vp(a_indices.ctypes.data), vp(a_indptr.ctypes.data), vp(b.ctypes.data), vp(out.ctypes.data),
+        i32(D.dtype_code(dt)), i32(np.dtype(idt).itemsize), i64(M), i64(K), i64(N), i64(len(a_data)),
+        vp(a_data.ctypes.data), vp(a_indices.ctypes.data), vp(a_indptr.ctypes.data), vp(b.ctypes.data),
+        vp(out.ctypes.data),
     )
     _lib.check(rc, "b2s_spmm_csr_dense_host")
     return out

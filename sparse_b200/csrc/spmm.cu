@@ -366,63 +366,4 @@ int b2s_spmm_csr_dense(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N
                                ldc, (cudaStream_t)stream);
 }
 
-int b2s_spmm_csr_dense_host(int dtype, int64_t M, int64_t K, int64_t N, int64_t nnz, const void *a_data_host,
-                            const int64_t *a_indices_host, const int64_t *a_indptr_host, const void *b_host,
-                            void *out_host) {
-    const size_t es = dtype_size(dtype);
-    B2S_REQUIRE(es != 0 && dtype != B2S_BOOL, B2S_ERR_UNSUPPORTED, "spmm_host: unsupported dtype %d", dtype);
-    B2S_REQUIRE(M >= 0 && K >= 0 && N >= 0 && nnz >= 0, B2S_ERR_INVALID, "spmm_host: negative size");
-    if (M == 0 || N == 0) return B2S_OK;
-    cudaStream_t s = nullptr;
-    const bool narrow = (K < 2147483647LL) && (nnz < 2147483647LL);
-    void *d_ad = nullptr, *d_ai64 = nullptr, *d_ap64 = nullptr, *d_ai = nullptr, *d_ap = nullptr, *d_b = nullptr,
-         *d_out = nullptr;
-    int rc = B2S_OK;
-#define B2S_TRY(x)                   \
-    do {                             \
-        rc = (x);                    \
-        if (rc != B2S_OK) goto done; \
-    } while (0)
-#define B2S_TRYCUDA(x)                                                              \
-    do {                                                                            \
-        cudaError_t _e = (x);                                                       \
-        if (_e != cudaSuccess) {                                                    \
-            set_error("%s: %s", #x, cudaGetErrorString(_e));                        \
-            rc = B2S_ERR_CUDA;                                                      \
-            goto done;                                                              \
-        }                                                                           \
-    } while (0)
-    B2S_TRY(scratch_alloc(&d_ad, (size_t)nnz * es, s));
-    B2S_TRY(scratch_alloc(&d_ai64, (size_t)nnz * 8, s));
-    B2S_TRY(scratch_alloc(&d_ap64, (size_t)(M + 1) * 8, s));
-    B2S_TRY(scratch_alloc(&d_b, (size_t)K * N * es, s));
-    B2S_TRY(scratch_alloc(&d_out, (size_t)M * N * es, s));
-    B2S_TRYCUDA(cudaMemcpyAsync(d_ad, a_data_host, (size_t)nnz * es, cudaMemcpyHostToDevice, s));
-    B2S_TRYCUDA(cudaMemcpyAsync(d_ai64, a_indices_host, (size_t)nnz * 8, cudaMemcpyHostToDevice, s));
-    B2S_TRYCUDA(cudaMemcpyAsync(d_ap64, a_indptr_host, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, s));
-    B2S_TRYCUDA(cudaMemcpyAsync(d_b, b_host, (size_t)K * N * es, cudaMemcpyHostToDevice, s));
-    if (narrow) {
-        B2S_TRY(scratch_alloc(&d_ai, (size_t)nnz * 4, s));
-        B2S_TRY(scratch_alloc(&d_ap, (size_t)(M + 1) * 4, s));
-        B2S_TRY(narrow_i64_i32((const int64_t *)d_ai64, (int32_t *)d_ai, nnz, s));
-        B2S_TRY(narrow_i64_i32((const int64_t *)d_ap64, (int32_t *)d_ap, M + 1, s));
-        B2S_TRY(spmm_csr_dense_impl(dtype, 4, M, K, N, d_ad, d_ai, d_ap, d_b, N, d_out, N, s));
-    } else {
-        B2S_TRY(spmm_csr_dense_impl(dtype, 8, M, K, N, d_ad, d_ai64, d_ap64, d_b, N, d_out, N, s));
-    }
-    B2S_TRYCUDA(cudaMemcpyAsync(out_host, d_out, (size_t)M * N * es, cudaMemcpyDeviceToHost, s));
-    B2S_TRYCUDA(cudaStreamSynchronize(s));
-done:
-    scratch_free(d_ad, s);
-    scratch_free(d_ai64, s);
-    scratch_free(d_ap64, s);
-    scratch_free(d_ai, s);
-    scratch_free(d_ap, s);
-    scratch_free(d_b, s);
-    scratch_free(d_out, s);
-#undef B2S_TRY
-#undef B2S_TRYCUDA
-    return rc;
-}
-
 }  // extern "C"
