@@ -361,15 +361,15 @@ def _dot(a, b, return_type=None):
         dtr = _dot_dtype(a.dtype, _dense_dtype(b))
         M, N = out_shape
         K = a.shape[1]
-        bd = _dense_dev(b, dtr)
         dense_out = return_type is None or return_type == np.ndarray
+        if (a.compressed_axes == (0,) and dense_out and a._data is None and isinstance(b, np.ndarray)
+                and a.dtype == dtr and b.dtype == dtr and a.nnz > 0):
+            # both operands live on the host: streamed H2D / K1 / D2H pipeline of the host-buffer ABI call
+            # (use a.to_device() first to keep A resident in HBM across calls instead)
+            out = D.pinned_empty((M, N), dtr)
+            return Kn.spmm_csr_dense_host(a._data_np, a._indices_np, a._indptr_np, b, out=out)
+        bd = _dense_dev(b, dtr)
         if a.compressed_axes == (0,):  # csr @ ndarray
-            if (dense_out and a._data is None and isinstance(b, np.ndarray) and a.dtype == dtr and b.dtype == dtr
-                    and a.nnz > 0):
-                # both operands live on the host: streamed H2D / K1 / D2H pipeline of the host-buffer ABI call
-                # (use a.to_device() first to keep A resident in HBM across calls instead)
-                out = D.pinned_empty((M, N), dtr)
-                return Kn.spmm_csr_dense_host(a._data_np, a._indices_np, a._indptr_np, b, out=out)
             ad, ai, ap = _csr_arrays(a, dtr)
             if dense_out:
                 return _return_dense(Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N), [b])

@@ -31,7 +31,23 @@ int num_sms() {
     return cached;
 }
 
+// Keep freed scratch in the stream-ordered pool instead of returning it to the OS at every synchronisation
+// (the default release threshold is 0, which makes every call re-map its gigabytes of temporaries).
+static void tune_pool_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
+}
+
 int scratch_alloc(void **p, size_t nbytes, cudaStream_t s) {
+    tune_pool_once();
     if (nbytes == 0) nbytes = 16;
     B2S_CUDA(cudaMallocAsync(p, nbytes, s));
     return B2S_OK;
