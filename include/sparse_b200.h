@@ -192,6 +192,15 @@ int b2s_ew_merge(int dtype, int op, const int64_t *keys_a_dev, const void *data_
                  const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb, const void *fill_a_host,
                  const void *fill_b_host, const void *out_fill_host, int64_t *out_keys_dev, void *out_vals_dev,
                  uint8_t *out_flags_dev, void *stream);
+/* Fused two-pass form of b2s_ew_merge (production path): begin() = merge + apply + per-tile counts, returns the
+ * output nnz (one stream sync); finish() = merge + apply again and write data, int64 coordinates [ndim, nnz] and
+ * (optionally) the sorted linear keys directly -- no union-sized temporaries in HBM. */
+int b2s_ew_merge_begin(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
+                       const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb,
+                       const void *fill_a_host, const void *fill_b_host, const void *out_fill_host, int ndim,
+                       const int64_t *shape_host, void **plan_out, int64_t *nnz_out, void *stream);
+int b2s_ew_merge_finish(void *plan, int64_t *coords_out_dev, int64_t coords_stride, void *vals_out_dev,
+                        int64_t *keys_out_or_null_dev);
 /* COO (x) scalar (mode 0: f(x,s), 1: f(s,x)) and unary maps (mode 2). */
 int b2s_ew_map(int dtype, int op, int mode, const void *x_dev, int64_t n, const void *scalar_host,
                const void *out_fill_host, void *out_vals_dev, uint8_t *out_flags_dev, void *stream);
@@ -215,6 +224,16 @@ int b2s_reduce_by_key(int dtype, int op, const int64_t *gid_dev, const void *val
 /* fill-value contribution of SparseArray.reduce (_sparse_array.py:405-422), in place. */
 int b2s_reduce_fill_fix(int dtype, int op, void *vals_dev, const int64_t *counts_dev, int64_t n_groups, int64_t ncols,
                         const void *fill_host, void *stream);
+
+/* Hand-written two-pass segmented-scan reduction (production path, reduce_fused.cu): begin() returns the number of
+ * groups; finish() writes group ids (= linear index over the kept axes), values with the fill-value contribution of
+ * _sparse_array.py:405-422 applied, and the group coordinates over shape_host[ndim]; it also reports how many results
+ * are bitwise equal to result_fill (so the prune compaction of _coo/core.py:713-723 can be skipped when 0). */
+int b2s_reduce_begin(int dtype, int op, const int64_t *keys_dev, const void *vals_dev, int64_t n, int64_t ncols,
+                     void **plan_out, int64_t *n_groups_out, void *stream);
+int b2s_reduce_finish(void *plan, const void *fill_host, int apply_fill_fix, const void *result_fill_host, int ndim,
+                      const int64_t *shape_host, int64_t *gid_out_dev, int64_t *coords_out_or_null_dev,
+                      int64_t coords_stride, void *vals_out_dev, int64_t *n_equal_fill_host);
 
 /* ---- fused example paths (K8 / K9, fused.cu) ---------------------------------------------- */
 /* examples/sddmm_example.py:51-52  s * (a @ b): out_vals[p] = s_vals[p] * dot(A[i_p,:], Bt[j_p,:]). */

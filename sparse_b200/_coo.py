@@ -372,6 +372,24 @@ class COO(SparseArray):
         new_coords = Kn.unravel(keys, new_shape, idt)
         return COO._from_device(new_coords, data, new_shape, self.fill_value, keys=keys)
 
+    def _permuted_keys(self, axes):
+        """(sorted linear keys over the permuted shape, matching data) without building coordinates."""
+        coords, data = self._dev()
+        axes = tuple(axes)
+        if axes == tuple(range(self.ndim)):
+            return self.sorted_keys(), data
+        perm_shape = tuple(self.shape[a] for a in axes)
+        st_perm = c_strides(perm_shape)
+        strides = [0] * self.ndim
+        for pos, a in enumerate(axes):
+            strides[a] = st_perm[pos]
+        keys = Kn.linearize(coords, strides)
+        unsorted, _ = Kn.keys_flags(keys)
+        if unsorted:
+            keys, perm = Kn.sort_keys(keys, key_bits(self.size))
+            data = Kn.gather(data, perm)
+        return keys, data
+
     def broadcast_to(self, shape):
         from ._elemwise import broadcast_to
 

@@ -111,7 +111,9 @@ def stream_ptr() -> int:
 
 
 def is_device_tensor(x) -> bool:
-    t = _torch
+    import sys
+
+    t = _torch or sys.modules.get("torch")  # a tensor can only exist if torch is already imported
     return t is not None and isinstance(x, t.Tensor) and (x.is_cuda or _TEST_CPU)
 
 

@@ -276,9 +276,9 @@ class _Elemwise:
                 return self._empty(out_dt, fill)
             ka, da, Ra = _stream(a, shape)
             kb, db, Rb = _stream(b, shape)
-            keys, vals, flags = Kn.ew_merge(op, ka, Kn.cast(da, T), Ra, kb, Kn.cast(db, T), Rb,
-                                            T.type(a.fill_value), T.type(b.fill_value), fill, out_dt)
-            return _finish(keys, vals, flags, shape, fill)
+            coords, vals, keys = Kn.ew_merge_fused(op, ka, Kn.cast(da, T), Ra, kb, Kn.cast(db, T), Rb,
+                                                   T.type(a.fill_value), T.type(b.fill_value), fill, out_dt, shape)
+            return COO._from_device(coords, vals, shape, fill, keys=keys)
 
         if (a_sp and not b_dn) or (b_sp and not a_dn):  # sparse (x) scalar
             sp, sc, mode = (a, b, 0) if a_sp else (b, a, 1)

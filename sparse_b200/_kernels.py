@@ -450,6 +450,30 @@ def ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fil
     return okeys, ovals, oflags
 
 
+def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape):
+    """Fused COO (x) COO coiteration -> (coords[ndim, nnz] int64, vals[nnz], keys[nnz]); canonical order."""
+    t = _t()
+    lib = _lib.load()
+    dt = D.np_dtype(data_a)
+    assert data_b.dtype == data_a.dtype
+    plan = ctypes.c_void_p(0)
+    nnz = ctypes.c_int64(0)
+    rc = lib.b2s_ew_merge_begin(
+        i32(D.dtype_code(dt)), i32(op), vp(D.ptr(keys_a)), vp(D.ptr(data_a)), i64(keys_a.shape[0]), i64(Ra),
+        vp(D.ptr(keys_b)), vp(D.ptr(data_b)), i64(keys_b.shape[0]), i64(Rb), _scalar_bytes(fill_a, dt),
+        _scalar_bytes(fill_b, dt), _scalar_bytes(out_fill, out_dtype), i32(len(shape)), _i64arr(shape),
+        ctypes.byref(plan), ctypes.byref(nnz), _sp())
+    _lib.check(rc, "b2s_ew_merge_begin")
+    n = int(nnz.value)
+    dev = data_a.device
+    coords = t.empty((len(shape), n), dtype=t.int64, device=dev)
+    vals = t.empty(n, dtype=D.torch_dtype(out_dtype), device=dev)
+    keys = t.empty(n, dtype=t.int64, device=dev)
+    rc = lib.b2s_ew_merge_finish(plan, vp(D.ptr(coords)), i64(max(n, 1)), vp(D.ptr(vals)), vp(D.ptr(keys)))
+    _lib.check(rc, "b2s_ew_merge_finish")
+    return coords, vals, keys
+
+
 def ew_map(op, mode, x, scalar, out_fill, out_dtype):
     """f(x, s) (mode 0), f(s, x) (mode 1) or unary f(x) (mode 2) -> (vals, flags)."""
     t = _t()
@@ -527,6 +551,30 @@ def reduce_by_key(op, gid, vals):
     _lib.check(rc, "b2s_reduce_by_key")
     g = int(ng.value)
     return groups[:g], ovals[:g], counts[:g]
+
+
+def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape):
+    """Segmented reduction over runs of key // ncols -> (coords[ndim, g] int64, group ids[g], values[g], n_equal_fill)."""
+    t = _t()
+    lib = _lib.load()
+    dt = D.np_dtype(vals)
+    plan = ctypes.c_void_p(0)
+    ng = ctypes.c_int64(0)
+    rc = lib.b2s_reduce_begin(i32(D.dtype_code(dt)), i32(op), vp(D.ptr(keys)), vp(D.ptr(vals)), i64(keys.shape[0]),
+                              i64(ncols), ctypes.byref(plan), ctypes.byref(ng), _sp())
+    _lib.check(rc, "b2s_reduce_begin")
+    g = int(ng.value)
+    dev = vals.device
+    nd = len(kept_shape)
+    coords = t.empty((nd, g), dtype=t.int64, device=dev)
+    gids = t.empty(g, dtype=t.int64, device=dev)
+    out = t.empty(g, dtype=vals.dtype, device=dev)
+    neq = ctypes.c_int64(0)
+    rc = lib.b2s_reduce_finish(plan, _scalar_bytes(fill_value, dt), i32(1), _scalar_bytes(result_fill, dt), i32(nd),
+                               _i64arr(kept_shape), vp(D.ptr(gids)), vp(D.ptr(coords) if nd else 0), i64(max(g, 1)),
+                               vp(D.ptr(out)), ctypes.byref(neq))
+    _lib.check(rc, "b2s_reduce_finish")
+    return coords, gids, out, int(neq.value)
 
 
 def reduce_fill_fix(op, vals, counts, ncols, fill_value):

@@ -66,28 +66,30 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
     if res_dt not in _RED_DTYPES:
         raise TypeError(f"sparse_b200: reduction dtype {res_dt} is outside the CUDA dtype matrix")
     work_dt = res_dt
-    a = x._permute_reshape(neg_axis + tuple(axis), (nrows, ncols)) if (neg_axis + tuple(axis)) != tuple(
-        range(x.ndim)) else x.reshape((nrows, ncols))
-    _, data = a._dev()
+    kept_shape = tuple(x.shape[d] for d in neg_axis)
     fill_in = x.fill_value
     if op in (4, 5):  # logical reductions work on truth values
-        data = Kn.cast(Kn.cast(data, np.bool_) if x.dtype != np.bool_ else data, np.bool_)
         fill_w = np.bool_(bool(fill_in))
+        work_dt = np.dtype(np.bool_)
     else:
-        data = Kn.cast(data, work_dt)
         fill_w = work_dt.type(fill_in)
     result_fill = fill_w
     if super_ufunc is not None:
         with np.errstate(all="ignore"):
             result_fill = np.asarray(super_ufunc(fill_w, ncols)).astype(work_dt)[()]
-    if a.nnz == 0:
-        return COO(np.zeros((len(neg_axis), 0), dtype=np.intp), np.empty(0, dtype=work_dt),
-                   shape=tuple(x.shape[d] for d in neg_axis), has_duplicates=False, sorted=True,
-                   fill_value=result_fill)
-    gid = Kn.group_ids(a.sorted_keys(), ncols)
-    groups, vals, counts = Kn.reduce_by_key(op, gid, data)
-    Kn.reduce_fill_fix(op, vals, counts, ncols, fill_w)
-    # _reduce_return: COO(coords=groups, data, sorted=True, prune=True).reshape(kept dims)
-    out = COO(groups[None, :], vals, shape=(nrows,), has_duplicates=False, sorted=True, prune=True,
-              fill_value=result_fill)
-    return out.reshape(tuple(x.shape[d] for d in neg_axis))
+    if x.nnz == 0:
+        return COO(np.zeros((len(neg_axis), 0), dtype=np.intp), np.empty(0, dtype=work_dt), shape=kept_shape,
+                   has_duplicates=False, sorted=True, fill_value=result_fill)
+    # kept axes first; keys over (kept..., reduced...) so that group id = key // ncols (sort only if not already so)
+    keys, data = x._permuted_keys(neg_axis + tuple(axis))
+    data = Kn.cast(data, work_dt)
+    # one fused segmented-scan pass pair: values with the fill-value contribution applied, group ids (= linear index
+    # over the kept axes) and their coordinates (_grouped_reduce + _sparse_array.py:405-422 + _reduce_return)
+    coords, gids, vals, n_eq = Kn.reduce_fused(op, keys, data, ncols, fill_w, result_fill, kept_shape)
+    if n_eq:  # prune=True of _reduce_return (_coo/core.py:713-723): drop results equal to the result fill value
+        flags = Kn.flag_not_fill(vals, result_fill)
+        pos, total = Kn.scan_flags(flags)
+        coords = Kn.compact_rows(coords, flags, pos, total)
+        vals = Kn.compact(vals, flags, pos, total)
+        gids = Kn.compact(gids, flags, pos, total)
+    return COO._from_device(coords, vals, kept_shape, result_fill, keys=gids)

@@ -323,6 +323,155 @@ ew_merge_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused two-pass form of the merge (the production path for COO (x) COO):
+//   pass 1 (EMIT = false): merge + apply, count the kept results of every 2048-position tile;
+//   exclusive scan of the tile counts (CUB) -> output offsets and the total (the only host sync);
+//   pass 2 (EMIT = true): merge + apply again, compact the kept (key, value) pairs of the tile in shared memory and
+//   write data, linear keys and the unravelled coordinate rows directly, coalesced.
+// No (key, value, flag) temporaries of union size ever touch HBM, and coordinates are produced in the same pass.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kEwMaxDims = 16;
+struct EwShape {
+    int ndim;
+    int64_t extent[kEwMaxDims];
+};
+
+template <typename T, typename O, bool PRED, bool EMIT>
+__global__ void __launch_bounds__(EW_THREADS)
+ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restrict__ db, T fill_a, T fill_b,
+                      O out_fill, int op, const int64_t *__restrict__ split_a, int64_t *__restrict__ tile_counts,
+                      const int64_t *__restrict__ tile_offsets, EwShape shp, int64_t *__restrict__ coords_out,
+                      int64_t coords_stride, O *__restrict__ vals_out, int64_t *__restrict__ keys_out) {
+    __shared__ int64_t sa[EW_TILE + 2];
+    __shared__ int64_t sb[EW_TILE + 2];
+    __shared__ int s_warp[EW_THREADS / 32];
+    const int64_t la = A.len(), lb = B.len();
+    const int64_t total = la + lb;
+    const int64_t tile = blockIdx.x;
+    const int64_t d0 = tile * EW_TILE;
+    const int64_t d1 = (d0 + EW_TILE < total) ? d0 + EW_TILE : total;
+    const int64_t a0 = split_a[tile], a1 = split_a[tile + 1];
+    const int64_t b0 = d0 - a0, b1 = d1 - a1;
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+    constexpr int64_t NEG = INT64_MIN, POS = INT64_MAX;
+    for (int i = threadIdx.x; i < na + 2; i += EW_THREADS) {
+        const int64_t p = a0 - 1 + i;
+        sa[i] = (p < 0) ? NEG : (p < la ? A.key(p) : POS);
+    }
+    for (int i = threadIdx.x; i < nb + 2; i += EW_THREADS) {
+        const int64_t p = b0 - 1 + i;
+        sb[i] = (p < 0) ? NEG : (p < lb ? B.key(p) : POS);
+    }
+    __syncthreads();
+    const int64_t *ka = sa + 1, *kb = sb + 1;
+    const int dloc = threadIdx.x * EW_ITEMS;
+    const int dn = (int)(d1 - d0);
+    int64_t rkey[EW_ITEMS];
+    O rval[EW_ITEMS];
+    unsigned keepmask = 0;
+    if (dloc < dn) {
+        int lo = dloc > nb ? dloc - nb : 0;
+        int hi = dloc < na ? dloc : na;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ka[mid] <= kb[dloc - 1 - mid]) lo = mid + 1;
+            else hi = mid;
+        }
+        int i = lo, j = dloc - lo;
+#pragma unroll
+        for (int it = 0; it < EW_ITEMS; ++it) {
+            const int d = dloc + it;
+            rkey[it] = 0;
+            rval[it] = O(0);
+            if (d < dn) {
+                const bool take_a = (j >= nb) || (i < na && ka[i] <= kb[j]);
+                int64_t key;
+                T va, vb;
+                bool emit = true;
+                if (take_a) {
+                    key = ka[i];
+                    va = da[A.src(a0 + i)];
+                    vb = (kb[j] == key) ? db[B.src(b0 + j)] : fill_b;
+                    ++i;
+                } else {
+                    key = kb[j];
+                    emit = (ka[i - 1] != key);
+                    va = fill_a;
+                    vb = db[B.src(b0 + j)];
+                    ++j;
+                }
+                O r;
+                if constexpr (PRED) r = (O)bin_pred<T>(op, va, vb);
+                else r = (O)bin_apply<T>(op, va, vb);
+                rkey[it] = key;
+                rval[it] = r;
+                if (emit && bits_differ<O>(r, out_fill)) keepmask |= 1u << it;
+            }
+        }
+    }
+    // block-wide exclusive scan of the per-thread keep counts
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int mine = __popc(keepmask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();  // also: every thread is done reading sa / sb
+    int woff = 0, tile_total = 0;
+#pragma unroll
+    for (int q = 0; q < EW_THREADS / 32; ++q) {
+        const int c = s_warp[q];
+        if (q < w) woff += c;
+        tile_total += c;
+    }
+    if constexpr (!EMIT) {
+        if (threadIdx.x == 0) tile_counts[tile] = tile_total;
+        return;
+    } else {
+        // compact into shared memory (reusing the key staging arrays), then coalesced write-out
+        int64_t *sk = sa;
+        O *sv = reinterpret_cast<O *>(sb);
+        int pos = woff + incl - mine;
+#pragma unroll
+        for (int it = 0; it < EW_ITEMS; ++it) {
+            if (keepmask & (1u << it)) {
+                sk[pos] = rkey[it];
+                sv[pos] = rval[it];
+                ++pos;
+            }
+        }
+        __syncthreads();
+        const int64_t base = tile_offsets[tile];
+        for (int t = threadIdx.x; t < tile_total; t += EW_THREADS) {
+            const int64_t key = sk[t];
+            vals_out[base + t] = sv[t];
+            if (keys_out) keys_out[base + t] = key;
+            int64_t k = key;
+            for (int d = shp.ndim - 1; d >= 0; --d) {
+                const int64_t e = shp.extent[d];
+                const int64_t q = k / e;
+                coords_out[(int64_t)d * coords_stride + base + t] = k - q * e;
+                k = q;
+            }
+        }
+    }
+}
+
+struct EwPlan {
+    int dtype, op, ndim;
+    Stream A, B;
+    const void *da, *db;
+    uint8_t fa[8], fb[8], fo[8];
+    int64_t ntiles, total_out;
+    int64_t *split, *offsets;
+    int64_t shape[kEwMaxDims];
+    cudaStream_t stream;
+};
+
 // ---- COO (x) scalar, scalar (x) COO, unary ---------------------------------------------------
 // mode: 0 = f(x, s), 1 = f(s, x), 2 = unary f(x)
 template <typename T, typename O, bool PRED>
@@ -345,7 +494,6 @@ __global__ void ew_map_kernel(const T *__restrict__ x, int64_t n, T scalar, int 
 }
 
 // ---- COO (x) dense ndarray: gather the dense operand at the (virtually expanded) coordinates ----
-constexpr int kEwMaxDims = 16;
 struct DenseIdx {
     int ndim;
     int64_t extent[kEwMaxDims];   // result shape
@@ -481,6 +629,99 @@ int b2s_ew_merge(int dtype, int op, const int64_t *keys_a_dev, const void *data_
                         (O *)out_vals_dev, out_flags_dev)));
     B2S_CHECK_LAUNCH();
     return scratch_free(split, s);
+}
+
+/*
+ * Fused COO (x) COO coiteration (production path): begin() runs the counting pass and returns the output nnz;
+ * finish() writes data, coordinates [ndim, nnz] (int64, row stride = nnz) and optionally the sorted linear keys.
+ */
+int b2s_ew_merge_begin(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
+                       const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb,
+                       const void *fill_a_host, const void *fill_b_host, const void *out_fill_host, int ndim,
+                       const int64_t *shape_host, void **plan_out, int64_t *nnz_out, void *stream) {
+    B2S_REQUIRE(plan_out && nnz_out, B2S_ERR_INVALID, "ew_merge_begin: NULL output");
+    B2S_REQUIRE(Ra >= 1 && Rb >= 1 && na >= 0 && nb >= 0, B2S_ERR_INVALID, "ew_merge_begin: bad sizes");
+    B2S_REQUIRE(ndim >= 0 && ndim <= kEwMaxDims, B2S_ERR_UNSUPPORTED, "ew_merge_begin: ndim %d", ndim);
+    cudaStream_t s = (cudaStream_t)stream;
+    EwPlan *pl = new EwPlan();
+    memset(pl, 0, sizeof(*pl));
+    pl->dtype = dtype;
+    pl->op = op;
+    pl->ndim = ndim;
+    pl->A = Stream{keys_a_dev, na, Ra};
+    pl->B = Stream{keys_b_dev, nb, Rb};
+    pl->da = data_a_dev;
+    pl->db = data_b_dev;
+    memcpy(pl->fa, fill_a_host, 8);
+    memcpy(pl->fb, fill_b_host, 8);
+    memcpy(pl->fo, out_fill_host, 8);
+    for (int d = 0; d < ndim; ++d) pl->shape[d] = shape_host[d];
+    pl->stream = s;
+    *plan_out = pl;
+    *nnz_out = 0;
+    const int64_t total = na * Ra + nb * Rb;
+    if (total == 0) return B2S_OK;
+    const int64_t ntiles = (total + EW_TILE - 1) / EW_TILE;
+    B2S_REQUIRE(ntiles < 2147483647LL, B2S_ERR_OVERFLOW, "ew_merge: too many tiles");
+    pl->ntiles = ntiles;
+    int rc;
+    if ((rc = scratch_alloc((void **)&pl->split, (size_t)(ntiles + 1) * 8, s))) return rc;
+    if ((rc = scratch_alloc((void **)&pl->offsets, (size_t)(ntiles + 1) * 8, s))) return rc;
+    int64_t *counts = nullptr;
+    if ((rc = scratch_alloc((void **)&counts, (size_t)(ntiles + 1) * 8, s))) return rc;
+    B2S_CUDA(cudaMemsetAsync(counts + ntiles, 0, 8, s));
+    ew_partition_kernel<<<(unsigned)((ntiles + 1 + 127) / 128), 128, 0, s>>>(pl->A, pl->B, ntiles, pl->split);
+    B2S_CHECK_LAUNCH();
+    const bool pred = op >= 32;
+    EwShape shp{};
+    shp.ndim = ndim;
+    B2S_EW_DISPATCH(dtype, pred,
+                    (ew_merge_fused_kernel<T, O, P, false><<<(unsigned)ntiles, EW_THREADS, 0, s>>>(
+                        pl->A, pl->B, (const T *)pl->da, (const T *)pl->db, scalar_from<T>(pl->fa),
+                        scalar_from<T>(pl->fb), scalar_from<O>(pl->fo), op, pl->split, counts, nullptr, shp, nullptr, 0,
+                        nullptr, nullptr)));
+    B2S_CHECK_LAUNCH();
+    size_t tb = 0;
+    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts, pl->offsets, (int)(ntiles + 1), s));
+    void *tmp = nullptr;
+    if ((rc = scratch_alloc(&tmp, tb, s))) return rc;
+    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, counts, pl->offsets, (int)(ntiles + 1), s));
+    count_launch(2);
+    B2S_CUDA(cudaMemcpyAsync(&pl->total_out, pl->offsets + ntiles, 8, cudaMemcpyDeviceToHost, s));
+    B2S_CUDA(cudaStreamSynchronize(s));
+    scratch_free(tmp, s);
+    scratch_free(counts, s);
+    *nnz_out = pl->total_out;
+    return B2S_OK;
+}
+
+int b2s_ew_merge_finish(void *plan, int64_t *coords_out_dev, int64_t coords_stride, void *vals_out_dev,
+                        int64_t *keys_out_or_null_dev) {
+    B2S_REQUIRE(plan != nullptr, B2S_ERR_INVALID, "ew_merge_finish: NULL plan");
+    EwPlan *pl = (EwPlan *)plan;
+    cudaStream_t s = pl->stream;
+    int rc = B2S_OK;
+    if (pl->ntiles > 0 && pl->total_out > 0) {
+        const bool pred = pl->op >= 32;
+        EwShape shp{};
+        shp.ndim = pl->ndim;
+        for (int d = 0; d < pl->ndim; ++d) shp.extent[d] = pl->shape[d];
+        const int dtype = pl->dtype;
+        const int op = pl->op;
+        rc = [&]() -> int {
+            B2S_EW_DISPATCH(dtype, pred,
+                            (ew_merge_fused_kernel<T, O, P, true><<<(unsigned)pl->ntiles, EW_THREADS, 0, s>>>(
+                                pl->A, pl->B, (const T *)pl->da, (const T *)pl->db, scalar_from<T>(pl->fa),
+                                scalar_from<T>(pl->fb), scalar_from<O>(pl->fo), op, pl->split, nullptr, pl->offsets,
+                                shp, coords_out_dev, coords_stride, (O *)vals_out_dev, keys_out_or_null_dev)));
+            B2S_CHECK_LAUNCH();
+            return B2S_OK;
+        }();
+    }
+    scratch_free(pl->split, s);
+    scratch_free(pl->offsets, s);
+    delete pl;
+    return rc;
 }
 
 /* mode 0: f(x, scalar); 1: f(scalar, x); 2: unary f(x).  op >= 32 (binary) / >= 64 (unary) -> bool output. */

@@ -103,21 +103,17 @@ __global__ void row_products_kernel(int64_t M, int64_t n_col, const I *__restric
     }
 }
 
-// classify rows into bins (atomic append; order inside a bin is irrelevant)
-__global__ void bin_rows_kernel(int64_t M, const int64_t *__restrict__ P, int64_t t0, int64_t t1,
-                                int64_t *__restrict__ list0, int64_t *__restrict__ list1,
-                                int64_t *__restrict__ list2, unsigned long long *__restrict__ counts,
+// classify rows into bins (atomic append; order inside a bin is irrelevant).  lists = 4 arrays of M entries.
+__global__ void bin_rows_kernel(int64_t M, const int64_t *__restrict__ P, int64_t t0, int64_t t1, int64_t t2,
+                                int64_t *__restrict__ lists, unsigned long long *__restrict__ counts,
                                 unsigned long long *__restrict__ maxP) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= M) return;
     const int64_t p = P[row];
     if (p == 0) return;
-    if (p <= t0) list0[atomicAdd(counts + 0, 1ull)] = row;
-    else if (p <= t1) list1[atomicAdd(counts + 1, 1ull)] = row;
-    else {
-        list2[atomicAdd(counts + 2, 1ull)] = row;
-        atomicMax(maxP, (unsigned long long)p);
-    }
+    const int bin = p <= t0 ? 0 : (p <= t1 ? 1 : (p <= t2 ? 2 : 3));
+    lists[(int64_t)bin * M + atomicAdd(counts + bin, 1ull)] = row;
+    if (bin == 3) atomicMax(maxP, (unsigned long long)p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -614,7 +610,7 @@ struct SpgemmPlan {
     cudaStream_t stream;
 };
 
-static int64_t g_t0 = 64, g_t1 = 256;  // bin thresholds on products per row (tests may lower them)
+static int64_t g_t0 = 64, g_t1 = 128, g_t2 = 256;  // bin thresholds on products per row (tests may lower them)
 
 static int exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t s) {
     if (n == 0) return B2S_OK;
@@ -648,14 +644,13 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
     // 2. bins
     int64_t *lists = nullptr;
     unsigned long long *counts = nullptr;
-    if ((rc = scratch_alloc((void **)&lists, (size_t)M * 3 * 8, s))) return rc;
-    if ((rc = scratch_alloc((void **)&counts, 4 * 8, s))) return rc;
-    B2S_CUDA(cudaMemsetAsync(counts, 0, 32, s));
-    bin_rows_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, pl->P, g_t0, g_t1, lists, lists + M, lists + 2 * M,
-                                                               counts, counts + 3);
+    if ((rc = scratch_alloc((void **)&lists, (size_t)M * 4 * 8, s))) return rc;
+    if ((rc = scratch_alloc((void **)&counts, 5 * 8, s))) return rc;
+    B2S_CUDA(cudaMemsetAsync(counts, 0, 40, s));
+    bin_rows_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, pl->P, g_t0, g_t1, g_t2, lists, counts, counts + 4);
     B2S_CHECK_LAUNCH();
-    unsigned long long hc[4];
-    B2S_CUDA(cudaMemcpyAsync(hc, counts, 32, cudaMemcpyDeviceToHost, s));
+    unsigned long long hc[5];
+    B2S_CUDA(cudaMemcpyAsync(hc, counts, 40, cudaMemcpyDeviceToHost, s));
     B2S_CUDA(cudaStreamSynchronize(s));
     // upper-bound output buffers
     if ((rc = scratch_alloc((void **)&pl->tmp_idx, (size_t)pl->ub_total * 8, s))) return rc;
@@ -664,36 +659,41 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
     zero_i64_kernel<<<(unsigned)((M + 255) / 256 > 2048 ? 2048 : (M + 255) / 256), 256, 0, s>>>(pl->row_nz, M + 1);
     count_launch(2);
     const int sms = num_sms();
-    // 3a. small rows
-    if (hc[0]) {
-        constexpr int WARPS = 8;
-        int64_t blocks = ((int64_t)hc[0] + WARPS - 1) / WARPS;
-        if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-        if (pl->sorted)
-            spgemm_warp_kernel<T, W, I, 128, WARPS, true><<<(unsigned)blocks, WARPS * 32, 0, s>>>(
-                lists, (int64_t)hc[0], ap, ai, ad, bp, bi, bd, pl->ub_off, pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);
-        else
-            spgemm_warp_kernel<T, W, I, 128, WARPS, false><<<(unsigned)blocks, WARPS * 32, 0, s>>>(
-                lists, (int64_t)hc[0], ap, ai, ad, bp, bi, bd, pl->ub_off, pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);
-        B2S_CHECK_LAUNCH();
+    // 3a. warp-per-row bins: persistent grids sized by the occupancy the shared-memory footprint allows
+#define B2S_WARP_BIN(BIN, H, WARPS)                                                                                  \
+    if (hc[BIN]) {                                                                                                   \
+        auto kern_s = spgemm_warp_kernel<T, W, I, H, WARPS, true>;                                                   \
+        auto kern_r = spgemm_warp_kernel<T, W, I, H, WARPS, false>;                                                  \
+        int occ = 1;                                                                                                 \
+        if (pl->sorted) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_s, WARPS * 32, 0);                  \
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_r, WARPS * 32, 0);                             \
+        if (occ < 1) occ = 1;                                                                                        \
+        int64_t blocks = ((int64_t)hc[BIN] + WARPS - 1) / WARPS;                                                     \
+        if (blocks > (int64_t)sms * occ) blocks = (int64_t)sms * occ;                                                \
+        const int64_t *lst = lists + (int64_t)BIN * M;                                                               \
+        if (pl->sorted)                                                                                              \
+            kern_s<<<(unsigned)blocks, WARPS * 32, 0, s>>>(lst, (int64_t)hc[BIN], ap, ai, ad, bp, bi, bd, pl->ub_off, \
+                                                           pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);   \
+        else                                                                                                         \
+            kern_r<<<(unsigned)blocks, WARPS * 32, 0, s>>>(lst, (int64_t)hc[BIN], ap, ai, ad, bp, bi, bd, pl->ub_off, \
+                                                           pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);   \
+        B2S_CHECK_LAUNCH();                                                                                          \
     }
-    if (hc[1]) {
-        constexpr int WARPS = (sizeof(W) + sizeof(I) > 8) ? 2 : 4;  // keep static shared memory under 48 KB
-        int64_t blocks = ((int64_t)hc[1] + WARPS - 1) / WARPS;
-        if (blocks > (int64_t)sms * 4) blocks = (int64_t)sms * 4;
-        if (pl->sorted)
-            spgemm_warp_kernel<T, W, I, 512, WARPS, true><<<(unsigned)blocks, WARPS * 32, 0, s>>>(
-                lists + M, (int64_t)hc[1], ap, ai, ad, bp, bi, bd, pl->ub_off, pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);
-        else
-            spgemm_warp_kernel<T, W, I, 512, WARPS, false><<<(unsigned)blocks, WARPS * 32, 0, s>>>(
-                lists + M, (int64_t)hc[1], ap, ai, ad, bp, bi, bd, pl->ub_off, pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);
-        B2S_CHECK_LAUNCH();
+    constexpr bool kWide = (sizeof(W) + sizeof(I)) > 8;  // keeps static shared memory under 48 KB
+    B2S_WARP_BIN(0, 128, 8)
+    if constexpr (kWide) {
+        B2S_WARP_BIN(1, 256, 4)
+        B2S_WARP_BIN(2, 512, 2)
+    } else {
+        B2S_WARP_BIN(1, 256, 8)
+        B2S_WARP_BIN(2, 512, 4)
     }
+#undef B2S_WARP_BIN
     // 3b. long rows
-    if (hc[2]) {
+    if (hc[3]) {
         constexpr int WARPS = 8;
         constexpr int TILE = 2048;
-        const int64_t Pmax = (int64_t)hc[3];
+        const int64_t Pmax = (int64_t)hc[4];
         const int64_t cap = Pmax < pl->n_col ? Pmax : pl->n_col;
         int64_t Hmax = 64;
         while (Hmax < 2 * cap) Hmax <<= 1;
@@ -701,13 +701,13 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
         size_t per_cta = (((size_t)Hmax * sizeof(I) + 15) & ~(size_t)15) + (size_t)Hmax * 8 + (size_t)Hmax * 8 +
                          ((nwords_max * 4 + 15) & ~(size_t)15) + nwords_max * 8 + 64;
         per_cta = (per_cta + 255) & ~(size_t)255;
-        int64_t ctas = (int64_t)hc[2] < (int64_t)sms * 2 ? (int64_t)hc[2] : (int64_t)sms * 2;
+        int64_t ctas = (int64_t)hc[3] < (int64_t)sms * 2 ? (int64_t)hc[3] : (int64_t)sms * 2;
         const size_t budget = (size_t)8 << 30;
         while (ctas > 1 && (size_t)ctas * per_cta > budget) ctas /= 2;
         unsigned char *scratch = nullptr;
         if ((rc = scratch_alloc((void **)&scratch, (size_t)ctas * per_cta, s))) return rc;
         spgemm_block_kernel<T, W, I, WARPS, TILE><<<(unsigned)ctas, WARPS * 32, 0, s>>>(
-            lists + 2 * M, (int64_t)hc[2], pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off, pl->tmp_idx,
+            lists + 3 * M, (int64_t)hc[3], pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off, pl->tmp_idx,
             (T *)pl->tmp_val, pl->row_nnz, pl->row_nz, scratch, per_cta, Hmax, Pmax);
         B2S_CHECK_LAUNCH();
         if (pl->sorted) {
@@ -715,7 +715,7 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
             T *sc_val = nullptr;
             if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->ub_total * 8, s))) return rc;
             if ((rc = scratch_alloc((void **)&sc_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
-            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(lists + 2 * M, (int64_t)hc[2], pl->ub_off, pl->row_nnz,
+            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(lists + 3 * M, (int64_t)hc[3], pl->ub_off, pl->row_nnz,
                                                                    pl->tmp_idx, (T *)pl->tmp_val, sc_idx, sc_val);
             B2S_CHECK_LAUNCH();
             scratch_free(sc_idx, s);
@@ -795,7 +795,9 @@ extern "C" {
 
 int b2s_spgemm_set_thresholds(int64_t t0, int64_t t1) {
     g_t0 = (t0 >= 1 && t0 <= 64) ? t0 : 64;
-    g_t1 = (t1 >= g_t0 && t1 <= 256) ? t1 : 256;
+    g_t2 = (t1 >= g_t0 && t1 <= 256) ? t1 : 256;
+    g_t1 = g_t2 < 128 ? g_t2 : (g_t0 > 128 ? g_t0 : 128);
+    if (g_t1 > g_t2) g_t1 = g_t2;
     return B2S_OK;
 }
 

@@ -279,6 +279,13 @@ def ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fil
     return T(keys), T(r), T(flags)
 
 
+def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape):
+    keys, vals, flags = ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype)
+    keep = n(flags).astype(bool)
+    k = T(n(keys)[keep])
+    return unravel(k, shape, np.int64), T(n(vals)[keep]), k
+
+
 def ew_map(op, mode, x, scalar, out_fill, out_dtype):
     a = n(x)
     with np.errstate(all="ignore"):
@@ -343,6 +350,14 @@ def reduce_by_key(op, gid, vals):
         r = _RED[op].reduceat(v, starts).astype(v.dtype)
     counts = np.diff(np.concatenate([starts, [len(g)]]))
     return T(g[starts]), T(r), T(counts.astype(np.int64))
+
+
+def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape):
+    gid = group_ids(keys, ncols)
+    groups, r, counts = reduce_by_key(op, gid, vals)
+    reduce_fill_fix(op, r, counts, ncols, fill_value)
+    neq = int((~bits_ne(n(r), n(r).dtype.type(result_fill))).sum())
+    return unravel(groups, kept_shape, np.int64), groups, r, neq
 
 
 def reduce_fill_fix(op, vals, counts, ncols, fill_value):
