@@ -121,7 +121,9 @@ class COO(SparseArray):
 
     @classmethod
     def _from_device(cls, coords, data, shape, fill_value=None, keys=None):
-        """Wrap canonical device arrays without any checks."""
+        """Wrap canonical device arrays without any checks.  coords may be None when `keys` (sorted linear keys over
+        `shape`) is given: the coordinate rows are then derived lazily."""
+        assert coords is not None or keys is not None
         self = cls.__new__(cls)
         SparseArray.__init__(self, tuple(int(s) for s in shape), fill_value=None)
         self._coords_np = self._data_np = None
@@ -174,17 +176,34 @@ class COO(SparseArray):
         return self
 
     def _dev(self):
-        """Ensure the device copies exist (one H2D, then resident)."""
+        """(coords, data) on the device.  Coordinates are LAZY: results of device operations carry only their sorted
+        linear keys (8 B/entry instead of 8*ndim B); the coordinate rows are unravelled the first time they are asked
+        for (a user reading `.coords`, or an axis permutation)."""
         if self._data is None:
             D.require_device()
             self._coords = D.upload(self._coords_np)
             self._data = D.upload(self._data_np)
+        if self._coords is None:
+            self._coords = Kn.unravel(self._keys, self.shape, np.int64)
         return self._coords, self._data
+
+    def _data_dev(self):
+        """Device data only (does not materialise lazy coordinates)."""
+        if self._data is None:
+            self._dev()
+        return self._data
+
+    def _idx_dtype(self):
+        if self._coords is not None:
+            return D.np_dtype(self._coords)
+        if self._coords_np is not None:
+            return self._coords_np.dtype
+        return np.dtype(np.int64)
 
     @property
     def coords(self):
         if self._coords_np is None:
-            self._coords_np = D.download(self._coords)
+            self._coords_np = D.download(self._dev()[0])
         return self._coords_np
 
     @property
@@ -201,11 +220,11 @@ class COO(SparseArray):
     def nnz(self):
         if self._data is not None:
             return int(self._data.shape[0])
-        return int(self._coords_np.shape[1])
+        return int(self._data_np.shape[0])
 
     @property
     def nbytes(self):
-        c_item = self._coords.element_size() if self._coords is not None else self._coords_np.itemsize
+        c_item = self._idx_dtype().itemsize
         return self.nnz * (self._dtype.itemsize + self.ndim * c_item)
 
     @property
@@ -249,11 +268,14 @@ class COO(SparseArray):
                 changed = True
         if changed:
             idt = D.np_dtype(coords)
-            self._coords = Kn.unravel(keys, self.shape, idt)
+            # keep the caller's index dtype when it is not int64; otherwise derive coordinates lazily from the keys
+            self._coords = Kn.unravel(keys, self.shape, idt) if idt != np.dtype(np.int64) else None
             self._data = data
             self._coords_np = self._data_np = None
         if not (unsorted and not check_sort):
             self._keys = keys  # keys are sorted (or the caller vouched for the order)
+        elif self._coords is None:
+            self._coords = Kn.unravel(keys, self.shape, np.int64)  # unsorted by request: no key cache
 
     # ---- conversions ----------------------------------------------------------------------------------
     def todense(self):
@@ -261,7 +283,7 @@ class COO(SparseArray):
         return D.download(self.todense_device())
 
     def todense_device(self):
-        coords, data = self._dev()
+        data = self._data_dev()
         out = Kn.full(max(self.size, 1) if self.ndim == 0 else self.size, self.fill_value, self._dtype)
         if self.ndim == 0:
             if self.nnz:
@@ -295,9 +317,9 @@ class COO(SparseArray):
         dtype = np.dtype(dtype)
         if self.dtype == dtype and not copy:
             return self
-        coords, data = self._dev()
-        out = COO._from_device(coords, Kn.cast(data, dtype) if self.dtype != dtype else data.clone(), self.shape,
-                               dtype.type(self.fill_value), keys=self._keys)
+        data = self._data_dev()
+        out = COO._from_device(self._coords, Kn.cast(data, dtype) if self.dtype != dtype else data.clone(), self.shape,
+                               dtype.type(self.fill_value), keys=self.sorted_keys() if self._coords is None else self._keys)
         return out
 
     def linear_loc(self):
@@ -345,10 +367,8 @@ class COO(SparseArray):
         if self.nnz == 0 and self._data is None:
             return COO(np.zeros((len(shape), 0), dtype=np.intp), self._data_np[:0], shape=shape, has_duplicates=False,
                        sorted=True, fill_value=self.fill_value)
-        coords, data = self._dev()
-        keys = self.sorted_keys()
-        new_coords = Kn.unravel(keys, shape, D.np_dtype(coords) if self.ndim else np.int64)
-        return COO._from_device(new_coords, data, shape, self.fill_value, keys=keys)
+        # only the (lazy) coordinates change; keys and data are shared
+        return COO._from_device(None, self._data_dev(), shape, self.fill_value, keys=self.sorted_keys())
 
     def _permute_reshape(self, axes, new_shape):
         """transpose(axes) followed by reshape(new_shape) in one pass: linearise with permuted strides,
@@ -359,7 +379,6 @@ class COO(SparseArray):
         strides = [0] * self.ndim
         for pos, a in enumerate(axes):
             strides[a] = st_perm[pos]
-        idt = D.np_dtype(coords) if self.ndim else np.int64
         if self.nnz == 0:
             t = D.torch()
             return COO._from_device(t.zeros((len(new_shape), 0), dtype=coords.dtype, device=coords.device), data,
@@ -369,8 +388,7 @@ class COO(SparseArray):
         if unsorted:
             keys, perm = Kn.sort_keys(keys, key_bits(self.size))
             data = Kn.gather(data, perm)
-        new_coords = Kn.unravel(keys, new_shape, idt)
-        return COO._from_device(new_coords, data, new_shape, self.fill_value, keys=keys)
+        return COO._from_device(None, data, new_shape, self.fill_value, keys=keys)
 
     def _permuted_keys(self, axes):
         """(sorted linear keys over the permuted shape, matching data) without building coordinates."""

@@ -60,14 +60,14 @@ def _csr_arrays(g, dtr):
 
 def _coo_as_csr(c, dtr, by_col=False):
     """2-D canonical COO -> CSR arrays (by_col: CSR of the transpose, i.e. CSC)."""
-    coords, data = c._dev()
+    data = c._data_dev()
     M, N = c.shape
     if not by_col:
         keys = c.sorted_keys()
         _, indices, indptr = Kn.csr_from_keys(keys, M, N, np.int64)
         d = data
     else:
-        keys = Kn.linearize(coords, [1, M])  # key over (col, row)
+        keys = Kn.linearize(c._dev()[0], [1, M])  # key over (col, row)
         unsorted, _ = Kn.keys_flags(keys)
         d = data
         if unsorted:
@@ -257,7 +257,7 @@ def _check_nan(x):
     if isinstance(x, COO):
         if x.dtype.kind != "f" or x.nnz == 0:
             return False
-        return Kn.any_nan(x._dev()[1])
+        return Kn.any_nan(x._data_dev())
     if isinstance(x, GCXS):
         if x.dtype.kind != "f" or x.nnz == 0:
             return False

@@ -108,8 +108,7 @@ def _finish(keys, vals, flags, shape, fill, idx_dtype=np.int64):
     if total != int(flags.shape[0]):
         keys = Kn.compact(keys, flags, pos, total)
         vals = Kn.compact(vals, flags, pos, total)
-    coords = Kn.unravel(keys, shape, idx_dtype)
-    return COO._from_device(coords, vals, shape, fill, keys=keys)
+    return COO._from_device(None, vals, shape, fill, keys=keys)
 
 
 def _stream(x, shape):
@@ -117,7 +116,7 @@ def _stream(x, shape):
 
     Trailing broadcast axes are expanded virtually (R > 1); any other broadcast pattern is materialised with the
     expansion kernel (+ a stable sort when the expansion is not already in key order)."""
-    coords, data = x._dev()
+    data = x._data_dev()
     nd, xn = len(shape), x.ndim
     off = nd - xn
     # result axis d is a broadcast axis of x iff the result is wider there than x (x lacks it or has extent 1)
@@ -125,19 +124,19 @@ def _stream(x, shape):
     if not any(bcast):
         if tuple(x.shape) == tuple(shape):
             return x.sorted_keys(), data, 1
-        st = c_strides(shape)
-        return Kn.linearize(coords, [st[d + off] for d in range(xn)]), data, 1
+        # same C-order layout up to leading extent-1 axes: the linear keys are identical
+        return x.sorted_keys(), data, 1
     first_b = bcast.index(True)
     trailing = all(bcast[d] or shape[d] == 1 for d in range(first_b, nd))
     if trailing:
         R = prod(shape[first_b:])
         st = c_strides(shape)
         strides = [(st[d + off] // R if (d + off) < first_b else 0) for d in range(xn)]
-        return Kn.linearize(coords, strides), data, R
+        return Kn.linearize(x._dev()[0], strides), data, R
     src_row = [(d - off if (d >= off and not bcast[d]) else -1) for d in range(nd)]
     # axes that x lacks but have extent 1 contribute coordinate 0: treat as broadcast of extent 1
     is_b = [1 if (bcast[d] or src_row[d] < 0) else 0 for d in range(nd)]
-    keys, src = Kn.ew_expand(coords, shape, is_b, src_row)
+    keys, src = Kn.ew_expand(x._dev()[0], shape, is_b, src_row)
     unsorted, _ = Kn.keys_flags(keys)
     if unsorted:
         keys, perm = Kn.sort_keys(keys, key_bits(prod(shape)))
@@ -230,7 +229,7 @@ class _Elemwise:
         _check_compute_dtype(T, func)
         with np.errstate(all="ignore"):
             fill = np.asarray(func(a.fill_value)).astype(out_dt)[()]
-        coords, data = a._dev()
+        data = a._data_dev()
         if any(s == 0 for s in self.shape):
             return COO(np.empty((len(self.shape), 0), dtype=np.intp), np.empty(0, dtype=out_dt), shape=self.shape,
                        has_duplicates=False, sorted=True, fill_value=fill)
@@ -238,14 +237,12 @@ class _Elemwise:
         return self._keep(a, vals, flags, fill)
 
     def _keep(self, a, vals, flags, fill):
-        coords, _ = a._dev()
         pos, total = Kn.scan_flags(flags)
-        keys = a._keys
-        if total != a.nnz:
-            coords = Kn.compact_rows(coords, flags, pos, total)
-            vals = Kn.compact(vals, flags, pos, total)
-            keys = Kn.compact(keys, flags, pos, total) if keys is not None else None
-        return COO._from_device(coords, vals, a.shape, fill, keys=keys)
+        if total == a.nnz:  # nothing pruned: coordinates (materialised or lazy) are shared with the operand
+            return COO._from_device(a._coords, vals, a.shape, fill,
+                                    keys=a._keys if a._coords is not None else a.sorted_keys())
+        keys = Kn.compact(a.sorted_keys(), flags, pos, total)
+        return COO._from_device(None, Kn.compact(vals, flags, pos, total), a.shape, fill, keys=keys)
 
     # ------------------------------------------------------------------------------------------------------
     def _binary(self):
@@ -276,9 +273,10 @@ class _Elemwise:
                 return self._empty(out_dt, fill)
             ka, da, Ra = _stream(a, shape)
             kb, db, Rb = _stream(b, shape)
-            coords, vals, keys = Kn.ew_merge_fused(op, ka, Kn.cast(da, T), Ra, kb, Kn.cast(db, T), Rb,
-                                                   T.type(a.fill_value), T.type(b.fill_value), fill, out_dt, shape)
-            return COO._from_device(coords, vals, shape, fill, keys=keys)
+            _, vals, keys = Kn.ew_merge_fused(op, ka, Kn.cast(da, T), Ra, kb, Kn.cast(db, T), Rb,
+                                              T.type(a.fill_value), T.type(b.fill_value), fill, out_dt, shape,
+                                              want_coords=False)
+            return COO._from_device(None, vals, shape, fill, keys=keys)
 
         if (a_sp and not b_dn) or (b_sp and not a_dn):  # sparse (x) scalar
             sp, sc, mode = (a, b, 0) if a_sp else (b, a, 1)
@@ -287,7 +285,7 @@ class _Elemwise:
                 fill = np.asarray(func(a.fill_value, sc) if a_sp else func(sc, b.fill_value)).astype(out_dt)[()]
             if empty:
                 return self._empty(out_dt, fill)
-            _, data = sp._dev()
+            data = sp._data_dev()
             vals, flags = Kn.ew_map(op, mode, Kn.cast(data, T), T.type(sc), fill, out_dt)
             return self._keep(sp, vals, flags, fill)
 
@@ -354,5 +352,4 @@ def broadcast_to(x, shape):
         is_b = [1 if (bc[d] or src_row[d] < 0) else 0 for d in range(nd)]
         keys, src = Kn.ew_expand(coords, result_shape, is_b, src_row)
         data = Kn.gather(data, src)
-    coords = Kn.unravel(keys, result_shape, np.int64)
-    return COO._from_device(coords, data, result_shape, x.fill_value, keys=keys)
+    return COO._from_device(None, data, result_shape, x.fill_value, keys=keys)

@@ -48,8 +48,7 @@ def sddmm(s, a, b, *, b_transposed=False):
     ad = _dense_dev(a, T)
     bt = _dense_dev(b, T) if b_transposed else Kn.transpose_dense(_dense_dev(b, T))  # (N, K): contiguous gathers
     out = Kn.sddmm(indptr, cols, vals, ad, bt, M, N, K)
-    coords, _ = c._dev()
-    res = COO._from_device(coords, out, s.shape, T.type(0), keys=c._keys)
+    res = COO._from_device(c._coords, out, s.shape, T.type(0), keys=c.sorted_keys())
     res._canonicalise(check_sort=False, sum_dups=False, prune=True)  # s * dense drops exact zeros (_umath.py:627-633)
     return res.asformat("gcxs", compressed_axes=s.compressed_axes) if was_gcxs else res
 

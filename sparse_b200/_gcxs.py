@@ -195,11 +195,12 @@ class GCXS(SparseArray):
         reordered_shape = tuple(x.shape[i] for i in axis_order)
         row_size, col_size = prod(reordered_shape[:axisptr]), prod(reordered_shape[axisptr:])
         check_linear_range(x.shape)
-        coords, data = x._dev()
-        idt = idx_dtype or D.np_dtype(coords)
+        data = x._data_dev()
+        idt = idx_dtype or x._idx_dtype()
         if axis_order == list(range(x.ndim)):
             keys = x.sorted_keys()
         else:
+            coords = x._dev()[0]
             st = c_strides(reordered_shape)
             strides = [0] * x.ndim
             for pos, a in enumerate(axis_order):
@@ -237,8 +238,7 @@ class GCXS(SparseArray):
         if unsorted:
             keys, perm = Kn.sort_keys(keys, key_bits(self.size))
             data = Kn.gather(data, perm)
-        coords = Kn.unravel(keys, self.shape, idt)
-        return COO._from_device(coords, data, self.shape, self.fill_value, keys=keys)
+        return COO._from_device(None, data, self.shape, self.fill_value, keys=keys)  # coordinates derived lazily
 
     @classmethod
     def from_numpy(cls, x, compressed_axes=None, fill_value=None, idx_dtype=None):

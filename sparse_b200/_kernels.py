@@ -450,7 +450,8 @@ def ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fil
     return okeys, ovals, oflags
 
 
-def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape):
+def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape,
+                   want_coords=True):
     """Fused COO (x) COO coiteration -> (coords[ndim, nnz] int64, vals[nnz], keys[nnz]); canonical order."""
     t = _t()
     lib = _lib.load()
@@ -466,10 +467,11 @@ def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, o
     _lib.check(rc, "b2s_ew_merge_begin")
     n = int(nnz.value)
     dev = data_a.device
-    coords = t.empty((len(shape), n), dtype=t.int64, device=dev)
+    coords = t.empty((len(shape), n), dtype=t.int64, device=dev) if want_coords else None
     vals = t.empty(n, dtype=D.torch_dtype(out_dtype), device=dev)
     keys = t.empty(n, dtype=t.int64, device=dev)
-    rc = lib.b2s_ew_merge_finish(plan, vp(D.ptr(coords)), i64(max(n, 1)), vp(D.ptr(vals)), vp(D.ptr(keys)))
+    rc = lib.b2s_ew_merge_finish(plan, vp(D.ptr(coords) if want_coords else 0), i64(max(n, 1)), vp(D.ptr(vals)),
+                                 vp(D.ptr(keys)))
     _lib.check(rc, "b2s_ew_merge_finish")
     return coords, vals, keys
 
@@ -553,7 +555,7 @@ def reduce_by_key(op, gid, vals):
     return groups[:g], ovals[:g], counts[:g]
 
 
-def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape):
+def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape, want_coords=True):
     """Segmented reduction over runs of key // ncols -> (coords[ndim, g] int64, group ids[g], values[g], n_equal_fill)."""
     t = _t()
     lib = _lib.load()
@@ -566,12 +568,13 @@ def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape):
     g = int(ng.value)
     dev = vals.device
     nd = len(kept_shape)
-    coords = t.empty((nd, g), dtype=t.int64, device=dev)
+    coords = t.empty((nd, g), dtype=t.int64, device=dev) if want_coords else None
     gids = t.empty(g, dtype=t.int64, device=dev)
     out = t.empty(g, dtype=vals.dtype, device=dev)
     neq = ctypes.c_int64(0)
     rc = lib.b2s_reduce_finish(plan, _scalar_bytes(fill_value, dt), i32(1), _scalar_bytes(result_fill, dt), i32(nd),
-                               _i64arr(kept_shape), vp(D.ptr(gids)), vp(D.ptr(coords) if nd else 0), i64(max(g, 1)),
+                               _i64arr(kept_shape), vp(D.ptr(gids)), vp(D.ptr(coords) if (nd and want_coords) else 0),
+                               i64(max(g, 1)),
                                vp(D.ptr(out)), ctypes.byref(neq))
     _lib.check(rc, "b2s_reduce_finish")
     return coords, gids, out, int(neq.value)

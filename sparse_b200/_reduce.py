@@ -85,11 +85,10 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
     data = Kn.cast(data, work_dt)
     # one fused segmented-scan pass pair: values with the fill-value contribution applied, group ids (= linear index
     # over the kept axes) and their coordinates (_grouped_reduce + _sparse_array.py:405-422 + _reduce_return)
-    coords, gids, vals, n_eq = Kn.reduce_fused(op, keys, data, ncols, fill_w, result_fill, kept_shape)
+    _, gids, vals, n_eq = Kn.reduce_fused(op, keys, data, ncols, fill_w, result_fill, kept_shape, want_coords=False)
     if n_eq:  # prune=True of _reduce_return (_coo/core.py:713-723): drop results equal to the result fill value
         flags = Kn.flag_not_fill(vals, result_fill)
         pos, total = Kn.scan_flags(flags)
-        coords = Kn.compact_rows(coords, flags, pos, total)
         vals = Kn.compact(vals, flags, pos, total)
         gids = Kn.compact(gids, flags, pos, total)
-    return COO._from_device(coords, vals, kept_shape, result_fill, keys=gids)
+    return COO._from_device(None, vals, kept_shape, result_fill, keys=gids)  # coordinates are derived lazily

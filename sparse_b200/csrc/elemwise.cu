@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "fastdiv.cuh"
 
 namespace b2s {
 
@@ -217,14 +218,23 @@ struct Stream {
     const int64_t *keys;  // prefix keys, sorted, unique
     int64_t n;            // stored entries
     int64_t R;            // trailing expansion factor (>= 1)
+    FastDiv fR;           // division by R without the 64-bit divide sequence
     __device__ __forceinline__ int64_t len() const { return n * R; }
     __device__ __forceinline__ int64_t key(int64_t p) const {
         if (R == 1) return keys[p];
-        const int64_t q = p / R;
+        const int64_t q = (int64_t)fR.div((uint64_t)p);
         return keys[q] * R + (p - q * R);
     }
-    __device__ __forceinline__ int64_t src(int64_t p) const { return R == 1 ? p : p / R; }
+    __device__ __forceinline__ int64_t src(int64_t p) const { return R == 1 ? p : (int64_t)fR.div((uint64_t)p); }
 };
+static inline Stream make_stream(const int64_t *keys, int64_t n, int64_t R) {
+    Stream s;
+    s.keys = keys;
+    s.n = n;
+    s.R = R;
+    s.fR = make_fastdiv((uint64_t)R);
+    return s;
+}
 
 constexpr int EW_THREADS = 256;
 constexpr int EW_ITEMS = 8;
@@ -334,7 +344,7 @@ ew_merge_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restric
 constexpr int kEwMaxDims = 16;
 struct EwShape {
     int ndim;
-    int64_t extent[kEwMaxDims];
+    FastDiv extent[kEwMaxDims];
 };
 
 template <typename T, typename O, bool PRED, bool EMIT>
@@ -450,12 +460,14 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
             const int64_t key = sk[t];
             vals_out[base + t] = sv[t];
             if (keys_out) keys_out[base + t] = key;
-            int64_t k = key;
-            for (int d = shp.ndim - 1; d >= 0; --d) {
-                const int64_t e = shp.extent[d];
-                const int64_t q = k / e;
-                coords_out[(int64_t)d * coords_stride + base + t] = k - q * e;
-                k = q;
+            if (coords_out) {
+                uint64_t k = (uint64_t)key;
+                for (int d = shp.ndim - 1; d >= 0; --d) {
+                    uint64_t q, r;
+                    shp.extent[d].divmod(k, q, r);
+                    coords_out[(int64_t)d * coords_stride + base + t] = (int64_t)r;
+                    k = q;
+                }
             }
         }
     }
@@ -496,7 +508,7 @@ __global__ void ew_map_kernel(const T *__restrict__ x, int64_t n, T scalar, int 
 // ---- COO (x) dense ndarray: gather the dense operand at the (virtually expanded) coordinates ----
 struct DenseIdx {
     int ndim;
-    int64_t extent[kEwMaxDims];   // result shape
+    FastDiv extent[kEwMaxDims];   // result shape
     int64_t dstride[kEwMaxDims];  // element strides of the dense operand broadcast to the result shape (0 on broadcast axes)
 };
 
@@ -507,11 +519,12 @@ __global__ void ew_dense_kernel(Stream A, const T *__restrict__ da, const T *__r
     const int64_t L = A.len();
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < L; p += (int64_t)gridDim.x * blockDim.x) {
         const int64_t key = A.key(p);
-        int64_t k = key, off = 0;
+        uint64_t k = (uint64_t)key;
+        int64_t off = 0;
         for (int d = di.ndim - 1; d >= 0; --d) {
-            const int64_t e = di.extent[d];
-            const int64_t q = k / e;
-            off += (k - q * e) * di.dstride[d];
+            uint64_t q, r;
+            di.extent[d].divmod(k, q, r);
+            off += (int64_t)r * di.dstride[d];
             k = q;
         }
         const T sv = da[A.src(p)];
@@ -613,7 +626,7 @@ int b2s_ew_merge(int dtype, int op, const int64_t *keys_a_dev, const void *data_
     const int64_t total = na * Ra + nb * Rb;
     if (total == 0) return B2S_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    Stream A{keys_a_dev, na, Ra}, B{keys_b_dev, nb, Rb};
+    Stream A = make_stream(keys_a_dev, na, Ra), B = make_stream(keys_b_dev, nb, Rb);
     const int64_t ntiles = (total + EW_TILE - 1) / EW_TILE;
     B2S_REQUIRE(ntiles < 2147483647LL, B2S_ERR_OVERFLOW, "ew_merge: too many tiles");
     int64_t *split = nullptr;
@@ -648,8 +661,8 @@ int b2s_ew_merge_begin(int dtype, int op, const int64_t *keys_a_dev, const void 
     pl->dtype = dtype;
     pl->op = op;
     pl->ndim = ndim;
-    pl->A = Stream{keys_a_dev, na, Ra};
-    pl->B = Stream{keys_b_dev, nb, Rb};
+    pl->A = make_stream(keys_a_dev, na, Ra);
+    pl->B = make_stream(keys_b_dev, nb, Rb);
     pl->da = data_a_dev;
     pl->db = data_b_dev;
     memcpy(pl->fa, fill_a_host, 8);
@@ -705,7 +718,7 @@ int b2s_ew_merge_finish(void *plan, int64_t *coords_out_dev, int64_t coords_stri
         const bool pred = pl->op >= 32;
         EwShape shp{};
         shp.ndim = pl->ndim;
-        for (int d = 0; d < pl->ndim; ++d) shp.extent[d] = pl->shape[d];
+        for (int d = 0; d < pl->ndim; ++d) shp.extent[d] = make_fastdiv((uint64_t)pl->shape[d]);
         const int dtype = pl->dtype;
         const int op = pl->op;
         rc = [&]() -> int {
@@ -747,11 +760,11 @@ int b2s_ew_dense(int dtype, int op, int swap, const int64_t *keys_a_dev, const v
     const int64_t L = na * Ra;
     if (L == 0) return B2S_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    Stream A{keys_a_dev, na, Ra};
+    Stream A = make_stream(keys_a_dev, na, Ra);
     DenseIdx di{};
     di.ndim = ndim;
     for (int d = 0; d < ndim; ++d) {
-        di.extent[d] = shape_host[d];
+        di.extent[d] = make_fastdiv((uint64_t)shape_host[d]);
         di.dstride[d] = dense_strides_host[d];
     }
     const bool pred = op >= 32;

@@ -13,13 +13,14 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "fastdiv.cuh"
 
 namespace b2s {
 
 constexpr int kMaxDims = 16;
 struct DimPack {
     int64_t stride[kMaxDims];  // multiplier of each *input* row (0 for dropped rows)
-    int64_t extent[kMaxDims];
+    FastDiv fext[kMaxDims];    // extents, prepared for multiply-high division
 };
 
 static inline unsigned grid_for(int64_t n, int threads = 256, int per_sm = 16) {
@@ -50,11 +51,11 @@ template <typename I>
 __global__ void unravel_kernel(int ndim, int64_t nnz, const int64_t *__restrict__ keys, DimPack dp,
                                I *__restrict__ coords, int64_t row_stride) {
     B2S_GRID_STRIDE(i, nnz) {
-        int64_t k = keys[i];
+        uint64_t k = (uint64_t)keys[i];
         for (int d = ndim - 1; d >= 0; --d) {
-            const int64_t e = dp.extent[d];
-            const int64_t q = k / e;
-            coords[(int64_t)d * row_stride + i] = (I)(k - q * e);
+            uint64_t q, r;
+            dp.fext[d].divmod(k, q, r);
+            coords[(int64_t)d * row_stride + i] = (I)r;
             k = q;
         }
     }
@@ -255,7 +256,7 @@ int b2s_coo_unravel(int idx_bytes, int ndim, int64_t nnz, const int64_t *keys_de
     B2S_REQUIRE(idx_bytes == 4 || idx_bytes == 8, B2S_ERR_INVALID, "unravel: idx_bytes");
     if (nnz == 0 || ndim == 0) return B2S_OK;
     DimPack dp{};
-    make_dims(ndim, shape_host, dp.extent);
+    for (int d = 0; d < ndim; ++d) dp.fext[d] = make_fastdiv((uint64_t)shape_host[d]);
     cudaStream_t s = (cudaStream_t)stream;
     if (idx_bytes == 4)
         unravel_kernel<int32_t><<<grid_for(nnz), 256, 0, s>>>(ndim, nnz, keys_dev, dp, (int32_t *)coords_out_dev,

@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "fastdiv.cuh"
 
 namespace b2s {
 
@@ -119,13 +120,14 @@ __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
 
 struct RdShape {
     int ndim;
-    int64_t extent[RD_MAXDIM];
+    FastDiv extent[RD_MAXDIM];
 };
 
 // One tile.  EMIT = false: write the tile summary.  EMIT = true: write finished runs.
 template <typename T, bool EMIT>
 __global__ void __launch_bounds__(RD_THREADS)
-reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols, int op,
+reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
+                   FastDiv fcols, int op,
                    // summaries (pass 1 out / pass 2 in)
                    int64_t *__restrict__ t_heads, int *__restrict__ t_flag, T *__restrict__ t_val,
                    int64_t *__restrict__ t_cnt, const int64_t *__restrict__ head_off, const int *__restrict__ c_flag,
@@ -146,12 +148,12 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     T v[RD_ITEMS];
     bool head[RD_ITEMS];
     int64_t gprev = -1;
-    if (base > 0 && base - 1 < n) gprev = keys[base - 1] / ncols;
+    if (base > 0 && base - 1 < n) gprev = (int64_t)fcols.div((uint64_t)keys[base - 1]);
 #pragma unroll
     for (int i = 0; i < RD_ITEMS; ++i) {
         const int64_t p = base + i;
         if (p < n) {
-            g[i] = keys[p] / ncols;
+            g[i] = (int64_t)fcols.div((uint64_t)keys[p]);
             v[i] = vals[p];
             head[i] = (p == 0) || (g[i] != (i == 0 ? gprev : g[i - 1]));
         } else {
@@ -248,7 +250,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         // walk the items again; a run ends where the next element is a head (or the array ends)
         int64_t gnext_thread = -1;
         const int64_t pn = base + RD_ITEMS;
-        if (pn < n) gnext_thread = keys[pn] / ncols;
+        if (pn < n) gnext_thread = (int64_t)fcols.div((uint64_t)keys[pn]);
         int eq = 0;
         T rv = st.val;
         int64_t rc = st.cnt;
@@ -271,11 +273,11 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                     out_val[idx] = outv;
                     out_gid[idx] = g[i];
                     if (out_coords) {
-                        int64_t k = g[i];
+                        uint64_t k = (uint64_t)g[i];
                         for (int d = shp.ndim - 1; d >= 0; --d) {
-                            const int64_t e = shp.extent[d];
-                            const int64_t q = k / e;
-                            out_coords[(int64_t)d * coords_stride + idx] = k - q * e;
+                            uint64_t q, r;
+                            shp.extent[d].divmod(k, q, r);
+                            out_coords[(int64_t)d * coords_stride + idx] = (int64_t)r;
                             k = q;
                         }
                     }
@@ -417,7 +419,7 @@ static int rd_begin_t(RdPlan *pl) {
     const int64_t nt = pl->ntiles;
     RdShape shp{};
     reduce_tile_kernel<T, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(
-        pl->keys, (const T *)pl->vals, pl->n, pl->ncols, pl->op, pl->t_heads, pl->t_flag, (T *)pl->t_val, pl->t_cnt,
+        pl->keys, (const T *)pl->vals, pl->n, pl->ncols, make_fastdiv((uint64_t)pl->ncols), pl->op, pl->t_heads, pl->t_flag, (T *)pl->t_val, pl->t_cnt,
         nullptr, nullptr, nullptr, nullptr, T(0), 0, T(0), shp, nullptr, nullptr, 0, nullptr, nullptr);
     B2S_CHECK_LAUNCH();
     reduce_scan_tiles_kernel<T><<<1, 1024, 0, s>>>(nt, pl->op, pl->t_heads, pl->t_flag, (const T *)pl->t_val, pl->t_cnt,
@@ -433,12 +435,13 @@ static int rd_finish_t(RdPlan *pl, const void *fill_host, int apply_fix, const v
     cudaStream_t s = pl->stream;
     RdShape shp{};
     shp.ndim = ndim;
-    for (int d = 0; d < ndim; ++d) shp.extent[d] = shape_host[d];
+    for (int d = 0; d < ndim; ++d) shp.extent[d] = make_fastdiv((uint64_t)shape_host[d]);
     T fill, rfill;
     memcpy(&fill, fill_host, sizeof(T));
     memcpy(&rfill, result_fill_host, sizeof(T));
     reduce_tile_kernel<T, true><<<(unsigned)pl->ntiles, RD_THREADS, 0, s>>>(
-        pl->keys, (const T *)pl->vals, pl->n, pl->ncols, pl->op, nullptr, nullptr, nullptr, nullptr, pl->head_off,
+        pl->keys, (const T *)pl->vals, pl->n, pl->ncols, make_fastdiv((uint64_t)pl->ncols), pl->op, nullptr, nullptr,
+        nullptr, nullptr, pl->head_off,
         pl->c_flag, (const T *)pl->c_val, pl->c_cnt, fill, apply_fix, rfill, shp, gid_out, coords_out, coords_stride,
         (T *)vals_out, pl->n_eq);
     B2S_CHECK_LAUNCH();

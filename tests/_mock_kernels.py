@@ -279,11 +279,12 @@ def ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fil
     return T(keys), T(r), T(flags)
 
 
-def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape):
+def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape,
+                   want_coords=True):
     keys, vals, flags = ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype)
     keep = n(flags).astype(bool)
     k = T(n(keys)[keep])
-    return unravel(k, shape, np.int64), T(n(vals)[keep]), k
+    return (unravel(k, shape, np.int64) if want_coords else None), T(n(vals)[keep]), k
 
 
 def ew_map(op, mode, x, scalar, out_fill, out_dtype):
@@ -352,12 +353,12 @@ def reduce_by_key(op, gid, vals):
     return T(g[starts]), T(r), T(counts.astype(np.int64))
 
 
-def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape):
+def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape, want_coords=True):
     gid = group_ids(keys, ncols)
     groups, r, counts = reduce_by_key(op, gid, vals)
     reduce_fill_fix(op, r, counts, ncols, fill_value)
     neq = int((~bits_ne(n(r), n(r).dtype.type(result_fill))).sum())
-    return unravel(groups, kept_shape, np.int64), groups, r, neq
+    return (unravel(groups, kept_shape, np.int64) if want_coords else None), groups, r, neq
 
 
 def reduce_fill_fix(op, vals, counts, ncols, fill_value):
