@@ -92,6 +92,19 @@ int b2s_spmm_csr_dense_host(int dtype, int idx_bytes, int64_t M, int64_t K, int6
                             const void *a_data_host, const void *a_indices_host, const void *a_indptr_host,
                             const void *b_host, void *out_host);
 
+/* 1 if every row of the CSR has non-decreasing column indices (precondition of the panel passes). Synchronises. */
+int b2s_csr_rows_sorted(int idx_bytes, int64_t M, const void *indptr_dev, const void *indices_dev, int *sorted_host,
+                        void *stream);
+/*
+ * K1 with explicit scheduling: n_panels <= 1 -> the one-pass kernel; n_panels >= 2 -> column-panel passes that keep
+ * the active slice of B resident in L2 (rows must be sorted by column: rows_sorted = 1; bit-identical results);
+ * n_panels == 0 -> choose from the size of B (~48 MB per panel) and nnz / M.  nnz < 0 = unknown.
+ */
+int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, int64_t nnz,
+                          const void *a_data_dev, const void *a_indices_dev, const void *a_indptr_dev,
+                          const void *b_dev, int64_t ldb, void *out_dev, int64_t ldc, int n_panels, int rows_sorted,
+                          void *stream);
+
 /* Tuning knob for K1 (0 = default).  variant: 1 = register-staged LDG gather,
  * 2 = 1-D bulk-TMA (cp.async.bulk) gather through a shared-memory ring. */
 int b2s_spmm_set_variant(int variant, int unroll);

@@ -166,6 +166,13 @@ class GCXS(SparseArray):
             self._indptr_np = D.download(self._indptr)
         return self._indptr_np
 
+    def _rows_sorted(self):
+        """Are the indices of every compressed row sorted?  (cached; decides whether K1 may use its panel passes)"""
+        if getattr(self, "_rows_sorted_flag", None) is None:
+            data, indices, indptr = self._dev()
+            self._rows_sorted_flag = Kn.csr_rows_sorted(indices, indptr, self._compressed_shape[0]) if self.ndim >= 2 else True
+        return self._rows_sorted_flag
+
     # ---- COO <-> GCXS ----------------------------------------------------------------------------------------
     @classmethod
     def from_coo(cls, x, compressed_axes=None, idx_dtype=None):

@@ -59,11 +59,14 @@ def empty(n, dtype, like=None):
 # ------------------------------------------------------------------------------------------------
 # K1
 # ------------------------------------------------------------------------------------------------
-def spmm_csr_dense(a_data, a_indices, a_indptr, b, M: int, K: int, N: int, out=None):
+def spmm_csr_dense(a_data, a_indices, a_indptr, b, M: int, K: int, N: int, out=None, *, n_panels=1,
+                   rows_sorted=None):
     """out[M,N] = CSR(A) @ B -- replaces _dot_csr_ndarray (_common.py:720-755).
 
     All arguments are CUDA tensors; `b` is (K, N) row-major (row stride may exceed N).
     Bit-identical to the reference loop (stored order, unfused multiply/add).
+    n_panels: 1 = one-pass kernel; >= 2 = column-panel passes (L2-resident slices of B; needs rows sorted by
+    column); 0 = let the library choose from the size of B and nnz / M.
     """
     lib = _lib.load()
     t = _t()
@@ -76,13 +79,23 @@ def spmm_csr_dense(a_data, a_indices, a_indptr, b, M: int, K: int, N: int, out=N
         out = t.empty((M, N), dtype=a_data.dtype, device=a_data.device)
     ldb = b.stride(0) if K > 1 else max(N, 1)
     ldc = out.stride(0) if M > 1 else max(N, 1)
-    rc = lib.b2s_spmm_csr_dense(
-        i32(D.dtype_code(dt)), i32(_idx_bytes(a_indices)), i64(M), i64(K), i64(N), vp(D.ptr(a_data)),
-        vp(D.ptr(a_indices)), vp(D.ptr(a_indptr)), vp(D.ptr(b)), i64(max(ldb, N)), vp(D.ptr(out)), i64(max(ldc, N)),
-        _sp(),
+    if n_panels != 1 and rows_sorted is None:
+        rows_sorted = csr_rows_sorted(a_indices, a_indptr, M)
+    rc = lib.b2s_spmm_csr_dense_ex(
+        i32(D.dtype_code(dt)), i32(_idx_bytes(a_indices)), i64(M), i64(K), i64(N), i64(a_data.shape[0]),
+        vp(D.ptr(a_data)), vp(D.ptr(a_indices)), vp(D.ptr(a_indptr)), vp(D.ptr(b)), i64(max(ldb, N)), vp(D.ptr(out)),
+        i64(max(ldc, N)), i32(n_panels if (n_panels == 1 or rows_sorted) else 1), i32(1 if rows_sorted else 0), _sp(),
     )
-    _lib.check(rc, "b2s_spmm_csr_dense")
+    _lib.check(rc, "b2s_spmm_csr_dense_ex")
     return out
+
+
+def csr_rows_sorted(a_indices, a_indptr, M) -> bool:
+    """True when every CSR row has non-decreasing column indices (precondition of the panel passes)."""
+    r = ctypes.c_int(1)
+    _lib.check(_lib.load().b2s_csr_rows_sorted(i32(_idx_bytes(a_indices)), i64(M), vp(D.ptr(a_indptr)),
+                                               vp(D.ptr(a_indices)), ctypes.byref(r), _sp()))
+    return bool(r.value)
 
 
 def spmm_csr_dense_host(a_data: np.ndarray, a_indices: np.ndarray, a_indptr: np.ndarray, b: np.ndarray,

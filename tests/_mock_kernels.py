@@ -49,7 +49,12 @@ def bits_ne(a, fill):
 
 
 # ---- K1 / prims ------------------------------------------------------------------------------------------
-def spmm_csr_dense(a_data, a_indices, a_indptr, b, M, K, N, out=None):
+def csr_rows_sorted(a_indices, a_indptr, M):
+    ip, ix = n(a_indptr), n(a_indices)
+    return all((np.diff(ix[ip[r]:ip[r + 1]]) >= 0).all() for r in range(M))
+
+
+def spmm_csr_dense(a_data, a_indices, a_indptr, b, M, K, N, out=None, n_panels=1, rows_sorted=None):
     r = oracle.dot_csr_ndarray((M, N), n(a_data), n(a_indices), n(a_indptr), np.ascontiguousarray(n(b)))
     r = T(r)
     if out is not None:

@@ -1,0 +1,125 @@
+"""Parity at BASELINE.json's full configuration sizes (C3, C4, C5) -- GPU only.
+
+Where the oracle (C port / NumPy restatement, pinned to the reference by the golden tests) finishes in seconds the
+comparison is exact and complete; otherwise size-independent properties are checked (linearity in a power of two,
+idempotence, sampled entries against a float64 restatement)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _sp():
+    import _mock_kernels
+    import sparse_b200
+
+    _mock_kernels.uninstall()
+    return sparse_b200
+
+
+def _union_oracle(ka, da, kb, db, f):
+    """NumPy restatement of elemwise on canonical key streams (zero fill values): union, f, drop zeros."""
+    keys = np.union1d(ka, kb)
+    va = np.zeros(len(keys), da.dtype)
+    vb = np.zeros(len(keys), db.dtype)
+    va[np.searchsorted(keys, ka)] = da
+    vb[np.searchsorted(keys, kb)] = db
+    r = f(va, vb)
+    keep = r.view(np.uint64) != 0
+    return keys[keep], r[keep]
+
+
+def test_c3_full_size_broadcast_add_and_multiply():
+    """C3: COO (512,512,512,64) + COO (512,512,512,1) at density 1e-4 (broadcast on axis 3), fp64."""
+    sp = _sp()
+    rng = np.random.default_rng(0)
+    shape_a, shape_b = (512, 512, 512, 64), (512, 512, 512, 1)
+    a = sp.random(shape_a, nnz=858_993, random_state=rng)
+    b = sp.random(shape_b, nnz=13_421, random_state=rng)
+    ka = np.ravel_multi_index(a.coords, shape_a)
+    kb3 = np.ravel_multi_index(b.coords[:3], shape_b[:3])
+    kb = (kb3[:, None] * 64 + np.arange(64)[None, :]).reshape(-1)
+    db = np.repeat(b.data, 64)
+    for f in (np.add, np.multiply, np.maximum):
+        got = f(a, b)
+        wk, wd = _union_oracle(ka, a.data, kb, db, f)
+        assert got.shape == shape_a and got.nnz == len(wk)
+        assert np.array_equal(np.ravel_multi_index(got.coords, shape_a), wk)
+        assert np.array_equal(got.data.view(np.uint64), wd.view(np.uint64))
+    # reductions on the same tensor against float64 NumPy
+    s3 = a.sum(axis=3)
+    dense_keys = np.ravel_multi_index(a.coords[:3], shape_a[:3])
+    uk, inv = np.unique(dense_keys, return_inverse=True)
+    want = np.bincount(inv, weights=a.data)
+    assert np.array_equal(np.ravel_multi_index(s3.coords, shape_a[:3]), uk)
+    assert np.allclose(s3.data, want, rtol=1e-12, atol=0)
+    m0 = a.max(axis=0)
+    k123 = np.ravel_multi_index(a.coords[1:], shape_a[1:])
+    uk2 = np.unique(k123)
+    want_max = np.zeros(len(uk2))
+    np.maximum.at(want_max, np.searchsorted(uk2, k123), a.data)
+    assert np.array_equal(np.ravel_multi_index(m0.coords, shape_a[1:]), uk2)
+    assert np.array_equal(m0.data, want_max)
+
+
+def test_c5_full_size_spgemm_bit_exact():
+    """C5: (1e6 x 1e6, density 1e-5)^2 -- indptr/indices/data identical to the oracle of _dot_csr_csr
+    (reverse-first-touch column order included)."""
+    sp = _sp()
+    rng = np.random.default_rng(3)
+    n = 1_000_000
+    A = sp.random((n, n), nnz=10_000_000, random_state=rng, format="gcxs", compressed_axes=(0,))
+    A = A.astype(np.float32)
+    got = sp.tensordot(A, A, axes=1)
+    d, i, p = oracle.dot_csr_csr((n, n), A.data, A.data, A.indices, A.indices, A.indptr, A.indptr)
+    keep = d.view(np.uint32) != 0  # prune=True
+    assert isinstance(got, sp.GCXS) and got.compressed_axes == (0,)
+    assert got.nnz == int(keep.sum())
+    if keep.all():
+        assert np.array_equal(got.indptr, p)
+    assert np.array_equal(got.indices, i[keep])
+    assert np.array_equal(got.data.view(np.uint32), d[keep].view(np.uint32))
+
+
+def test_c4_sddmm_large_properties():
+    """C4-shaped SDDMM (1e6 x 1e6 mask, K = 256, fp32; nnz reduced to 2e7 to keep the test short):
+    exact linearity in a power of two, coordinates preserved, sampled entries vs a float64 restatement."""
+    sp = _sp()
+    import torch
+
+    rng = np.random.default_rng(4)
+    n, K = 1_000_000, 256
+    s = sp.random((n, n), nnz=20_000_000, random_state=rng).astype(np.float32)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.rand((n, K), generator=g, device="cuda", dtype=torch.float32)
+    b = torch.rand((K, n), generator=g, device="cuda", dtype=torch.float32)
+    r1 = sp.sddmm(s, a, b)
+    r2 = sp.sddmm(s * np.float32(2.0), a, b)
+    assert r1.nnz == s.nnz and np.array_equal(r1.coords, s.coords)
+    assert np.array_equal(r2.data, r1.data * np.float32(2.0))
+    sel = rng.choice(s.nnz, 2000, replace=False)
+    ii, jj = s.coords[0, sel], s.coords[1, sel]
+    ah = a[torch.from_numpy(ii).cuda()].double().cpu().numpy()
+    bh = b[:, torch.from_numpy(jj).cuda()].double().cpu().numpy().T
+    want = s.data[sel].astype(np.float64) * np.einsum("nk,nk->n", ah, bh)
+    assert np.allclose(r1.data[sel], want, rtol=2e-5, atol=0)
+
+
+def test_c1_coo_tensordot_matches_oracle():
+    """C1: COO(1000^2 @ 0.01) . COO -> COO, benchmark seed 42 (benchmarks/conftest.py:6-8 upstream)."""
+    sp = _sp()
+    rng = np.random.default_rng(42)
+    a = sp.random((1000, 1000), density=0.01, random_state=rng)
+    b = sp.random((1000, 1000), density=0.01, random_state=rng)
+    got = sp.tensordot(a, b, axes=1)
+    ip_a = np.searchsorted(a.coords[0], np.arange(1001))
+    ip_b = np.searchsorted(b.coords[0], np.arange(1001))
+    co, d = oracle.dot_coo_coo((1000, 1000), a.coords, b.coords, a.data, b.data, ip_a, ip_b)
+    order = np.lexsort((co[1], co[0]))
+    assert np.array_equal(got.coords, co[:, order])
+    assert np.array_equal(got.data.view(np.uint64), d[order].view(np.uint64))
+    dense = sp.tensordot(a, b.todense(), axes=1)
+    assert np.array_equal(dense.view(np.uint64),
+                          oracle.dot_coo_ndarray(a.coords, a.data, b.todense().T, (1000, 1000)).view(np.uint64))

@@ -127,3 +127,42 @@ def test_large_linearity_and_row_checksum():
     take = np.concatenate([np.arange(ip[r], ip[r + 1]) for r in sel])
     want = oracle.dot_csr_ndarray((len(sel), 128), vd[take], ci[take], sub_ptr, Bh)
     assert bits_equal(D.download(C)[sel], want)
+
+
+@pytest.mark.parametrize("n_panels", [2, 3, 8, 0])
+@pytest.mark.parametrize("dtype,N", [(np.float32, 128), (np.float32, 256), (np.float64, 64), (np.float32, 36)])
+def test_column_panel_passes_are_bit_identical(n_panels, dtype, N):
+    """K1p: panel passes carry partial sums through C; results must equal the one-pass kernel and the oracle."""
+    from sparse_b200 import _device as D
+    from sparse_b200 import _kernels as Kn
+
+    rng = np.random.default_rng(77)
+    M, K = 3000, 5000
+    a_data, a_indices, a_indptr = rand_csr(rng, M, K, 0.02, dtype)
+    # long rows spanning every panel and a few empty rows
+    b = rand_dense(rng, (K, N), dtype)
+    want = oracle.dot_csr_ndarray((M, N), a_data, a_indices, a_indptr, b)
+    ad, ai, ap, bd = (D.upload(a_data), D.upload(a_indices.astype(np.int32)), D.upload(a_indptr.astype(np.int32)),
+                      D.upload(b))
+    assert Kn.csr_rows_sorted(ai, ap, M)
+    got = Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N, n_panels=n_panels, rows_sorted=True)
+    assert bits_equal(D.download(got), want)
+
+
+def test_panel_mode_refuses_unsorted_rows():
+    from sparse_b200 import _device as D
+    from sparse_b200 import _kernels as Kn
+
+    rng = np.random.default_rng(78)
+    M, K, N = 200, 300, 128
+    a_data, a_indices, a_indptr = rand_csr(rng, M, K, 0.1, np.float32)
+    for r in range(M):  # reverse every row: still a valid CSR, no longer column-sorted
+        s, e = a_indptr[r], a_indptr[r + 1]
+        a_indices[s:e] = a_indices[s:e][::-1].copy()
+        a_data[s:e] = a_data[s:e][::-1].copy()
+    b = rand_dense(rng, (K, N), np.float32)
+    ad, ai, ap, bd = (D.upload(a_data), D.upload(a_indices.astype(np.int32)), D.upload(a_indptr.astype(np.int32)),
+                      D.upload(b))
+    assert not Kn.csr_rows_sorted(ai, ap, M)
+    got = Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N, n_panels=4)  # falls back to the one-pass kernel
+    assert bits_equal(D.download(got), oracle.dot_csr_ndarray((M, N), a_data, a_indices, a_indptr, b))
