@@ -372,9 +372,7 @@ def _dot(a, b, return_type=None):
         if a.compressed_axes == (0,):  # csr @ ndarray
             ad, ai, ap = _csr_arrays(a, dtr)
             if dense_out:
-                big = K * N * dtr.itemsize > 96e6  # B beyond L2: let K1 choose column-panel passes if rows are sorted
-                return _return_dense(Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N, n_panels=0 if big else 1,
-                                                       rows_sorted=a._rows_sorted() if big else None), [b])
+                return _return_dense(Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N), [b])
             out, flags = Kn.spmm_csr_dense_flagged(ad, ai, ap, bd, M, K, N)
             _, cols, data, indptr = Kn.dense_to_csr(out, flags=flags)
             g = GCXS._from_device(data, cols, indptr, out_shape, (0,))

@@ -195,15 +195,12 @@ int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_
     const bool vec_ok = (dtype == B2S_F32 || dtype == B2S_F64) && es != 0 && (N * es) % 16 == 0 &&
                         (ldb * es) % 16 == 0 && (ldc * es) % 16 == 0 && (((uintptr_t)b_dev | (uintptr_t)out_dev) & 15) == 0;
     if (n_panels == 0) {
+        // Measured on B200 (profiles/r01_k1_panels.json): 7.74 ms one-pass vs 8.5 / 9.2 / 13.4 ms with 2 / 8 / 16 panels
+        // at C2.  The one-pass kernel already runs at the L2 (LTS) throughput ceiling (~6.8 TB/s of gathered bytes), so
+        // turning DRAM misses into L2 hits buys nothing and every extra pass adds its C read-modify-write.  The
+        // automatic choice is therefore always the one-pass kernel; panels stay available on explicit request.
+        (void)nnz;
         n_panels = 1;
-        const double b_bytes = (double)K * (double)N * (double)es;
-        if (rows_sorted == 1 && vec_ok && nnz > 0 && M > 0 && b_bytes > 96e6) {
-            int p = (int)((b_bytes + 48e6 - 1) / 48e6);
-            if (p > 32) p = 32;
-            // every pass touches each row once (cursor, chunk, C read-modify-write): worth it only for long rows
-            while (p > 1 && (double)nnz / (double)M < 4.0 * p) p /= 2;
-            n_panels = p < 2 ? 1 : p;
-        }
     }
     if (n_panels <= 1 || !vec_ok || M == 0 || N == 0)
         return spmm_csr_dense_impl(dtype, idx_bytes, M, K, N, a_data_dev, a_indices_dev, a_indptr_dev, b_dev, ldb,
