@@ -108,6 +108,9 @@ int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_
 /* Tuning knob for K1 (0 = default).  variant: 1 = register-staged LDG gather,
  * 2 = 1-D bulk-TMA (cp.async.bulk) gather through a shared-memory ring. */
 int b2s_spmm_set_variant(int variant, int unroll);
+/* nnz-balanced handling of long rows (> 4096 stored entries): a column-split kernel runs them on a side stream,
+ * concurrently with the row-split kernel (default on; results stay bit-identical). */
+int b2s_spmm_set_skew(int enabled);
 
 
 /* ---- streaming primitives (prims.cu): COO canonicalisation / format conversion ------------ */

@@ -53,7 +53,7 @@ template <typename T, typename I, int VEC, int G, int U>
 __global__ void __launch_bounds__(256)
 spmm_csr_dense_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const I *__restrict__ a_indices,
                       const I *__restrict__ a_indptr, const T *__restrict__ B, int64_t ldb, T *__restrict__ C,
-                      int64_t ldc) {
+                      int64_t ldc, const uint8_t *__restrict__ skip) {
     static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two <= 32");
     static_assert(U <= G && G % U == 0, "U must divide G");
     constexpr unsigned FULL = 0xffffffffu;
@@ -67,7 +67,9 @@ spmm_csr_dense_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const 
     const bool col_ok = col0 < N;
 
     int64_t base = 0, end = 0;
-    if (row_ok) {
+    // rows marked in `skip` are long rows handled by the column-split kernel (spmm_skew.cu)
+    const bool skipped = skip != nullptr && row_ok && skip[row] != 0;
+    if (row_ok && !skipped) {
         base = (int64_t)a_indptr[row];
         end = (int64_t)a_indptr[row + 1];
     }
@@ -121,7 +123,7 @@ spmm_csr_dense_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const 
         }
         base = nb;
     }
-    if (row_ok && col_ok) store_c<T, VEC>(C + row * ldc + col0, acc);
+    if (row_ok && col_ok && !skipped) store_c<T, VEC>(C + row * ldc + col0, acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -247,10 +249,17 @@ spmm_csr_dense_tma_kernel(int64_t M, int N, const T *__restrict__ a_data, const 
 // ---------------------------------------------------------------------------
 static int g_variant = 1;
 static int g_unroll = 8;
+static int g_skew = 1;  // long-row (nnz-balanced) handling on by default
+
+// spmm_skew.cu
+template <typename T, typename I>
+int skew_begin(int64_t M, int64_t N, const void *ad, const void *ai, const void *ap, const void *b, int64_t ldb,
+               void *out, int64_t ldc, cudaStream_t s, uint8_t **skip_out);
+int skew_end(cudaStream_t s, uint8_t *skip);
 
 template <typename T, typename I, int VEC, int G, int U>
 static int launch_v1(int64_t M, int64_t N, const void *ad, const void *ai, const void *ap, const void *b, int64_t ldb,
-                     void *out, int64_t ldc, cudaStream_t s) {
+                     void *out, int64_t ldc, cudaStream_t s, const uint8_t *skip = nullptr) {
     constexpr int THREADS = 256;
     constexpr int rows_per_block = (THREADS / 32) * (32 / G);
     const int64_t gx = (M + rows_per_block - 1) / rows_per_block;
@@ -259,7 +268,7 @@ static int launch_v1(int64_t M, int64_t N, const void *ad, const void *ai, const
                 (long long)M, (long long)N);
     dim3 grid((unsigned)gx, (unsigned)gy);
     spmm_csr_dense_kernel<T, I, VEC, G, U><<<grid, THREADS, 0, s>>>(M, N, (const T *)ad, (const I *)ai, (const I *)ap,
-                                                                    (const T *)b, ldb, (T *)out, ldc);
+                                                                    (const T *)b, ldb, (T *)out, ldc, skip);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }
@@ -270,6 +279,16 @@ static int dispatch_g(int64_t M, int64_t N, const void *ad, const void *ai, cons
     const int64_t packs = (N + VEC - 1) / VEC;  // column packs per row
 #define B2S_GO(G, U) return launch_v1<T, I, VEC, G, U>(M, N, ad, ai, ap, b, ldb, out, ldc, s)
     if (packs >= 32) {
+        if (g_skew && g_variant == 1 && M >= 4096) {
+            // nnz-balanced mode: rows longer than kLongRow go to the column-split kernel on a side stream (they start
+            // first and run concurrently with the row-split kernel, which skips them)
+            uint8_t *skip = nullptr;
+            int rc = skew_begin<T, I>(M, N, ad, ai, ap, b, ldb, out, ldc, s, &skip);
+            if (rc) return rc;
+            rc = launch_v1<T, I, VEC, 32, 8>(M, N, ad, ai, ap, b, ldb, out, ldc, s, skip);
+            const int rc2 = skew_end(s, skip);
+            return rc ? rc : rc2;
+        }
         if (g_unroll == 4) B2S_GO(32, 4);
         if (g_unroll == 16) B2S_GO(32, 16);
         if (g_unroll == 32) B2S_GO(32, 32);
@@ -352,6 +371,11 @@ int narrow_i64_i32(const int64_t *in, int32_t *out, int64_t n, cudaStream_t s) {
 using namespace b2s;
 
 extern "C" {
+
+int b2s_spmm_set_skew(int enabled) {
+    g_skew = enabled ? 1 : 0;
+    return B2S_OK;
+}
 
 int b2s_spmm_set_variant(int variant, int unroll) {
     g_variant = (variant == 2) ? 2 : 1;

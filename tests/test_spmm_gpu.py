@@ -166,3 +166,30 @@ def test_panel_mode_refuses_unsorted_rows():
     assert not Kn.csr_rows_sorted(ai, ap, M)
     got = Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N, n_panels=4)  # falls back to the one-pass kernel
     assert bits_equal(D.download(got), oracle.dot_csr_ndarray((M, N), a_data, a_indices, a_indptr, b))
+
+
+@pytest.mark.parametrize("dtype,N", [(np.float32, 128), (np.float64, 64), (np.float32, 256), (np.int64, 128)])
+def test_long_rows_take_the_column_split_kernel(dtype, N):
+    """nnz-balanced mode: rows with more than 4096 entries are computed by the column-split kernel on a side stream;
+    the row-split kernel skips them.  Results must stay bit-identical to the oracle."""
+    from sparse_b200 import _device as D
+    from sparse_b200 import _kernels as Kn
+
+    rng = np.random.default_rng(91)
+    M, K = 5000, 30000
+    lens = rng.integers(0, 40, M)
+    long_rows = [3, 77, 1234, 4999]
+    for r, n in zip(long_rows, (4097, 9000, 25000, 30000)):
+        lens[r] = n
+    indptr = np.zeros(M + 1, np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(K, n, replace=False)) for n in lens]).astype(np.int64)
+    if np.issubdtype(np.dtype(dtype), np.integer):
+        data = rng.integers(-3, 4, len(indices)).astype(dtype)
+    else:
+        data = (rng.random(len(indices)) - 0.5).astype(dtype)
+    b = rand_dense(rng, (K, N), dtype)
+    want = oracle.dot_csr_ndarray((M, N), data, indices, indptr, b)
+    got = Kn.spmm_csr_dense(D.upload(data), D.upload(indices.astype(np.int32)), D.upload(indptr.astype(np.int32)),
+                            D.upload(b), M, K, N)
+    assert bits_equal(D.download(got), want)
