@@ -103,13 +103,16 @@ int b2s_csr_rows_sorted(int idx_bytes, int64_t M, const void *indptr_dev, const 
 int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, int64_t nnz,
                           const void *a_data_dev, const void *a_indices_dev, const void *a_indptr_dev,
                           const void *b_dev, int64_t ldb, void *out_dev, int64_t ldc, int n_panels, int rows_sorted,
-                          void *stream);
+                          int long_rows, void *stream);
+/* Largest number of stored entries in a row: callers enable `long_rows` (the nnz-balanced column-split kernel for rows
+ * with more than 4096 entries, run concurrently on a side stream) only for matrices that have such rows. */
+int b2s_csr_max_row_nnz(int idx_bytes, int64_t M, const void *indptr_dev, int64_t *max_host, void *stream);
 
 /* Tuning knob for K1 (0 = default).  variant: 1 = register-staged LDG gather,
  * 2 = 1-D bulk-TMA (cp.async.bulk) gather through a shared-memory ring. */
 int b2s_spmm_set_variant(int variant, int unroll);
-/* nnz-balanced handling of long rows (> 4096 stored entries): a column-split kernel runs them on a side stream,
- * concurrently with the row-split kernel (default on; results stay bit-identical). */
+/* process-wide default of the nnz-balanced long-row path used by b2s_spmm_csr_dense (default off; b2s_spmm_csr_dense_ex
+ * selects it per call; results stay bit-identical). */
 int b2s_spmm_set_skew(int enabled);
 
 

@@ -372,7 +372,7 @@ def _dot(a, b, return_type=None):
         if a.compressed_axes == (0,):  # csr @ ndarray
             ad, ai, ap = _csr_arrays(a, dtr)
             if dense_out:
-                return _return_dense(Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N), [b])
+                return _return_dense(Kn.spmm_csr_dense(ad, ai, ap, bd, M, K, N, long_rows=a._has_long_rows()), [b])
             out, flags = Kn.spmm_csr_dense_flagged(ad, ai, ap, bd, M, K, N)
             _, cols, data, indptr = Kn.dense_to_csr(out, flags=flags)
             g = GCXS._from_device(data, cols, indptr, out_shape, (0,))

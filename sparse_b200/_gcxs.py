@@ -166,6 +166,14 @@ class GCXS(SparseArray):
             self._indptr_np = D.download(self._indptr)
         return self._indptr_np
 
+    def _has_long_rows(self):
+        """Does some compressed row hold more than 4096 entries?  (cached; enables K1's nnz-balanced long-row kernel)"""
+        if getattr(self, "_long_rows_flag", None) is None:
+            _, _, indptr = self._dev()
+            self._long_rows_flag = (self.ndim >= 2 and self.nnz > 4096
+                                    and Kn.csr_max_row_nnz(indptr, self._compressed_shape[0]) > 4096)
+        return self._long_rows_flag
+
     def _rows_sorted(self):
         """Are the indices of every compressed row sorted?  (cached; decides whether K1 may use its panel passes)"""
         if getattr(self, "_rows_sorted_flag", None) is None:

@@ -60,7 +60,7 @@ def empty(n, dtype, like=None):
 # K1
 # ------------------------------------------------------------------------------------------------
 def spmm_csr_dense(a_data, a_indices, a_indptr, b, M: int, K: int, N: int, out=None, *, n_panels=1,
-                   rows_sorted=None):
+                   rows_sorted=None, long_rows=False):
     """out[M,N] = CSR(A) @ B -- replaces _dot_csr_ndarray (_common.py:720-755).
 
     All arguments are CUDA tensors; `b` is (K, N) row-major (row stride may exceed N).
@@ -84,10 +84,19 @@ def spmm_csr_dense(a_data, a_indices, a_indptr, b, M: int, K: int, N: int, out=N
     rc = lib.b2s_spmm_csr_dense_ex(
         i32(D.dtype_code(dt)), i32(_idx_bytes(a_indices)), i64(M), i64(K), i64(N), i64(a_data.shape[0]),
         vp(D.ptr(a_data)), vp(D.ptr(a_indices)), vp(D.ptr(a_indptr)), vp(D.ptr(b)), i64(max(ldb, N)), vp(D.ptr(out)),
-        i64(max(ldc, N)), i32(n_panels if (n_panels == 1 or rows_sorted) else 1), i32(1 if rows_sorted else 0), _sp(),
+        i64(max(ldc, N)), i32(n_panels if (n_panels == 1 or rows_sorted) else 1), i32(1 if rows_sorted else 0),
+        i32(1 if long_rows else 0), _sp(),
     )
     _lib.check(rc, "b2s_spmm_csr_dense_ex")
     return out
+
+
+def csr_max_row_nnz(a_indptr, M) -> int:
+    """Largest row length of a CSR (one device reduction + sync)."""
+    r = ctypes.c_int64(0)
+    _lib.check(_lib.load().b2s_csr_max_row_nnz(i32(_idx_bytes(a_indptr)), i64(M), vp(D.ptr(a_indptr)), ctypes.byref(r),
+                                               _sp()))
+    return int(r.value)
 
 
 def csr_rows_sorted(a_indices, a_indptr, M) -> bool:

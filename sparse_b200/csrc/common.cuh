@@ -68,6 +68,7 @@ int scratch_free(void *p, cudaStream_t s);
 int spmm_csr_dense_impl(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, const void *ad, const void *ai,
                         const void *ap, const void *b, int64_t ldb, void *out, int64_t ldc, cudaStream_t s);
 int narrow_i64_i32(const int64_t *in, int32_t *out, int64_t n, cudaStream_t s);
+void set_call_skew(int v);  // per-call override of the long-row path (-1 = process default)
 
 // ---------------------------------------------------------------------------
 // exact (non-contracted) arithmetic: the reference rounds a*b and (+) separately

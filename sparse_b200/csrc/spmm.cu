@@ -249,7 +249,9 @@ spmm_csr_dense_tma_kernel(int64_t M, int N, const T *__restrict__ a_data, const 
 // ---------------------------------------------------------------------------
 static int g_variant = 1;
 static int g_unroll = 8;
-static int g_skew = 1;  // long-row (nnz-balanced) handling on by default
+static int g_skew = 0;  // process-wide default of the long-row (nnz-balanced) path; per-call override below
+static thread_local int t_skew = -1;
+void set_call_skew(int v) { t_skew = v; }
 
 // spmm_skew.cu
 template <typename T, typename I>
@@ -279,7 +281,7 @@ static int dispatch_g(int64_t M, int64_t N, const void *ad, const void *ai, cons
     const int64_t packs = (N + VEC - 1) / VEC;  // column packs per row
 #define B2S_GO(G, U) return launch_v1<T, I, VEC, G, U>(M, N, ad, ai, ap, b, ldb, out, ldc, s)
     if (packs >= 32) {
-        if (g_skew && g_variant == 1 && M >= 4096) {
+        if ((t_skew >= 0 ? t_skew : g_skew) && g_variant == 1 && M >= 4096) {
             // nnz-balanced mode: rows longer than kLongRow go to the column-split kernel on a side stream (they start
             // first and run concurrently with the row-split kernel, which skips them)
             uint8_t *skip = nullptr;

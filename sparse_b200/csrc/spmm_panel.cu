@@ -126,6 +126,21 @@ __global__ void rows_sorted_kernel(int64_t M, const I *__restrict__ indptr, cons
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 1);
 }
 
+template <typename I>
+__global__ void max_row_kernel(int64_t M, const I *__restrict__ indptr, unsigned long long *__restrict__ out) {
+    unsigned long long m = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long n = (unsigned long long)((int64_t)indptr[r + 1] - (int64_t)indptr[r]);
+        m = n > m ? n : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 template <typename T, typename I>
 static int run_panels(int64_t M, int64_t K, int64_t N, const void *ad, const void *ai, const void *ap, const void *b,
                       int64_t ldb, void *out, int64_t ldc, int n_panels, cudaStream_t s) {
@@ -180,6 +195,30 @@ int b2s_csr_rows_sorted(int idx_bytes, int64_t M, const void *indptr_dev, const 
     return B2S_OK;
 }
 
+/* Largest number of stored entries in a row (decides whether the nnz-balanced long-row path is worth enabling). */
+int b2s_csr_max_row_nnz(int idx_bytes, int64_t M, const void *indptr_dev, int64_t *max_host, void *stream) {
+    B2S_REQUIRE(max_host != nullptr, B2S_ERR_INVALID, "csr_max_row_nnz: NULL output");
+    *max_host = 0;
+    if (M == 0) return B2S_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *d = nullptr;
+    int rc = scratch_alloc((void **)&d, 8, s);
+    if (rc) return rc;
+    B2S_CUDA(cudaMemsetAsync(d, 0, 8, s));
+    int64_t blocks = (M + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (idx_bytes == 4) max_row_kernel<int32_t><<<(unsigned)blocks, 256, 0, s>>>(M, (const int32_t *)indptr_dev, d);
+    else max_row_kernel<int64_t><<<(unsigned)blocks, 256, 0, s>>>(M, (const int64_t *)indptr_dev, d);
+    B2S_CHECK_LAUNCH();
+    unsigned long long h = 0;
+    B2S_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s));
+    B2S_CUDA(cudaStreamSynchronize(s));
+    scratch_free(d, s);
+    *max_host = (int64_t)h;
+    return B2S_OK;
+}
+
 /*
  * K1 with explicit scheduling control.  n_panels <= 1: the one-pass kernel (same as b2s_spmm_csr_dense).
  * n_panels >= 2: column-panel passes (rows MUST be sorted by column -- check with b2s_csr_rows_sorted; 16-byte aligned
@@ -189,7 +228,7 @@ int b2s_csr_rows_sorted(int idx_bytes, int64_t M, const void *indptr_dev, const 
 int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, int64_t nnz,
                           const void *a_data_dev, const void *a_indices_dev, const void *a_indptr_dev,
                           const void *b_dev, int64_t ldb, void *out_dev, int64_t ldc, int n_panels, int rows_sorted,
-                          void *stream) {
+                          int long_rows, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const size_t es = dtype_size(dtype);
     const bool vec_ok = (dtype == B2S_F32 || dtype == B2S_F64) && es != 0 && (N * es) % 16 == 0 &&
@@ -202,9 +241,13 @@ int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_
         (void)nnz;
         n_panels = 1;
     }
-    if (n_panels <= 1 || !vec_ok || M == 0 || N == 0)
-        return spmm_csr_dense_impl(dtype, idx_bytes, M, K, N, a_data_dev, a_indices_dev, a_indptr_dev, b_dev, ldb,
-                                   out_dev, ldc, s);
+    if (n_panels <= 1 || !vec_ok || M == 0 || N == 0) {
+        set_call_skew(long_rows ? 1 : 0);
+        const int rc = spmm_csr_dense_impl(dtype, idx_bytes, M, K, N, a_data_dev, a_indices_dev, a_indptr_dev, b_dev,
+                                           ldb, out_dev, ldc, s);
+        set_call_skew(-1);
+        return rc;
+    }
     B2S_REQUIRE(rows_sorted == 1, B2S_ERR_INVALID, "spmm panels: rows must be sorted by column (rows_sorted=1)");
     B2S_REQUIRE(idx_bytes == 4 || idx_bytes == 8, B2S_ERR_INVALID, "spmm panels: idx_bytes");
     if (dtype == B2S_F32) {

@@ -54,7 +54,12 @@ def csr_rows_sorted(a_indices, a_indptr, M):
     return all((np.diff(ix[ip[r]:ip[r + 1]]) >= 0).all() for r in range(M))
 
 
-def spmm_csr_dense(a_data, a_indices, a_indptr, b, M, K, N, out=None, n_panels=1, rows_sorted=None):
+def csr_max_row_nnz(a_indptr, M):
+    ip = n(a_indptr)
+    return int(np.diff(ip).max()) if M else 0
+
+
+def spmm_csr_dense(a_data, a_indices, a_indptr, b, M, K, N, out=None, n_panels=1, rows_sorted=None, long_rows=False):
     r = oracle.dot_csr_ndarray((M, N), n(a_data), n(a_indices), n(a_indptr), np.ascontiguousarray(n(b)))
     r = T(r)
     if out is not None:

@@ -190,6 +190,8 @@ def test_long_rows_take_the_column_split_kernel(dtype, N):
         data = (rng.random(len(indices)) - 0.5).astype(dtype)
     b = rand_dense(rng, (K, N), dtype)
     want = oracle.dot_csr_ndarray((M, N), data, indices, indptr, b)
-    got = Kn.spmm_csr_dense(D.upload(data), D.upload(indices.astype(np.int32)), D.upload(indptr.astype(np.int32)),
-                            D.upload(b), M, K, N)
+    ipd = D.upload(indptr.astype(np.int32))
+    assert Kn.csr_max_row_nnz(ipd, M) == 30000
+    got = Kn.spmm_csr_dense(D.upload(data), D.upload(indices.astype(np.int32)), ipd, D.upload(b), M, K, N,
+                            long_rows=True)
     assert bits_equal(D.download(got), want)
