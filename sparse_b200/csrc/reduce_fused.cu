@@ -124,6 +124,13 @@ struct RdShape {
 };
 
 // One tile.  EMIT = false: write the tile summary.  EMIT = true: write finished runs.
+// Loads and stores go through shared memory so that global accesses are fully coalesced: the tile's 2048 (key, value)
+// pairs are loaded with unit stride, each thread then reads its 8 consecutive pairs from a padded layout
+// (index e + e/8: 2-way instead of 16-way bank conflicts), and in the emit pass the finished runs of the tile -- which
+// occupy one contiguous range of output slots -- are staged in the same buffers and written out with unit stride.
+constexpr int RD_PAD = RD_TILE + RD_TILE / 8 + 8;
+__device__ __forceinline__ int rd_pad(int e) { return e + (e >> 3); }
+
 template <typename T, bool EMIT>
 __global__ void __launch_bounds__(RD_THREADS)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
@@ -136,31 +143,50 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                    T fill, int apply_fix, T result_fill, RdShape shp, int64_t *__restrict__ out_gid,
                    int64_t *__restrict__ out_coords, int64_t coords_stride, T *__restrict__ out_val,
                    unsigned long long *__restrict__ n_equal_fill) {
+    __shared__ int64_t sk[RD_PAD];
+    __shared__ T sv[RD_PAD];
     __shared__ int s_flag[RD_THREADS / 32];
     __shared__ T s_val[RD_THREADS / 32];
     __shared__ int64_t s_cnt[RD_THREADS / 32];
     __shared__ int s_heads[RD_THREADS / 32];
     const int64_t tile = blockIdx.x;
-    const int64_t base = tile * RD_TILE + (int64_t)threadIdx.x * RD_ITEMS;
+    const int64_t tile_base = tile * RD_TILE;
+    const int64_t base = tile_base + (int64_t)threadIdx.x * RD_ITEMS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    // coalesced tile load: slot e holds element tile_base + e (group id, value); slot -1 / RD_TILE = neighbours
+#pragma unroll
+    for (int i = 0; i < RD_ITEMS; ++i) {
+        const int e = threadIdx.x + i * RD_THREADS;
+        const int64_t p = tile_base + e;
+        int64_t gk = -1;
+        T vv = T(0);
+        if (p < n) {
+            gk = (int64_t)fcols.div((uint64_t)keys[p]);
+            vv = vals[p];
+        }
+        sk[rd_pad(e)] = gk;
+        sv[rd_pad(e)] = vv;
+    }
+    __shared__ int64_t s_edge[2];
+    if (threadIdx.x == 0) {
+        s_edge[0] = (tile_base > 0) ? (int64_t)fcols.div((uint64_t)keys[tile_base - 1]) : -1;
+        s_edge[1] = (tile_base + RD_TILE < n) ? (int64_t)fcols.div((uint64_t)keys[tile_base + RD_TILE]) : -1;
+    }
+    __syncthreads();
 
     int64_t g[RD_ITEMS];
     T v[RD_ITEMS];
     bool head[RD_ITEMS];
-    int64_t gprev = -1;
-    if (base > 0 && base - 1 < n) gprev = (int64_t)fcols.div((uint64_t)keys[base - 1]);
+    const int e0 = threadIdx.x * RD_ITEMS;
+    const int64_t gprev = (threadIdx.x == 0) ? s_edge[0] : sk[rd_pad(e0 - 1)];
+    const int64_t gnext_thread = (threadIdx.x == RD_THREADS - 1) ? s_edge[1] : sk[rd_pad(e0 + RD_ITEMS)];
 #pragma unroll
     for (int i = 0; i < RD_ITEMS; ++i) {
         const int64_t p = base + i;
-        if (p < n) {
-            g[i] = (int64_t)fcols.div((uint64_t)keys[p]);
-            v[i] = vals[p];
-            head[i] = (p == 0) || (g[i] != (i == 0 ? gprev : g[i - 1]));
-        } else {
-            g[i] = -1;
-            v[i] = T(0);
-            head[i] = false;
-        }
+        g[i] = sk[rd_pad(e0 + i)];
+        v[i] = sv[rd_pad(e0 + i)];
+        head[i] = (p < n) && ((p == 0) || (g[i] != (i == 0 ? gprev : g[i - 1])));
     }
     // thread summary: run still open at the end of the thread's range
     Run<T> mine;
@@ -200,8 +226,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         s_cnt[w] = incl.cnt;
         s_heads[w] = hincl;
     }
-    __syncthreads();
-    // carry entering this warp = combination of the previous warps' totals (and, in pass 2, the tile carry-in)
+    __syncthreads();  // (also: every thread has copied its inputs out of sk / sv)
     Run<T> carry;
     carry.flag = 0;
     carry.val = T(0);
@@ -230,7 +255,6 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     }
     if constexpr (!EMIT) {
         if (threadIdx.x == 0) {
-            // summary WITHOUT carry-in (tile_total was seeded with an empty run)
             t_heads[tile] = tile_heads;
             t_flag[tile] = tile_total.flag;
             t_val[tile] = tile_total.val;
@@ -238,7 +262,10 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         }
         return;
     } else {
-        // exclusive state for this thread = carry (+) inclusive state of the previous lane
+        const int64_t slot0 = head_off[tile] - 1;  // output slot of a run that started before this tile
+        // the staging buffers alias the input buffers: mark every slot empty first
+        for (int i = threadIdx.x; i < RD_TILE + 1; i += RD_THREADS) sk[i] = -1;
+        __syncthreads();
         Run<T> prev = run_shfl_up(incl, 1);
         int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
         Run<T> st = carry;
@@ -247,11 +274,6 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
             st = run_combine<T>(op, carry, prev);
             hcount += hprev;
         }
-        // walk the items again; a run ends where the next element is a head (or the array ends)
-        int64_t gnext_thread = -1;
-        const int64_t pn = base + RD_ITEMS;
-        if (pn < n) gnext_thread = (int64_t)fcols.div((uint64_t)keys[pn]);
-        int eq = 0;
         T rv = st.val;
         int64_t rc = st.cnt;
 #pragma unroll
@@ -266,36 +288,47 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                     rv = rc == 0 ? v[i] : red_apply<T>(op, rv, v[i]);
                     rc += 1;
                 }
-                const bool last = (p == n - 1) || ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1] ) : (g[i] != gnext_thread));
+                const bool last = (p == n - 1) ||
+                                  ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1]) : (g[i] != gnext_thread));
                 if (last) {
-                    const int64_t idx = hcount - 1;
-                    T outv = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
-                    out_val[idx] = outv;
-                    out_gid[idx] = g[i];
-                    if (out_coords) {
-                        uint64_t k = (uint64_t)g[i];
-                        for (int d = shp.ndim - 1; d >= 0; --d) {
-                            uint64_t q, r;
-                            shp.extent[d].divmod(k, q, r);
-                            out_coords[(int64_t)d * coords_stride + idx] = (int64_t)r;
-                            k = q;
-                        }
-                    }
-                    bool same;
-                    if constexpr (sizeof(T) == 1) same = (*(const uint8_t *)&outv) == (*(const uint8_t *)&result_fill);
-                    else if constexpr (sizeof(T) == 4) {
-                        uint32_t x, y;
-                        memcpy(&x, &outv, 4);
-                        memcpy(&y, &result_fill, 4);
-                        same = x == y;
-                    } else {
-                        uint64_t x, y;
-                        memcpy(&x, &outv, 8);
-                        memcpy(&y, &result_fill, 8);
-                        same = x == y;
-                    }
-                    eq += same ? 1 : 0;
+                    const int loc = (int)(hcount - 1 - slot0);  // 0 .. RD_TILE
+                    sk[loc] = g[i];
+                    sv[loc] = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
                 }
+            }
+        }
+        __syncthreads();
+        int eq = 0;
+        for (int l = threadIdx.x; l < RD_TILE + 1; l += RD_THREADS) {
+            const int64_t gid = sk[l];
+            if (gid >= 0) {
+                const int64_t idx = slot0 + l;
+                const T outv = sv[l];
+                out_val[idx] = outv;
+                out_gid[idx] = gid;
+                if (out_coords) {
+                    uint64_t k = (uint64_t)gid;
+                    for (int d = shp.ndim - 1; d >= 0; --d) {
+                        uint64_t q, r;
+                        shp.extent[d].divmod(k, q, r);
+                        out_coords[(int64_t)d * coords_stride + idx] = (int64_t)r;
+                        k = q;
+                    }
+                }
+                bool same;
+                if constexpr (sizeof(T) == 1) same = (*(const uint8_t *)&outv) == (*(const uint8_t *)&result_fill);
+                else if constexpr (sizeof(T) == 4) {
+                    uint32_t x, y;
+                    memcpy(&x, &outv, 4);
+                    memcpy(&y, &result_fill, 4);
+                    same = x == y;
+                } else {
+                    uint64_t x, y;
+                    memcpy(&x, &outv, 8);
+                    memcpy(&y, &result_fill, 8);
+                    same = x == y;
+                }
+                eq += same ? 1 : 0;
             }
         }
         eq = __reduce_add_sync(0xffffffffu, eq);
