@@ -206,12 +206,7 @@ int b2s_indptr_remap(int idx_bytes, const void *old_indptr_dev, int64_t nrows, c
  * 32..40 predicates (gt ge lt le eq ne land lor lxor); unary 0..31 value ops, 64..68 predicates (see elemwise.cu). */
 /* Replaces _Elemwise._match_coo + _match_arrays + _get_func_coords_data (_umath.py:656-751, 53-92, 576-654) for two
  * COO operands: merge-path union of two sorted key streams, each optionally expanded virtually by a trailing
- * broadcast factor R.  Outputs have na*Ra + nb*Rb slots; flags mark the entries to keep. */
-int b2s_ew_merge(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
-                 const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb, const void *fill_a_host,
-                 const void *fill_b_host, const void *out_fill_host, int64_t *out_keys_dev, void *out_vals_dev,
-                 uint8_t *out_flags_dev, void *stream);
-/* Fused two-pass form of b2s_ew_merge (production path): begin() = merge + apply + per-tile counts, returns the
+ * broadcast factor R.  Fused two-pass form: begin() = merge + apply + per-tile counts, returns the
  * output nnz (one stream sync); finish() = merge + apply again and write data, int64 coordinates [ndim, nnz] and
  * (optionally) the sorted linear keys directly -- no union-sized temporaries in HBM. */
 int b2s_ew_merge_begin(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
@@ -233,17 +228,9 @@ int b2s_ew_expand(int idx_bytes, const void *coords_dev, int64_t row_stride, int
                   const int64_t *result_shape_host, const int32_t *is_bcast_host, const int32_t *src_row_host,
                   int64_t *out_keys_dev, int64_t *out_src_dev, void *stream);
 
-/* ---- grouped reductions (K7, reduce.cu) ---------------------------------------------------- */
-/* Operator codes: 0 add, 1 multiply, 2 maximum, 3 minimum, 4 logical_and, 5 logical_or, 6..8 bitwise and/or/xor. */
-int b2s_group_ids(const int64_t *keys_dev, int64_t n, int64_t ncols, int64_t *gid_out_dev, void *stream);
-/* _grouped_reduce = _calc_counts_invidx + ufunc.reduceat (_coo/core.py:1601-1661). Outputs sized n. */
-int b2s_reduce_by_key(int dtype, int op, const int64_t *gid_dev, const void *vals_dev, int64_t n,
-                      int64_t *groups_out_dev, void *vals_out_dev, int64_t *counts_out_dev, int64_t *n_groups_host,
-                      void *stream);
-/* fill-value contribution of SparseArray.reduce (_sparse_array.py:405-422), in place. */
-int b2s_reduce_fill_fix(int dtype, int op, void *vals_dev, const int64_t *counts_dev, int64_t n_groups, int64_t ncols,
-                        const void *fill_host, void *stream);
-
+/* ---- grouped reductions (K7, reduce_fused.cu) ------------------------------------------------ */
+/* Operator codes: 0 add, 1 multiply, 2 maximum, 3 minimum, 4 logical_and, 5 logical_or, 6..8 bitwise and/or/xor.
+ * Replaces _grouped_reduce = _calc_counts_invidx + ufunc.reduceat (_coo/core.py:1601-1661). */
 /* Hand-written two-pass segmented-scan reduction (production path, reduce_fused.cu): begin() returns the number of
  * groups; finish() writes group ids (= linear index over the kept axes), values with the fill-value contribution of
  * _sparse_array.py:405-422 applied, and the group coordinates over shape_host[ndim]; it also reports how many results

@@ -453,25 +453,6 @@ def dense_to_csr(x, flags=None, mode=0, want_rows=False, want_indptr=True):
 # ------------------------------------------------------------------------------------------------
 # K5 elemwise
 # ------------------------------------------------------------------------------------------------
-def ew_merge(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype):
-    """Union coiteration of two sorted key streams -> (keys, vals, flags) with na*Ra + nb*Rb slots."""
-    t = _t()
-    dt = D.np_dtype(data_a)
-    assert data_b.dtype == data_a.dtype
-    na, nb = keys_a.shape[0], keys_b.shape[0]
-    total = na * Ra + nb * Rb
-    dev = data_a.device
-    okeys = t.empty(total, dtype=t.int64, device=dev)
-    ovals = t.empty(total, dtype=D.torch_dtype(out_dtype), device=dev)
-    oflags = t.empty(total, dtype=t.uint8, device=dev)
-    rc = _lib.load().b2s_ew_merge(
-        i32(D.dtype_code(dt)), i32(op), vp(D.ptr(keys_a)), vp(D.ptr(data_a)), i64(na), i64(Ra), vp(D.ptr(keys_b)),
-        vp(D.ptr(data_b)), i64(nb), i64(Rb), _scalar_bytes(fill_a, dt), _scalar_bytes(fill_b, dt),
-        _scalar_bytes(out_fill, out_dtype), vp(D.ptr(okeys)), vp(D.ptr(ovals)), vp(D.ptr(oflags)), _sp())
-    _lib.check(rc, "b2s_ew_merge")
-    return okeys, ovals, oflags
-
-
 def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, out_fill, out_dtype, shape,
                    want_coords=True):
     """Fused COO (x) COO coiteration -> (coords[ndim, nnz] int64, vals[nnz], keys[nnz]); canonical order."""
@@ -554,29 +535,6 @@ def ew_expand(coords, result_shape, is_bcast, src_row):
 # ------------------------------------------------------------------------------------------------
 # K7 reductions
 # ------------------------------------------------------------------------------------------------
-def group_ids(keys, ncols):
-    t = _t()
-    out = t.empty_like(keys)
-    _lib.check(_lib.load().b2s_group_ids(vp(D.ptr(keys)), i64(keys.shape[0]), i64(ncols), vp(D.ptr(out)), _sp()))
-    return out
-
-
-def reduce_by_key(op, gid, vals):
-    """_grouped_reduce (_coo/core.py:1631-1661) -> (groups, values, counts), each of length n_groups."""
-    t = _t()
-    n = gid.shape[0]
-    dt = D.np_dtype(vals)
-    groups = t.empty(n, dtype=t.int64, device=gid.device)
-    ovals = t.empty(n, dtype=vals.dtype, device=gid.device)
-    counts = t.empty(n, dtype=t.int64, device=gid.device)
-    ng = ctypes.c_int64(0)
-    rc = _lib.load().b2s_reduce_by_key(i32(D.dtype_code(dt)), i32(op), vp(D.ptr(gid)), vp(D.ptr(vals)), i64(n),
-                                      vp(D.ptr(groups)), vp(D.ptr(ovals)), vp(D.ptr(counts)), ctypes.byref(ng), _sp())
-    _lib.check(rc, "b2s_reduce_by_key")
-    g = int(ng.value)
-    return groups[:g], ovals[:g], counts[:g]
-
-
 def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape, want_coords=True):
     """Segmented reduction over runs of key // ncols -> (coords[ndim, g] int64, group ids[g], values[g], n_equal_fill)."""
     t = _t()
@@ -600,14 +558,6 @@ def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape, wan
                                vp(D.ptr(out)), ctypes.byref(neq))
     _lib.check(rc, "b2s_reduce_finish")
     return coords, gids, out, int(neq.value)
-
-
-def reduce_fill_fix(op, vals, counts, ncols, fill_value):
-    dt = D.np_dtype(vals)
-    rc = _lib.load().b2s_reduce_fill_fix(i32(D.dtype_code(dt)), i32(op), vp(D.ptr(vals)), vp(D.ptr(counts)),
-                                        i64(vals.shape[0]), i64(ncols), _scalar_bytes(fill_value, dt), _sp())
-    _lib.check(rc, "b2s_reduce_fill_fix")
-    return vals
 
 
 # ------------------------------------------------------------------------------------------------

@@ -262,77 +262,6 @@ __global__ void ew_partition_kernel(Stream A, Stream B, int64_t ntiles, int64_t 
     split_a[t] = merge_split(A, B, d);
 }
 
-// One CTA per tile of EW_TILE merged positions.  Output slot = merged position; a matched b-item gets flag 0.
-template <typename T, typename O, bool PRED>
-__global__ void __launch_bounds__(EW_THREADS)
-ew_merge_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restrict__ db, T fill_a, T fill_b, O out_fill,
-                int op, const int64_t *__restrict__ split_a, int64_t *__restrict__ out_keys, O *__restrict__ out_vals,
-                uint8_t *__restrict__ out_flags) {
-    __shared__ int64_t sa[EW_TILE + 2];
-    __shared__ int64_t sb[EW_TILE + 2];
-    const int64_t la = A.len(), lb = B.len();
-    const int64_t total = la + lb;
-    const int64_t tile = blockIdx.x;
-    const int64_t d0 = tile * EW_TILE;
-    const int64_t d1 = (d0 + EW_TILE < total) ? d0 + EW_TILE : total;
-    const int64_t a0 = split_a[tile], a1 = split_a[tile + 1];
-    const int64_t b0 = d0 - a0, b1 = d1 - a1;
-    const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
-    constexpr int64_t NEG = INT64_MIN, POS = INT64_MAX;
-    // sa[0] = key before the tile's a-range (for "b matched by previous a"), sa[1..na], sa[na+1] = sentinel
-    for (int i = threadIdx.x; i < na + 2; i += EW_THREADS) {
-        const int64_t p = a0 - 1 + i;
-        sa[i] = (p < 0) ? NEG : (p < la ? A.key(p) : POS);
-    }
-    for (int i = threadIdx.x; i < nb + 2; i += EW_THREADS) {
-        const int64_t p = b0 - 1 + i;
-        sb[i] = (p < 0) ? NEG : (p < lb ? B.key(p) : POS);
-    }
-    __syncthreads();
-    const int64_t *ka = sa + 1, *kb = sb + 1;  // ka[-1] and kb[nb] are valid sentinels
-    const int dloc = threadIdx.x * EW_ITEMS;
-    const int dn = (int)(d1 - d0);
-    if (dloc >= dn) return;
-    // thread-level merge-path search inside the tile
-    int lo = dloc > nb ? dloc - nb : 0;
-    int hi = dloc < na ? dloc : na;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ka[mid] <= kb[dloc - 1 - mid]) lo = mid + 1;
-        else hi = mid;
-    }
-    int i = lo, j = dloc - lo;
-#pragma unroll
-    for (int it = 0; it < EW_ITEMS; ++it) {
-        const int d = dloc + it;
-        if (d >= dn) break;
-        const bool take_a = (j >= nb) || (i < na && ka[i] <= kb[j]);
-        int64_t key;
-        T va, vb;
-        bool emit = true;
-        if (take_a) {
-            key = ka[i];
-            va = da[A.src(a0 + i)];
-            // kb[j] is readable up to j == nb (next tile's first b key or +inf)
-            vb = (kb[j] == key) ? db[B.src(b0 + j)] : fill_b;
-            ++i;
-        } else {
-            key = kb[j];
-            emit = (ka[i - 1] != key);  // ka[-1] = previous tile's last a key or -inf
-            va = fill_a;
-            vb = db[B.src(b0 + j)];
-            ++j;
-        }
-        O r;
-        if constexpr (PRED) r = (O)bin_pred<T>(op, va, vb);
-        else r = (O)bin_apply<T>(op, va, vb);
-        const int64_t o = d0 + d;
-        out_keys[o] = key;
-        out_vals[o] = r;
-        out_flags[o] = (emit && bits_differ<O>(r, out_fill)) ? 1 : 0;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Fused two-pass form of the merge (the production path for COO (x) COO):
 //   pass 1 (EMIT = false): merge + apply, count the kept results of every 2048-position tile;
@@ -616,33 +545,6 @@ using namespace b2s;
     } while (0)
 
 extern "C" {
-
-/* Union coiteration of two sorted key streams (see file header).  Outputs have na*Ra + nb*Rb slots. */
-int b2s_ew_merge(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
-                 const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb, const void *fill_a_host,
-                 const void *fill_b_host, const void *out_fill_host, int64_t *out_keys_dev, void *out_vals_dev,
-                 uint8_t *out_flags_dev, void *stream) {
-    B2S_REQUIRE(Ra >= 1 && Rb >= 1 && na >= 0 && nb >= 0, B2S_ERR_INVALID, "ew_merge: bad sizes");
-    const int64_t total = na * Ra + nb * Rb;
-    if (total == 0) return B2S_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    Stream A = make_stream(keys_a_dev, na, Ra), B = make_stream(keys_b_dev, nb, Rb);
-    const int64_t ntiles = (total + EW_TILE - 1) / EW_TILE;
-    B2S_REQUIRE(ntiles < 2147483647LL, B2S_ERR_OVERFLOW, "ew_merge: too many tiles");
-    int64_t *split = nullptr;
-    int rc = scratch_alloc((void **)&split, (size_t)(ntiles + 1) * 8, s);
-    if (rc) return rc;
-    ew_partition_kernel<<<(unsigned)((ntiles + 1 + 127) / 128), 128, 0, s>>>(A, B, ntiles, split);
-    B2S_CHECK_LAUNCH();
-    const bool pred = op >= 32;
-    B2S_EW_DISPATCH(dtype, pred,
-                    (ew_merge_kernel<T, O, P><<<(unsigned)ntiles, EW_THREADS, 0, s>>>(
-                        A, B, (const T *)data_a_dev, (const T *)data_b_dev, scalar_from<T>(fill_a_host),
-                        scalar_from<T>(fill_b_host), scalar_from<O>(out_fill_host), op, split, out_keys_dev,
-                        (O *)out_vals_dev, out_flags_dev)));
-    B2S_CHECK_LAUNCH();
-    return scratch_free(split, s);
-}
 
 /*
  * Fused COO (x) COO coiteration (production path): begin() runs the counting pass and returns the output nnz;
