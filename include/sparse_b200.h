@@ -121,6 +121,10 @@ int b2s_spmm_set_skew(int enabled);
  * keys[i] = sum_d coords[d][i] * strides_host[d]. coords is [ndim, nnz] with row stride `row_stride` elements. */
 int b2s_coo_linearize(int idx_bytes, int ndim, int64_t nnz, const void *coords_dev, int64_t row_stride,
                       const int64_t *strides_host, int64_t *keys_out_dev, void *stream);
+/* trace selector of _einsum_single (_common.py:1378-1392): flags[i] = 1 iff coords[d][i] == coords[first_host[d]][i]
+ * for every d (first_host[d] = first axis carrying the same subscript label, == d for unrepeated labels). */
+int b2s_coo_diag_flags(int idx_bytes, int ndim, int64_t nnz, const void *coords_dev, int64_t row_stride,
+                       const int32_t *first_host, uint8_t *flags_out_dev, void *stream);
 /* inverse of linear_loc for C-order `shape_host`; writes coords [ndim, nnz] of width idx_bytes. */
 int b2s_coo_unravel(int idx_bytes, int ndim, int64_t nnz, const int64_t *keys_dev, const int64_t *shape_host,
                     void *coords_out_dev, int64_t row_stride, void *stream);

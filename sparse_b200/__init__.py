@@ -1,7 +1,7 @@
 """sparse_b200 -- a B200-native (sm_100a) implementation of pydata/sparse's data-parallel hot path.
 
 Drop-in names for that path: ``COO``, ``GCXS`` (``CSR``/``CSC``), ``tensordot``, ``matmul``, ``dot``,
-``elemwise``, reductions (``sum``/``max``/``min``/``prod``/``mean``/``any``/``all``) and the NumPy protocols
+``elemwise``, reductions (``sum``/``max``/``min``/``prod``/``mean``/``any``/``all`` and the ``nan*`` forms) and the NumPy protocols
 (``__array_ufunc__``, ``__array_function__``, ``@``), plus the fused ``sddmm`` and ``mttkrp`` example paths.
 Host code is Python; every data-path step is a hand-written CUDA kernel in ``libsparse_b200.so`` reached through a
 thin C ABI (``include/sparse_b200.h``) via ctypes.  There is no CPU fallback: without the library or a CUDA device
@@ -9,9 +9,11 @@ operations raise.
 """
 from ._coo import COO, as_coo
 from ._dot import dot, matmul, stack, tensordot
+from ._einsum import einsum
 from ._elemwise import broadcast_to, elemwise
 from ._fused import mttkrp, sddmm
 from ._gcxs import CSC, CSR, GCXS
+from ._nanreduce import nanmax, nanmean, nanmin, nanprod, nanreduce, nansum
 from ._random import random
 from ._sparse_array import SparseArray
 
@@ -53,4 +55,5 @@ def all(x, /, *, axis=None, keepdims=False):
 
 
 __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
-           "elemwise", "broadcast_to", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all"]
+           "elemwise", "broadcast_to", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
+           "einsum", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce"]

@@ -20,11 +20,17 @@ from ._coo import COO, _is_scipy_sparse
 from ._sparse_array import SparseArray
 from ._utils import c_strides, isscalar, key_bits, prod
 
+def nan_replace(a, b):
+    """where(isnan(a), b, a): NumPy meaning of device op 14 (`_replace_nan`, _coo/common.py:674-693); type resolution
+    and fill values run through this definition, the stored values through the map kernel."""
+    return np.where(np.isnan(a), b, a)
+
+
 # ufunc -> device op code (csrc/elemwise.cu)
 _BINARY = {
     np.add: 0, np.subtract: 1, np.multiply: 2, np.true_divide: 3, np.maximum: 4, np.minimum: 5, np.fmax: 6,
     np.fmin: 7, np.power: 8, np.floor_divide: 9, np.remainder: 10, np.bitwise_and: 11, np.bitwise_or: 12,
-    np.bitwise_xor: 13, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
+    np.bitwise_xor: 13, nan_replace: 14, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
     np.not_equal: 37, np.logical_and: 38, np.logical_or: 39, np.logical_xor: 40,
 }
 _UNARY = {

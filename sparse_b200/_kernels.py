@@ -153,6 +153,21 @@ def linearize(coords, strides):
     return keys
 
 
+def diag_flags(coords, first):
+    """uint8 flags: entry i kept iff coords[d, i] == coords[first[d], i] for all d (einsum trace selector)."""
+    t = _t()
+    ndim, nnz = coords.shape
+    flags = t.empty(nnz, dtype=t.uint8, device=coords.device)
+    if nnz == 0:
+        return flags
+    if coords.stride(1) != 1:
+        coords = coords.contiguous()
+    rc = _lib.load().b2s_coo_diag_flags(i32(_idx_bytes(coords)), i32(ndim), i64(nnz), vp(D.ptr(coords)),
+                                        i64(coords.stride(0)), _i32arr(first), vp(D.ptr(flags)), _sp())
+    _lib.check(rc, "b2s_coo_diag_flags")
+    return flags
+
+
 def unravel(keys, shape, idx_dtype=np.int64):
     """coords[ndim, nnz] of C-order linear `keys` over `shape`."""
     t = _t()

@@ -17,7 +17,7 @@ from ._sparse_array import _reduce_super_ufunc
 from ._utils import equivalent, normalize_axis, prod
 
 _RED = {np.add: 0, np.multiply: 1, np.maximum: 2, np.minimum: 3, np.logical_and: 4, np.logical_or: 5,
-        np.bitwise_and: 6, np.bitwise_or: 7, np.bitwise_xor: 8}
+        np.bitwise_and: 6, np.bitwise_or: 7, np.bitwise_xor: 8, np.fmax: 9, np.fmin: 10}
 _RED_DTYPES = (np.dtype("float32"), np.dtype("float64"), np.dtype("int32"), np.dtype("int64"), np.dtype("bool"))
 
 

@@ -155,6 +155,24 @@ class SparseArray(NDArrayOperatorsMixin):
             out = (num / den) if not isinstance(num, SparseArray) else np.true_divide(num, den)
         return out.astype(dtype) if hasattr(out, "astype") else out
 
+    # ---- scalar conversion (_sparse_array.py:970-993) ---------------------------------------------------
+    def _to_scalar(self, builtin):
+        if self.size != 1 or self.shape != ():
+            raise ValueError(f"{builtin} can be computed for one-element arrays only.")
+        return builtin(self.todense().flatten()[0])
+
+    def __bool__(self):
+        return self._to_scalar(bool)
+
+    def __float__(self):
+        return self._to_scalar(float)
+
+    def __int__(self):
+        return self._to_scalar(int)
+
+    def __index__(self):
+        return self._to_scalar(int)
+
     # ---- misc -----------------------------------------------------------------------------------------
     @property
     def real(self):

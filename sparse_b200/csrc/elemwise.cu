@@ -23,6 +23,7 @@ namespace b2s {
 enum BinOp {
     OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_MAXIMUM = 4, OP_MINIMUM = 5, OP_FMAX = 6, OP_FMIN = 7,
     OP_POW = 8, OP_FLOORDIV = 9, OP_MOD = 10, OP_BAND = 11, OP_BOR = 12, OP_BXOR = 13,
+    OP_NANREPLACE = 14,  // where(isnan(a), b, a): _replace_nan of the nan-reductions (_coo/common.py:293-310)
     // predicates (bool output)
     OP_GT = 32, OP_GE = 33, OP_LT = 34, OP_LE = 35, OP_EQ = 36, OP_NE = 37, OP_LAND = 38, OP_LOR = 39, OP_LXOR = 40
 };
@@ -54,6 +55,7 @@ __device__ __forceinline__ T bin_apply(int op, T a, T b) {
             case OP_MINIMUM: return (is_nan(a) || is_nan(b)) ? (is_nan(a) ? a : b) : (a < b ? a : b);
             case OP_FMAX: return is_nan(a) ? b : (is_nan(b) ? a : (a > b ? a : b));
             case OP_FMIN: return is_nan(a) ? b : (is_nan(b) ? a : (a < b ? a : b));
+            case OP_NANREPLACE: return is_nan(a) ? b : a;
             case OP_POW: return pow(a, b);
             case OP_FLOORDIV: {
                 if (b == T(0)) return a / b;
@@ -101,6 +103,7 @@ __device__ __forceinline__ T bin_apply(int op, T a, T b) {
             case OP_BAND: return a & b;
             case OP_BOR: return a | b;
             case OP_BXOR: return a ^ b;
+            case OP_NANREPLACE: return a;
             default: return T(0);
         }
     }

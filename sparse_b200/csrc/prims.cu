@@ -46,6 +46,23 @@ __global__ void linearize_kernel(int ndim, int64_t nnz, const I *__restrict__ co
     }
 }
 
+// ---- trace selector of einsum: keep entry i iff coords[d][i] == coords[first[d]][i] for every d ---
+struct DiagPack {
+    int first[kMaxDims];
+};
+template <typename I>
+__global__ void diag_flags_kernel(int ndim, int64_t nnz, const I *__restrict__ coords, int64_t row_stride, DiagPack dg,
+                                  uint8_t *__restrict__ flags) {
+    B2S_GRID_STRIDE(i, nnz) {
+        bool keep = true;
+        for (int d = 0; d < ndim; ++d) {
+            const int f = dg.first[d];
+            if (f != d) keep &= coords[(int64_t)d * row_stride + i] == coords[(int64_t)f * row_stride + i];
+        }
+        flags[i] = keep ? 1 : 0;
+    }
+}
+
 // ---- unravel: coords[d][i] = (key / stride[d]) % extent[d] ----------------------------------
 template <typename I>
 __global__ void unravel_kernel(int ndim, int64_t nnz, const int64_t *__restrict__ keys, DimPack dp,
@@ -246,6 +263,28 @@ int b2s_coo_linearize(int idx_bytes, int ndim, int64_t nnz, const void *coords_d
     else
         linearize_kernel<int64_t><<<grid_for(nnz), 256, 0, s>>>(ndim, nnz, (const int64_t *)coords_dev, row_stride, dp,
                                                                keys_out_dev);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+int b2s_coo_diag_flags(int idx_bytes, int ndim, int64_t nnz, const void *coords_dev, int64_t row_stride,
+                        const int32_t *first_host, uint8_t *flags_out_dev, void *stream) {
+    B2S_REQUIRE(ndim >= 0 && ndim <= kMaxDims, B2S_ERR_UNSUPPORTED, "diag_flags: ndim %d > %d", ndim, kMaxDims);
+    B2S_REQUIRE(idx_bytes == 4 || idx_bytes == 8, B2S_ERR_INVALID, "diag_flags: idx_bytes");
+    if (nnz == 0) return B2S_OK;
+    DiagPack dg{};
+    for (int d = 0; d < ndim; ++d) {
+        B2S_REQUIRE(first_host[d] >= 0 && first_host[d] <= d, B2S_ERR_INVALID, "diag_flags: first[%d] = %d", d,
+                    first_host[d]);
+        dg.first[d] = first_host[d];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (idx_bytes == 4)
+        diag_flags_kernel<int32_t><<<grid_for(nnz), 256, 0, s>>>(ndim, nnz, (const int32_t *)coords_dev, row_stride, dg,
+                                                                flags_out_dev);
+    else
+        diag_flags_kernel<int64_t><<<grid_for(nnz), 256, 0, s>>>(ndim, nnz, (const int64_t *)coords_dev, row_stride, dg,
+                                                                flags_out_dev);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }

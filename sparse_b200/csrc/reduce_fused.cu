@@ -22,7 +22,8 @@
 
 namespace b2s {
 
-enum RedOp2 { RF_ADD = 0, RF_MUL = 1, RF_MAX = 2, RF_MIN = 3, RF_AND = 4, RF_OR = 5, RF_BAND = 6, RF_BOR = 7, RF_BXOR = 8 };
+enum RedOp2 { RF_ADD = 0, RF_MUL = 1, RF_MAX = 2, RF_MIN = 3, RF_AND = 4, RF_OR = 5, RF_BAND = 6, RF_BOR = 7, RF_BXOR = 8,
+              RF_FMAX = 9, RF_FMIN = 10 };  // NaN-ignoring (np.fmax / np.fmin: nanmax / nanmin)
 
 constexpr int RD_THREADS = 256;
 constexpr int RD_ITEMS = 8;
@@ -37,14 +38,16 @@ __device__ __forceinline__ T red_apply(int op, T a, T b) {
             case RF_MUL: return mul_rn(a, b);
             case RF_MAX: return (a != a) ? a : ((b != b) ? b : (a >= b ? a : b));  // NaN propagates (np.maximum)
             case RF_MIN: return (a != a) ? a : ((b != b) ? b : (a <= b ? a : b));
+            case RF_FMAX: return (a >= b || b != b) ? a : b;  // the other operand when one is NaN
+            case RF_FMIN: return (a <= b || b != b) ? a : b;
             default: return a;
         }
     } else {
         switch (op) {
             case RF_ADD: return (T)(a + b);
             case RF_MUL: return (T)(a * b);
-            case RF_MAX: return a >= b ? a : b;
-            case RF_MIN: return a <= b ? a : b;
+            case RF_MAX: case RF_FMAX: return a >= b ? a : b;
+            case RF_MIN: case RF_FMIN: return a <= b ? a : b;
             case RF_AND: return (T)((a != T(0)) && (b != T(0)));
             case RF_OR: return (T)((a != T(0)) || (b != T(0)));
             case RF_BAND: return (T)(a & b);

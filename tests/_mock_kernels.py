@@ -19,7 +19,7 @@ _ORIG = {}
 
 _BIN = {0: np.add, 1: np.subtract, 2: np.multiply, 3: np.true_divide, 4: np.maximum, 5: np.minimum, 6: np.fmax,
         7: np.fmin, 8: np.power, 9: np.floor_divide, 10: np.remainder, 11: np.bitwise_and, 12: np.bitwise_or,
-        13: np.bitwise_xor, 32: np.greater, 33: np.greater_equal, 34: np.less, 35: np.less_equal, 36: np.equal,
+        13: np.bitwise_xor, 14: lambda a, b: np.where(np.isnan(a), b, a), 32: np.greater, 33: np.greater_equal, 34: np.less, 35: np.less_equal, 36: np.equal,
         37: np.not_equal, 38: np.logical_and, 39: np.logical_or, 40: np.logical_xor}
 _UN = {0: np.negative, 1: np.absolute, 2: np.sqrt, 3: np.square, 4: np.sign, 5: np.exp, 6: np.expm1, 7: np.log,
        8: np.log1p, 9: np.sin, 10: np.cos, 11: np.tan, 12: np.tanh, 13: np.sinh, 14: np.cosh, 15: np.arcsin,
@@ -27,7 +27,7 @@ _UN = {0: np.negative, 1: np.absolute, 2: np.sqrt, 3: np.square, 4: np.sign, 5: 
        23: np.invert, 24: np.arcsinh, 25: np.arctanh, 26: np.deg2rad, 27: np.rad2deg, 28: np.exp2, 29: np.log2,
        30: np.log10, 31: np.cbrt, 64: np.isnan, 65: np.isinf, 66: np.isfinite, 67: np.logical_not, 68: np.signbit}
 _RED = {0: np.add, 1: np.multiply, 2: np.maximum, 3: np.minimum, 4: np.logical_and, 5: np.logical_or,
-        6: np.bitwise_and, 7: np.bitwise_or, 8: np.bitwise_xor}
+        6: np.bitwise_and, 7: np.bitwise_or, 8: np.bitwise_xor, 9: np.fmax, 10: np.fmin}
 
 
 def n(x):
@@ -74,6 +74,15 @@ def linearize(coords, strides):
     for d in range(c.shape[0]):
         k += c[d] * int(strides[d])
     return T(k)
+
+
+def diag_flags(coords, first):
+    c = n(coords)
+    keep = np.ones(c.shape[1], dtype=bool)
+    for d, f in enumerate(first):
+        if f != d:
+            keep &= c[d] == c[f]
+    return T(keep.astype(np.uint8))
 
 
 def unravel(keys, shape, idx_dtype=np.int64):

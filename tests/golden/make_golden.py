@@ -381,6 +381,115 @@ def gen_reduce():
                    **enc("a_", x), **enc("out_", r))
     bk.save()
 
+# --------------------------------------------------------------------------
+def gen_nanreduce():
+    """NaN-skipping reductions (_coo/common.py:346-531, 674-732; tests/test_coo.py:196-263 upstream)."""
+    bk = Book("nanreduce_api")
+    rng = np.random.default_rng(29)
+    axes_list = [None, 0, 2, (0, 2), (1, 2), -1]
+    arrays = []
+    for dt in ("float64", "float32"):
+        x = rand_sparse(rng, (5, 6, 7), 0.35, dt)
+        d = x.data.copy()
+        d[rng.random(d.shape[0]) < 0.25] = np.nan
+        arrays.append((dt, "", sparse.COO(x.coords, d, shape=x.shape)))
+    # NaN fill value: every implicit entry is skipped as well
+    x = rand_sparse(rng, (4, 5, 6), 0.4, "float64")
+    d = x.data.copy()
+    d[::5] = np.nan
+    arrays.append(("float64", "nanfill", sparse.COO(x.coords, d, shape=x.shape, fill_value=np.nan)))
+    # one fully stored all-NaN slice (warns "All-NaN slice" / "Mean of empty slice")
+    dn = rng.random((3, 4))
+    dn[dn < 0.5] = 0.0
+    dn[1, :] = np.nan
+    arrays.append(("float64", "allnan", sparse.COO.from_numpy(dn)))
+    # integer input: nan-functions degenerate to the plain reductions
+    arrays.append(("int64", "", rand_sparse(rng, (5, 6, 7), 0.3, "int64")))
+    for dt, note, x in arrays:
+        for name in ("nansum", "nanprod", "nanmax", "nanmin", "nanmean"):
+            for axis in axes_list:
+                if x.ndim == 2 and axis in (2, (0, 2), (1, 2)):
+                    continue
+                for keepdims in (False, True):
+                    with np.errstate(all="ignore"):
+                        r = getattr(sparse, name)(x, axis=axis, keepdims=keepdims)
+                    ax = axis if axis is None or isinstance(axis, int) else list(axis)
+                    bk.add({"op": name, "dtype": dt, "axis": ax, "keepdims": keepdims, "fmt": "coo", "note": note},
+                           **enc("a_", x), **enc("out_", r))
+    # GCXS input goes through asCOO
+    g = arrays[0][2].asformat("gcxs")
+    for name in ("nansum", "nanmax", "nanmean"):
+        for axis in (0, (0, 2), None):
+            with np.errstate(all="ignore"):
+                r = getattr(sparse, name)(g, axis=axis)
+            ax = axis if axis is None or isinstance(axis, int) else list(axis)
+            bk.add({"op": name, "dtype": "float64", "axis": ax, "keepdims": False, "fmt": "gcxs", "note": ""},
+                   **enc("a_", arrays[0][2]), **enc("out_", r), a_ca=np.array(g.compressed_axes))
+    bk.save()
+
+# --------------------------------------------------------------------------
+EINSUM_CASES = [
+    "a,->a", "ab,->ab", ",ab,->ab", ",,->", "a,ab,abc->abc", "a,b,ab->ab", "ea,fb,gc,hd,abcd->efgh",
+    "ea,fb,abcd,gc,hd->efgh", "abcd,ea,fb,gc,hd->efgh", "acdf,jbje,gihb,hfac,gfac,gifabc,hfac",
+    "cd,bdhe,aidb,hgca,gc,hgibcd,hgac", "abhe,hidj,jgba,hiab,gab", "bde,cdh,agdb,hica,ibd,hgicd,hiac",
+    "chd,bde,agbc,hiad,hgc,hgi,hiad", "chd,bde,agbc,hiad,bdi,cgh,agdb", "bdhe,acad,hiab,agac,hibd", "ab,ab,c->",
+    "ab,ab,c->c", "ab,ab,cd,cd->", "ab,ab,cd,cd->ac", "ab,ab,cd,cd->cd", "ab,ab,cd,cd,ef,ef->", "ab,cd,ef->abcdef",
+    "ab,cd,ef->acdf", "ab,cd,de->abcde", "ab,cd,de->be", "ab,bcd,cd->abcd", "ab,bcd,cd->abd", "eb,cb,fb->cef",
+    "dd,fb,be,cdb->cef", "bca,cdb,dbf,afc->", "dcc,fce,ea,dbf->ab", "fdf,cdd,ccd,afe->ae", "abcd,ad",
+    "ed,fcd,ff,bcf->be", "baa,dcf,af,cde->be", "bd,db,eac->ace", "fff,fae,bef,def->abd", "efc,dbc,acf,fd->abe",
+    "ab,ab", "ab,ba", "abc,abc", "abc,bac", "abc,cba", "ab,bc", "ab,cb", "ba,bc", "ba,cb", "abcd,cd", "abcd,ab",
+    "abcd,cdef", "abcd,cdef->feba", "abcd,efdc", "aab,bc->ac", "ab,bcc->ac", "aab,bcc->ac", "baa,bcc->ac",
+    "aab,ccb->ac", "aab,fa,df,ecc->bde", "ecb,fef,bad,ed->ac", "bcf,bbb,fbf,fc->", "bb,ff,be->e", "bcb,bb,fc,fff->",
+    "fbb,dfd,fc,fc->", "afd,ba,cc,dc->bf", "adb,bc,fa,cfc->d", "bbd,bda,fc,db->acf", "dba,ead,cad->bce",
+    "aef,fbc,dca->bde", "abab->ba", "...ab,...ab", "...ab,...b->...a", "a...,a...", "ab->ba", "abc->", "abc->b",
+    "aa", "aa->a", "aab->b",
+]  # the reference's own test list (tests/test_einsum.py:7-82 upstream) + single-term forms
+
+
+def gen_einsum():
+    """einsum (_common.py:1150-1476; tests/test_einsum.py upstream)."""
+    bk = Book("einsum_api")
+    rng = np.random.default_rng(31)
+    d = 4
+    for sub in EINSUM_CASES:
+        terms = sub.split("->")[0].split(",")
+        for density in (0.3, 1.0):
+            arrays = [sparse.random((d,) * len(t.replace("...", "xy")), density=density, random_state=rng)
+                      for t in terms]
+            r = sparse.einsum(sub, *arrays)
+            ops = {}
+            for i, a in enumerate(arrays):
+                ops.update(enc(f"op{i}_", a))
+            bk.add({"op": "einsum", "sub": sub, "n": len(arrays), "fmts": ["coo"] * len(arrays), "dtype": None,
+                    "note": f"d{density}"}, **ops, **enc("out_", r))
+    # operand formats -> result format (tests/test_einsum.py:143-183 upstream, without DOK)
+    for fmts in (("coo",), ("gcxs",), ("coo", "coo"), ("coo", "dense"), ("dense", "coo"), ("gcxs", "dense"),
+                 ("dense", "gcxs"), ("gcxs", "gcxs"), ("dense", "coo", "gcxs"), ("dense", "dense", "coo")):
+        arrays = [sparse.random((3, 3, 3), density=0.5, random_state=rng) for _ in fmts]
+        ins = [a.todense() if f == "dense" else a.asformat(f) for a, f in zip(arrays, fmts)]
+        eq = {1: "abc->bc", 2: "abc,cda->abd", 3: "abc,cad,dea->abe"}[len(fmts)]
+        r = sparse.einsum(eq, *ins)
+        ops = {}
+        for i, a in enumerate(arrays):
+            ops.update(enc(f"op{i}_", a))
+        bk.add({"op": "einsum", "sub": eq, "n": len(arrays), "fmts": list(fmts), "dtype": None, "note": "fmt"},
+               **ops, **enc("out_", r))
+    # dtype=
+    x = (sparse.random((3, 3), density=0.5, random_state=rng) * 10.0).astype(np.float64)
+    y = sparse.COO.from_numpy(np.ones((3, 1)))
+    for dt in ("int64", "float32"):
+        r = sparse.einsum("ij,i->j", x, y.reshape((3,)), dtype=np.dtype(dt))
+        bk.add({"op": "einsum", "sub": "ij,i->j", "n": 2, "fmts": ["coo", "coo"], "dtype": dt, "note": "dtype"},
+               **enc("op0_", x), **enc("op1_", y.reshape((3,))), **enc("out_", r))
+    # interleaved (sublist) call form (tests/test_einsum.py:103-115 upstream); Ellipsis encoded as -1
+    x = sparse.random((d, d), density=0.5, random_state=rng)
+    for lists in ([[0, 0]], [[0, Ellipsis]], [[Ellipsis, 1], [Ellipsis]], [[0, 1], [0]], [[0, 1], [1, 0]]):
+        r = sparse.einsum(x, *lists)
+        enc_lists = [[-1 if s is Ellipsis else s for s in li] for li in lists]
+        bk.add({"op": "einsum_lists", "lists": enc_lists, "n": 1, "fmts": ["coo"], "dtype": None, "note": "lists"},
+               **enc("op0_", x), **enc("out_", r))
+    bk.save()
+
 
 # --------------------------------------------------------------------------
 def gen_formats():
@@ -440,7 +549,7 @@ def gen_examples():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dot", "tensordot", "elemwise", "reduce", "formats", "examples"]
+    which = sys.argv[1:] or ["dot", "tensordot", "elemwise", "reduce", "nanreduce", "einsum", "formats", "examples"]
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         if "dot" in which:
@@ -451,6 +560,10 @@ if __name__ == "__main__":
             gen_elemwise()
         if "reduce" in which:
             gen_reduce()
+        if "nanreduce" in which:
+            gen_nanreduce()
+        if "einsum" in which:
+            gen_einsum()
         if "formats" in which:
             gen_formats()
         if "examples" in which:
