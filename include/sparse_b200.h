@@ -125,6 +125,13 @@ int b2s_coo_linearize(int idx_bytes, int ndim, int64_t nnz, const void *coords_d
  * for every d (first_host[d] = first axis carrying the same subscript label, == d for unrepeated labels). */
 int b2s_coo_diag_flags(int idx_bytes, int ndim, int64_t nnz, const void *coords_dev, int64_t row_stride,
                        const int32_t *first_host, uint8_t *flags_out_dev, void *stream);
+/* basic indexing x[ints / slices] (_coo/indexing.py:12-133: _mask + the coordinate transform `(c - start) // step`).
+ * keys_dev: C-order linear keys over shape_host.  Axis d keeps coordinate c iff c = start + j*step for some
+ * 0 <= j < count (an integer index is start = i, step = 1, count = 1); flags[i] = all axes keep, and
+ * keys_out[i] = sum_d j_d * out_stride_host[d] (out_stride 0 drops the axis).  Compaction is the caller's. */
+int b2s_coo_slice_keys(int ndim, int64_t nnz, const int64_t *keys_dev, const int64_t *shape_host,
+                       const int64_t *start_host, const int64_t *step_host, const int64_t *count_host,
+                       const int64_t *out_stride_host, uint8_t *flags_out_dev, int64_t *keys_out_dev, void *stream);
 /* inverse of linear_loc for C-order `shape_host`; writes coords [ndim, nnz] of width idx_bytes. */
 int b2s_coo_unravel(int idx_bytes, int ndim, int64_t nnz, const int64_t *keys_dev, const int64_t *shape_host,
                     void *coords_out_dev, int64_t row_stride, void *stream);

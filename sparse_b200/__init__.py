@@ -13,6 +13,7 @@ from ._einsum import einsum
 from ._elemwise import broadcast_to, elemwise
 from ._fused import mttkrp, sddmm
 from ._gcxs import CSC, CSR, GCXS
+from ._io import load_npz, save_npz
 from ._nanreduce import nanmax, nanmean, nanmin, nanprod, nanreduce, nansum
 from ._random import random
 from ._sparse_array import SparseArray
@@ -56,4 +57,4 @@ def all(x, /, *, axis=None, keepdims=False):
 
 __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
            "elemwise", "broadcast_to", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
-           "einsum", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce"]
+           "einsum", "save_npz", "load_npz", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce"]

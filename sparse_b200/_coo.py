@@ -413,31 +413,13 @@ class COO(SparseArray):
 
         return broadcast_to(self, shape)
 
-    # ---- indexing: only what the hot path's callers need ------------------------------------------------
+    # ---- indexing ---------------------------------------------------------------------------------------
     def __getitem__(self, index):
-        """Supports `None` insertion, full slices and Ellipsis (`x[:, :, None]`, used by the MTTKRP expression
-        and by `outer`), plus an integer on the leading axis (batched matmul, _common.py:278-282)."""
-        if not isinstance(index, tuple):
-            index = (index,)
-        if any(i is Ellipsis for i in index):
-            n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
-            e = index.index(Ellipsis)
-            index = index[:e] + (slice(None),) * (self.ndim - n_real) + index[e + 1:]
-        if all(i is None or (isinstance(i, slice) and i == slice(None)) for i in index):
-            n_real = sum(1 for i in index if i is not None)
-            index = index + (slice(None),) * (self.ndim - n_real)
-            new_shape, d = [], 0
-            for i in index:
-                if i is None:
-                    new_shape.append(1)
-                else:
-                    new_shape.append(self.shape[d])
-                    d += 1
-            return self.reshape(tuple(new_shape))
-        if isinstance(index[0], (int, np.integer)) and all(
-                isinstance(i, slice) and i == slice(None) for i in index[1:]):
-            return self._take_leading(int(index[0]))
-        raise NotImplementedError("sparse_b200.COO supports only None/full-slice indexing and x[i] on the leading axis")
+        """Integers, slices (any step), None and Ellipsis -- one streaming kernel over the linear keys
+        (_coo/indexing.py:12-133); see _indexing.py."""
+        from ._indexing import coo_getitem
+
+        return coo_getitem(self, index)
 
     def _take_leading(self, i):
         if i < 0:

@@ -364,8 +364,10 @@ class GCXS(SparseArray):
         return self.reshape(-1)
 
     def __getitem__(self, index):
-        """`None` insertion / full slices only (the MTTKRP expression, examples/mttkrp_example.py:51)."""
-        return GCXS.from_coo(self.tocoo()[index])
+        """Integers, slices, None, Ellipsis (_compressed/indexing.py:14-174); see _indexing.py."""
+        from ._indexing import gcxs_getitem
+
+        return gcxs_getitem(self, index)
 
     # ---- prune (compressed.py:816-842) ---------------------------------------------------------------------------
     def _prune(self):

@@ -1,0 +1,158 @@
+"""Basic indexing (integers, slices with any step, None, Ellipsis) of COO and GCXS arrays on the device.
+
+Host-side mirror of sparse/numba_backend/_coo/indexing.py:12-133 (`getitem`), _slicing.py (`normalize_index`) and
+_compressed/indexing.py:14-174.  The reference narrows the sorted coordinate rows axis by axis with binary searches
+(`_compute_mask`, numba) and then transforms the surviving coordinates; here one streaming kernel
+(`b2s_coo_slice_keys`, csrc/prims.cu) unravels each entry's linear key, tests every axis against its
+(start, step, count) range and emits the key over the RESULT shape, followed by the usual flag-scan-compact (and a
+sort only when a negative step reverses an axis).  Advanced (integer-array / boolean-mask) indexing is not on the
+CUDA path and raises.
+"""
+from __future__ import annotations
+
+import operator
+
+import numpy as np
+
+from . import _device as D
+from . import _kernels as Kn
+from ._utils import c_strides, key_bits, prod
+
+
+def _normalize(index, shape):
+    """Canonical per-entry items: ("int", i) | ("slice", start, step, count) | ("none",), Ellipsis expanded and
+    missing trailing axes filled with full slices (NumPy's rules and error types)."""
+    ells = [k for k, i in enumerate(index) if i is Ellipsis]
+    if len(ells) > 1:
+        raise IndexError("an index can only have a single ellipsis ('...')")
+    n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
+    ndim = len(shape)
+    if n_real > ndim:
+        raise IndexError(f"too many indices for array: array is {ndim}-dimensional, but {n_real} were indexed")
+    fill = (slice(None),) * (ndim - n_real)
+    if ells:
+        index = index[:ells[0]] + fill + index[ells[0] + 1:]
+    else:
+        index = index + fill
+    items, d = [], 0
+    for ind in index:
+        if ind is None:
+            items.append(("none",))
+            continue
+        extent = shape[d]
+        if isinstance(ind, slice):
+            start, stop, step = ind.indices(extent)
+            items.append(("slice", start, step, len(range(start, stop, step))))
+        elif isinstance(ind, (bool, np.bool_)) or isinstance(ind, (list, np.ndarray)) or D.is_device_tensor(ind):
+            raise NotImplementedError("sparse_b200: advanced (integer-array / boolean-mask) indexing is not on the "
+                                      "CUDA path; only integers, slices, None and Ellipsis are")
+        else:
+            try:
+                i = operator.index(ind)
+            except TypeError:
+                raise IndexError("only integers, slices (`:`), ellipsis (`...`) and None are valid indices") from None
+            if not -extent <= i < extent:
+                raise IndexError(f"index {i} is out of bounds for axis {d} with size {extent}")
+            items.append(("int", i + extent if i < 0 else i))
+        d += 1
+    return items
+
+
+def coo_getitem(x, index):
+    """COO.__getitem__ (_coo/indexing.py:12-133)."""
+    from ._coo import COO
+
+    if isinstance(index, str):
+        raise NotImplementedError("sparse_b200: structured dtypes are outside the CUDA dtype matrix")
+    if not isinstance(index, tuple):
+        index = (index,)
+    last_ellipsis = len(index) > 0 and index[-1] is Ellipsis
+    items = _normalize(index, x.shape)
+    if len(index) != 0 and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items, x.shape)) \
+            and len(items) == x.ndim:
+        return x
+    new_shape = tuple(1 if it[0] == "none" else it[3] for it in items if it[0] != "int")
+    real = [it for it in items if it[0] != "none"]
+
+    # leading integer on a canonical array: contiguous run of the sorted entries (the batched-matmul slice a[i])
+    if (x.ndim > 1 and real[0][0] == "int" and x._coords is not None
+            and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items[1:], x.shape[1:]))
+            and len(items) == x.ndim):
+        return x._take_leading(real[0][1])
+
+    if x.nnz == 0 or x.ndim == 0:
+        data = x._data_dev() if x.nnz else None
+        total = x.nnz
+        keys = None
+    else:
+        st_new = c_strides(new_shape)
+        start, step, count, ostride = [], [], [], []
+        p = 0
+        for it in items:
+            if it[0] == "none":
+                p += 1
+            elif it[0] == "int":
+                start.append(it[1]); step.append(1); count.append(1); ostride.append(0)
+            else:
+                start.append(it[1]); step.append(it[2]); count.append(it[3]); ostride.append(st_new[p])
+                p += 1
+        flags, keys = Kn.slice_keys(x.sorted_keys(), x.shape, start, step, count, ostride)
+        pos, total = Kn.scan_flags(flags)
+        data = x._data_dev()
+        if total != x.nnz:
+            keys = Kn.compact(keys, flags, pos, total)
+            data = Kn.compact(data, flags, pos, total)
+        if total > 1 and any(s < 0 for s in step):
+            unsorted, _ = Kn.keys_flags(keys)
+            if unsorted:
+                keys, perm = Kn.sort_keys(keys, key_bits(prod(new_shape)))
+                data = Kn.gather(data, perm)
+
+    if not new_shape:
+        if not last_ellipsis:  # a single element: the stored value, else the fill value
+            return D.download(data[:1])[0] if total else x.fill_value
+        host = D.download(data[:total]) if total else np.empty(0, dtype=x.dtype)
+        return COO(np.empty((0, total), dtype=np.intp), host, shape=(), has_duplicates=False, sorted=True,
+                   fill_value=x.fill_value)
+    if total == 0:
+        return COO(np.zeros((len(new_shape), 0), dtype=np.intp), np.empty(0, dtype=x.dtype), shape=new_shape,
+                   has_duplicates=False, sorted=True, fill_value=x.fill_value)
+    if keys is None:  # 0-D input with None axes
+        keys = Kn.full(total, 0, np.int64)
+    return COO._from_device(None, data, new_shape, x.fill_value, keys=keys)
+
+
+def gcxs_getitem(x, index):
+    """GCXS.__getitem__ (_compressed/indexing.py:14-174): same selection, result compressed along the surviving
+    compressed axes of the operand."""
+    from ._gcxs import GCXS
+
+    if not isinstance(index, tuple):
+        index = (index,)
+    if x.ndim == 1:
+        r = coo_getitem(x.tocoo(), index)
+        return GCXS.from_coo(r) if hasattr(r, "nnz") else r
+    items = _normalize(index, x.shape)
+    if len(index) != 0 and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items, x.shape)) \
+            and len(items) == x.ndim:
+        return x
+    real = [it for it in items if it[0] != "none"]
+    if all(it[0] == "int" for it in real) and len(real) == len(items):
+        return coo_getitem(x.tocoo(), tuple(it[1] for it in real))  # get_single_element: always a scalar
+    comp, n_comp_kept, n_uncomp_kept, pos = [], 0, 0, 0
+    for axis, it in enumerate(real):
+        if it[0] == "int":
+            continue
+        if axis in x.compressed_axes:
+            comp.append(pos)
+            n_comp_kept += 1
+        else:
+            n_uncomp_kept += 1
+        pos += 1
+    if n_comp_kept == 0 or n_uncomp_kept == 0:
+        comp = [0]
+    for k, it in enumerate(items):
+        if it[0] == "none":
+            comp = [c + 1 if c >= k else c for c in comp]
+    r = coo_getitem(x.tocoo(), index)
+    return GCXS.from_coo(r, None if r.ndim == 1 else tuple(comp))

@@ -168,6 +168,20 @@ def diag_flags(coords, first):
     return flags
 
 
+def slice_keys(keys, shape, start, step, count, out_stride):
+    """(flags, new keys) of basic indexing: axis d keeps c = start[d] + j*step[d], 0 <= j < count[d]."""
+    t = _t()
+    n = keys.shape[0]
+    flags = t.empty(n, dtype=t.uint8, device=keys.device)
+    okeys = t.empty(n, dtype=t.int64, device=keys.device)
+    if n:
+        rc = _lib.load().b2s_coo_slice_keys(i32(len(shape)), i64(n), vp(D.ptr(keys)), _i64arr(shape), _i64arr(start),
+                                            _i64arr(step), _i64arr(count), _i64arr(out_stride), vp(D.ptr(flags)),
+                                            vp(D.ptr(okeys)), _sp())
+        _lib.check(rc, "b2s_coo_slice_keys")
+    return flags, okeys
+
+
 def unravel(keys, shape, idx_dtype=np.int64):
     """coords[ndim, nnz] of C-order linear `keys` over `shape`."""
     t = _t()

@@ -78,6 +78,37 @@ __global__ void unravel_kernel(int ndim, int64_t nnz, const int64_t *__restrict_
     }
 }
 
+// ---- basic indexing x[ints / slices]: per entry, test every axis against its (start, step, count) range and emit the
+// ---- key over the result shape (integer-indexed axes carry out_stride 0) -----------------------------------------
+struct SlicePack {
+    FastDiv fext[kMaxDims];     // input extents
+    FastDiv fstep[kMaxDims];    // |step|
+    int64_t start[kMaxDims];
+    int64_t count[kMaxDims];    // len(range(start, stop, step)); 1 for an integer index
+    int64_t ostride[kMaxDims];  // stride of the axis in the result (0 when dropped)
+    int neg[kMaxDims];          // step < 0
+};
+__global__ void slice_keys_kernel(int ndim, int64_t nnz, const int64_t *__restrict__ keys, SlicePack sp,
+                                  uint8_t *__restrict__ flags, int64_t *__restrict__ okeys) {
+    B2S_GRID_STRIDE(i, nnz) {
+        uint64_t k = (uint64_t)keys[i];
+        int64_t ok = 0;
+        bool keep = true;
+        for (int d = ndim - 1; d >= 0; --d) {
+            uint64_t q, c;
+            sp.fext[d].divmod(k, q, c);
+            k = q;
+            const int64_t off = sp.neg[d] ? sp.start[d] - (int64_t)c : (int64_t)c - sp.start[d];
+            uint64_t j = 0, r = 0;
+            if (off >= 0) sp.fstep[d].divmod((uint64_t)off, j, r);
+            keep &= off >= 0 && r == 0 && (int64_t)j < sp.count[d];
+            ok += (int64_t)j * sp.ostride[d];
+        }
+        flags[i] = keep ? 1 : 0;
+        okeys[i] = ok;
+    }
+}
+
 // ---- sortedness / duplicate flags over a key array ------------------------------------------
 __global__ void keys_flags_kernel(const int64_t *__restrict__ keys, int64_t n, int32_t *__restrict__ flags) {
     bool unsorted = false, dup = false;
@@ -285,6 +316,27 @@ int b2s_coo_diag_flags(int idx_bytes, int ndim, int64_t nnz, const void *coords_
     else
         diag_flags_kernel<int64_t><<<grid_for(nnz), 256, 0, s>>>(ndim, nnz, (const int64_t *)coords_dev, row_stride, dg,
                                                                 flags_out_dev);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
+int b2s_coo_slice_keys(int ndim, int64_t nnz, const int64_t *keys_dev, const int64_t *shape_host,
+                       const int64_t *start_host, const int64_t *step_host, const int64_t *count_host,
+                       const int64_t *out_stride_host, uint8_t *flags_out_dev, int64_t *keys_out_dev, void *stream) {
+    B2S_REQUIRE(ndim >= 1 && ndim <= kMaxDims, B2S_ERR_UNSUPPORTED, "slice_keys: ndim %d not in 1..%d", ndim, kMaxDims);
+    if (nnz == 0) return B2S_OK;
+    SlicePack sp{};
+    for (int d = 0; d < ndim; ++d) {
+        B2S_REQUIRE(step_host[d] != 0, B2S_ERR_INVALID, "slice_keys: step[%d] == 0", d);
+        sp.fext[d] = make_fastdiv((uint64_t)shape_host[d]);
+        sp.neg[d] = step_host[d] < 0;
+        sp.fstep[d] = make_fastdiv((uint64_t)(step_host[d] < 0 ? -step_host[d] : step_host[d]));
+        sp.start[d] = start_host[d];
+        sp.count[d] = count_host[d];
+        sp.ostride[d] = out_stride_host[d];
+    }
+    slice_keys_kernel<<<grid_for(nnz), 256, 0, (cudaStream_t)stream>>>(ndim, nnz, keys_dev, sp, flags_out_dev,
+                                                                      keys_out_dev);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }

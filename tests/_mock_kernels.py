@@ -85,6 +85,19 @@ def diag_flags(coords, first):
     return T(keep.astype(np.uint8))
 
 
+def slice_keys(keys, shape, start, step, count, out_stride):
+    k = n(keys)
+    c = np.stack(np.unravel_index(k, shape)) if len(k) else np.zeros((len(shape), 0), np.int64)
+    keep = np.ones(len(k), dtype=bool)
+    ok = np.zeros(len(k), dtype=np.int64)
+    for d in range(len(shape)):
+        off = (c[d] - start[d]) * (1 if step[d] > 0 else -1)
+        j = off // abs(step[d])
+        keep &= (off >= 0) & (off % abs(step[d]) == 0) & (j < count[d])
+        ok += np.where(keep, j, 0) * out_stride[d]
+    return T(keep.astype(np.uint8)), T(ok)
+
+
 def unravel(keys, shape, idx_dtype=np.int64):
     k = n(keys)
     if len(shape) == 0:
