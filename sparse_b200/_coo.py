@@ -310,8 +310,41 @@ class COO(SparseArray):
             return self.todense()
         raise NotImplementedError(f"The given format is not supported: {format}")
 
+    # ---- SciPy interop (_coo/core.py:1166-1260): host objects built from one D2H of the component arrays -------
+    def to_scipy_sparse(self, /, *, accept_fv=None):
+        import scipy.sparse
+
+        from ._utils import check_fill_value
+
+        check_fill_value(self, accept_fv=accept_fv)
+        if self.ndim != 2:
+            raise ValueError("Can only convert a 2-dimensional array to a Scipy sparse matrix.")
+        result = scipy.sparse.coo_array((self.data, self.coords), shape=self.shape)
+        result.has_canonical_format = True
+        return result
+
     def tocsr(self):
-        return self.asformat("gcxs", compressed_axes=(0,))
+        """scipy.sparse.csr_array (row pointer built on the device by the CSR conversion kernels)."""
+        import scipy.sparse
+
+        from ._utils import check_zero_fill_value
+
+        check_zero_fill_value(self)
+        if self.ndim != 2:
+            raise ValueError("This array must be two-dimensional for this conversion to work.")
+        g = self.asformat("gcxs", compressed_axes=(0,))
+        return scipy.sparse.csr_array((g.data, g.indices, g.indptr), shape=self.shape)
+
+    def tocsc(self):
+        import scipy.sparse
+
+        from ._utils import check_zero_fill_value
+
+        check_zero_fill_value(self)
+        if self.ndim != 2:
+            raise ValueError("This array must be two-dimensional for this conversion to work.")
+        g = self.asformat("gcxs", compressed_axes=(1,))
+        return scipy.sparse.csc_array((g.data, g.indices, g.indptr), shape=self.shape)
 
     def astype(self, dtype, casting="unsafe", copy=True):
         dtype = np.dtype(dtype)

@@ -133,3 +133,85 @@ def sddmm_rowblock(s_local, a_local, b_cols_shard, group=None):
     bt_shard = Kn.transpose_dense(b_cols_shard)  # (N/world, K)
     Bt = all_gather_rows(bt_shard, group)        # (N, K)
     return sddmm(s_local, a_local, Bt, b_transposed=True)
+
+
+# ---- element-wise operations and reductions: range partition on the leading coordinate -------------
+def leading_splits(arrays, world: int):
+    """Boundaries on the LEADING axis shared by every operand such that each rank holds ~1/world of the stored
+    entries of all operands together (operands whose leading extent is 1 are broadcast there and are not split)."""
+    ext = max(a.shape[0] for a in arrays)
+    counts = np.zeros(ext, dtype=np.int64)
+    for a in arrays:
+        if a.shape[0] != ext:
+            continue
+        lead = a.coords[0] if a.nnz else np.empty(0, dtype=np.int64)
+        counts += np.bincount(lead, minlength=ext)
+    return nnz_balanced_splits(np.concatenate([[0], np.cumsum(counts)]), world)
+
+
+def leading_block(x, r0: int, r1: int):
+    """Entries of COO `x` whose leading coordinate lies in [r0, r1) (one pass of the slice kernel); an operand that is
+    broadcast on the leading axis (extent 1) is replicated."""
+    if x.shape[0] == 1 and r1 - r0 != 1:
+        return x
+    return x[r0:r1]
+
+
+def elemwise_leading(func, *local_blocks, **kwargs):
+    """Local block of ``elemwise(func, *operands)``: every operand was cut at the same leading-axis boundaries
+    (`leading_splits` / `leading_block`), so the blocks are independent -- no collective."""
+    from ._elemwise import elemwise
+
+    return elemwise(func, *local_blocks, **kwargs)
+
+
+def reduce_leading(x_local, method, axis=None, keepdims=False, group=None, **kwargs):
+    """``x.reduce(method, axis)`` for an array range-partitioned on axis 0.
+
+    Axis 0 kept: the local result IS this rank's block of the answer (no collective).  Axis 0 reduced: every rank
+    reduces its block to a sparse partial over the kept axes, the partials' (key, value) streams are all-gathered
+    (variable length) and stacked on a new leading axis of extent `world`, and one more device reduction over that
+    axis combines them -- the same result on every rank.  Requires a fill value that the reduction leaves unchanged
+    (0 for add, 0/1 for multiply, anything for max/min/and/or), the only case in which partial fill values agree."""
+    from ._coo import COO
+    from ._utils import equivalent, normalize_axis
+
+    dist = _dist()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    ax = normalize_axis(axis, x_local.ndim)
+    ax = tuple(range(x_local.ndim)) if ax is None or ax == (None,) else (ax if isinstance(ax, tuple) else (ax,))
+    if 0 not in ax or world == 1:
+        return x_local.reduce(method, axis=ax, keepdims=keepdims, **kwargs)
+    part = x_local.reduce(method, axis=ax, keepdims=False, **kwargs)
+    t = D.torch()
+    kept = tuple(part.shape)
+    size = int(np.prod(kept)) if kept else 1
+    if not kept:
+        # full reduction: the partial is one dense element (its own fill value); combine the `world` elements
+        keys = Kn.full(1, 0, np.int64)
+        vals = D.upload(np.asarray(part.todense()).reshape(1))
+        part_fill = vals.new_zeros(1)[0].item()
+    else:
+        if not equivalent(part.fill_value, part.dtype.type(x_local.fill_value)):
+            raise ValueError("reduce_leading: the reduction changes the fill value, so row-block partials cannot be "
+                             "combined; gather the operand instead")
+        part_fill = part.fill_value
+        c = part if isinstance(part, COO) else part.tocoo()
+        if c.nnz:
+            keys, vals = c.sorted_keys(), c._data_dev()
+        else:
+            keys, vals = Kn.full(0, 0, np.int64), Kn.full(0, 0, part.dtype)
+    all_keys = all_gather_varlen(keys, group)
+    all_vals = all_gather_varlen(vals, group)
+    stacked_keys = t.cat([k + r * size for r, k in enumerate(all_keys)])
+    stacked = COO._from_device(None, t.cat(all_vals), (world,) + kept, part_fill, keys=stacked_keys) \
+        if int(stacked_keys.shape[0]) else COO(np.zeros((1 + len(kept), 0), dtype=np.intp),
+                                               np.empty(0, dtype=part.dtype), shape=(world,) + kept,
+                                               fill_value=part_fill)
+    out = stacked.reduce(method, axis=(0,), **{k: v for k, v in kwargs.items() if k != "dtype"})
+    if keepdims:
+        shape = list(x_local.shape)
+        for a in ax:
+            shape[a] = 1
+        out = out.reshape(tuple(shape)) if out.ndim or shape else out
+    return out

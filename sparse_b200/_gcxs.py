@@ -278,6 +278,18 @@ class GCXS(SparseArray):
     def copy(self, deep=True):
         return GCXS(self)
 
+    def to_scipy_sparse(self, accept_fv=None):
+        """compressed.py:495-525: csr_array when axis 0 is compressed, else csc_array."""
+        import scipy.sparse
+
+        from ._utils import check_fill_value
+
+        check_fill_value(self, accept_fv=accept_fv)
+        if self.ndim != 2:
+            raise ValueError("Can only convert a 2-dimensional array to a Scipy sparse matrix.")
+        cls = scipy.sparse.csr_array if 0 in self.compressed_axes else scipy.sparse.csc_array
+        return cls((self.data, self.indices, self.indptr), shape=self.shape)
+
     def asformat(self, format, **kwargs):
         if format in ("gcxs", GCXS) or (isinstance(format, type) and issubclass(format, GCXS)):
             ca = kwargs.pop("compressed_axes", None)

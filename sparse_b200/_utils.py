@@ -43,6 +43,16 @@ def check_zero_fill_value(*args, loose=True):
             )
 
 
+def check_fill_value(x, /, *, accept_fv=None):
+    """_utils.py:531-560: raise unless the fill value is one of `accept_fv` (default: zero only)."""
+    if accept_fv is None:
+        accept_fv = [0]
+    if not isinstance(accept_fv, Iterable):
+        accept_fv = [accept_fv]
+    if not any(equivalent(fv, x.fill_value, loose=True) for fv in accept_fv):
+        raise ValueError(f"{x.fill_value} not in accepted fill-values: {accept_fv}")
+
+
 def normalize_axis(axis, ndim):
     """_utils.py:normalize_axis."""
     if axis is None:

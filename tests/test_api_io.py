@@ -51,3 +51,38 @@ def test_load_invalid_file_raises(sp, tmp_path):
     np.savez(p, a=np.arange(3))
     with pytest.raises(RuntimeError):
         sp.load_npz(p)
+
+
+# ---- SciPy interop (tests/test_coo.py:1113-1172, tests/test_compressed.py upstream) ---------------------------------------
+def test_scipy_round_trips(sp):
+    import scipy.sparse as ss
+
+    rng = np.random.default_rng(4)
+    m = ss.random(30, 40, density=0.1, format="csr", random_state=rng, dtype=np.float64)
+    x = sp.COO.from_scipy_sparse(m)
+    assert np.array_equal(x.todense(), m.toarray())
+    back = x.to_scipy_sparse()
+    assert back.format == "coo" and (abs(back - m)).nnz == 0
+    csr, csc = x.tocsr(), x.tocsc()
+    assert csr.format == "csr" and csc.format == "csc"
+    assert np.array_equal(csr.indptr, m.indptr) and np.array_equal(csr.indices, m.indices)
+    assert np.array_equal(csr.data, m.data) and np.array_equal(csc.toarray(), m.toarray())
+    for ca, fmt in (((0,), "csr"), ((1,), "csc")):
+        g = sp.GCXS.from_scipy_sparse(m.asformat(fmt))
+        assert g.compressed_axes == ca
+        s = g.to_scipy_sparse()
+        assert s.format == fmt and np.array_equal(s.toarray(), m.toarray())
+    # scipy operands are accepted by the products directly (_common.py:128-131)
+    d = rng.random((40, 5))
+    assert np.allclose(sp.tensordot(x, d, axes=1), m @ d, rtol=1e-12)
+    assert np.allclose(sp.matmul(m, sp.COO.from_numpy(d)).todense(), m @ d, rtol=1e-12)
+
+
+def test_scipy_export_checks(sp):
+    x = sp.random((3, 4, 5), density=0.5, random_state=1)
+    with pytest.raises(ValueError):
+        x.to_scipy_sparse()
+    y = sp.random((3, 4), density=0.5, random_state=1, fill_value=1.0)
+    with pytest.raises(ValueError):
+        y.to_scipy_sparse()
+    assert y.to_scipy_sparse(accept_fv=1.0).shape == (3, 4)
