@@ -91,6 +91,13 @@ int b2s_spmm_csr_dense(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N
 int b2s_spmm_csr_dense_host(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t N, int64_t nnz,
                             const void *a_data_host, const void *a_indices_host, const void *a_indptr_host,
                             const void *b_host, void *out_host);
+/* Host threads that narrow int64 column indices to int32 into pinned staging before the upload of
+ * b2s_spmm_csr_dense_host (-1 = auto, 0 = upload the raw int64 indices and narrow on the device). */
+int b2s_spmm_host_set_threads(int n);
+/* Pipeline shape of b2s_spmm_csr_dense_host: number of nnz-balanced row chunks and of pinned staging slots. */
+int b2s_spmm_host_set_pipeline(int chunks, int slots);
+/* The host-side narrowing step on its own (same thread pool): dst[i] = (int32) src[i]. */
+int b2s_host_narrow_i64_i32(const int64_t *src_host, int32_t *dst_host, int64_t n);
 
 /* 1 if every row of the CSR has non-decreasing column indices (precondition of the panel passes). Synchronises. */
 int b2s_csr_rows_sorted(int idx_bytes, int64_t M, const void *indptr_dev, const void *indices_dev, int *sorted_host,

@@ -135,6 +135,22 @@ def spmm_set_variant(variant: int = 1, unroll: int = 8):
     _lib.check(_lib.load().b2s_spmm_set_variant(i32(variant), i32(unroll)))
 
 
+def spmm_host_set_threads(n: int = -1):
+    """Host threads narrowing int64 indices before the upload of the host-buffer product (-1 auto, 0 device-side)."""
+    _lib.check(_lib.load().b2s_spmm_host_set_threads(i32(n)))
+
+
+def spmm_host_set_pipeline(chunks: int = 16, slots: int = 4):
+    _lib.check(_lib.load().b2s_spmm_host_set_pipeline(i32(chunks), i32(slots)))
+
+
+def host_narrow(src: np.ndarray, dst: np.ndarray):
+    """dst[i] = int32(src[i]) on the host thread pool of the library (both C-contiguous host arrays)."""
+    assert src.dtype == np.int64 and dst.dtype == np.int32 and src.size == dst.size
+    _lib.check(_lib.load().b2s_host_narrow_i64_i32(vp(src.ctypes.data), vp(dst.ctypes.data), i64(src.size)))
+    return dst
+
+
 # ------------------------------------------------------------------------------------------------
 # prims
 # ------------------------------------------------------------------------------------------------

@@ -435,6 +435,19 @@ def spmm_set_variant(variant=1, unroll=8):
     return None
 
 
+def spmm_host_set_threads(n=-1):
+    return None
+
+
+def spmm_host_set_pipeline(chunks=16, slots=4):
+    return None
+
+
+def host_narrow(src, dst):
+    dst[...] = src.astype(np.int32)
+    return dst
+
+
 _NAMES = [k for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and hasattr(Kn, k)
           and k not in ("n", "T", "bits_ne", "install", "uninstall")]
 
