@@ -347,12 +347,17 @@ def main():
             tt = torch.tensor([e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e_ms = float(tt.item())
-        h2d = int(h_vals.numel() * 4 + h_cols.numel() * 8 + h_ptr.numel() * 8 + h_B.numel() * 4)
+        # bytes that cross PCIe per step: values, column indices (int64 on the host, narrowed to int32 by the
+        # library's host thread pool into pinned staging before the copy), int64 indptr, B; and C coming back
+        host_in = int(h_vals.numel() * 4 + h_cols.numel() * 8 + h_ptr.numel() * 8 + h_B.numel() * 4)
+        h2d = int(h_vals.numel() * 4 + h_cols.numel() * 4 + h_ptr.numel() * 8 + h_B.numel() * 4)
         d2h = int(h_C.numel() * 4)
         e2e = {"value": round(nnz_all / (e_ms * 1e-3) / 1e9, 4), "unit": "GNNZ/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": round(e_ms, 3), "steps": esteps,
+               "d2h_bytes_per_step": d2h, "host_input_bytes_per_step": host_in, "ms_per_step": round(e_ms, 3),
+               "steps": esteps,
                "api": "sparse_b200.tensordot(GCXS(host arrays, int64 indices), np.ndarray) -> np.ndarray "
-                      "(b2s_spmm_csr_dense_host: 3-stream H2D/K1/D2H pipeline, pinned buffers)"}
+                      "(b2s_spmm_csr_dense_host: host-side int64->int32 index narrowing + 3-stream H2D/K1/D2H "
+                      "pipeline, pinned buffers)"}
         C_ref = C if world == 1 else Kn.spmm_csr_dense(vals, cols, indptr, B, M, K, ncols)
         same = bool(torch.equal(h_C.to(dev), C_ref))
         e2e["matches_device_path"] = same

@@ -224,15 +224,15 @@ int b2s_indptr_remap(int idx_bytes, const void *old_indptr_dev, int64_t nrows, c
  * 32..40 predicates (gt ge lt le eq ne land lor lxor); unary 0..31 value ops, 64..68 predicates (see elemwise.cu). */
 /* Replaces _Elemwise._match_coo + _match_arrays + _get_func_coords_data (_umath.py:656-751, 53-92, 576-654) for two
  * COO operands: merge-path union of two sorted key streams, each optionally expanded virtually by a trailing
- * broadcast factor R.  Fused two-pass form: begin() = merge + apply + per-tile counts, returns the
- * output nnz (one stream sync); finish() = merge + apply again and write data, int64 coordinates [ndim, nnz] and
- * (optionally) the sorted linear keys directly -- no union-sized temporaries in HBM. */
-int b2s_ew_merge_begin(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
-                       const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb,
-                       const void *fill_a_host, const void *fill_b_host, const void *out_fill_host, int ndim,
-                       const int64_t *shape_host, void **plan_out, int64_t *nnz_out, void *stream);
-int b2s_ew_merge_finish(void *plan, int64_t *coords_out_dev, int64_t coords_stride, void *vals_out_dev,
-                        int64_t *keys_out_or_null_dev);
+ * broadcast factor R; the operator is applied and results equal to the output fill value are dropped in the same
+ * pass.  SINGLE pass (decoupled look-back instead of count + scan + emit): the caller passes output buffers with room
+ * for `capacity` >= na*Ra + nb*Rb entries (the union can never be larger); kept (key, value) pairs are written
+ * densely from offset 0 in key order and their number is returned in *nnz_out (synchronises the stream once).
+ * Coordinates are b2s_coo_unravel of the keys. */
+int b2s_ew_merge_single(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
+                        const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb,
+                        const void *fill_a_host, const void *fill_b_host, const void *out_fill_host, int64_t capacity,
+                        void *vals_out_dev, int64_t *keys_out_dev, int64_t *nnz_out, void *stream);
 /* COO (x) scalar (mode 0: f(x,s), 1: f(s,x)) and unary maps (mode 2). */
 int b2s_ew_map(int dtype, int op, int mode, const void *x_dev, int64_t n, const void *scalar_host,
                const void *out_fill_host, void *out_vals_dev, uint8_t *out_flags_dev, void *stream);

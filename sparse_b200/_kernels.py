@@ -505,23 +505,22 @@ def ew_merge_fused(op, keys_a, data_a, Ra, keys_b, data_b, Rb, fill_a, fill_b, o
     lib = _lib.load()
     dt = D.np_dtype(data_a)
     assert data_b.dtype == data_a.dtype
-    plan = ctypes.c_void_p(0)
+    cap = int(keys_a.shape[0]) * int(Ra) + int(keys_b.shape[0]) * int(Rb)
+    dev = data_a.device
+    vals = t.empty(cap, dtype=D.torch_dtype(out_dtype), device=dev)
+    keys = t.empty(cap, dtype=t.int64, device=dev)
     nnz = ctypes.c_int64(0)
-    rc = lib.b2s_ew_merge_begin(
+    rc = lib.b2s_ew_merge_single(
         i32(D.dtype_code(dt)), i32(op), vp(D.ptr(keys_a)), vp(D.ptr(data_a)), i64(keys_a.shape[0]), i64(Ra),
         vp(D.ptr(keys_b)), vp(D.ptr(data_b)), i64(keys_b.shape[0]), i64(Rb), _scalar_bytes(fill_a, dt),
-        _scalar_bytes(fill_b, dt), _scalar_bytes(out_fill, out_dtype), i32(len(shape)), _i64arr(shape),
-        ctypes.byref(plan), ctypes.byref(nnz), _sp())
-    _lib.check(rc, "b2s_ew_merge_begin")
+        _scalar_bytes(fill_b, dt), _scalar_bytes(out_fill, out_dtype), i64(cap), vp(D.ptr(vals)), vp(D.ptr(keys)),
+        ctypes.byref(nnz), _sp())
+    _lib.check(rc, "b2s_ew_merge_single")
     n = int(nnz.value)
-    dev = data_a.device
-    coords = t.empty((len(shape), n), dtype=t.int64, device=dev) if want_coords else None
-    vals = t.empty(n, dtype=D.torch_dtype(out_dtype), device=dev)
-    keys = t.empty(n, dtype=t.int64, device=dev)
-    rc = lib.b2s_ew_merge_finish(plan, vp(D.ptr(coords) if want_coords else 0), i64(max(n, 1)), vp(D.ptr(vals)),
-                                 vp(D.ptr(keys)))
-    _lib.check(rc, "b2s_ew_merge_finish")
-    return coords, vals, keys
+    if n != cap:
+        # views keep the worst-case buffers alive: give them back when more than a quarter would be wasted
+        vals, keys = (vals[:n].clone(), keys[:n].clone()) if 4 * n < 3 * cap else (vals[:n], keys[:n])
+    return (unravel(keys, shape, np.int64) if want_coords else None), vals, keys
 
 
 def ew_map(op, mode, x, scalar, out_fill, out_dtype):

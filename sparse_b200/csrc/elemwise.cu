@@ -240,7 +240,7 @@ static inline Stream make_stream(const int64_t *keys, int64_t n, int64_t R) {
 }
 
 constexpr int EW_THREADS = 256;
-constexpr int EW_ITEMS = 8;
+constexpr int EW_ITEMS = 7;  // odd: per-thread merge ranges start 7 keys (56 B) apart -> no shared-memory bank conflicts
 constexpr int EW_TILE = EW_THREADS * EW_ITEMS;
 
 // merge-path split of diagonal d: number of a-items among the first d merged items (ties: a first)
@@ -266,31 +266,34 @@ __global__ void ew_partition_kernel(Stream A, Stream B, int64_t ntiles, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fused two-pass form of the merge (the production path for COO (x) COO):
-//   pass 1 (EMIT = false): merge + apply, count the kept results of every 2048-position tile;
-//   exclusive scan of the tile counts (CUB) -> output offsets and the total (the only host sync);
-//   pass 2 (EMIT = true): merge + apply again, compact the kept (key, value) pairs of the tile in shared memory and
-//   write data, linear keys and the unravelled coordinate rows directly, coalesced.
-// No (key, value, flag) temporaries of union size ever touch HBM, and coordinates are produced in the same pass.
+// Fused SINGLE-pass merge (the production path for COO (x) COO): every 1792-position tile of the merge path is
+// merged, the operator applied and the kept (key, value) pairs compacted in shared memory; the tile's offset in the
+// output comes from a decoupled look-back over the (status | count) words of its predecessors (Merrill & Garland,
+// "Single-pass parallel prefix scan with decoupled look-back").  Tiles are taken in TICKET order (atomic counter),
+// every tile publishes its own count before it waits for anything, and it only ever waits on tiles with smaller
+// tickets, i.e. on CTAs that are already running -- so the wait cannot deadlock.  No (key, value, flag) temporaries
+// of union size ever touch HBM and the merge runs once; coordinates are derived lazily from the keys by the caller.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kEwMaxDims = 16;
-struct EwShape {
-    int ndim;
-    FastDiv extent[kEwMaxDims];
-};
+constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull << 62) - 1;
+__device__ __forceinline__ uint64_t lb_load(const uint64_t *p) { return *(const volatile uint64_t *)p; }
+__device__ __forceinline__ void lb_store(uint64_t *p, uint64_t v) { *(volatile uint64_t *)p = v; }
 
-template <typename T, typename O, bool PRED, bool EMIT>
+template <typename T, typename O, bool PRED>
 __global__ void __launch_bounds__(EW_THREADS)
 ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restrict__ db, T fill_a, T fill_b,
-                      O out_fill, int op, const int64_t *__restrict__ split_a, int64_t *__restrict__ tile_counts,
-                      const int64_t *__restrict__ tile_offsets, EwShape shp, int64_t *__restrict__ coords_out,
-                      int64_t coords_stride, O *__restrict__ vals_out, int64_t *__restrict__ keys_out) {
+                      O out_fill, int op, const int64_t *__restrict__ split_a, O *__restrict__ vals_out,
+                      int64_t *__restrict__ keys_out, uint64_t *__restrict__ lb_status,
+                      unsigned int *__restrict__ lb_ticket, int64_t *__restrict__ total_out) {
     __shared__ int64_t sa[EW_TILE + 2];
     __shared__ int64_t sb[EW_TILE + 2];
     __shared__ int s_warp[EW_THREADS / 32];
+    __shared__ int64_t s_tile, s_base;
     const int64_t la = A.len(), lb = B.len();
     const int64_t total = la + lb;
-    const int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(lb_ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
     const int64_t d0 = tile * EW_TILE;
     const int64_t d1 = (d0 + EW_TILE < total) ? d0 + EW_TILE : total;
     const int64_t a0 = split_a[tile], a1 = split_a[tile + 1];
@@ -370,51 +373,54 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
         if (q < w) woff += c;
         tile_total += c;
     }
-    if constexpr (!EMIT) {
-        if (threadIdx.x == 0) tile_counts[tile] = tile_total;
-        return;
-    } else {
-        // compact into shared memory (reusing the key staging arrays), then coalesced write-out
-        int64_t *sk = sa;
-        O *sv = reinterpret_cast<O *>(sb);
-        int pos = woff + incl - mine;
+    // publish this tile's count as early as possible: successors can start summing while we compact
+    if (threadIdx.x == 0) lb_store(&lb_status[tile], (tile == 0 ? LB_PREFIX : LB_AGG) | (uint64_t)tile_total);
+    // compact into shared memory (reusing the key staging arrays), then coalesced write-out
+    int64_t *sk = sa;
+    O *sv = reinterpret_cast<O *>(sb);
+    int pos = woff + incl - mine;
 #pragma unroll
-        for (int it = 0; it < EW_ITEMS; ++it) {
-            if (keepmask & (1u << it)) {
-                sk[pos] = rkey[it];
-                sv[pos] = rval[it];
-                ++pos;
-            }
-        }
-        __syncthreads();
-        const int64_t base = tile_offsets[tile];
-        for (int t = threadIdx.x; t < tile_total; t += EW_THREADS) {
-            const int64_t key = sk[t];
-            vals_out[base + t] = sv[t];
-            if (keys_out) keys_out[base + t] = key;
-            if (coords_out) {
-                uint64_t k = (uint64_t)key;
-                for (int d = shp.ndim - 1; d >= 0; --d) {
-                    uint64_t q, r;
-                    shp.extent[d].divmod(k, q, r);
-                    coords_out[(int64_t)d * coords_stride + base + t] = (int64_t)r;
-                    k = q;
-                }
-            }
+    for (int it = 0; it < EW_ITEMS; ++it) {
+        if (keepmask & (1u << it)) {
+            sk[pos] = rkey[it];
+            sv[pos] = rval[it];
+            ++pos;
         }
     }
+    __syncthreads();
+    if (w == 0) {  // decoupled look-back: 32 predecessors per step, nearest in lane 0
+        int64_t excl = 0;
+        if (tile != 0) {
+            int64_t p = tile - 1;
+            for (;;) {
+                const int64_t idx = p - lane;
+                uint64_t v = idx >= 0 ? lb_load(&lb_status[idx]) : LB_PREFIX;  // virtual prefix 0 before tile 0
+                while (__any_sync(0xffffffffu, (v >> 62) == 0)) {
+                    if ((v >> 62) == 0) v = lb_load(&lb_status[idx]);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int first = pm ? __ffs(pm) - 1 : 31;  // nearest lane that already holds a full prefix
+                int64_t c = lane <= first ? (int64_t)(v & LB_VALUE) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+                excl += __shfl_sync(0xffffffffu, c, 0);
+                if (pm) break;
+                p -= 32;
+            }
+            if (lane == 0) lb_store(&lb_status[tile], LB_PREFIX | (uint64_t)(excl + tile_total));
+        }
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == (int64_t)gridDim.x - 1) *total_out = excl + tile_total;
+        }
+    }
+    __syncthreads();
+    const int64_t base = s_base;
+    for (int t = threadIdx.x; t < tile_total; t += EW_THREADS) {
+        vals_out[base + t] = sv[t];
+        keys_out[base + t] = sk[t];
+    }
 }
-
-struct EwPlan {
-    int dtype, op, ndim;
-    Stream A, B;
-    const void *da, *db;
-    uint8_t fa[8], fb[8], fo[8];
-    int64_t ntiles, total_out;
-    int64_t *split, *offsets;
-    int64_t shape[kEwMaxDims];
-    cudaStream_t stream;
-};
 
 // ---- COO (x) scalar, scalar (x) COO, unary ---------------------------------------------------
 // mode: 0 = f(x, s), 1 = f(s, x), 2 = unary f(x)
@@ -550,96 +556,50 @@ using namespace b2s;
 extern "C" {
 
 /*
- * Fused COO (x) COO coiteration (production path): begin() runs the counting pass and returns the output nnz;
- * finish() writes data, coordinates [ndim, nnz] (int64, row stride = nnz) and optionally the sorted linear keys.
+ * Single-pass form: the caller provides output buffers of `capacity` >= na*Ra + nb*Rb entries (the union can never be
+ * larger); one merge kernel with a decoupled look-back writes the kept (key, value) pairs densely from offset 0 and
+ * the output nnz comes back through nnz_out (one host sync).  No second merge, no scan kernel.
  */
-int b2s_ew_merge_begin(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
-                       const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb,
-                       const void *fill_a_host, const void *fill_b_host, const void *out_fill_host, int ndim,
-                       const int64_t *shape_host, void **plan_out, int64_t *nnz_out, void *stream) {
-    B2S_REQUIRE(plan_out && nnz_out, B2S_ERR_INVALID, "ew_merge_begin: NULL output");
-    B2S_REQUIRE(Ra >= 1 && Rb >= 1 && na >= 0 && nb >= 0, B2S_ERR_INVALID, "ew_merge_begin: bad sizes");
-    B2S_REQUIRE(ndim >= 0 && ndim <= kEwMaxDims, B2S_ERR_UNSUPPORTED, "ew_merge_begin: ndim %d", ndim);
-    cudaStream_t s = (cudaStream_t)stream;
-    EwPlan *pl = new EwPlan();
-    memset(pl, 0, sizeof(*pl));
-    pl->dtype = dtype;
-    pl->op = op;
-    pl->ndim = ndim;
-    pl->A = make_stream(keys_a_dev, na, Ra);
-    pl->B = make_stream(keys_b_dev, nb, Rb);
-    pl->da = data_a_dev;
-    pl->db = data_b_dev;
-    memcpy(pl->fa, fill_a_host, 8);
-    memcpy(pl->fb, fill_b_host, 8);
-    memcpy(pl->fo, out_fill_host, 8);
-    for (int d = 0; d < ndim; ++d) pl->shape[d] = shape_host[d];
-    pl->stream = s;
-    *plan_out = pl;
+int b2s_ew_merge_single(int dtype, int op, const int64_t *keys_a_dev, const void *data_a_dev, int64_t na, int64_t Ra,
+                        const int64_t *keys_b_dev, const void *data_b_dev, int64_t nb, int64_t Rb,
+                        const void *fill_a_host, const void *fill_b_host, const void *out_fill_host, int64_t capacity,
+                        void *vals_out_dev, int64_t *keys_out_dev, int64_t *nnz_out, void *stream) {
+    B2S_REQUIRE(nnz_out != nullptr, B2S_ERR_INVALID, "ew_merge_single: NULL nnz_out");
+    B2S_REQUIRE(Ra >= 1 && Rb >= 1 && na >= 0 && nb >= 0, B2S_ERR_INVALID, "ew_merge_single: bad sizes");
     *nnz_out = 0;
     const int64_t total = na * Ra + nb * Rb;
     if (total == 0) return B2S_OK;
+    B2S_REQUIRE(keys_out_dev && vals_out_dev, B2S_ERR_INVALID, "ew_merge_single: NULL output");
+    B2S_REQUIRE(capacity >= total, B2S_ERR_INVALID, "ew_merge_single: capacity %lld < %lld candidates",
+                (long long)capacity, (long long)total);
     const int64_t ntiles = (total + EW_TILE - 1) / EW_TILE;
     B2S_REQUIRE(ntiles < 2147483647LL, B2S_ERR_OVERFLOW, "ew_merge: too many tiles");
-    pl->ntiles = ntiles;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Stream A = make_stream(keys_a_dev, na, Ra), B = make_stream(keys_b_dev, nb, Rb);
+    int64_t *split = nullptr;
+    uint64_t *status = nullptr;  // [ntiles] status words, then the ticket counter and the total
     int rc;
-    if ((rc = scratch_alloc((void **)&pl->split, (size_t)(ntiles + 1) * 8, s))) return rc;
-    if ((rc = scratch_alloc((void **)&pl->offsets, (size_t)(ntiles + 1) * 8, s))) return rc;
-    int64_t *counts = nullptr;
-    if ((rc = scratch_alloc((void **)&counts, (size_t)(ntiles + 1) * 8, s))) return rc;
-    B2S_CUDA(cudaMemsetAsync(counts + ntiles, 0, 8, s));
-    ew_partition_kernel<<<(unsigned)((ntiles + 1 + 127) / 128), 128, 0, s>>>(pl->A, pl->B, ntiles, pl->split);
+    if ((rc = scratch_alloc((void **)&split, (size_t)(ntiles + 1) * 8, s))) return rc;
+    if ((rc = scratch_alloc((void **)&status, (size_t)(ntiles + 2) * 8, s))) return rc;
+    B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)(ntiles + 2) * 8, s));
+    unsigned int *ticket = (unsigned int *)(status + ntiles);
+    int64_t *total_dev = (int64_t *)(status + ntiles + 1);
+    ew_partition_kernel<<<(unsigned)((ntiles + 1 + 127) / 128), 128, 0, s>>>(A, B, ntiles, split);
     B2S_CHECK_LAUNCH();
     const bool pred = op >= 32;
-    EwShape shp{};
-    shp.ndim = ndim;
     B2S_EW_DISPATCH(dtype, pred,
-                    (ew_merge_fused_kernel<T, O, P, false><<<(unsigned)ntiles, EW_THREADS, 0, s>>>(
-                        pl->A, pl->B, (const T *)pl->da, (const T *)pl->db, scalar_from<T>(pl->fa),
-                        scalar_from<T>(pl->fb), scalar_from<O>(pl->fo), op, pl->split, counts, nullptr, shp, nullptr, 0,
-                        nullptr, nullptr)));
+                    (ew_merge_fused_kernel<T, O, P><<<(unsigned)ntiles, EW_THREADS, 0, s>>>(
+                        A, B, (const T *)data_a_dev, (const T *)data_b_dev, scalar_from<T>(fill_a_host),
+                        scalar_from<T>(fill_b_host), scalar_from<O>(out_fill_host), op, split, (O *)vals_out_dev,
+                        keys_out_dev, status, ticket, total_dev)));
     B2S_CHECK_LAUNCH();
-    size_t tb = 0;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts, pl->offsets, (int)(ntiles + 1), s));
-    void *tmp = nullptr;
-    if ((rc = scratch_alloc(&tmp, tb, s))) return rc;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, counts, pl->offsets, (int)(ntiles + 1), s));
-    count_launch(2);
-    B2S_CUDA(cudaMemcpyAsync(&pl->total_out, pl->offsets + ntiles, 8, cudaMemcpyDeviceToHost, s));
+    int64_t total_out = 0;
+    B2S_CUDA(cudaMemcpyAsync(&total_out, total_dev, 8, cudaMemcpyDeviceToHost, s));
     B2S_CUDA(cudaStreamSynchronize(s));
-    scratch_free(tmp, s);
-    scratch_free(counts, s);
-    *nnz_out = pl->total_out;
+    scratch_free(split, s);
+    scratch_free(status, s);
+    *nnz_out = total_out;
     return B2S_OK;
-}
-
-int b2s_ew_merge_finish(void *plan, int64_t *coords_out_dev, int64_t coords_stride, void *vals_out_dev,
-                        int64_t *keys_out_or_null_dev) {
-    B2S_REQUIRE(plan != nullptr, B2S_ERR_INVALID, "ew_merge_finish: NULL plan");
-    EwPlan *pl = (EwPlan *)plan;
-    cudaStream_t s = pl->stream;
-    int rc = B2S_OK;
-    if (pl->ntiles > 0 && pl->total_out > 0) {
-        const bool pred = pl->op >= 32;
-        EwShape shp{};
-        shp.ndim = pl->ndim;
-        for (int d = 0; d < pl->ndim; ++d) shp.extent[d] = make_fastdiv((uint64_t)pl->shape[d]);
-        const int dtype = pl->dtype;
-        const int op = pl->op;
-        rc = [&]() -> int {
-            B2S_EW_DISPATCH(dtype, pred,
-                            (ew_merge_fused_kernel<T, O, P, true><<<(unsigned)pl->ntiles, EW_THREADS, 0, s>>>(
-                                pl->A, pl->B, (const T *)pl->da, (const T *)pl->db, scalar_from<T>(pl->fa),
-                                scalar_from<T>(pl->fb), scalar_from<O>(pl->fo), op, pl->split, nullptr, pl->offsets,
-                                shp, coords_out_dev, coords_stride, (O *)vals_out_dev, keys_out_or_null_dev)));
-            B2S_CHECK_LAUNCH();
-            return B2S_OK;
-        }();
-    }
-    scratch_free(pl->split, s);
-    scratch_free(pl->offsets, s);
-    delete pl;
-    return rc;
 }
 
 /* mode 0: f(x, scalar); 1: f(scalar, x); 2: unary f(x).  op >= 32 (binary) / >= 64 (unary) -> bool output. */
