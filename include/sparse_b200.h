@@ -249,15 +249,17 @@ int b2s_ew_expand(int idx_bytes, const void *coords_dev, int64_t row_stride, int
 /* ---- grouped reductions (K7, reduce_fused.cu) ------------------------------------------------ */
 /* Operator codes: 0 add, 1 multiply, 2 maximum, 3 minimum, 4 logical_and, 5 logical_or, 6..8 bitwise and/or/xor.
  * Replaces _grouped_reduce = _calc_counts_invidx + ufunc.reduceat (_coo/core.py:1601-1661). */
-/* Hand-written two-pass segmented-scan reduction (production path, reduce_fused.cu): begin() returns the number of
- * groups; finish() writes group ids (= linear index over the kept axes), values with the fill-value contribution of
- * _sparse_array.py:405-422 applied, and the group coordinates over shape_host[ndim]; it also reports how many results
- * are bitwise equal to result_fill (so the prune compaction of _coo/core.py:713-723 can be skipped when 0). */
-int b2s_reduce_begin(int dtype, int op, const int64_t *keys_dev, const void *vals_dev, int64_t n, int64_t ncols,
-                     void **plan_out, int64_t *n_groups_out, void *stream);
-int b2s_reduce_finish(void *plan, const void *fill_host, int apply_fill_fix, const void *result_fill_host, int ndim,
-                      const int64_t *shape_host, int64_t *gid_out_dev, int64_t *coords_out_or_null_dev,
-                      int64_t coords_stride, void *vals_out_dev, int64_t *n_equal_fill_host);
+/* Hand-written SINGLE-pass segmented-scan reduction (reduce_fused.cu; replaces _grouped_reduce / _calc_counts_invidx +
+ * ufunc.reduceat, _coo/core.py:1601-1661, and the fill-value correction of _sparse_array.py:405-422): runs of equal
+ * group id (= key / ncols) of the sorted keys are reduced with `op` (0 add, 1 mul, 2 max, 3 min, 4 and, 5 or, 6 band,
+ * 7 bor, 8 bxor, 9 fmax, 10 fmin); group ids (= linear index over the kept axes) and values are written densely from
+ * offset 0 into caller buffers of `capacity` >= n entries; tile carries come from a decoupled look-back.  Returns the
+ * number of groups and how many results are bitwise equal to result_fill (so the prune compaction of
+ * _coo/core.py:713-723 can be skipped when 0).  Synchronises the stream once. */
+int b2s_reduce_single(int dtype, int op, const int64_t *keys_dev, const void *vals_dev, int64_t n, int64_t ncols,
+                      const void *fill_host, int apply_fill_fix, const void *result_fill_host, int64_t capacity,
+                      int64_t *gid_out_dev, void *vals_out_dev, int64_t *n_groups_out, int64_t *n_equal_fill_out,
+                      void *stream);
 
 /* ---- fused example paths (K8 / K9, fused.cu) ---------------------------------------------- */
 /* examples/sddmm_example.py:51-52  s * (a @ b): out_vals[p] = s_vals[p] * dot(A[i_p,:], Bt[j_p,:]). */

@@ -580,27 +580,26 @@ def ew_expand(coords, result_shape, is_bcast, src_row):
 # K7 reductions
 # ------------------------------------------------------------------------------------------------
 def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape, want_coords=True):
-    """Segmented reduction over runs of key // ncols -> (coords[ndim, g] int64, group ids[g], values[g], n_equal_fill)."""
+    """Segmented reduction over runs of key // ncols -> (coords[ndim, g] int64, group ids[g], values[g], n_equal_fill).
+    One pass: outputs are allocated for the worst case (one group per entry) and trimmed."""
     t = _t()
     lib = _lib.load()
     dt = D.np_dtype(vals)
-    plan = ctypes.c_void_p(0)
-    ng = ctypes.c_int64(0)
-    rc = lib.b2s_reduce_begin(i32(D.dtype_code(dt)), i32(op), vp(D.ptr(keys)), vp(D.ptr(vals)), i64(keys.shape[0]),
-                              i64(ncols), ctypes.byref(plan), ctypes.byref(ng), _sp())
-    _lib.check(rc, "b2s_reduce_begin")
-    g = int(ng.value)
+    n = int(keys.shape[0])
     dev = vals.device
-    nd = len(kept_shape)
-    coords = t.empty((nd, g), dtype=t.int64, device=dev) if want_coords else None
-    gids = t.empty(g, dtype=t.int64, device=dev)
-    out = t.empty(g, dtype=vals.dtype, device=dev)
+    gids = t.empty(n, dtype=t.int64, device=dev)
+    out = t.empty(n, dtype=vals.dtype, device=dev)
+    ng = ctypes.c_int64(0)
     neq = ctypes.c_int64(0)
-    rc = lib.b2s_reduce_finish(plan, _scalar_bytes(fill_value, dt), i32(1), _scalar_bytes(result_fill, dt), i32(nd),
-                               _i64arr(kept_shape), vp(D.ptr(gids)), vp(D.ptr(coords) if (nd and want_coords) else 0),
-                               i64(max(g, 1)),
-                               vp(D.ptr(out)), ctypes.byref(neq))
-    _lib.check(rc, "b2s_reduce_finish")
+    rc = lib.b2s_reduce_single(i32(D.dtype_code(dt)), i32(op), vp(D.ptr(keys)), vp(D.ptr(vals)), i64(n), i64(ncols),
+                               _scalar_bytes(fill_value, dt), i32(1), _scalar_bytes(result_fill, dt), i64(n),
+                               vp(D.ptr(gids)), vp(D.ptr(out)), ctypes.byref(ng), ctypes.byref(neq), _sp())
+    _lib.check(rc, "b2s_reduce_single")
+    g = int(ng.value)
+    if g != n:
+        # views keep the worst-case buffers alive: give them back when more than half would be wasted
+        gids, out = (gids[:g].clone(), out[:g].clone()) if 2 * g < n else (gids[:g], out[:g])
+    coords = unravel(gids, kept_shape, np.int64) if want_coords else None
     return coords, gids, out, int(neq.value)
 
 

@@ -374,7 +374,7 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
         tile_total += c;
     }
     // publish this tile's count as early as possible: successors can start summing while we compact
-    if (threadIdx.x == 0) lb_store(&lb_status[tile], (tile == 0 ? LB_PREFIX : LB_AGG) | (uint64_t)tile_total);
+    if (threadIdx.x == 0) lb_store(&lb_status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | (uint64_t)tile_total);
     // compact into shared memory (reusing the key staging arrays), then coalesced write-out
     int64_t *sk = sa;
     O *sv = reinterpret_cast<O *>(sb);
@@ -388,24 +388,36 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
         }
     }
     __syncthreads();
-    if (w == 0) {  // decoupled look-back: 32 predecessors per step, nearest in lane 0
+    if (w == 0) {  // decoupled look-back: 64 predecessors per step (two per lane), nearest in lane 0
         int64_t excl = 0;
         if (tile != 0) {
             int64_t p = tile - 1;
             for (;;) {
-                const int64_t idx = p - lane;
-                uint64_t v = idx >= 0 ? lb_load(&lb_status[idx]) : LB_PREFIX;  // virtual prefix 0 before tile 0
-                while (__any_sync(0xffffffffu, (v >> 62) == 0)) {
-                    if ((v >> 62) == 0) v = lb_load(&lb_status[idx]);
+                const int64_t i0 = p - lane, i1 = p - 32 - lane;
+                uint64_t v0 = i0 >= 0 ? lb_load(&lb_status[i0]) : LB_PREFIX;  // virtual prefix 0 before tile 0
+                uint64_t v1 = i1 >= 0 ? lb_load(&lb_status[i1]) : LB_PREFIX;
+                while (__any_sync(0xffffffffu, (v0 >> 62) == 0)) {
+                    if ((v0 >> 62) == 0) v0 = lb_load(&lb_status[i0]);
                 }
-                const unsigned pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                const int first = pm ? __ffs(pm) - 1 : 31;  // nearest lane that already holds a full prefix
-                int64_t c = lane <= first ? (int64_t)(v & LB_VALUE) : 0;
+                const unsigned pm0 = __ballot_sync(0xffffffffu, (v0 >> 62) == 2);
+                int64_t c;
+                unsigned done = pm0;
+                if (pm0) {
+                    c = lane <= __ffs(pm0) - 1 ? (int64_t)(v0 & LB_VALUE) : 0;  // up to the nearest full prefix
+                } else {
+                    while (__any_sync(0xffffffffu, (v1 >> 62) == 0)) {
+                        if ((v1 >> 62) == 0) v1 = lb_load(&lb_status[i1]);
+                    }
+                    const unsigned pm1 = __ballot_sync(0xffffffffu, (v1 >> 62) == 2);
+                    const int first1 = pm1 ? __ffs(pm1) - 1 : 31;
+                    c = (int64_t)(v0 & LB_VALUE) + (lane <= first1 ? (int64_t)(v1 & LB_VALUE) : 0);
+                    done = pm1;
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
                 excl += __shfl_sync(0xffffffffu, c, 0);
-                if (pm) break;
-                p -= 32;
+                if (done) break;
+                p -= 64;
             }
             if (lane == 0) lb_store(&lb_status[tile], LB_PREFIX | (uint64_t)(excl + tile_total));
         }

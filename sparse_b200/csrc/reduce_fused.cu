@@ -1,19 +1,17 @@
 // reduce_fused.cu -- K7 production path: hand-written segmented-scan reduction over sorted COO keys.
 //
 // Replaces _calc_counts_invidx + ufunc.reduceat + the fill-value correction + the result's coordinate build
-// (sparse/numba_backend/_coo/core.py:1601-1661, 693-723; _sparse_array.py:405-422) with two streaming passes:
+// (sparse/numba_backend/_coo/core.py:1601-1661, 693-723; _sparse_array.py:405-422) with ONE streaming pass:
 //
-//   pass 1  per 2048-element tile: head flags (group id = key / n_cols changes), a segmented reduction inside
-//           every thread's 8 consecutive elements and a block-level segmented scan -> tile summary
-//           (number of heads, "contains a head", value and count of the run that is still open at the tile end);
-//   scan    one CTA turns the tile summaries into per-tile head offsets and carry-in runs (segmented scan);
-//   pass 2  recomputes the tile, seeds the block scan with the carry-in and lets the thread that owns the LAST element
-//           of every run write its group id, its value with the fill-value contribution already applied
-//           (add: + fill*n_fill, multiply: * fill**n_fill, others: op(v, fill) when the group is incomplete)
-//           and the unravelled coordinates of the kept axes.  It also counts results equal to the result fill value
-//           so the (rare) prune compaction only runs when needed.
+//   per 2048-element tile: head flags (group id = key / n_cols changes), a segmented reduction inside every thread's
+//   8 consecutive elements and a block-level segmented scan -> tile aggregate (number of heads, "contains a head",
+//   value and count of the run that is still open at the tile end); the tile's carry-in comes from a decoupled
+//   look-back over its predecessors' descriptors; then the thread that owns the LAST element of every run writes its
+//   group id and its value with the fill-value contribution already applied (add: + fill*n_fill, multiply:
+//   * fill**n_fill, others: op(v, fill) when the group is incomplete).  Results equal to the result fill value are
+//   counted so the (rare) prune compaction only runs when needed.  Coordinates are derived lazily from the group ids.
 //
-// Traffic: 2 x n x (8 + sizeof(T)) bytes read, n_groups x (8 x (1 + ndim_out) + sizeof(T)) written.
+// Traffic: n x (8 + sizeof(T)) bytes read, n_groups x (8 + sizeof(T)) written.
 // Association order differs from NumPy's reduceat (itself unspecified) -> tolerance parity for float add/multiply.
 #include <type_traits>
 
@@ -28,7 +26,6 @@ enum RedOp2 { RF_ADD = 0, RF_MUL = 1, RF_MAX = 2, RF_MIN = 3, RF_AND = 4, RF_OR 
 constexpr int RD_THREADS = 256;
 constexpr int RD_ITEMS = 8;
 constexpr int RD_TILE = RD_THREADS * RD_ITEMS;
-constexpr int RD_MAXDIM = 16;
 
 template <typename T>
 __device__ __forceinline__ T red_apply(int op, T a, T b) {
@@ -121,38 +118,47 @@ __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
     return r;
 }
 
-struct RdShape {
-    int ndim;
-    FastDiv extent[RD_MAXDIM];
-};
-
-// One tile.  EMIT = false: write the tile summary.  EMIT = true: write finished runs.
+// One tile of the SINGLE-pass segmented reduction.
 // Loads and stores go through shared memory so that global accesses are fully coalesced: the tile's 2048 (key, value)
 // pairs are loaded with unit stride, each thread then reads its 8 consecutive pairs from a padded layout
-// (index e + e/8: 2-way instead of 16-way bank conflicts), and in the emit pass the finished runs of the tile -- which
-// occupy one contiguous range of output slots -- are staged in the same buffers and written out with unit stride.
+// (index e + e/8: 2-way instead of 16-way bank conflicts), and the finished runs of the tile -- which occupy one
+// contiguous range of output slots -- are staged in the same buffers and written out with unit stride.
+// The carry-in of a tile (the run still open at its first element + the number of run heads before it) comes from a
+// decoupled look-back over the tile descriptors of its predecessors (Merrill & Garland): tiles are taken in TICKET
+// order, every tile publishes its own aggregate before it waits for anything and only ever waits on smaller tickets
+// (CTAs that are already running), so the wait cannot deadlock.  The head count travels in ONE word with its status
+// (aggregate / inclusive prefix), so its look-back needs no fences; the carry-in RUN only ever needs the predecessors'
+// aggregates back to the nearest tile that contains a head (usually the immediate predecessor), which are published
+// (payload, __threadfence, status) before that tile waits for anything.
 constexpr int RD_PAD = RD_TILE + RD_TILE / 8 + 8;
 __device__ __forceinline__ int rd_pad(int e) { return e + (e >> 3); }
 
-template <typename T, bool EMIT>
+enum : uint64_t { RD_AGG = 1ull << 62, RD_PREFIX = 2ull << 62, RD_VALUE = (1ull << 62) - 1 };
+template <typename T>
+struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entries each)
+    uint64_t *heads;     // (status << 62) | number of run heads: the tile's own (AGG) or the inclusive prefix (PREFIX)
+    T *run_val;          // the tile's aggregate run (no carry-in): value ...
+    int64_t *run_meta;   // ... and (count << 1) | "the tile contains a head"; valid once heads[] is non-zero
+};
+
+template <typename T>
 __global__ void __launch_bounds__(RD_THREADS)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
-                   FastDiv fcols, int op,
-                   // summaries (pass 1 out / pass 2 in)
-                   int64_t *__restrict__ t_heads, int *__restrict__ t_flag, T *__restrict__ t_val,
-                   int64_t *__restrict__ t_cnt, const int64_t *__restrict__ head_off, const int *__restrict__ c_flag,
-                   const T *__restrict__ c_val, const int64_t *__restrict__ c_cnt,
-                   // outputs (pass 2)
-                   T fill, int apply_fix, T result_fill, RdShape shp, int64_t *__restrict__ out_gid,
-                   int64_t *__restrict__ out_coords, int64_t coords_stride, T *__restrict__ out_val,
-                   unsigned long long *__restrict__ n_equal_fill) {
+                   FastDiv fcols, int op, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
+                   T result_fill, int64_t *__restrict__ out_gid, T *__restrict__ out_val,
+                   unsigned long long *__restrict__ counters /* [0] results equal to result_fill, [1] groups */) {
     __shared__ int64_t sk[RD_PAD];
     __shared__ T sv[RD_PAD];
     __shared__ int s_flag[RD_THREADS / 32];
     __shared__ T s_val[RD_THREADS / 32];
     __shared__ int64_t s_cnt[RD_THREADS / 32];
     __shared__ int s_heads[RD_THREADS / 32];
-    const int64_t tile = blockIdx.x;
+    __shared__ int64_t s_tile, s_hexcl, s_ccnt;
+    __shared__ int s_cflag;
+    __shared__ T s_cval;
+    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
     const int64_t tile_base = tile * RD_TILE;
     const int64_t base = tile_base + (int64_t)threadIdx.x * RD_ITEMS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -230,19 +236,12 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         s_heads[w] = hincl;
     }
     __syncthreads();  // (also: every thread has copied its inputs out of sk / sv)
-    Run<T> carry;
-    carry.flag = 0;
-    carry.val = T(0);
-    carry.cnt = 0;
-    int64_t hbefore = 0;
-    if constexpr (EMIT) {
-        carry.flag = c_flag[tile];
-        carry.val = c_val[tile];
-        carry.cnt = c_cnt[tile];
-        hbefore = head_off[tile];
-    }
-    Run<T> tile_total = carry;
-    int tile_heads = 0;
+    Run<T> wcarry;  // warps before this one, no carry-in yet
+    wcarry.flag = 0;
+    wcarry.val = T(0);
+    wcarry.cnt = 0;
+    Run<T> tile_agg = wcarry;
+    int hbefore_local = 0, tile_heads = 0;
 #pragma unroll
     for (int q = 0; q < RD_THREADS / 32; ++q) {
         Run<T> wq;
@@ -250,236 +249,195 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         wq.val = s_val[q];
         wq.cnt = s_cnt[q];
         if (q < w) {
-            carry = run_combine<T>(op, carry, wq);
-            hbefore += s_heads[q];
+            wcarry = run_combine<T>(op, wcarry, wq);
+            hbefore_local += s_heads[q];
         }
-        tile_total = run_combine<T>(op, tile_total, wq);
+        tile_agg = run_combine<T>(op, tile_agg, wq);
         tile_heads += s_heads[q];
     }
-    if constexpr (!EMIT) {
-        if (threadIdx.x == 0) {
-            t_heads[tile] = tile_heads;
-            t_flag[tile] = tile_total.flag;
-            t_val[tile] = tile_total.val;
-            t_cnt[tile] = tile_total.cnt;
-        }
-        return;
-    } else {
-        const int64_t slot0 = head_off[tile] - 1;  // output slot of a run that started before this tile
-        // the staging buffers alias the input buffers: mark every slot empty first
-        for (int i = threadIdx.x; i < RD_TILE + 1; i += RD_THREADS) sk[i] = -1;
-        __syncthreads();
-        Run<T> prev = run_shfl_up(incl, 1);
-        int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
-        Run<T> st = carry;
-        int64_t hcount = hbefore;  // heads strictly before this thread's first element
-        if (lane > 0) {
-            st = run_combine<T>(op, carry, prev);
-            hcount += hprev;
-        }
-        T rv = st.val;
-        int64_t rc = st.cnt;
-#pragma unroll
-        for (int i = 0; i < RD_ITEMS; ++i) {
-            const int64_t p = base + i;
-            if (p < n) {
-                if (head[i]) {
-                    rv = v[i];
-                    rc = 1;
-                    ++hcount;
-                } else {
-                    rv = rc == 0 ? v[i] : red_apply<T>(op, rv, v[i]);
-                    rc += 1;
+    // publish the aggregate (tile 0: already the inclusive prefix) before waiting for anybody: run payload first,
+    // then the status word that makes it visible
+    if (threadIdx.x == 0) {
+        *(volatile T *)&desc.run_val[tile] = tile_agg.val;
+        *(volatile int64_t *)&desc.run_meta[tile] = (tile_agg.cnt << 1) | (int64_t)tile_agg.flag;
+        __threadfence();
+        *(volatile uint64_t *)&desc.heads[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (uint64_t)tile_heads;
+    }
+    // the staging buffers alias the input buffers: mark every slot empty
+    for (int i = threadIdx.x; i < RD_TILE + 1; i += RD_THREADS) sk[i] = -1;
+    if (w == 0) {
+        Run<T> excl;
+        excl.flag = 0;
+        excl.val = T(0);
+        excl.cnt = 0;
+        int64_t hexcl = 0;
+        if (tile != 0) {
+            int64_t p = tile - 1;  // lane 0 looks at the nearest predecessor
+            // (1) the carry-in RUN: predecessors' aggregates, nearest first, up to the nearest tile that contains a
+            //     head -- almost always the immediate predecessor, so one window is the common case
+            for (int64_t q = p;;) {
+                const int64_t idx = q - lane;
+                uint64_t hv = idx >= 0 ? *(volatile uint64_t *)&desc.heads[idx] : (uint64_t)RD_PREFIX;
+                while (__any_sync(0xffffffffu, (hv >> 62) == 0)) {
+                    if ((hv >> 62) == 0) hv = *(volatile uint64_t *)&desc.heads[idx];
                 }
-                const bool last = (p == n - 1) ||
-                                  ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1]) : (g[i] != gnext_thread));
-                if (last) {
-                    const int loc = (int)(hcount - 1 - slot0);  // 0 .. RD_TILE
-                    sk[loc] = g[i];
-                    sv[loc] = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
+                __threadfence();
+                const int64_t meta = idx >= 0 ? *(volatile int64_t *)&desc.run_meta[idx] : 1;  // before tile 0: a head
+                const unsigned fm = __ballot_sync(0xffffffffu, (meta & 1) != 0);
+                const int firstf = fm ? __ffs(fm) - 1 : 31;
+                Run<T> x;
+                x.flag = 0;
+                x.val = T(0);
+                x.cnt = 0;
+                if (lane <= firstf && idx >= 0) {
+                    x.flag = (int)(meta & 1);
+                    x.cnt = meta >> 1;
+                    x.val = *(volatile T *)&desc.run_val[idx];
                 }
+                // ordered reduction: lane + o holds an EARLIER tile, so it goes on the left
+                const int steps = firstf == 0 ? 0 : 32;
+                for (int o = 1; o < steps; o <<= 1) {
+                    Run<T> other;
+                    other.flag = __shfl_down_sync(0xffffffffu, x.flag, o);
+                    other.val = __shfl_down_sync(0xffffffffu, x.val, o);
+                    other.cnt = __shfl_down_sync(0xffffffffu, x.cnt, o);
+                    if (lane + o < 32) x = run_combine<T>(op, other, x);
+                }
+                Run<T> win;
+                win.flag = __shfl_sync(0xffffffffu, x.flag, 0);
+                win.val = __shfl_sync(0xffffffffu, x.val, 0);
+                win.cnt = __shfl_sync(0xffffffffu, x.cnt, 0);
+                excl = run_combine<T>(op, win, excl);  // this window lies before everything gathered so far
+                if (fm) break;
+                q -= 32;
             }
-        }
-        __syncthreads();
-        int eq = 0;
-        for (int l = threadIdx.x; l < RD_TILE + 1; l += RD_THREADS) {
-            const int64_t gid = sk[l];
-            if (gid >= 0) {
-                const int64_t idx = slot0 + l;
-                const T outv = sv[l];
-                out_val[idx] = outv;
-                out_gid[idx] = gid;
-                if (out_coords) {
-                    uint64_t k = (uint64_t)gid;
-                    for (int d = shp.ndim - 1; d >= 0; --d) {
-                        uint64_t q, r;
-                        shp.extent[d].divmod(k, q, r);
-                        out_coords[(int64_t)d * coords_stride + idx] = (int64_t)r;
-                        k = q;
+            // (2) the number of heads before this tile: single-word look-back, 64 predecessors per step
+            for (;;) {
+                const int64_t i0 = p - lane, i1 = p - 32 - lane;
+                uint64_t v0 = i0 >= 0 ? *(volatile uint64_t *)&desc.heads[i0] : (uint64_t)RD_PREFIX;
+                uint64_t v1 = i1 >= 0 ? *(volatile uint64_t *)&desc.heads[i1] : (uint64_t)RD_PREFIX;
+                while (__any_sync(0xffffffffu, (v0 >> 62) == 0)) {
+                    if ((v0 >> 62) == 0) v0 = *(volatile uint64_t *)&desc.heads[i0];
+                }
+                const unsigned pm0 = __ballot_sync(0xffffffffu, (v0 >> 62) == 2);
+                int64_t c;
+                unsigned done = pm0;
+                if (pm0) {
+                    c = lane <= __ffs(pm0) - 1 ? (int64_t)(v0 & RD_VALUE) : 0;  // up to the nearest inclusive prefix
+                } else {
+                    while (__any_sync(0xffffffffu, (v1 >> 62) == 0)) {
+                        if ((v1 >> 62) == 0) v1 = *(volatile uint64_t *)&desc.heads[i1];
                     }
+                    const unsigned pm1 = __ballot_sync(0xffffffffu, (v1 >> 62) == 2);
+                    const int first1 = pm1 ? __ffs(pm1) - 1 : 31;
+                    c = (int64_t)(v0 & RD_VALUE) + (lane <= first1 ? (int64_t)(v1 & RD_VALUE) : 0);
+                    done = pm1;
                 }
-                bool same;
-                if constexpr (sizeof(T) == 1) same = (*(const uint8_t *)&outv) == (*(const uint8_t *)&result_fill);
-                else if constexpr (sizeof(T) == 4) {
-                    uint32_t x, y;
-                    memcpy(&x, &outv, 4);
-                    memcpy(&y, &result_fill, 4);
-                    same = x == y;
-                } else {
-                    uint64_t x, y;
-                    memcpy(&x, &outv, 8);
-                    memcpy(&y, &result_fill, 8);
-                    same = x == y;
-                }
-                eq += same ? 1 : 0;
-            }
-        }
-        eq = __reduce_add_sync(0xffffffffu, eq);
-        if (lane == 0 && eq) atomicAdd(n_equal_fill, (unsigned long long)eq);
-    }
-}
-
-// single-CTA segmented scan over the tile summaries -> per-tile head offsets and carry-in runs
-template <typename T>
-__global__ void __launch_bounds__(1024)
-reduce_scan_tiles_kernel(int64_t ntiles, int op, const int64_t *__restrict__ t_heads, const int *__restrict__ t_flag,
-                         const T *__restrict__ t_val, const int64_t *__restrict__ t_cnt,
-                         int64_t *__restrict__ head_off, int *__restrict__ c_flag, T *__restrict__ c_val,
-                         int64_t *__restrict__ c_cnt) {
-    __shared__ int s_flag[32];
-    __shared__ T s_val[32];
-    __shared__ int64_t s_cnt[32];
-    __shared__ int64_t s_heads[32];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int64_t per = (ntiles + 1023) / 1024;
-    const int64_t lo = (int64_t)tid * per, hi = (lo + per < ntiles) ? lo + per : ntiles;
-    Run<T> mine;
-    mine.flag = 0;
-    mine.val = T(0);
-    mine.cnt = 0;
-    int64_t hsum = 0;
-    for (int64_t t = lo; t < hi; ++t) {
-        Run<T> x;
-        x.flag = t_flag[t];
-        x.val = t_val[t];
-        x.cnt = t_cnt[t];
-        mine = run_combine<T>(op, mine, x);
-        hsum += t_heads[t];
-    }
-    Run<T> incl = mine;
-    int64_t hincl = hsum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const Run<T> up = run_shfl_up(incl, o);
-        const int64_t hu = __shfl_up_sync(0xffffffffu, hincl, o);
-        if (lane >= o) {
-            incl = run_combine<T>(op, up, incl);
-            hincl += hu;
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+                hexcl += __shfl_sync(0xffffffffu, c, 0);
+                if (done) break;
+                p -= 64;
+            }
+            if (lane == 0) *(volatile uint64_t *)&desc.heads[tile] = RD_PREFIX | (uint64_t)(hexcl + tile_heads);
         }
-    }
-    if (lane == 31) {
-        s_flag[w] = incl.flag;
-        s_val[w] = incl.val;
-        s_cnt[w] = incl.cnt;
-        s_heads[w] = hincl;
+        if (lane == 0) {
+            s_hexcl = hexcl;
+            s_cflag = excl.flag;
+            s_cval = excl.val;
+            s_ccnt = excl.cnt;
+            if (tile == (int64_t)gridDim.x - 1) counters[1] = (unsigned long long)(hexcl + tile_heads);
+        }
     }
     __syncthreads();
     Run<T> carry;
-    carry.flag = 0;
-    carry.val = T(0);
-    carry.cnt = 0;
-    int64_t hbefore = 0, htotal = 0;
-    for (int q = 0; q < 32; ++q) {
-        Run<T> wq;
-        wq.flag = s_flag[q];
-        wq.val = s_val[q];
-        wq.cnt = s_cnt[q];
-        if (q < w) {
-            carry = run_combine<T>(op, carry, wq);
-            hbefore += s_heads[q];
-        }
-        htotal += s_heads[q];
-    }
+    carry.flag = s_cflag;
+    carry.val = s_cval;
+    carry.cnt = s_ccnt;
+    carry = run_combine<T>(op, carry, wcarry);
+    const int64_t hbefore = s_hexcl + hbefore_local;
+    const int64_t slot0 = s_hexcl - 1;  // output slot of a run that started before this tile
     Run<T> prev = run_shfl_up(incl, 1);
-    int64_t hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
+    int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
     Run<T> st = carry;
-    int64_t hc = hbefore;
+    int64_t hcount = hbefore;  // heads strictly before this thread's first element
     if (lane > 0) {
         st = run_combine<T>(op, carry, prev);
-        hc += hprev;
+        hcount += hprev;
     }
-    for (int64_t t = lo; t < hi; ++t) {
-        head_off[t] = hc;
-        c_flag[t] = st.flag;
-        c_val[t] = st.val;
-        c_cnt[t] = st.cnt;
-        Run<T> x;
-        x.flag = t_flag[t];
-        x.val = t_val[t];
-        x.cnt = t_cnt[t];
-        st = run_combine<T>(op, st, x);
-        hc += t_heads[t];
+    T rv = st.val;
+    int64_t rc = st.cnt;
+#pragma unroll
+    for (int i = 0; i < RD_ITEMS; ++i) {
+        const int64_t p = base + i;
+        if (p < n) {
+            if (head[i]) {
+                rv = v[i];
+                rc = 1;
+                ++hcount;
+            } else {
+                rv = rc == 0 ? v[i] : red_apply<T>(op, rv, v[i]);
+                rc += 1;
+            }
+            const bool last = (p == n - 1) ||
+                              ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1]) : (g[i] != gnext_thread));
+            if (last) {
+                const int loc = (int)(hcount - 1 - slot0);  // 0 .. RD_TILE
+                sk[loc] = g[i];
+                sv[loc] = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
+            }
+        }
     }
-    if (tid == 0) head_off[ntiles] = htotal;
-}
-
-struct RdPlan {
-    int dtype, op;
-    int64_t n, ncols, ntiles, ngroups;
-    const int64_t *keys;
-    const void *vals;
-    int64_t *t_heads, *t_cnt, *head_off, *c_cnt;
-    int *t_flag, *c_flag;
-    void *t_val, *c_val;
-    unsigned long long *n_eq;
-    cudaStream_t stream;
-};
-
-static void rd_free(RdPlan *pl) {
-    cudaStream_t s = pl->stream;
-    scratch_free(pl->t_heads, s);
-    scratch_free(pl->t_cnt, s);
-    scratch_free(pl->head_off, s);
-    scratch_free(pl->c_cnt, s);
-    scratch_free(pl->t_flag, s);
-    scratch_free(pl->c_flag, s);
-    scratch_free(pl->t_val, s);
-    scratch_free(pl->c_val, s);
-    scratch_free(pl->n_eq, s);
-    delete pl;
+    __syncthreads();
+    int eq = 0;
+    for (int l = threadIdx.x; l < RD_TILE + 1; l += RD_THREADS) {
+        const int64_t gid = sk[l];
+        if (gid >= 0) {
+            const int64_t idx = slot0 + l;
+            const T outv = sv[l];
+            out_val[idx] = outv;
+            out_gid[idx] = gid;
+            bool same;
+            if constexpr (sizeof(T) == 1) same = (*(const uint8_t *)&outv) == (*(const uint8_t *)&result_fill);
+            else if constexpr (sizeof(T) == 4) {
+                uint32_t x, y;
+                memcpy(&x, &outv, 4);
+                memcpy(&y, &result_fill, 4);
+                same = x == y;
+            } else {
+                uint64_t x, y;
+                memcpy(&x, &outv, 8);
+                memcpy(&y, &result_fill, 8);
+                same = x == y;
+            }
+            eq += same ? 1 : 0;
+        }
+    }
+    eq = __reduce_add_sync(0xffffffffu, eq);
+    if (lane == 0 && eq) atomicAdd(&counters[0], (unsigned long long)eq);
 }
 
 template <typename T>
-static int rd_begin_t(RdPlan *pl) {
-    cudaStream_t s = pl->stream;
-    const int64_t nt = pl->ntiles;
-    RdShape shp{};
-    reduce_tile_kernel<T, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(
-        pl->keys, (const T *)pl->vals, pl->n, pl->ncols, make_fastdiv((uint64_t)pl->ncols), pl->op, pl->t_heads, pl->t_flag, (T *)pl->t_val, pl->t_cnt,
-        nullptr, nullptr, nullptr, nullptr, T(0), 0, T(0), shp, nullptr, nullptr, 0, nullptr, nullptr);
-    B2S_CHECK_LAUNCH();
-    reduce_scan_tiles_kernel<T><<<1, 1024, 0, s>>>(nt, pl->op, pl->t_heads, pl->t_flag, (const T *)pl->t_val, pl->t_cnt,
-                                                   pl->head_off, pl->c_flag, (T *)pl->c_val, pl->c_cnt);
-    B2S_CHECK_LAUNCH();
-    return B2S_OK;
-}
-
-template <typename T>
-static int rd_finish_t(RdPlan *pl, const void *fill_host, int apply_fix, const void *result_fill_host, int ndim,
-                       const int64_t *shape_host, int64_t *gid_out, int64_t *coords_out, int64_t coords_stride,
-                       void *vals_out) {
-    cudaStream_t s = pl->stream;
-    RdShape shp{};
-    shp.ndim = ndim;
-    for (int d = 0; d < ndim; ++d) shp.extent[d] = make_fastdiv((uint64_t)shape_host[d]);
+static int rd_single_t(const int64_t *keys, const void *vals, int64_t n, int64_t ncols, int op, const void *fill_host,
+                       int apply_fix, const void *result_fill_host, int64_t *gid_out, void *vals_out, int64_t nt,
+                       void *scratch, cudaStream_t s) {
+    // scratch layout: counters[2] (u64) | ticket (u64 slot) | heads u64[nt] | run_meta i64[nt] | run_val T[nt] (8-B slots)
+    char *b = (char *)scratch;
+    unsigned long long *counters = (unsigned long long *)b;
+    unsigned int *ticket = (unsigned int *)(b + 16);
+    b += 24;
+    RdDesc<T> d;
+    d.heads = (uint64_t *)b;
+    b += (size_t)nt * 8;
+    d.run_meta = (int64_t *)b;
+    b += (size_t)nt * 8;
+    d.run_val = (T *)b;
     T fill, rfill;
     memcpy(&fill, fill_host, sizeof(T));
     memcpy(&rfill, result_fill_host, sizeof(T));
-    reduce_tile_kernel<T, true><<<(unsigned)pl->ntiles, RD_THREADS, 0, s>>>(
-        pl->keys, (const T *)pl->vals, pl->n, pl->ncols, make_fastdiv((uint64_t)pl->ncols), pl->op, nullptr, nullptr,
-        nullptr, nullptr, pl->head_off,
-        pl->c_flag, (const T *)pl->c_val, pl->c_cnt, fill, apply_fix, rfill, shp, gid_out, coords_out, coords_stride,
-        (T *)vals_out, pl->n_eq);
+    reduce_tile_kernel<T><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
+                                                             make_fastdiv((uint64_t)ncols), op, d, ticket, fill,
+                                                             apply_fix, rfill, gid_out, (T *)vals_out, counters);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }
@@ -491,91 +449,51 @@ using namespace b2s;
 extern "C" {
 
 /*
- * Segmented reduction of `vals` over runs of equal group id (= key / ncols) of the sorted `keys`.
- * begin(): pass 1 + tile scan, returns the number of groups (one stream sync).
- * finish(): pass 2 writes group ids, values (fill-value contribution applied when apply_fill_fix) and, if
- * coords_out is given, the coordinates of every group id unravelled over shape_host[ndim]; returns the number of
- * results bitwise equal to result_fill (one stream sync) so the caller can skip the prune compaction when it is 0.
+ * Segmented reduction of `vals` over runs of equal group id (= key / ncols) of the sorted `keys`, in ONE pass:
+ * group ids and values (fill-value contribution applied when apply_fill_fix) are written densely from offset 0 into
+ * caller buffers with room for `capacity` >= n entries (there cannot be more groups than entries); returns the
+ * number of groups and the number of results bitwise equal to result_fill (so the caller can skip the prune
+ * compaction when it is 0).  One stream sync.
  */
-int b2s_reduce_begin(int dtype, int op, const int64_t *keys_dev, const void *vals_dev, int64_t n, int64_t ncols,
-                     void **plan_out, int64_t *n_groups_out, void *stream) {
-    B2S_REQUIRE(plan_out && n_groups_out, B2S_ERR_INVALID, "reduce_begin: NULL output");
-    B2S_REQUIRE(n >= 0 && ncols >= 1, B2S_ERR_INVALID, "reduce_begin: bad sizes");
-    cudaStream_t s = (cudaStream_t)stream;
-    RdPlan *pl = new RdPlan();
-    memset(pl, 0, sizeof(*pl));
-    pl->dtype = dtype;
-    pl->op = op;
-    pl->n = n;
-    pl->ncols = ncols;
-    pl->keys = keys_dev;
-    pl->vals = vals_dev;
-    pl->stream = s;
-    *plan_out = pl;
+int b2s_reduce_single(int dtype, int op, const int64_t *keys_dev, const void *vals_dev, int64_t n, int64_t ncols,
+                      const void *fill_host, int apply_fill_fix, const void *result_fill_host, int64_t capacity,
+                      int64_t *gid_out_dev, void *vals_out_dev, int64_t *n_groups_out, int64_t *n_equal_fill_out,
+                      void *stream) {
+    B2S_REQUIRE(n_groups_out && n_equal_fill_out, B2S_ERR_INVALID, "reduce_single: NULL output");
+    B2S_REQUIRE(n >= 0 && ncols >= 1, B2S_ERR_INVALID, "reduce_single: bad sizes");
     *n_groups_out = 0;
+    *n_equal_fill_out = 0;
     if (n == 0) return B2S_OK;
+    B2S_REQUIRE(capacity >= n && gid_out_dev && vals_out_dev, B2S_ERR_INVALID,
+                "reduce_single: output capacity %lld < %lld entries", (long long)capacity, (long long)n);
+    cudaStream_t s = (cudaStream_t)stream;
     const int64_t nt = (n + RD_TILE - 1) / RD_TILE;
     B2S_REQUIRE(nt < 2147483647LL, B2S_ERR_OVERFLOW, "reduce: too many tiles");
-    pl->ntiles = nt;
-    int rc;
-    const size_t es = dtype_size(dtype);
-    if ((rc = scratch_alloc((void **)&pl->t_heads, (size_t)nt * 8, s)) ||
-        (rc = scratch_alloc((void **)&pl->t_cnt, (size_t)nt * 8, s)) ||
-        (rc = scratch_alloc((void **)&pl->head_off, (size_t)(nt + 1) * 8, s)) ||
-        (rc = scratch_alloc((void **)&pl->c_cnt, (size_t)nt * 8, s)) ||
-        (rc = scratch_alloc((void **)&pl->t_flag, (size_t)nt * 4, s)) ||
-        (rc = scratch_alloc((void **)&pl->c_flag, (size_t)nt * 4, s)) ||
-        (rc = scratch_alloc((void **)&pl->t_val, (size_t)nt * es, s)) ||
-        (rc = scratch_alloc((void **)&pl->c_val, (size_t)nt * es, s)) ||
-        (rc = scratch_alloc((void **)&pl->n_eq, 8, s)))
-        return rc;
-    B2S_CUDA(cudaMemsetAsync(pl->n_eq, 0, 8, s));
-    switch (dtype) {
-        case B2S_F32: rc = rd_begin_t<float>(pl); break;
-        case B2S_F64: rc = rd_begin_t<double>(pl); break;
-        case B2S_I32: rc = rd_begin_t<int32_t>(pl); break;
-        case B2S_I64: rc = rd_begin_t<int64_t>(pl); break;
-        case B2S_BOOL: rc = rd_begin_t<uint8_t>(pl); break;
-        default: set_error("reduce_begin: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
-    }
+    const size_t bytes = 24 + (size_t)nt * 3 * 8;
+    void *scratch = nullptr;
+    int rc = scratch_alloc(&scratch, bytes, s);
     if (rc) return rc;
-    B2S_CUDA(cudaMemcpyAsync(&pl->ngroups, pl->head_off + nt, 8, cudaMemcpyDeviceToHost, s));
-    B2S_CUDA(cudaStreamSynchronize(s));
-    *n_groups_out = pl->ngroups;
-    return B2S_OK;
-}
-
-int b2s_reduce_finish(void *plan, const void *fill_host, int apply_fill_fix, const void *result_fill_host, int ndim,
-                      const int64_t *shape_host, int64_t *gid_out_dev, int64_t *coords_out_or_null_dev,
-                      int64_t coords_stride, void *vals_out_dev, int64_t *n_equal_fill_host) {
-    B2S_REQUIRE(plan != nullptr, B2S_ERR_INVALID, "reduce_finish: NULL plan");
-    RdPlan *pl = (RdPlan *)plan;
-    int rc = B2S_OK;
-    if (n_equal_fill_host) *n_equal_fill_host = 0;
-    if (ndim < 0 || ndim > RD_MAXDIM) {
-        set_error("reduce_finish: ndim %d", ndim);
-        rc = B2S_ERR_UNSUPPORTED;
-    } else if (pl->n > 0 && pl->ngroups > 0) {
-        switch (pl->dtype) {
-            case B2S_F32: rc = rd_finish_t<float>(pl, fill_host, apply_fill_fix, result_fill_host, ndim, shape_host, gid_out_dev, coords_out_or_null_dev, coords_stride, vals_out_dev); break;
-            case B2S_F64: rc = rd_finish_t<double>(pl, fill_host, apply_fill_fix, result_fill_host, ndim, shape_host, gid_out_dev, coords_out_or_null_dev, coords_stride, vals_out_dev); break;
-            case B2S_I32: rc = rd_finish_t<int32_t>(pl, fill_host, apply_fill_fix, result_fill_host, ndim, shape_host, gid_out_dev, coords_out_or_null_dev, coords_stride, vals_out_dev); break;
-            case B2S_I64: rc = rd_finish_t<int64_t>(pl, fill_host, apply_fill_fix, result_fill_host, ndim, shape_host, gid_out_dev, coords_out_or_null_dev, coords_stride, vals_out_dev); break;
-            case B2S_BOOL: rc = rd_finish_t<uint8_t>(pl, fill_host, apply_fill_fix, result_fill_host, ndim, shape_host, gid_out_dev, coords_out_or_null_dev, coords_stride, vals_out_dev); break;
-            default: rc = B2S_ERR_UNSUPPORTED;
-        }
-        if (rc == B2S_OK && n_equal_fill_host) {
-            unsigned long long h = 0;
-            cudaError_t e = cudaMemcpyAsync(&h, pl->n_eq, 8, cudaMemcpyDeviceToHost, pl->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(pl->stream);
-            if (e != cudaSuccess) {
-                set_error("reduce_finish: %s", cudaGetErrorString(e));
-                rc = B2S_ERR_CUDA;
-            }
-            *n_equal_fill_host = (int64_t)h;
+    B2S_CUDA(cudaMemsetAsync(scratch, 0, 24 + (size_t)nt * 8, s));  // counters, ticket and every status word start at 0
+    switch (dtype) {
+        case B2S_F32: rc = rd_single_t<float>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+        case B2S_F64: rc = rd_single_t<double>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+        case B2S_I32: rc = rd_single_t<int32_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+        case B2S_I64: rc = rd_single_t<int64_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+        case B2S_BOOL: rc = rd_single_t<uint8_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+        default: set_error("reduce_single: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
+    }
+    unsigned long long h[2] = {0, 0};
+    if (rc == B2S_OK) {
+        cudaError_t e = cudaMemcpyAsync(h, scratch, 16, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            set_error("reduce_single: %s", cudaGetErrorString(e));
+            rc = B2S_ERR_CUDA;
         }
     }
-    rd_free(pl);
+    scratch_free(scratch, s);
+    *n_equal_fill_out = (int64_t)h[0];
+    *n_groups_out = (int64_t)h[1];
     return rc;
 }
 
