@@ -300,13 +300,24 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
     const int64_t b0 = d0 - a0, b1 = d1 - a1;
     const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
     constexpr int64_t NEG = INT64_MIN, POS = INT64_MAX;
-    for (int i = threadIdx.x; i < na + 2; i += EW_THREADS) {
-        const int64_t p = a0 - 1 + i;
-        sa[i] = (p < 0) ? NEG : (p < la ? A.key(p) : POS);
-    }
-    for (int i = threadIdx.x; i < nb + 2; i += EW_THREADS) {
-        const int64_t p = b0 - 1 + i;
-        sb[i] = (p < 0) ? NEG : (p < lb ? B.key(p) : POS);
+    // stage both key ranges (+ one sentinel on each side); all global loads of a thread are issued before the first
+    // shared-memory store so that up to 2 x EW_LD of them are in flight per thread
+    constexpr int EW_LD = (EW_TILE + 2 + EW_THREADS - 1) / EW_THREADS;
+    {
+        int64_t ra[EW_LD], rb[EW_LD];
+#pragma unroll
+        for (int k = 0; k < EW_LD; ++k) {
+            const int i = threadIdx.x + k * EW_THREADS;
+            const int64_t pa = a0 - 1 + i, pb = b0 - 1 + i;
+            ra[k] = (i < na + 2) ? ((pa < 0) ? NEG : (pa < la ? A.key(pa) : POS)) : POS;
+            rb[k] = (i < nb + 2) ? ((pb < 0) ? NEG : (pb < lb ? B.key(pb) : POS)) : POS;
+        }
+#pragma unroll
+        for (int k = 0; k < EW_LD; ++k) {
+            const int i = threadIdx.x + k * EW_THREADS;
+            if (i < na + 2) sa[i] = ra[k];
+            if (i < nb + 2) sb[i] = rb[k];
+        }
     }
     __syncthreads();
     const int64_t *ka = sa + 1, *kb = sb + 1;
@@ -397,6 +408,7 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
                 uint64_t v0 = i0 >= 0 ? lb_load(&lb_status[i0]) : LB_PREFIX;  // virtual prefix 0 before tile 0
                 uint64_t v1 = i1 >= 0 ? lb_load(&lb_status[i1]) : LB_PREFIX;
                 while (__any_sync(0xffffffffu, (v0 >> 62) == 0)) {
+                    __nanosleep(64);  // leave the issue slots to the warps that are still merging
                     if ((v0 >> 62) == 0) v0 = lb_load(&lb_status[i0]);
                 }
                 const unsigned pm0 = __ballot_sync(0xffffffffu, (v0 >> 62) == 2);
@@ -406,6 +418,7 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
                     c = lane <= __ffs(pm0) - 1 ? (int64_t)(v0 & LB_VALUE) : 0;  // up to the nearest full prefix
                 } else {
                     while (__any_sync(0xffffffffu, (v1 >> 62) == 0)) {
+                        __nanosleep(64);
                         if ((v1 >> 62) == 0) v1 = lb_load(&lb_status[i1]);
                     }
                     const unsigned pm1 = __ballot_sync(0xffffffffu, (v1 >> 62) == 2);

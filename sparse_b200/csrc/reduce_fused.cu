@@ -142,7 +142,7 @@ struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entr
 };
 
 template <typename T>
-__global__ void __launch_bounds__(RD_THREADS)
+__global__ void __launch_bounds__(RD_THREADS, 4)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
                    FastDiv fcols, int op, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
                    T result_fill, int64_t *__restrict__ out_gid, T *__restrict__ out_val,
@@ -279,6 +279,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                 const int64_t idx = q - lane;
                 uint64_t hv = idx >= 0 ? *(volatile uint64_t *)&desc.heads[idx] : (uint64_t)RD_PREFIX;
                 while (__any_sync(0xffffffffu, (hv >> 62) == 0)) {
+                    __nanosleep(64);  // leave the issue slots to the warps that still have work
                     if ((hv >> 62) == 0) hv = *(volatile uint64_t *)&desc.heads[idx];
                 }
                 __threadfence();
@@ -317,6 +318,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                 uint64_t v0 = i0 >= 0 ? *(volatile uint64_t *)&desc.heads[i0] : (uint64_t)RD_PREFIX;
                 uint64_t v1 = i1 >= 0 ? *(volatile uint64_t *)&desc.heads[i1] : (uint64_t)RD_PREFIX;
                 while (__any_sync(0xffffffffu, (v0 >> 62) == 0)) {
+                    __nanosleep(64);
                     if ((v0 >> 62) == 0) v0 = *(volatile uint64_t *)&desc.heads[i0];
                 }
                 const unsigned pm0 = __ballot_sync(0xffffffffu, (v0 >> 62) == 2);
@@ -326,6 +328,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                     c = lane <= __ffs(pm0) - 1 ? (int64_t)(v0 & RD_VALUE) : 0;  // up to the nearest inclusive prefix
                 } else {
                     while (__any_sync(0xffffffffu, (v1 >> 62) == 0)) {
+                        __nanosleep(64);
                         if ((v1 >> 62) == 0) v1 = *(volatile uint64_t *)&desc.heads[i1];
                     }
                     const unsigned pm1 = __ballot_sync(0xffffffffu, (v1 >> 62) == 2);
