@@ -123,3 +123,53 @@ def test_c1_coo_tensordot_matches_oracle():
     dense = sp.tensordot(a, b.todense(), axes=1)
     assert np.array_equal(dense.view(np.uint64),
                           oracle.dot_coo_ndarray(a.coords, a.data, b.todense().T, (1000, 1000)).view(np.uint64))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
+def test_reductions_with_runs_spanning_many_tiles(dtype):
+    """Single-pass reduction kernel: groups that span hundreds of 2048-entry tiles (carry-in runs folded through
+    several look-back windows), groups that end exactly on tile boundaries, and a full reduction to one value."""
+    sp = _sp()
+    rng = np.random.default_rng(12)
+    shape = (6, 1_500_000)
+    nnz = 3_000_000
+    x = sp.random(shape, nnz=nnz, random_state=rng)
+    if dtype == np.int64:
+        x = sp.COO(x.coords, rng.integers(-5, 6, x.nnz), shape=shape, has_duplicates=False, sorted=True)
+    else:
+        x = x.astype(dtype)
+    rows = x.coords[0]
+    d = x.data
+    tol = dict(rtol=1e-5 if dtype == np.float32 else 1e-11, atol=0)
+    s1 = x.sum(axis=1).todense()
+    want = np.array([d[rows == r].astype(np.float64 if dtype != np.int64 else np.int64).sum() for r in range(6)])
+    assert np.allclose(s1, want, **tol) if dtype != np.int64 else np.array_equal(s1, want)
+    m1 = x.max(axis=1).todense()
+    want_max = np.array([max(d[rows == r].max(), 0) for r in range(6)], dtype=dtype)
+    assert np.array_equal(m1, want_max)
+    tot = x.sum()
+    ref = d.astype(np.float64).sum() if dtype != np.int64 else d.sum()
+    assert np.allclose(tot.todense(), ref, **tol) if dtype != np.int64 else tot.todense() == ref
+    # every group exactly one tile long (2048 entries), fully stored: runs end on every tile boundary
+    y = sp.COO.from_numpy(np.arange(1, 2048 * 300 + 1, dtype=dtype).reshape(300, 2048))
+    assert np.array_equal(y.sum(axis=1).todense(), np.arange(1, 2048 * 300 + 1, dtype=np.float64 if dtype != np.int64
+                                                           else np.int64).reshape(300, 2048).sum(axis=1).astype(
+        y.sum(axis=1).dtype))
+    assert np.array_equal(y.min(axis=1).todense(), np.arange(300, dtype=dtype) * 2048 + 1)
+
+
+def test_elemwise_union_over_thousands_of_tiles_int_exact():
+    """Single-pass merge kernel at ~3300 tiles with integer data (exact), equal keys in both operands on every tile
+    boundary pattern, results pruned where a + b == 0."""
+    sp = _sp()
+    rng = np.random.default_rng(13)
+    shape = (3000, 4000)
+    a = sp.random(shape, nnz=3_000_000, random_state=rng)
+    b = sp.random(shape, nnz=3_000_000, random_state=rng)
+    a = sp.COO(a.coords, rng.integers(-3, 4, a.nnz), shape=shape, has_duplicates=False, sorted=True, prune=True)
+    b = sp.COO(b.coords, rng.integers(-3, 4, b.nnz), shape=shape, has_duplicates=False, sorted=True, prune=True)
+    for f in (np.add, np.multiply, np.maximum, np.not_equal):
+        got = f(a, b)
+        want = f(a.todense(), b.todense())
+        assert np.array_equal(got.todense(), want), f.__name__
+        assert got.nnz == np.count_nonzero(want), f.__name__
