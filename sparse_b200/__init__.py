@@ -10,7 +10,7 @@ operations raise.
 from ._coo import COO, as_coo
 from ._dot import dot, matmul, stack, tensordot
 from ._einsum import einsum
-from ._elemwise import broadcast_to, elemwise
+from ._elemwise import broadcast_to, elemwise, where
 from ._fused import mttkrp, sddmm
 from ._gcxs import CSC, CSR, GCXS
 from ._io import load_npz, save_npz
@@ -56,5 +56,5 @@ def all(x, /, *, axis=None, keepdims=False):
 
 
 __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
-           "elemwise", "broadcast_to", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
+           "elemwise", "broadcast_to", "where", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
            "einsum", "save_npz", "load_npz", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce"]

@@ -53,7 +53,8 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
+    hdrs = (sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.h")))
+            + sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))))
     os.makedirs(OBJ, exist_ok=True)
     nvcc = nvcc_path()
     jobs = []

@@ -26,11 +26,31 @@ def nan_replace(a, b):
     return np.where(np.isnan(a), b, a)
 
 
+def _sel_x(c, x):
+    """c != 0 ? x : +0 (device op 15; first half of the three-operand where)."""
+    x = np.asarray(x)
+    return np.where(np.asarray(c) != 0, x, x.dtype.type(0))
+
+
+def _sel_y(c, y):
+    """c != 0 ? +0 : y (device op 16)."""
+    y = np.asarray(y)
+    return np.where(np.asarray(c) != 0, y.dtype.type(0), y)
+
+
+def _bitor_raw(a, b):
+    """OR of the raw bit patterns (device op 17): merges the two selections without touching -0.0 / NaN payloads."""
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.result_type(a, b)
+    u = np.dtype(f"u{dt.itemsize}")
+    return (a.astype(dt).view(u) | b.astype(dt).view(u)).view(dt)
+
+
 # ufunc -> device op code (csrc/elemwise.cu)
 _BINARY = {
     np.add: 0, np.subtract: 1, np.multiply: 2, np.true_divide: 3, np.maximum: 4, np.minimum: 5, np.fmax: 6,
     np.fmin: 7, np.power: 8, np.floor_divide: 9, np.remainder: 10, np.bitwise_and: 11, np.bitwise_or: 12,
-    np.bitwise_xor: 13, nan_replace: 14, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
+    np.bitwise_xor: 13, nan_replace: 14, _sel_x: 15, _sel_y: 16, _bitor_raw: 17, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
     np.not_equal: 37, np.logical_and: 38, np.logical_or: 39, np.logical_xor: 40,
 }
 _UNARY = {
@@ -214,12 +234,15 @@ class _Elemwise:
             if self.dtype is not None:
                 res = res.astype(self.dtype)
             return COO.from_numpy(res) if res.ndim == 0 else res
-        if n == 1:
+        composite = not isinstance(self.func, np.ufunc) and self.func not in _BINARY and self.func not in _UNARY
+        if composite:
+            out = self._composite()
+        elif n == 1:
             out = self._unary()
         elif n == 2:
             out = self._binary()
         else:
-            raise NotImplementedError("sparse_b200.elemwise: only unary and binary functions run on the CUDA path")
+            out = self._composite()
         if isinstance(out, COO):
             if self.dtype is not None and np.dtype(self.dtype) != out.dtype:
                 out = out.astype(self.dtype)
@@ -227,6 +250,28 @@ class _Elemwise:
         return out
 
     # ------------------------------------------------------------------------------------------------------
+    def _composite(self):
+        """n-ary / user-defined `func` (e.g. `lambda x, y, z: (x + y) * z`, tests/test_elemwise.py:252-305 upstream).
+
+        The reference evaluates `func` with NumPy on the matched data of every mask combination (_umath.py:576-654).
+        A Python callable cannot run inside a CUDA kernel, so it is evaluated ONCE on the sparse operands themselves:
+        every operator / ufunc inside it dispatches back to the unary / binary device kernels through
+        `__array_ufunc__`, and the intermediate results stay canonical COO arrays on the device.  Element for element
+        the same IEEE operations run in the same order as in the reference, so values and the final fill value are
+        identical; a `func` that leaves the ufunc protocol (or an n-ary ufunc, n > 2) raises."""
+        if isinstance(self.func, np.ufunc):
+            raise TypeError(f"sparse_b200: {self.func.__name__} with {len(self.args)} operands is not in the CUDA op "
+                            "set; there is no CPU fallback.")
+        out = self.func(*self.args)
+        if out is NotImplemented or not (isinstance(out, (SparseArray, np.ndarray)) or isscalar(out)):
+            raise TypeError("sparse_b200.elemwise: the function did not evaluate to an array through the NumPy ufunc "
+                            "protocol; only compositions of the supported ufuncs run on the CUDA path")
+        if isscalar(out):
+            out = COO.from_numpy(np.asarray(out))
+        if isinstance(out, SparseArray) and tuple(out.shape) != tuple(self.shape):
+            out = broadcast_to(out.asformat("coo"), self.shape)
+        return out.asformat("coo") if isinstance(out, SparseArray) else out
+
     def _unary(self):
         (a,) = self.args
         func = self.func
@@ -340,6 +385,47 @@ class _Elemwise:
 def elemwise(func, *args, **kwargs):
     """Apply a function to any number of arguments (reference: _umath.py:13-50)."""
     return _Elemwise(func, *args, **kwargs).get_result()
+
+
+def where(condition, x=None, y=None):
+    """numpy.where for sparse operands (reference: _coo/common.py:533-579).
+
+    One argument: the coordinates of the non-zero entries.  Three arguments: `elemwise(np.where, condition, x, y)` in
+    the reference; here two selections and one OR of raw bit patterns, each a pass of the binary coiteration kernel:
+    `(c ? x : +0) | (c ? +0 : y)` -- exact for every value (signed zeros, NaN payloads, infinities), and the fill
+    value of the result is `where(fill_c, fill_x, fill_y)` by the same formula."""
+    from ._utils import check_zero_fill_value
+
+    x_given, y_given = x is not None, y is not None
+    if not (x_given or y_given):
+        if not isinstance(condition, SparseArray) and not _is_scipy_sparse(condition):
+            raise ValueError(f"Performing this operation would produce a dense result: {np.where!s}")
+        check_zero_fill_value(condition)
+        c = condition.asformat("coo") if isinstance(condition, SparseArray) else COO.from_scipy_sparse(condition)
+        return tuple(c.coords)
+    if x_given != y_given:
+        raise ValueError("either both or neither of x and y should be given")
+    with np.errstate(all="ignore"):
+        T = np.result_type(_stand_in(x), _stand_in(y))
+    work = np.dtype("int32") if T == np.bool_ else T
+    _check_compute_dtype(work, np.where)
+
+    def as_t(v):
+        if isinstance(v, SparseArray):
+            return v.astype(work) if v.dtype != work else v
+        if D.is_device_tensor(v):
+            return Kn.cast(v, work)
+        if isinstance(v, np.ndarray) and v.ndim > 0:
+            return v.astype(work)
+        return work.type(v)
+
+    c = condition
+    cdt = c.dtype if hasattr(c, "dtype") else np.asarray(c).dtype
+    if cdt != np.bool_:
+        c = c != 0  # truth value first: a narrowing cast could flush a tiny non-zero to zero
+    c = c.astype(work) if hasattr(c, "astype") else work.type(bool(c))
+    out = elemwise(_bitor_raw, elemwise(_sel_x, c, as_t(x)), elemwise(_sel_y, c, as_t(y)))
+    return out.astype(np.bool_) if T == np.bool_ else out
 
 
 def broadcast_to(x, shape):

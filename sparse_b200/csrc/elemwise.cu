@@ -24,6 +24,10 @@ enum BinOp {
     OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_MAXIMUM = 4, OP_MINIMUM = 5, OP_FMAX = 6, OP_FMIN = 7,
     OP_POW = 8, OP_FLOORDIV = 9, OP_MOD = 10, OP_BAND = 11, OP_BOR = 12, OP_BXOR = 13,
     OP_NANREPLACE = 14,  // where(isnan(a), b, a): _replace_nan of the nan-reductions (_coo/common.py:293-310)
+    // three-operand where(c, x, y) (_coo/common.py:533-579) as two selections and an OR of the raw bit patterns
+    OP_SEL_X = 15,   // a != 0 ? b : +0
+    OP_SEL_Y = 16,   // a != 0 ? +0 : b
+    OP_BITOR_RAW = 17,
     // predicates (bool output)
     OP_GT = 32, OP_GE = 33, OP_LT = 34, OP_LE = 35, OP_EQ = 36, OP_NE = 37, OP_LAND = 38, OP_LOR = 39, OP_LXOR = 40
 };
@@ -43,7 +47,33 @@ __device__ __forceinline__ bool is_nan(T x) {
 }
 
 template <typename T>
+__device__ __forceinline__ T raw_or(T a, T b) {
+    if constexpr (sizeof(T) == 4) {
+        uint32_t x, y;
+        memcpy(&x, &a, 4);
+        memcpy(&y, &b, 4);
+        x |= y;
+        T r;
+        memcpy(&r, &x, 4);
+        return r;
+    } else {
+        uint64_t x, y;
+        memcpy(&x, &a, 8);
+        memcpy(&y, &b, 8);
+        x |= y;
+        T r;
+        memcpy(&r, &x, 8);
+        return r;
+    }
+}
+
+template <typename T>
 __device__ __forceinline__ T bin_apply(int op, T a, T b) {
+    if (op >= OP_SEL_X && op <= OP_BITOR_RAW) {
+        if (op == OP_SEL_X) return a != T(0) ? b : T(0);
+        if (op == OP_SEL_Y) return a != T(0) ? T(0) : b;
+        return raw_or<T>(a, b);
+    }
     if constexpr (std::is_floating_point<T>::value) {
         switch (op) {
             case OP_ADD: return add_rn(a, b);

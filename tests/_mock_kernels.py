@@ -19,7 +19,11 @@ _ORIG = {}
 
 _BIN = {0: np.add, 1: np.subtract, 2: np.multiply, 3: np.true_divide, 4: np.maximum, 5: np.minimum, 6: np.fmax,
         7: np.fmin, 8: np.power, 9: np.floor_divide, 10: np.remainder, 11: np.bitwise_and, 12: np.bitwise_or,
-        13: np.bitwise_xor, 14: lambda a, b: np.where(np.isnan(a), b, a), 32: np.greater, 33: np.greater_equal, 34: np.less, 35: np.less_equal, 36: np.equal,
+        13: np.bitwise_xor, 14: lambda a, b: np.where(np.isnan(a), b, a),
+        15: lambda a, b: np.where(a != 0, b, np.asarray(b).dtype.type(0)),
+        16: lambda a, b: np.where(a != 0, np.asarray(b).dtype.type(0), b),
+        17: lambda a, b: (np.asarray(a).view(f"u{np.asarray(a).dtype.itemsize}") | np.asarray(b).view(f"u{np.asarray(b).dtype.itemsize}")).view(np.asarray(a).dtype),
+        32: np.greater, 33: np.greater_equal, 34: np.less, 35: np.less_equal, 36: np.equal,
         37: np.not_equal, 38: np.logical_and, 39: np.logical_or, 40: np.logical_xor}
 _UN = {0: np.negative, 1: np.absolute, 2: np.sqrt, 3: np.square, 4: np.sign, 5: np.exp, 6: np.expm1, 7: np.log,
        8: np.log1p, 9: np.sin, 10: np.cos, 11: np.tan, 12: np.tanh, 13: np.sinh, 14: np.cosh, 15: np.arcsin,

@@ -577,6 +577,82 @@ def gen_indexing():
         bk.add({"op": "getitem", "fmt": "coo", "index": _enc_index(index)}, **enc("a_", x), **enc("out_", x[index]))
     bk.save()
 
+# --------------------------------------------------------------------------
+def gen_elemwise_nary():
+    """n-ary / user-defined functions through elemwise (tests/test_elemwise.py:252-305 upstream)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import _nary_funcs as NF
+
+    bk = Book("elemwise_nary_api")
+    rng = np.random.default_rng(43)
+    shape_sets = [[(2,), (3, 2), (4, 3, 2)], [(3,), (2, 3), (2, 2, 3)], [(2,), (2, 2), (2, 2, 2)],
+                  [(4,), (4, 4), (4, 4, 4)], [(1, 1, 2), (1, 3, 1), (4, 1, 1)], [(2,), (2, 1), (2, 1, 1)]]
+    for shapes in shape_sets:
+        args = [sparse.random(sh, density=0.5, random_state=rng) for sh in shapes]
+        for fi, f in enumerate(NF.TRINARY):
+            r = sparse.elemwise(f, *args)
+            ops = {}
+            for i, a in enumerate(args):
+                ops.update(enc(f"op{i}_", a))
+            bk.add({"op": "trinary", "func": fi, "n": 3, "note": ""}, **ops, **enc("out_", r))
+    patho = [([(2,), (3, 2), (4, 3, 2)], 0), ([(3,), (2, 3), (2, 2, 3)], 1), ([(2,), (2, 2), (2, 2, 2)], 2),
+             ([(4,), (4, 4), (4, 4, 4)], 3)]
+    for shapes, fi in patho:
+        for value in (np.nan, np.inf, -np.inf):
+            for fraction in (0.25, 0.5, 1.0):
+                def rvs(n, value=value, fraction=fraction):
+                    i = int(n * fraction)
+                    ar = np.empty((n,), dtype=np.float64)
+                    ar[:i] = value
+                    ar[i:] = rng.random(n - i)
+                    return ar
+                args = [sparse.random(sh, density=0.5, random_state=rng, data_rvs=rvs) for sh in shapes]
+                with np.errstate(all="ignore"):
+                    r = sparse.elemwise(NF.TRINARY[fi], *args)
+                ops = {}
+                for i, a in enumerate(args):
+                    ops.update(enc(f"op{i}_", a))
+                bk.add({"op": "trinary", "func": fi, "n": 3, "note": f"patho-{value}-{fraction}"}, **ops,
+                       **enc("out_", r))
+    # three-operand where (tests/test_coo.py:955-984 upstream) + signed zeros / NaN / inf / non-zero fills / scalars
+    where_shapes = [[(2,), (3, 2), (4, 3, 2)], [(3,), (2, 3), (2, 2, 3)], [(4,), (4, 4), (4, 4, 4)],
+                    [(1, 1, 2), (1, 3, 1), (4, 1, 1)], [(2,), (2, 1), (2, 1, 1)], [(3,), (), (2, 3)], [(4, 4), (), ()]]
+    for shapes in where_shapes:
+        for dt in ("float64", "float32", "int64"):
+            cs = sparse.random(shapes[0], density=0.5, random_state=rng).astype(np.bool_)
+            xs = rand_sparse(rng, shapes[1], 0.5, dt)
+            ys = rand_sparse(rng, shapes[2], 0.5, dt)
+            r = sparse.where(cs, xs, ys)
+            bk.add({"op": "where", "func": -1, "n": 3, "note": f"{dt}"}, **enc("op0_", cs), **enc("op1_", xs),
+                   **enc("op2_", ys), **enc("out_", r))
+    cs = sparse.random((6, 7), density=0.5, random_state=rng).astype(np.bool_)
+    xs = sparse.random((6, 7), density=0.6, random_state=rng)
+    ys = sparse.random((6, 7), density=0.6, random_state=rng)
+    dx, dy = xs.data.copy(), ys.data.copy()
+    dx[::4], dx[1::4], dy[::3], dy[1::5] = -0.0, np.nan, np.inf, -0.0
+    xs2 = sparse.COO(xs.coords, dx, shape=xs.shape)
+    ys2 = sparse.COO(ys.coords, dy, shape=ys.shape, fill_value=2.5)
+    for note, args in (("special", (cs, xs2, ys2)), ("scalar_x", (cs, 0, ys2)), ("scalar_y", (cs, xs2, -1.5)),
+                       ("float_cond", (xs2, xs, ys))):
+        with np.errstate(all="ignore"):
+            r = sparse.where(*args)
+        ops = {}
+        for i, a in enumerate(args):
+            ops.update(enc(f"op{i}_", a))
+        bk.add({"op": "where", "func": -1, "n": 3, "note": note}, **ops, **enc("out_", r))
+    x = sparse.random((5, 6), density=0.4, random_state=rng)
+    y = sparse.random((5, 6), density=0.4, random_state=rng)
+    for fi, f in enumerate(NF.UNARY_BINARY):
+        n = f.__code__.co_argcount
+        args = [x, y][:n]
+        with np.errstate(all="ignore"):
+            r = sparse.elemwise(f, *args)
+        ops = {}
+        for i, a in enumerate(args):
+            ops.update(enc(f"op{i}_", a))
+        bk.add({"op": "unary_binary", "func": fi, "n": n, "note": ""}, **ops, **enc("out_", r))
+    bk.save()
+
 
 # --------------------------------------------------------------------------
 def gen_formats():
@@ -636,7 +712,7 @@ def gen_examples():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dot", "tensordot", "elemwise", "reduce", "nanreduce", "einsum", "io", "indexing", "formats", "examples"]
+    which = sys.argv[1:] or ["dot", "tensordot", "elemwise", "reduce", "nanreduce", "einsum", "io", "indexing", "nary", "formats", "examples"]
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         if "dot" in which:
@@ -655,6 +731,8 @@ if __name__ == "__main__":
             gen_io()
         if "indexing" in which:
             gen_indexing()
+        if "nary" in which:
+            gen_elemwise_nary()
         if "formats" in which:
             gen_formats()
         if "examples" in which:
