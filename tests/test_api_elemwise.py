@@ -48,12 +48,13 @@ def test_elemwise(sp, c):
 
 def test_unsupported_function_raises(sp):
     x = sp.COO(np.array([[0, 1]]), np.array([1.0, 2.0]), shape=(3,), has_duplicates=False, sorted=True)
-    with pytest.raises(TypeError, match="CUDA op set"):
-        sp.elemwise(lambda a, b: a + b, x, x)
+    assert np.array_equal(sp.elemwise(lambda a, b: a + b, x, x).todense(), [2.0, 4.0, 0.0])  # composite: evaluated
     with pytest.raises(TypeError, match="CUDA op set"):
         np.arctan2(x, x)
+    with pytest.raises(TypeError, match="CUDA op set"):
+        sp.elemwise(lambda a, b: np.arctan2(a, b), x, x)
     with pytest.raises(ValueError, match="could not be broadcast"):
         y = sp.COO(np.array([[0, 1]]), np.array([1.0, 2.0]), shape=(4,), has_duplicates=False, sorted=True)
         x + y
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError, match="CUDA op set"):
         sp.elemwise(np.add, x, x, x)
