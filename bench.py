@@ -375,17 +375,23 @@ def main():
             "metric": "CSR x dense tensordot throughput (GNNZ/s)", "value": round(value, 4), "unit": "GNNZ/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: GCXS/CSR({M}x{K}, nnz={nnz} per GPU, uniform) @ dense({K}x{ncols}) fp32 -> dense",
-                       "index_dtype_device": "int32", "l2": "inputs>L2 (2.2 GB operands vs 126 MB L2), no flush",
-                       "parallelism": "1-D row blocks of A per GPU; B row-sharded, one NCCL all-gather per step, double-buffered on a side stream (overlaps the previous step's K1)"
-                       if world > 1 else "single GPU",
-                       "exact_order": True},
+            "config": workload_config(M, K, nnz, ncols, world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def workload_config(M, K, nnz, ncols, world):
+    """The `config` object of the JSON line -- identical for the product arm and the reference arm."""
+    return {"workload": f"C2: GCXS/CSR({M}x{K}, nnz={nnz} per GPU, uniform) @ dense({K}x{ncols}) fp32 -> dense",
+            "index_dtype_device": "int32", "l2": "inputs>L2 (2.2 GB operands vs 126 MB L2), no flush",
+            "parallelism": "1-D row blocks of A per GPU; B row-sharded, one NCCL all-gather per step, "
+                           "double-buffered on a side stream (overlaps the previous step's K1)"
+            if world > 1 else "single GPU",
+            "exact_order": True}
 
 
 def reference_arm(args, rank, world):
@@ -425,7 +431,7 @@ def reference_arm(args, rank, world):
         "unit": "GNNZ/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2 sample: {sample}"},
+        "config": workload_config(M, K, args.nnz, ncols, world),
         "cpu_baseline": {"value": round(val, 5), "unit": "GNNZ/s", "cores": oracle.max_threads(), "kind": "port",
                          "sample": sample + "; oracle/dot_oracle.c = C restatement of _dot_csr_ndarray "
                                             "(the numba reference itself is single-threaded and cannot travel)"},
