@@ -141,10 +141,11 @@ struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entr
     int64_t *run_meta;   // ... and (count << 1) | "the tile contains a head"; valid once heads[] is non-zero
 };
 
-template <typename T>
+// IS_ADD: the operator is known at compile time for sums (the common case): no per-element switch
+template <typename T, bool IS_ADD>
 __global__ void __launch_bounds__(RD_THREADS, 4)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
-                   FastDiv fcols, int op, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
+                   FastDiv fcols, int op_rt, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
                    T result_fill, int64_t *__restrict__ out_gid, T *__restrict__ out_val,
                    unsigned long long *__restrict__ counters /* [0] results equal to result_fill, [1] groups */) {
     __shared__ int64_t sk[RD_PAD];
@@ -156,6 +157,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     __shared__ int64_t s_tile, s_hexcl, s_ccnt;
     __shared__ int s_cflag;
     __shared__ T s_cval;
+    const int op = IS_ADD ? (int)RF_ADD : op_rt;
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
     __syncthreads();
     const int64_t tile = s_tile;
@@ -438,9 +440,16 @@ static int rd_single_t(const int64_t *keys, const void *vals, int64_t n, int64_t
     T fill, rfill;
     memcpy(&fill, fill_host, sizeof(T));
     memcpy(&rfill, result_fill_host, sizeof(T));
-    reduce_tile_kernel<T><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
-                                                             make_fastdiv((uint64_t)ncols), op, d, ticket, fill,
-                                                             apply_fix, rfill, gid_out, (T *)vals_out, counters);
+    if (op == RF_ADD)
+        reduce_tile_kernel<T, true><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
+                                                                       make_fastdiv((uint64_t)ncols), op, d, ticket,
+                                                                       fill, apply_fix, rfill, gid_out, (T *)vals_out,
+                                                                       counters);
+    else
+        reduce_tile_kernel<T, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
+                                                                        make_fastdiv((uint64_t)ncols), op, d, ticket,
+                                                                        fill, apply_fix, rfill, gid_out,
+                                                                        (T *)vals_out, counters);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }
