@@ -3,8 +3,8 @@
 Host-side mirror of SparseArray.reduce (sparse/numba_backend/_sparse_array.py:372-437),
 COO._reduce_calc/_reduce_return (_coo/core.py:693-723) and GCXS._reduce_calc/_reduce_return
 (_compressed/compressed.py:354-386).  The grouped reduction itself (transpose -> 2-D -> reduceat over runs) runs on
-the device: permuted linearisation + stable sort (only when the reduced axes are not trailing), then one
-segmented reduce-by-key pass and the fill-value correction kernel (csrc/reduce.cu).
+the device: permuted linearisation + stable sort (only when the reduced axes are not trailing), then ONE single-pass
+segmented-scan kernel that also applies the fill-value correction (csrc/reduce_fused.cu, `b2s_reduce_single`).
 """
 from __future__ import annotations
 
