@@ -232,7 +232,7 @@ class GCXS(SparseArray):
         """compressed.py:425-460: rows from indptr, then undo the axis reordering (COO rebuild + sort)."""
         data, indices, indptr = self._dev()
         if self.ndim == 0:
-            return COO._from_device(indices.reshape(0, -1), data, self.shape, self.fill_value)
+            return COO._from_device(indices.reshape(0, int(data.shape[0])), data, self.shape, self.fill_value)
         if self.ndim == 1:
             return COO(indices[None, :], data, shape=self.shape, fill_value=self.fill_value)
         nrows, ncols = self._compressed_shape
