@@ -242,3 +242,51 @@ def test_sparse_dense_elemwise_and_matmul(data):
     assert np.allclose(np.asarray(x @ w), dx @ w, rtol=1e-12, atol=1e-12)
     ws, _ = _rand((shape[-1], k), data.draw(st.integers(0, 99)), 0.7)
     assert np.allclose((x @ ws).todense(), dx @ ws.todense(), rtol=1e-12, atol=1e-12)
+
+
+@SET
+@given(st.data())
+def test_matmul_and_dot_broadcasting(data):
+    batch = data.draw(st.lists(st.integers(1, 3), min_size=0, max_size=2).map(tuple))
+    m, k, n = (data.draw(st.integers(1, 4)) for _ in range(3))
+    b_batch = tuple(data.draw(st.sampled_from([s, 1])) for s in batch)[data.draw(st.integers(0, len(batch))):]
+    a, da = _rand(batch + (m, k), data.draw(st.integers(0, 99)), 0.6)
+    b, db = _rand(b_batch + (k, n), data.draw(st.integers(0, 99)), 0.6)
+    sp = _sp()
+    fa = data.draw(st.sampled_from(["coo", "gcxs"]))
+    fb = data.draw(st.sampled_from(["coo", "gcxs", "dense"]))
+    A = a.asformat(fa)
+    B = db if fb == "dense" else b.asformat(fb)
+    got = sp.matmul(A, B)
+    want = np.matmul(da, db)
+    got_d = got.todense() if hasattr(got, "todense") else np.asarray(got)
+    assert got_d.shape == want.shape and np.allclose(got_d, want, rtol=1e-12, atol=1e-12)
+    got = sp.dot(A, B)
+    want = np.dot(da, db)
+    got_d = got.todense() if hasattr(got, "todense") else np.asarray(got)
+    assert got_d.shape == want.shape and np.allclose(got_d, want, rtol=1e-12, atol=1e-12)
+
+
+@SET
+@given(st.data())
+def test_gcxs_views_match_numpy(data):
+    shape = data.draw(st.lists(st.integers(1, 4), min_size=2, max_size=4).map(tuple))
+    x, d = _rand(shape, data.draw(st.integers(0, 99)), 0.5)
+    nd = len(shape)
+    ca = tuple(sorted(data.draw(st.lists(st.integers(0, nd - 1), min_size=1, max_size=nd - 1, unique=True))))
+    g = x.asformat("gcxs", compressed_axes=ca)
+    assert g.compressed_axes == ca and np.array_equal(g.todense(), d)
+    ca2 = tuple(sorted(data.draw(st.lists(st.integers(0, nd - 1), min_size=1, max_size=nd - 1, unique=True))))
+    g2 = g.change_compressed_axes(ca2)
+    assert g2.compressed_axes == ca2 and np.array_equal(g2.todense(), d)
+    index = tuple(data.draw(st.sampled_from([slice(None), slice(0, 1), slice(None, None, -1), 0, -1, slice(1, None, 2)]))
+                  for _ in range(data.draw(st.integers(1, nd))))
+    want = d[index]
+    got = g[index]
+    if np.ndim(want) == 0:
+        assert got == want
+    else:
+        assert isinstance(got, _sp().GCXS) and np.array_equal(got.todense(), want)
+    tgt = data.draw(st.sampled_from([shape, (2,) + shape, tuple(3 if e == 1 else e for e in shape)]))
+    assert np.array_equal(x.broadcast_to(tgt).todense(), np.broadcast_to(d, tgt))
+    assert np.array_equal(g.astype(np.float32).todense(), d.astype(np.float32))
