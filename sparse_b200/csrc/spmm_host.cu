@@ -92,6 +92,11 @@ void narrow_range(const int64_t *src, int32_t *dst, int64_t n) {
     for (int64_t i = 0; i < n; ++i) dst[i] = (int32_t)src[i];
 }
 
+std::mutex &host_pipe_mutex() {
+    static std::mutex m;
+    return m;
+}
+
 HostPool &host_pool() {
     static HostPool *p = nullptr;  // leaked on purpose, see host_pool.h
     static int built_for = -2;
@@ -137,6 +142,7 @@ extern "C" int b2s_spmm_host_set_pipeline(int chunks, int slots) {
 }
 
 extern "C" int b2s_host_narrow_i64_i32(const int64_t *src_host, int32_t *dst_host, int64_t n) {
+    std::lock_guard<std::mutex> guard(host_pipe_mutex());
     host_pool().parallel_for(n, [src_host, dst_host](int64_t b, int64_t e) {
         narrow_range(src_host + b, dst_host + b, e - b);
     });
@@ -151,6 +157,9 @@ extern "C" int b2s_spmm_csr_dense_host(int dtype, int idx_bytes, int64_t M, int6
     B2S_REQUIRE(idx_bytes == 4 || idx_bytes == 8, B2S_ERR_INVALID, "spmm_host: idx_bytes must be 4 or 8");
     B2S_REQUIRE(M >= 0 && K >= 0 && N >= 0 && nnz >= 0, B2S_ERR_INVALID, "spmm_host: negative size");
     if (M == 0 || N == 0) return B2S_OK;
+    // the three pipeline streams, the pinned staging ring and the host thread pool are process-wide: callers that come
+    // in from several threads (ctypes releases the GIL) take turns -- they would share the PCIe link anyway
+    std::lock_guard<std::mutex> guard(host_pipe_mutex());
     HostPipe &P = pipe();
     B2S_REQUIRE(P.ok, B2S_ERR_CUDA, "spmm_host: could not create CUDA streams");
     const bool narrow = idx_bytes == 8 && (K < 2147483647LL) && (nnz < 2147483647LL);

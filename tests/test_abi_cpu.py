@@ -3,6 +3,7 @@ include/sparse_b200.h declares, and fails loudly without a device (no CPU fallba
 import ctypes
 import subprocess
 
+import numpy as np
 import pytest
 
 from sparse_b200 import _lib
@@ -48,3 +49,27 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text, f
+
+
+def test_host_side_index_narrowing_is_thread_safe():
+    """b2s_host_narrow_i64_i32 (the staging step of the host-buffer product) needs no GPU: several Python threads
+    calling it at once (ctypes releases the GIL) share one thread pool behind a mutex and all get exact results."""
+    import threading
+
+    from sparse_b200 import _kernels as Kn
+
+    rng = np.random.default_rng(0)
+    srcs = [rng.integers(0, 2**31 - 1, 1_000_003 + 17 * i, dtype=np.int64) for i in range(4)]
+    dsts = [np.zeros(s.size, np.int32) for s in srcs]
+
+    def work(i):
+        for _ in range(3):
+            Kn.host_narrow(srcs[i], dsts[i])
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for s, d in zip(srcs, dsts):
+        assert np.array_equal(d, s.astype(np.int32))
+    small = np.arange(5, dtype=np.int64)
+    assert np.array_equal(Kn.host_narrow(small, np.empty(5, np.int32)), small.astype(np.int32))
