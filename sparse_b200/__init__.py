@@ -8,12 +8,17 @@ thin C ABI (``include/sparse_b200.h``) via ctypes.  There is no CPU fallback: wi
 operations raise.
 """
 from ._coo import COO, as_coo
-from ._dot import dot, matmul, stack, tensordot
+from ._creation import (abs, argwhere, asarray, asnumpy, astype, can_cast, diff, empty, empty_like, equal, eye,
+                        full, full_like, imag, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
+                        reshape, result_type, round, std, var, vecdot, zeros, zeros_like)
+from ._dot import dot, matmul, tensordot
 from ._einsum import einsum
 from ._elemwise import broadcast_to, elemwise, where
 from ._fused import mttkrp, sddmm
 from ._gcxs import CSC, CSR, GCXS
 from ._io import load_npz, save_npz
+from ._manip import (concatenate, diagonal, diagonalize, expand_dims, flip, kron, matrix_transpose, moveaxis, outer,
+                     pad, permute_dims, repeat, roll, squeeze, stack, swapaxes, take, tile, tril, triu, unstack)
 from ._nanreduce import nanmax, nanmean, nanmin, nanprod, nanreduce, nansum
 from ._random import random
 from ._sparse_array import SparseArray
@@ -21,10 +26,12 @@ from ._sparse_array import SparseArray
 __version__ = "0.1.0"
 
 
-def asarray(x, /, *, format="coo", **kwargs):
-    if isinstance(x, SparseArray):
-        return x.asformat(format, **kwargs)
-    return as_coo(x).asformat(format, **kwargs)
+def clip(a, min=None, max=None, out=None):
+    """_coo/common.py:1028-1071."""
+    return (a if isinstance(a, SparseArray) else as_coo(a)).clip(min, max, out=out)
+
+
+concat = concatenate
 
 
 def sum(x, /, *, axis=None, dtype=None, keepdims=False):
@@ -57,4 +64,10 @@ def all(x, /, *, axis=None, keepdims=False):
 
 __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
            "elemwise", "broadcast_to", "where", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
-           "einsum", "save_npz", "load_npz", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce"]
+           "einsum", "save_npz", "load_npz", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce",
+           # array manipulation and creation next to the hot path (widened per SURVEY.md s8f)
+           "concatenate", "concat", "unstack", "moveaxis", "swapaxes", "permute_dims", "matrix_transpose", "squeeze",
+           "expand_dims", "flip", "roll", "triu", "tril", "diagonal", "diagonalize", "pad", "repeat", "tile", "outer",
+           "kron", "take", "clip", "eye", "full", "full_like", "zeros", "zeros_like", "ones", "ones_like", "empty",
+           "empty_like", "asnumpy", "can_cast", "result_type", "std", "var", "abs", "reshape", "astype", "equal",
+           "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]

@@ -15,7 +15,7 @@ import numpy as np
 from . import _device as D
 from . import _kernels as Kn
 from ._sparse_array import SparseArray
-from ._utils import _zero_of_dtype, c_strides, can_store, check_linear_range, key_bits, prod
+from ._utils import _zero_of_dtype, c_strides, can_store, check_linear_range, key_bits, normalize_axis, prod
 
 
 def _is_scipy_sparse(x):
@@ -45,6 +45,9 @@ class COO(SparseArray):
         if data is None:
             arr = as_coo(coords, shape=shape, fill_value=fill_value, idx_dtype=idx_dtype)
             self._copy_from(arr)
+            if idx_dtype is not None and self.ndim:
+                if not can_store(idx_dtype, max(self.shape)):
+                    raise ValueError(f"cannot cast array with shape {self.shape} to dtype {idx_dtype}.")
             return
 
         dev_in = D.is_device_tensor(coords) or D.is_device_tensor(data)
@@ -119,6 +122,10 @@ class COO(SparseArray):
         self._dtype = other._dtype
         self.fill_value = other.fill_value
 
+    def _make_shallow_copy_of(self, other):
+        """`out=` target of a ufunc (_coo/core.py:_make_shallow_copy_of): adopt the result's arrays."""
+        self._copy_from(other.asformat("coo") if not isinstance(other, COO) else other)
+
     @classmethod
     def _from_device(cls, coords, data, shape, fill_value=None, keys=None):
         """Wrap canonical device arrays without any checks.  coords may be None when `keys` (sorted linear keys over
@@ -136,6 +143,8 @@ class COO(SparseArray):
     def from_numpy(cls, x, fill_value=None, idx_dtype=None):
         """Dense ndarray -> COO (_coo/core.py:from_numpy): entries bitwise different from the fill value."""
         x = np.asanyarray(x).view(type=np.ndarray)
+        if idx_dtype is not None and x.ndim and not can_store(idx_dtype, max(x.shape)):
+            raise ValueError(f"cannot cast array with shape {x.shape} to dtype {idx_dtype}.")
         if fill_value is None:
             # 0-D: the element itself becomes the fill value (nnz = 0), _coo/core.py:371-372
             fill_value = _zero_of_dtype(x.dtype) if x.shape else x[()]
@@ -163,15 +172,23 @@ class COO(SparseArray):
         return cls._from_device(coords, data, shape, fill_value, keys=keys)
 
     @classmethod
-    def from_scipy_sparse(cls, x):
-        x = x.tocoo()
-        coords = np.stack([x.row, x.col])
-        return cls(coords, x.data, shape=x.shape, has_duplicates=not getattr(x, "has_canonical_format", False),
-                   sorted=False)
+    def from_scipy_sparse(cls, x, /, *, fill_value=None):
+        """_coo/core.py:424-467; non-canonical input is canonicalised by SciPy on the host before the upload."""
+        x = x.asformat("coo")
+        if not x.has_canonical_format:
+            x = x.copy()
+            x.eliminate_zeros()
+            x.sum_duplicates()
+        coords = np.stack([x.row, x.col]) if not hasattr(x, "coords") else np.stack(x.coords)
+        return cls(coords, x.data, shape=x.shape, has_duplicates=not x.has_canonical_format,
+                   sorted=x.has_canonical_format, fill_value=fill_value)
 
     # ---- device / host mirrors -----------------------------------------------------------------------
-    def to_device(self):
+    def to_device(self, device=None, /, *, stream=None):
         """Move the arrays to HBM now (they stay resident); returns self."""
+        from ._creation import _check_device
+
+        _check_device(device)
         self._dev()
         return self
 
@@ -347,13 +364,28 @@ class COO(SparseArray):
         return scipy.sparse.csc_array((g.data, g.indices, g.indptr), shape=self.shape)
 
     def astype(self, dtype, casting="unsafe", copy=True):
+        """Cast of the stored values and the fill value.  Upstream routes this through `elemwise`
+        (_sparse_array.py:626-643), so values that BECOME equal to the fill value under the cast (0.4 -> int 0, a
+        double that underflows to float32 0) are dropped from the result; same here (flag, scan, compact)."""
         dtype = np.dtype(dtype)
         if self.dtype == dtype and not copy:
             return self
+        if not np.can_cast(self.dtype, dtype, casting=casting):
+            raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
         data = self._data_dev()
-        out = COO._from_device(self._coords, Kn.cast(data, dtype) if self.dtype != dtype else data.clone(), self.shape,
-                               dtype.type(self.fill_value), keys=self.sorted_keys() if self._coords is None else self._keys)
-        return out
+        fill = np.asarray(self.fill_value).astype(dtype)[()]
+        if self.dtype == dtype:
+            return COO._from_device(self._coords, data.clone(), self.shape, fill,
+                                    keys=self.sorted_keys() if self._coords is None else self._keys)
+        vals = Kn.cast(data, dtype)
+        if self.nnz and not np.can_cast(self.dtype, dtype, casting="safe"):
+            flags = Kn.flag_not_fill(vals, fill)
+            pos, total = Kn.scan_flags(flags)
+            if total != self.nnz:
+                return COO._from_device(None, Kn.compact(vals, flags, pos, total), self.shape, fill,
+                                        keys=Kn.compact(self.sorted_keys(), flags, pos, total))
+        return COO._from_device(self._coords, vals, self.shape, fill,
+                                keys=self.sorted_keys() if self._coords is None else self._keys)
 
     def linear_loc(self):
         return D.download(self.sorted_keys())
@@ -362,7 +394,9 @@ class COO(SparseArray):
     def transpose(self, axes=None):
         if axes is None:
             axes = tuple(reversed(range(self.ndim)))
-        axes = tuple(int(a) + self.ndim if int(a) < 0 else int(a) for a in axes)
+        if not isinstance(axes, Iterable) or any(isinstance(a, Iterable) for a in axes):
+            raise ValueError(f"axes must be a sequence of integers, got {axes!r}")
+        axes = normalize_axis(tuple(axes), self.ndim)
         if len(np.unique(axes)) < len(axes):
             raise ValueError("repeated axis in transpose")
         if not len(axes) == self.ndim:
@@ -494,12 +528,24 @@ def as_coo(x, shape=None, fill_value=None, idx_dtype=None):
     """_coo/common.py:as_coo."""
     from ._gcxs import GCXS
 
+    from ._sparse_array import SparseArray
+
+    if hasattr(x, "shape") and shape is not None:
+        raise ValueError("Cannot provide a shape in combination with something that already has a shape.")
+    if hasattr(x, "fill_value") and fill_value is not None:
+        raise ValueError("Cannot provide a fill-value in combination with something that already has a fill-value.")
     if isinstance(x, COO):
         return x
-    if isinstance(x, GCXS):
+    if isinstance(x, SparseArray):
         return x.tocoo()
     if _is_scipy_sparse(x):
         return COO.from_scipy_sparse(x)
     if isinstance(x, np.ndarray) or np.isscalar(x):
+        if idx_dtype is not None and np.ndim(x) and not can_store(idx_dtype, max(np.shape(x))):
+            raise ValueError(f"cannot cast array with shape {np.shape(x)} to dtype {idx_dtype}.")
         return COO.from_numpy(np.asarray(x), fill_value=fill_value, idx_dtype=idx_dtype)
-    raise NotImplementedError(f"Format not supported for conversion: {type(x)}")
+    if isinstance(x, (list, tuple)) and not (len(x) and isinstance(x[0], (list, tuple)) and len(x[0]) == 2
+                                               and isinstance(x[0][0], (list, tuple))):
+        return COO.from_numpy(np.asarray(x), fill_value=fill_value, idx_dtype=idx_dtype)
+    raise NotImplementedError(f"Format not supported for conversion. Supplied type is {type(x)}, "
+                              "see help(sparse.as_coo) for supported formats.")

@@ -270,25 +270,10 @@ def _check_nan(x):
 
 
 def stack(arrays, axis=0):
-    """Stack sparse results of the batched matmul (_common.py:288); axis=0 only, via key offsets."""
-    all_gcxs = builtins.all(isinstance(x, GCXS) for x in arrays)
-    arrays = [as_coo(x) if not isinstance(x, COO) else x for x in arrays]
-    if axis != 0:
-        raise NotImplementedError("sparse_b200.stack supports axis=0 only")
-    if all_gcxs:  # _compressed/common.py:52-96: GCXS in -> GCXS out, compressed along the stacking axis
-        return GCXS.from_coo(stack(arrays, axis=0), (0,))
-    t = D.torch()
-    shape = arrays[0].shape
-    parts_c, parts_d = [], []
-    for i, x in enumerate(arrays):
-        assert x.shape == shape
-        coords, data = x._dev()
-        lead = Kn.full(x.nnz, i, D.np_dtype(coords))
-        parts_c.append(t.cat([lead[None, :], coords], dim=0))
-        parts_d.append(data)
-    coords = t.cat(parts_c, dim=1)
-    data = t.cat(parts_d)
-    return COO._from_device(coords, data, (len(arrays),) + tuple(shape), arrays[0].fill_value)
+    """Stack the sparse results of the batched matmul (_common.py:288): device re-keying in `_manip.stack`."""
+    from ._manip import stack as _stack
+
+    return _stack(arrays, axis)
 
 
 def dot(a, b):

@@ -234,6 +234,14 @@ class _Elemwise:
             if self.dtype is not None:
                 res = res.astype(self.dtype)
             return COO.from_numpy(res) if res.ndim == 0 else res
+        if self.dtype is not None and isinstance(self.func, np.ufunc):
+            # ufunc(..., dtype=T) (what `out=` turns into, _sparse_array.py:344) selects the T loop: array operands
+            # are cast to T BEFORE the operation.  Predicates (bool result whatever the input) keep their operands.
+            dt = np.dtype(self.dtype)
+            code = _BINARY.get(self.func, 0) if n == 2 else _UNARY.get(self.func, 0)
+            if dt != np.bool_ and code < (32 if n == 2 else 64):
+                self.args = tuple(a.astype(dt) if isinstance(a, (COO, np.ndarray)) and getattr(a, "ndim", 0) > 0
+                                  and a.dtype != dt else a for a in self.args)
         composite = not isinstance(self.func, np.ufunc) and self.func not in _BINARY and self.func not in _UNARY
         if composite:
             out = self._composite()
@@ -275,6 +283,8 @@ class _Elemwise:
     def _unary(self):
         (a,) = self.args
         func = self.func
+        if func is np.conjugate and a.dtype.kind in "fiu":
+            func = np.positive  # conj of a real array is the array itself
         op = _op_code(func, _UNARY, "unary")
         out_dt, T = _resolve(func, _stand_in(a))
         _check_compute_dtype(T, func)

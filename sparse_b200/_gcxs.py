@@ -14,7 +14,7 @@ from . import _device as D
 from . import _kernels as Kn
 from ._coo import COO, _is_scipy_sparse
 from ._sparse_array import SparseArray
-from ._utils import _zero_of_dtype, c_strides, check_compressed_axes, check_linear_range, key_bits, normalize_axis, prod
+from ._utils import _zero_of_dtype, c_strides, can_store, check_compressed_axes, check_linear_range, key_bits, normalize_axis, prod
 
 
 class GCXS(SparseArray):
@@ -75,6 +75,10 @@ class GCXS(SparseArray):
         self._compressed_axes = o._compressed_axes
         self.fill_value = o.fill_value
 
+    def _make_shallow_copy_of(self, other):
+        """`out=` target of a ufunc (compressed.py:_make_shallow_copy_of)."""
+        self._adopt(other if isinstance(other, GCXS) else GCXS.from_coo(other.asformat("coo"), self.compressed_axes))
+
     @classmethod
     def _from_device(cls, data, indices, indptr, shape, compressed_axes, fill_value=None):
         self = cls.__new__(cls)
@@ -129,8 +133,11 @@ class GCXS(SparseArray):
         return self.nnz * (self._dtype.itemsize + isz) + nptr * isz
 
     # ---- mirrors ---------------------------------------------------------------------------------------------
-    def to_device(self):
+    def to_device(self, device=None, /, *, stream=None):
         """Move the arrays to HBM now (they stay resident); returns self."""
+        from ._creation import _check_device
+
+        _check_device(device)
         self._dev()
         return self
 
@@ -198,6 +205,8 @@ class GCXS(SparseArray):
             return cls._from_device(data, coords[0].contiguous(),
                                     D.torch().zeros(0, dtype=coords.dtype, device=data.device), x.shape, None,
                                     x.fill_value)
+        if idx_dtype is not None and not can_store(idx_dtype, max(x.shape)):
+            raise ValueError(f"cannot cast array with shape {x.shape} to dtype {idx_dtype}.")
         compressed_axes = normalize_axis(compressed_axes, x.ndim)
         if compressed_axes is None:
             compressed_axes = (int(np.argmin(x.shape)),)
@@ -260,14 +269,18 @@ class GCXS(SparseArray):
         return cls.from_coo(COO.from_numpy(x, fill_value=fill_value, idx_dtype=idx_dtype), compressed_axes)
 
     @classmethod
-    def from_scipy_sparse(cls, x):
-        if x.format == "csc":
-            x.sort_indices() if not x.has_sorted_indices else None
-            return cls((x.data, x.indices, x.indptr), shape=x.shape, compressed_axes=(1,))
-        x = x.asformat("csr")
-        if not x.has_sorted_indices:
-            x.sort_indices()
-        return cls((x.data, x.indices, x.indptr), shape=x.shape, compressed_axes=(0,))
+    def from_scipy_sparse(cls, x, /, *, fill_value=None):
+        """compressed.py:210-219: CSC input stays column-compressed, anything else goes through CSR; non-canonical
+        input (duplicates, explicit zeros, unsorted rows) is canonicalised by SciPy on the host before the upload."""
+        is_csc = x.format == "csc"
+        ca = (1,) if is_csc else (0,)
+        if not is_csc:
+            x = x.asformat("csr")
+        if not x.has_canonical_format:
+            x = x.copy()
+            x.eliminate_zeros()
+            x.sum_duplicates()
+        return cls((x.data, x.indices, x.indptr), shape=x.shape, compressed_axes=ca, fill_value=fill_value)
 
     def todense(self):
         return self.tocoo().todense()
@@ -276,7 +289,15 @@ class GCXS(SparseArray):
         return self.tocoo().todense_device()
 
     def copy(self, deep=True):
-        return GCXS(self)
+        """compressed.py:copy -- deep: the three arrays are cloned (device clone and host mirrors alike)."""
+        out = type(self).__new__(type(self))
+        out._adopt(self)
+        if deep:
+            for name in ("_data", "_indices", "_indptr"):
+                dev, host = getattr(self, name), getattr(self, name + "_np")
+                setattr(out, name, dev.clone() if dev is not None else None)
+                setattr(out, name + "_np", host.copy() if host is not None else None)
+        return out
 
     def to_scipy_sparse(self, accept_fv=None):
         """compressed.py:495-525: csr_array when axis 0 is compressed, else csc_array."""
@@ -291,24 +312,41 @@ class GCXS(SparseArray):
         return cls((self.data, self.indices, self.indptr), shape=self.shape)
 
     def asformat(self, format, **kwargs):
-        if format in ("gcxs", GCXS) or (isinstance(format, type) and issubclass(format, GCXS)):
+        """compressed.py:asformat -- "gcxs" / "csr" / "csc" / "coo" / "dense" (names or classes)."""
+        if isinstance(format, str):
+            format = {"gcxs": GCXS, "csr": CSR, "csc": CSC, "coo": COO, "dense": np.ndarray}.get(format, format)
+        if isinstance(format, type) and issubclass(format, (CSR, CSC)):
+            if kwargs:
+                raise ValueError(f"Extra kwargs found: {kwargs}")
+            return format(self)
+        if format is GCXS or (isinstance(format, type) and issubclass(format, GCXS)):
             ca = kwargs.pop("compressed_axes", None)
+            if kwargs:
+                raise ValueError(f"Extra kwargs found: {kwargs}")
             if ca is None:
-                return self
-            return self.change_compressed_axes(ca)
-        if format in ("coo", COO) or (isinstance(format, type) and issubclass(format, COO)):
+                return self if type(self) is GCXS else GCXS(self)
+            return GCXS(self).change_compressed_axes(ca) if type(self) is not GCXS else self.change_compressed_axes(ca)
+        if kwargs:
+            raise ValueError(f"Extra kwargs found: {kwargs}")
+        if format is COO or (isinstance(format, type) and issubclass(format, COO)):
             return self.tocoo()
-        if format in (np.ndarray, "dense"):
+        if format is np.ndarray:
             return self.todense()
         raise NotImplementedError(f"The given format is not supported: {format}")
 
     def astype(self, dtype, casting="unsafe", copy=True):
+        """Cast; entries that become equal to the fill value are pruned, as upstream's elemwise-based astype does."""
         dtype = np.dtype(dtype)
         if self.dtype == dtype and not copy:
             return self
+        if not np.can_cast(self.dtype, dtype, casting=casting):
+            raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
         data, indices, indptr = self._dev()
-        return GCXS._from_device(Kn.cast(data, dtype) if dtype != self.dtype else data.clone(), indices, indptr,
-                                 self.shape, self.compressed_axes, dtype.type(self.fill_value))
+        out = GCXS._from_device(Kn.cast(data, dtype) if dtype != self.dtype else data.clone(), indices, indptr,
+                                self.shape, self.compressed_axes, np.asarray(self.fill_value).astype(dtype)[()])
+        if dtype != self.dtype and not np.can_cast(self.dtype, dtype, casting="safe"):
+            out._prune()
+        return out
 
     def change_compressed_axes(self, new_compressed_axes):
         """compressed.py:388-423."""
@@ -419,15 +457,75 @@ class GCXS(SparseArray):
             return NotImplemented
 
 
-class CSR(GCXS):
+class _Compressed2d(GCXS):
+    """2-D specialisations (compressed.py:851-949): fixed compressed axis, O(1) transpose into the sibling class."""
+
+    class_compressed_axes = None
+
+    def __init__(self, arg, shape=None, compressed_axes=None, prune=False, fill_value=None):
+        if compressed_axes is None:
+            compressed_axes = self.class_compressed_axes
+        if tuple(compressed_axes) != self.class_compressed_axes:
+            what = "rows" if self.class_compressed_axes == (0,) else "columns"
+            raise ValueError(f"{type(self).__name__} only accepts {what} as compressed axis but got: {compressed_axes}")
+        if not hasattr(arg, "shape") and shape is None:
+            raise ValueError("missing `shape` argument")
+        if shape is not None and hasattr(arg, "shape"):
+            raise NotImplementedError("Cannot change shape in constructor")
+        nd = len(shape if shape is not None else arg.shape)
+        if nd != 2:
+            raise ValueError(f"{type(self).__name__} must be 2-d, passed {nd}-d shape.")
+        super().__init__(arg, shape=shape, compressed_axes=self.class_compressed_axes, prune=prune,
+                         fill_value=fill_value)
+
+    @property
+    def ndim(self):
+        return 2
+
+    @classmethod
+    def from_numpy(cls, x, fill_value=0, idx_dtype=None):
+        return cls(GCXS.from_coo(COO.from_numpy(x, fill_value=fill_value, idx_dtype=idx_dtype),
+                                 cls.class_compressed_axes, idx_dtype))
+
+    @classmethod
+    def from_coo(cls, x, compressed_axes=None, idx_dtype=None):
+        return cls(GCXS.from_coo(x, cls.class_compressed_axes, idx_dtype))
+
+    @classmethod
+    def from_scipy_sparse(cls, x, /, *, fill_value=None):
+        fmt = "csr" if cls.class_compressed_axes == (0,) else "csc"
+        x = x.asformat(fmt, copy=False)
+        if not x.has_canonical_format:
+            x = x.copy()
+            x.eliminate_zeros()
+            x.sum_duplicates()
+        return cls((x.data, x.indices, x.indptr), shape=x.shape, fill_value=fill_value)
+
+    def transpose(self, axes=None, copy=False, compressed_axes=None):
+        """compressed.py:915-923: CSR of (m, n) IS the CSC of (n, m) -- the three arrays are shared, not copied."""
+        axes = normalize_axis(axes, self.ndim) if axes is not None else None
+        if axes not in [(0, 1), (1, 0), None]:
+            raise ValueError(f"Invalid transpose axes: {axes}")
+        src = self.copy() if copy else self
+        if axes == (0, 1):
+            return src
+        if not copy and src.nbytes <= (64 << 20):
+            src.data, src.indices, src.indptr  # small arrays: both views hand out the SAME host mirrors
+        other = CSC if isinstance(self, CSR) else CSR
+        out = other.__new__(other)
+        out._adopt(src)
+        out.shape = src.shape[::-1]
+        out._compressed_axes = other.class_compressed_axes
+        return out
+
+
+class CSR(_Compressed2d):
     """2-D GCXS with compressed_axes=(0,)."""
 
-    def __init__(self, arg, shape=None, prune=False, fill_value=None):
-        super().__init__(arg, shape=shape, compressed_axes=(0,), prune=prune, fill_value=fill_value)
+    class_compressed_axes = (0,)
 
 
-class CSC(GCXS):
+class CSC(_Compressed2d):
     """2-D GCXS with compressed_axes=(1,)."""
 
-    def __init__(self, arg, shape=None, prune=False, fill_value=None):
-        super().__init__(arg, shape=shape, compressed_axes=(1,), prune=prune, fill_value=fill_value)
+    class_compressed_axes = (1,)

@@ -5,8 +5,10 @@ _compressed/indexing.py:14-174.  The reference narrows the sorted coordinate row
 (`_compute_mask`, numba) and then transforms the surviving coordinates; here one streaming kernel
 (`b2s_coo_slice_keys`, csrc/prims.cu) unravels each entry's linear key, tests every axis against its
 (start, step, count) range and emits the key over the RESULT shape, followed by the usual flag-scan-compact (and a
-sort only when a negative step reverses an axis).  Advanced (integer-array / boolean-mask) indexing is not on the
-CUDA path and raises.
+sort only when a negative step reverses an axis).  ONE one-dimensional advanced index (integer list / array or
+boolean mask, _coo/indexing.py:136-172) is served by `_manip.take_axis` after the basic part of the index: a lookup
+table over the axis extent is scattered on the device and every surviving entry gathers its slot from it.  Several
+advanced indices in one subscript are not on the CUDA path and raise.
 """
 from __future__ import annotations
 
@@ -44,8 +46,8 @@ def _normalize(index, shape):
             start, stop, step = ind.indices(extent)
             items.append(("slice", start, step, len(range(start, stop, step))))
         elif isinstance(ind, (bool, np.bool_)) or isinstance(ind, (list, np.ndarray)) or D.is_device_tensor(ind):
-            raise NotImplementedError("sparse_b200: advanced (integer-array / boolean-mask) indexing is not on the "
-                                      "CUDA path; only integers, slices, None and Ellipsis are")
+            raise NotImplementedError("sparse_b200: scalar booleans and nested advanced indices are not on the CUDA "
+                                      "path; integers, slices, None, Ellipsis and one 1-D integer / boolean array are")
         else:
             try:
                 i = operator.index(ind)
@@ -58,6 +60,56 @@ def _normalize(index, shape):
     return items
 
 
+def _split_advanced(index, shape):
+    """(index with the advanced entry replaced by a full slice, its position in the RESULT, integer list) or None."""
+    adv = [k for k, i in enumerate(index)
+           if isinstance(i, (list, np.ndarray)) or (D.is_device_tensor(i) and not isinstance(i, (bool, np.bool_)))]
+    if not adv:
+        return None
+    if len(adv) > 1:
+        raise NotImplementedError("sparse_b200: more than one advanced (integer-array / boolean-mask) index in a "
+                                  "subscript is not on the CUDA path")
+    k = adv[0]
+    arr = D.download(index[k]) if D.is_device_tensor(index[k]) else np.asarray(index[k])
+    if arr.ndim != 1:
+        raise IndexError("Only one-dimensional iterable indices supported.")
+    # the axis of x the advanced index addresses: entries before it that consume an axis (Ellipsis expands)
+    n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
+    axis = 0
+    for i in index[:k]:
+        if i is Ellipsis:
+            axis += len(shape) - n_real
+        elif i is not None:
+            axis += 1
+    if axis >= len(shape):
+        raise IndexError(f"too many indices for array: array is {len(shape)}-dimensional")
+    extent = shape[axis]
+    if arr.size == 0:
+        arr = arr.astype(np.int64)
+    if arr.dtype == np.bool_:
+        if len(arr) != extent:
+            raise IndexError(f"boolean index did not match indexed array; dimension is {extent:d} "
+                             f"but corresponding boolean dimension is {len(arr):d}")
+        arr = np.flatnonzero(arr)
+    elif arr.dtype.kind not in "iu":
+        raise IndexError("only integers, slices (`:`), ellipsis (`...`), numpy.newaxis (`None`) and integer or "
+                         "boolean arrays are valid indices")
+    arr = arr.astype(np.int64)
+    if arr.size and (arr.min() < -extent or arr.max() >= extent):
+        bad = arr[(arr < -extent) | (arr >= extent)][0]
+        raise IndexError(f"index {bad} is out of bounds for axis {axis} with size {extent}")
+    arr = np.where(arr < 0, arr + extent, arr)
+    basic = index[:k] + (slice(None),) + index[k + 1:]
+    # position of that axis in the result of the basic part: integers before it drop out, None adds one
+    pos = 0
+    for i in index[:k]:
+        if i is Ellipsis:
+            pos += len(shape) - n_real
+        elif i is None or isinstance(i, slice):
+            pos += 1
+    return basic, pos, arr
+
+
 def coo_getitem(x, index):
     """COO.__getitem__ (_coo/indexing.py:12-133)."""
     from ._coo import COO
@@ -66,6 +118,13 @@ def coo_getitem(x, index):
         raise NotImplementedError("sparse_b200: structured dtypes are outside the CUDA dtype matrix")
     if not isinstance(index, tuple):
         index = (index,)
+    split = _split_advanced(index, x.shape)
+    if split is not None:
+        from ._manip import take_axis
+
+        basic, pos, arr = split
+        y = coo_getitem(x, basic)
+        return take_axis(y, arr, pos)
     last_ellipsis = len(index) > 0 and index[-1] is Ellipsis
     items = _normalize(index, x.shape)
     if len(index) != 0 and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items, x.shape)) \
@@ -132,9 +191,11 @@ def gcxs_getitem(x, index):
     if x.ndim == 1:
         r = coo_getitem(x.tocoo(), index)
         return GCXS.from_coo(r) if hasattr(r, "nnz") else r
-    items = _normalize(index, x.shape)
-    if len(index) != 0 and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items, x.shape)) \
-            and len(items) == x.ndim:
+    split = _split_advanced(index, x.shape)
+    layout_index = split[0] if split is not None else index  # an advanced index keeps its axis, like a slice
+    items = _normalize(layout_index, x.shape)
+    if split is None and len(index) != 0 and len(items) == x.ndim \
+            and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items, x.shape)):
         return x
     real = [it for it in items if it[0] != "none"]
     if all(it[0] == "int" for it in real) and len(real) == len(items):

@@ -6,7 +6,7 @@ from __future__ import annotations
 import numpy as np
 
 from ._coo import COO
-from ._utils import prod
+from ._utils import can_store, prod
 
 
 def random(shape, density=None, nnz=None, random_state=None, data_rvs=None, format="coo", fill_value=None,
@@ -21,6 +21,8 @@ def random(shape, density=None, nnz=None, random_state=None, data_rvs=None, form
     if not (0 <= density <= 1):
         raise ValueError(f"density {density} is not in the unit interval")
     elements = prod(shape)
+    if idx_dtype is not None and shape and not can_store(idx_dtype, max(shape)):
+        raise ValueError(f"cannot cast array with shape {shape} to dtype {idx_dtype}.")
     if nnz is None:
         nnz = int(elements * density)
     if not (0 <= nnz <= elements):

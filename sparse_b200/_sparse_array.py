@@ -7,6 +7,7 @@ np.tensordot / np.matmul / np.dot / np.sum ... to this package's functions.
 from __future__ import annotations
 
 import operator
+import warnings
 from functools import reduce as _functools_reduce
 
 import numpy as np
@@ -51,9 +52,14 @@ class SparseArray(NDArrayOperatorsMixin):
             raise TypeError("len() of unsized object")
         return self.shape[0]
 
-    def __array__(self, dtype=None, copy=None):
-        x = self.todense()
-        return x.astype(dtype) if dtype is not None and x.dtype != dtype else x
+    def __array__(self, *args, **kwargs):
+        """No silent densification (_sparse_array.py:270-280): opt in with SPARSE_AUTO_DENSIFY=1 or call todense()."""
+        import os
+
+        if os.environ.get("SPARSE_AUTO_DENSIFY", "0") not in ("1", "true", "True"):
+            raise RuntimeError("Cannot convert a sparse array to dense automatically. To manually densify, use the "
+                               "todense method.")
+        return np.asarray(self.todense(), *args, **kwargs)
 
     def __repr__(self):
         return (f"<{type(self).__name__}: shape={self.shape}, dtype={self.dtype}, nnz={self.nnz}, "
@@ -74,27 +80,51 @@ class SparseArray(NDArrayOperatorsMixin):
         return sparse_func(*args, **kwargs)
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """_sparse_array.py:322-370: `__call__` -> elemwise, `reduce` -> reduce, `outer` -> broadcast call.
+
+        `out=` (and therefore the in-place operators `+=`, `*=` ... of NDArrayOperatorsMixin) is honoured the way
+        upstream does it: NumPy's own casting check is run on one-element stand-ins (so an illegal cast raises the
+        same `UFuncTypeError`), the operation is computed in `out`'s dtype, and `out` then adopts the result's device
+        arrays (a shallow re-point, no copy)."""
         from ._elemwise import elemwise
 
         out = kwargs.pop("out", None)
-        if out is not None:
-            raise NotImplementedError("sparse_b200: the `out=` argument of ufuncs is not supported on the CUDA path")
+        if out is not None and not isinstance(out, tuple):
+            out = (out,)
+        if out is not None and not all(isinstance(x, type(self)) for x in out):
+            return NotImplemented
         if getattr(ufunc, "signature", None) is not None:
             return self.__array_function__(ufunc, (np.ndarray, type(self)), inputs, kwargs)
+        if out is not None:
+            test_args = [np.empty((1,), dtype=a.dtype) if hasattr(a, "dtype") else a for a in inputs]
+            test_kwargs = kwargs.copy()
+            if method == "reduce":
+                test_kwargs["axis"] = None
+            test_out = tuple(np.empty(() if method == "reduce" else (1,), dtype=a.dtype) for a in out)
+            with np.errstate(all="ignore"):
+                getattr(ufunc, method)(*test_args, out=test_out[0] if len(test_out) == 1 else test_out, **test_kwargs)
+            kwargs["dtype"] = out[0].dtype
         if method == "outer":
             method = "__call__"
             cum_ndim = 0
             inputs_transformed = []
-            for inp in inputs:
+            for inp in reversed(inputs):  # the LAST operand keeps its axes, earlier ones get trailing unit axes
                 inputs_transformed.append(inp[(Ellipsis,) + (None,) * cum_ndim])
                 cum_ndim += inp.ndim
-            inputs = tuple(inputs_transformed)
+            inputs = tuple(reversed(inputs_transformed))
         if method == "__call__":
             result = elemwise(ufunc, *inputs, **kwargs)
         elif method == "reduce":
             result = SparseArray._reduce(ufunc, *inputs, **kwargs)
         else:
             return NotImplemented
+        if out is not None and result is not NotImplemented:
+            (out,) = out
+            if tuple(out.shape) != tuple(result.shape):
+                raise ValueError(f"non-broadcastable output operand with shape {out.shape} "
+                                 f"doesn't match the broadcast shape {result.shape}")
+            out._make_shallow_copy_of(result)
+            return out
         return result
 
     # ---- reductions (reference: _sparse_array.py:310-437) ------------------------------------------
@@ -155,6 +185,118 @@ class SparseArray(NDArrayOperatorsMixin):
             out = (num / den) if not isinstance(num, SparseArray) else np.true_divide(num, den)
         return out.astype(dtype) if hasattr(out, "astype") else out
 
+    def var(self, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
+        """Variance along `axis` (_sparse_array.py:725-813): two-pass form, mean first, then the mean of the squared
+        deviations; every step is an element-wise or reduction kernel on the device."""
+        axis = normalize_axis(axis, self.ndim)
+        if axis is None:
+            axis = tuple(range(self.ndim))
+        if not isinstance(axis, tuple):
+            axis = (axis,)
+        rcount = _functools_reduce(operator.mul, (self.shape[a] for a in axis), 1)
+        if ddof >= rcount:
+            warnings.warn("Degrees of freedom <= 0 for slice", RuntimeWarning, stacklevel=1)
+        if dtype is None and issubclass(self.dtype.type, (np.integer, np.bool_)):
+            dtype = np.dtype("f8")
+        with np.errstate(all="ignore"):
+            arrmean = np.true_divide(self.sum(axis, dtype=dtype, keepdims=True), rcount)
+            x = self - arrmean
+            x = np.multiply(x, x)
+            ret = x.sum(axis=axis, dtype=dtype, keepdims=keepdims)
+            rcount = max(rcount - ddof, 0)
+            res = np.true_divide(ret, rcount)
+            if hasattr(res, "astype") and res.dtype != ret.dtype:
+                res = res.astype(ret.dtype)
+        if out is not None:
+            out._make_shallow_copy_of(res)
+            return out
+        return res
+
+    def std(self, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
+        """Standard deviation = sqrt(var) (_sparse_array.py:815-877)."""
+        ret = self.var(axis=axis, dtype=dtype, ddof=ddof, keepdims=keepdims)
+        with np.errstate(all="ignore"):
+            res = np.sqrt(ret)
+        if out is not None:
+            out._make_shallow_copy_of(res)
+            return out
+        return res
+
+    def round(self, decimals=0, out=None):
+        """numpy.round semantics (_sparse_array.py:592-606): round-half-even at `decimals` places, as NumPy computes
+        it -- scale by 10**|decimals|, rint, scale back (integers with decimals >= 0 are returned unchanged)."""
+        if out is not None and not isinstance(out, tuple):
+            out = (out,)
+        decimals = operator.index(decimals)
+        kw = {"out": out} if out is not None else {}
+        if issubclass(self.dtype.type, (np.integer, np.bool_)) and decimals >= 0:
+            return np.positive(self, **kw) if self.dtype != np.bool_ else self.copy()
+        if decimals == 0:
+            return np.rint(self, **kw)
+        with np.errstate(all="ignore"):
+            if issubclass(self.dtype.type, np.integer):
+                p = self.dtype.type(10 ** -decimals)
+                q = np.floor_divide(self, p)
+                r = np.subtract(self, np.multiply(q, p))
+                # integers, negative decimals: multiples of 10**-decimals, ties to even multiple like NumPy
+                half = p // 2
+                up = np.logical_or(np.greater(r, half), np.logical_and(np.equal(r, half), np.not_equal(
+                    np.remainder(q, 2), 0))) if p % 2 == 0 else np.greater(r, half)
+                res = np.multiply(np.add(q, up.astype(self.dtype)), p)
+                if out is not None:
+                    out[0]._make_shallow_copy_of(res)
+                    return out[0]
+                return res
+            p = self.dtype.type(10.0 ** abs(decimals))
+            if decimals > 0:
+                return np.true_divide(np.rint(np.multiply(self, p)), p, **kw)
+            return np.multiply(np.rint(np.true_divide(self, p)), p, **kw)
+
+    round_ = round
+
+    def clip(self, min=None, max=None, out=None):
+        """numpy.clip (_sparse_array.py:610-624): maximum(x, min) then minimum(., max)."""
+        if min is None and max is None:
+            raise ValueError("One of max or min must be given.")
+        if out is not None and not isinstance(out, tuple):
+            out = (out,)
+        kw = {"out": out} if out is not None else {}
+        if max is None:
+            return np.maximum(self, min, **kw)
+        if min is None:
+            return np.minimum(self, max, **kw)
+        return np.minimum(np.maximum(self, min), max, **kw)
+
+    def conj(self):
+        return np.conj(self)
+
+    # ---- structure (thin forwards to _manip; `COO.flatten/swapaxes/squeeze/nonzero`, _coo/core.py) ----------
+    def flatten(self, order="C"):
+        if order not in {"C", None}:
+            raise NotImplementedError("The `order` parameter is not supported")
+        return self.reshape(-1)
+
+    def swapaxes(self, axis1, axis2):
+        from ._manip import swapaxes
+
+        return swapaxes(self, axis1, axis2)
+
+    def squeeze(self, axis=None):
+        from ._manip import squeeze
+
+        return squeeze(self, axis)
+
+    def nonzero(self):
+        from ._creation import nonzero
+
+        return nonzero(self)
+
+    def isinf(self):
+        return np.isinf(self)
+
+    def isnan(self):
+        return np.isnan(self)
+
     # ---- scalar conversion (_sparse_array.py:970-993) ---------------------------------------------------
     def _to_scalar(self, builtin):
         if self.size != 1 or self.shape != ():
@@ -177,6 +319,23 @@ class SparseArray(NDArrayOperatorsMixin):
     @property
     def real(self):
         return self
+
+    @property
+    def imag(self):
+        """Real dtypes: an all-zero array of the same dtype (numpy.imag)."""
+        return np.multiply(self, self.dtype.type(0)) if self._zero_fill() else np.subtract(self, self)
+
+    def __complex__(self):
+        return self._to_scalar(complex)
+
+    def __array_namespace__(self, *, api_version=None):
+        if api_version is None:
+            api_version = "2024.12"
+        if api_version not in {"2021.12", "2022.12", "2023.12", "2024.12"}:
+            raise ValueError(f'"{api_version}" Array API version not supported.')
+        import sparse_b200
+
+        return sparse_b200
 
     def _zero_fill(self):
         return bool(equivalent(self.fill_value, _zero_of_dtype(self.dtype), loose=True))

@@ -50,7 +50,7 @@ def check_fill_value(x, /, *, accept_fv=None):
     if not isinstance(accept_fv, Iterable):
         accept_fv = [accept_fv]
     if not any(equivalent(fv, x.fill_value, loose=True) for fv in accept_fv):
-        raise ValueError(f"{x.fill_value} not in accepted fill-values: {accept_fv}")
+        raise ValueError(f"{x.fill_value=} but should be in {accept_fv}.")
 
 
 def normalize_axis(axis, ndim):

@@ -45,9 +45,11 @@ def test_indexing_errors(sp):
         with pytest.raises(IndexError):
             x[bad]
     with pytest.raises(NotImplementedError):
-        x[[0, 1]]
-    with pytest.raises(NotImplementedError):
-        x[np.array([True, False])]
+        x[[0, 1], [1, 2]]  # several advanced indices in one subscript are not on the CUDA path
+    with pytest.raises(IndexError):
+        x[np.array([True, False, True])]  # boolean mask of the wrong length
+    with pytest.raises(IndexError):
+        x[[0, 2]]
 
 
 def test_large_slices_match_numpy(sp):
