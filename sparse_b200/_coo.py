@@ -317,13 +317,22 @@ class COO(SparseArray):
         return COO(self)
 
     def asformat(self, format, **kwargs):
-        from ._gcxs import GCXS
+        """_coo/core.py:asformat -- "coo" / "gcxs" / "csr" / "csc" / "dense" (names or classes)."""
+        from ._gcxs import CSC, CSR, GCXS
 
-        if format in ("coo", COO) or (isinstance(format, type) and issubclass(format, COO)):
-            return self
-        if format in ("gcxs", GCXS) or (isinstance(format, type) and issubclass(format, GCXS)):
+        if isinstance(format, str):
+            format = {"coo": COO, "gcxs": GCXS, "csr": CSR, "csc": CSC, "dense": np.ndarray}.get(format, format)
+        if isinstance(format, type) and issubclass(format, (CSR, CSC)):
+            if kwargs:
+                raise ValueError(f"Extra kwargs found: {kwargs}")
+            return format(self)
+        if isinstance(format, type) and issubclass(format, GCXS):
             return GCXS.from_coo(self, **kwargs)
-        if format in (np.ndarray, "dense"):
+        if kwargs:
+            raise ValueError(f"Extra kwargs found: {kwargs}")
+        if isinstance(format, type) and issubclass(format, COO):
+            return self
+        if format is np.ndarray:
             return self.todense()
         raise NotImplementedError(f"The given format is not supported: {format}")
 

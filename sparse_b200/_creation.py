@@ -121,8 +121,8 @@ def asnumpy(a, dtype=None, order=None):
 
 def can_cast(from_, to, /, *, casting="safe"):
     """_common.py:1863-1892."""
-    from_ = from_.dtype if hasattr(from_, "dtype") else np.dtype(from_)
-    to = to.dtype if hasattr(to, "dtype") else np.dtype(to)
+    from_ = from_.dtype if isinstance(from_, (SparseArray, np.ndarray)) else np.dtype(from_)
+    to = to.dtype if isinstance(to, (SparseArray, np.ndarray)) else np.dtype(to)
     return np.can_cast(from_, to, casting=casting)
 
 

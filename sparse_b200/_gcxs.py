@@ -386,6 +386,14 @@ class GCXS(SparseArray):
     def T(self):
         return self.transpose()
 
+    @property
+    def mT(self):
+        if self.ndim < 2:
+            raise ValueError("Cannot compute matrix transpose if `ndim < 2`.")
+        axes = list(range(self.ndim))
+        axes[-1], axes[-2] = axes[-2], axes[-1]
+        return self.transpose(axes)
+
     def reshape(self, shape, order="C", compressed_axes=None):
         """compressed.py:622-682."""
         shape = tuple(shape) if isinstance(shape, Iterable) else (shape,)

@@ -230,7 +230,7 @@ def squeeze(x, /, axis=None):
     return x.reshape(tuple(s for d, s in enumerate(x.shape) if d not in axis))
 
 
-def expand_dims(x, /, *, axis=0):
+def expand_dims(x, /, axis=0):
     """numpy.expand_dims (_coo/common.py:1074-1133)."""
     if not isinstance(axis, (int, np.integer, tuple, list)):
         raise IndexError(f"Invalid axis position: type={type(axis)}, axis={axis}")
@@ -247,7 +247,7 @@ def expand_dims(x, /, *, axis=0):
     return x.reshape(tuple(1 if d in norm else next(it) for d in range(out_ndim)))
 
 
-def flip(x, /, *, axis=None):
+def flip(x, /, axis=None):
     """numpy.flip (_coo/common.py:1136-1186): a slice with step -1 on every flipped axis."""
     if axis is None:
         axis = tuple(range(x.ndim))
@@ -546,7 +546,7 @@ def take_axis(x, idx, axis):
     return _join(keys_parts, data_parts, shape, x.dtype, x.fill_value)
 
 
-def take(x, indices, /, *, axis=None):
+def take(x, indices, /, axis=None):
     """numpy.take along one axis (_coo/common.py:1349-1383)."""
     from ._gcxs import GCXS
 
