@@ -46,7 +46,11 @@ typedef enum {
     B2S_ERR_NO_DEVICE = -5    /* no CUDA device visible                             */
 } b2s_status;
 
-typedef enum { B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2, B2S_I64 = 3, B2S_BOOL = 4 } b2s_dtype;
+typedef enum {
+    B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2, B2S_I64 = 3, B2S_BOOL = 4,
+    /* storage-only integer widths: accepted by b2s_cast alone (every arithmetic entry point rejects them) */
+    B2S_I8 = 5, B2S_I16 = 6, B2S_U8 = 7, B2S_U16 = 8, B2S_U32 = 9, B2S_U64 = 10
+} b2s_dtype;
 
 /* ---- runtime ---------------------------------------------------------- */
 int b2s_abi_version(void);

@@ -33,6 +33,7 @@ class COO(SparseArray):
         self._coords = None  # device [ndim, nnz]
         self._data = None    # device [nnz]
         self._keys = None    # device sorted linear keys (cache)
+        self._idx_vis = None  # index dtype shown to the caller when it is not the device one (int32 / int64)
 
         if isinstance(coords, COO):
             if data is not None or shape is not None:
@@ -54,7 +55,7 @@ class COO(SparseArray):
         if dev_in:
             t = D.torch()
             if not D.is_device_tensor(coords):
-                coords = D.upload(np.asarray(coords))
+                coords = D.upload_index(np.asarray(coords))
             if not D.is_device_tensor(data):
                 data = D.upload(np.asarray(data))
             if coords.dim() == 1:
@@ -78,6 +79,10 @@ class COO(SparseArray):
                 data = np.broadcast_to(data, coords.shape[1])
             if data.ndim != 1:
                 raise ValueError("`data` must be a scalar or 1-dimensional.")
+            if coords.dtype.kind not in "iu":
+                coords = coords.astype(np.intp)
+            if D.device_index_dtype(coords.dtype) != coords.dtype:
+                self._idx_vis = coords.dtype
             self._coords_np, self._data_np = coords, data
             nnz, ndim_c = int(coords.shape[1]), int(coords.shape[0])
             self._dtype = data.dtype
@@ -98,10 +103,13 @@ class COO(SparseArray):
         if idx_dtype:
             if not can_store(idx_dtype, max(shape) if shape else 0):
                 raise ValueError(f"cannot cast array with shape {shape} to dtype {idx_dtype}.")
+            idx_dtype = np.dtype(idx_dtype)
+            dev_dt = D.device_index_dtype(idx_dtype)
+            self._idx_vis = idx_dtype if dev_dt != idx_dtype else None
             if self._coords_np is not None:
                 self._coords_np = self._coords_np.astype(idx_dtype)
             else:
-                self._coords = Kn.cast(self._coords, idx_dtype)
+                self._coords = Kn.cast(self._coords, dev_dt)
         if self.shape:
             dlen = int(self._data.shape[0]) if self._data is not None else len(self._data_np)
             if dlen != nnz:
@@ -119,6 +127,7 @@ class COO(SparseArray):
         SparseArray.__init__(self, other.shape, fill_value=None)
         self._coords_np, self._data_np = other._coords_np, other._data_np
         self._coords, self._data, self._keys = other._coords, other._data, other._keys
+        self._idx_vis = other._idx_vis
         self._dtype = other._dtype
         self.fill_value = other.fill_value
 
@@ -135,6 +144,7 @@ class COO(SparseArray):
         SparseArray.__init__(self, tuple(int(s) for s in shape), fill_value=None)
         self._coords_np = self._data_np = None
         self._coords, self._data, self._keys = coords, data, keys
+        self._idx_vis = None
         self._dtype = D.np_dtype(data)
         self.fill_value = self._dtype.type(0 if fill_value is None else fill_value)
         return self
@@ -163,13 +173,22 @@ class COO(SparseArray):
     def _from_dense_device(cls, xd, shape, fill_value, idx_dtype=None):
         n = prod(shape)
         flat = xd.reshape(1, n)
-        if np.dtype(D.np_dtype(xd)).type(fill_value).tobytes() == b"\0" * xd.element_size():
+        if D.np_dtype(xd) not in D._CODES:
+            # storage-only dtypes (narrow / unsigned integers, float16, complex): element-size generic flag + compact
+            flags = Kn.flag_not_fill(flat.reshape(-1), fill_value)
+            pos, total = Kn.scan_flags(flags)
+            keys = Kn.compact(Kn.iota(n), flags, pos, total)
+            data = Kn.compact(flat.reshape(-1), flags, pos, total)
+        elif np.dtype(D.np_dtype(xd)).type(fill_value).tobytes() == b"\0" * xd.element_size():
             _, keys, data, _ = Kn.dense_to_csr(flat, mode=1, want_indptr=False)
         else:
             flags = Kn.flag_not_fill(flat.reshape(-1), fill_value)
             _, keys, data, _ = Kn.dense_to_csr(flat, flags=flags.reshape(1, n), want_indptr=False)
-        coords = Kn.unravel(keys, shape, idx_dtype or np.int64)
-        return cls._from_device(coords, data, shape, fill_value, keys=keys)
+        dev_dt = D.device_index_dtype(idx_dtype or np.int64)
+        out = cls._from_device(Kn.unravel(keys, shape, dev_dt), data, shape, fill_value, keys=keys)
+        if idx_dtype is not None and np.dtype(idx_dtype) != dev_dt:
+            out._idx_vis = np.dtype(idx_dtype)
+        return out
 
     @classmethod
     def from_scipy_sparse(cls, x, /, *, fill_value=None):
@@ -198,7 +217,7 @@ class COO(SparseArray):
         for (a user reading `.coords`, or an axis permutation)."""
         if self._data is None:
             D.require_device()
-            self._coords = D.upload(self._coords_np)
+            self._coords = D.upload_index(self._coords_np)
             self._data = D.upload(self._data_np)
         if self._coords is None:
             self._coords = Kn.unravel(self._keys, self.shape, np.int64)
@@ -211,6 +230,8 @@ class COO(SparseArray):
         return self._data
 
     def _idx_dtype(self):
+        if self._idx_vis is not None:
+            return self._idx_vis
         if self._coords is not None:
             return D.np_dtype(self._coords)
         if self._coords_np is not None:
@@ -220,7 +241,8 @@ class COO(SparseArray):
     @property
     def coords(self):
         if self._coords_np is None:
-            self._coords_np = D.download(self._dev()[0])
+            c = D.download(self._dev()[0])
+            self._coords_np = c.astype(self._idx_vis) if self._idx_vis is not None else c
         return self._coords_np
 
     @property
@@ -393,8 +415,10 @@ class COO(SparseArray):
             if total != self.nnz:
                 return COO._from_device(None, Kn.compact(vals, flags, pos, total), self.shape, fill,
                                         keys=Kn.compact(self.sorted_keys(), flags, pos, total))
-        return COO._from_device(self._coords, vals, self.shape, fill,
-                                keys=self.sorted_keys() if self._coords is None else self._keys)
+        out = COO._from_device(self._coords, vals, self.shape, fill,
+                               keys=self.sorted_keys() if self._coords is None else self._keys)
+        out._idx_vis = self._idx_vis
+        return out
 
     def linear_loc(self):
         return D.download(self.sorted_keys())

@@ -43,6 +43,11 @@ def _np2t():
             np.dtype("uint8"): t.uint8,
             np.dtype("bool"): t.bool,
         }
+        # storage-only dtypes: containers hold them and every structural (element-size generic) kernel moves them;
+        # arithmetic on them raises TypeError in the op layer (outside the CUDA dtype matrix)
+        for name in ("uint16", "uint32", "uint64", "float16", "complex64", "complex128"):
+            if hasattr(t, name):
+                _NP2T[np.dtype(name)] = getattr(t, name)
     return _NP2T
 
 
@@ -61,6 +66,19 @@ def dtype_code(dt) -> int:
         raise TypeError(f"sparse_b200: dtype {dt} is outside the supported CUDA dtype matrix "
                         f"({', '.join(str(k) for k in _CODES)})")
     return _CODES[dt]
+
+
+# b2s_cast alone also takes the storage-only integer widths (include/sparse_b200.h: B2S_I8 .. B2S_U64)
+_CAST_CODES = {**_CODES, np.dtype("int8"): 5, np.dtype("int16"): 6, np.dtype("uint8"): 7, np.dtype("uint16"): 8,
+               np.dtype("uint32"): 9, np.dtype("uint64"): 10}
+
+
+def cast_code(dt) -> int:
+    dt = np.dtype(dt)
+    if dt not in _CAST_CODES:
+        raise TypeError(f"sparse_b200: no device cast to / from dtype {dt} "
+                        f"({', '.join(str(k) for k in _CAST_CODES)})")
+    return _CAST_CODES[dt]
 
 
 def torch_dtype(dt):
@@ -124,13 +142,30 @@ def upload(arr, dtype=None):
     a = np.asarray(arr)
     if dtype is not None and a.dtype != np.dtype(dtype):
         a = a.astype(dtype)
-    if a.dtype.kind == "u" and a.dtype.itemsize > 1:  # uintp coords etc.
-        a = a.astype(np.int64)
     torch_dtype(a.dtype)
     a = np.ascontiguousarray(a)
     if not a.flags.writeable:
         a = a.copy()
     return t.from_numpy(a).to(device(), non_blocking=True)
+
+
+def device_index_dtype(dt) -> np.dtype:
+    """Index arrays live on the device as int32 or int64 only (what the kernels take); narrower or unsigned index
+    dtypes a caller asks for are a host-side view of the same numbers (`_idx_vis` on the containers)."""
+    dt = np.dtype(dt)
+    if dt in (np.dtype(np.int32), np.dtype(np.int64)):
+        return dt
+    if dt.kind in "iu" and (dt.itemsize < 4):
+        return np.dtype(np.int32)
+    return np.dtype(np.int64)
+
+
+def upload_index(arr):
+    """Host index array (coords / indices / indptr) -> device int32 / int64 tensor."""
+    a = np.asarray(arr)
+    if a.dtype.kind not in "iub":
+        raise ValueError(f"index arrays must be integers, got {a.dtype}")
+    return upload(a, device_index_dtype(a.dtype))
 
 
 _PIN_MIN_BYTES = 1 << 20

@@ -21,6 +21,7 @@ class GCXS(SparseArray):
     def __init__(self, arg, shape=None, compressed_axes=None, prune=False, fill_value=None, idx_dtype=None):
         self._data_np = self._indices_np = self._indptr_np = None
         self._data = self._indices = self._indptr = None
+        self._idx_vis = None  # index dtype shown to the caller when it is not the device one (int32 / int64)
         if _is_scipy_sparse(arg):
             arg = GCXS.from_scipy_sparse(arg)
         if isinstance(arg, np.ndarray):
@@ -56,6 +57,8 @@ class GCXS(SparseArray):
             self._data_np = np.asarray(data)
             self._indices_np = np.asarray(indices)
             self._indptr_np = np.asarray(indptr)
+            if self._indices_np.dtype.kind in "iu" and D.device_index_dtype(self._indices_np.dtype) != self._indices_np.dtype:
+                self._idx_vis = self._indices_np.dtype
             if self._data_np.ndim != 1:
                 raise ValueError("data must be a scalar or 1-dimensional.")
             self._dtype = self._data_np.dtype
@@ -71,6 +74,7 @@ class GCXS(SparseArray):
         SparseArray.__init__(self, o.shape, fill_value=None)
         self._data_np, self._indices_np, self._indptr_np = o._data_np, o._indices_np, o._indptr_np
         self._data, self._indices, self._indptr = o._data, o._indices, o._indptr
+        self._idx_vis = o._idx_vis
         self._dtype = o._dtype
         self._compressed_axes = o._compressed_axes
         self.fill_value = o.fill_value
@@ -85,6 +89,7 @@ class GCXS(SparseArray):
         SparseArray.__init__(self, tuple(int(s) for s in shape), fill_value=None)
         self._data_np = self._indices_np = self._indptr_np = None
         self._data, self._indices, self._indptr = data, indices, indptr
+        self._idx_vis = None
         self._dtype = D.np_dtype(data)
         self._compressed_axes = tuple(int(a) for a in compressed_axes) if compressed_axes is not None else None
         self.fill_value = self._dtype.type(0 if fill_value is None else fill_value)
@@ -145,12 +150,12 @@ class GCXS(SparseArray):
         if self._data is None:
             D.require_device()
             self._data = D.upload(self._data_np)
-            self._indices = D.upload(self._indices_np)
+            self._indices = D.upload_index(self._indices_np)
         if self._indptr is None:
             ip = np.asarray(self._indptr_np)
             if ip.size == 0:
                 ip = np.zeros(0, dtype=np.int64)
-            self._indptr = D.upload(ip.astype(D.np_dtype(self._indices)) if ip.dtype != D.np_dtype(self._indices) else ip)
+            self._indptr = D.upload_index(ip.astype(D.np_dtype(self._indices)) if ip.dtype != D.np_dtype(self._indices) else ip)
         if self._indptr.dtype != self._indices.dtype:
             self._indptr = Kn.cast(self._indptr, D.np_dtype(self._indices))
         return self._data, self._indices, self._indptr
@@ -164,13 +169,15 @@ class GCXS(SparseArray):
     @property
     def indices(self):
         if self._indices_np is None:
-            self._indices_np = D.download(self._indices)
+            a = D.download(self._indices)
+            self._indices_np = a.astype(self._idx_vis) if self._idx_vis is not None else a
         return self._indices_np
 
     @property
     def indptr(self):
         if self._indptr_np is None:
-            self._indptr_np = D.download(self._indptr)
+            a = D.download(self._indptr)
+            self._indptr_np = a.astype(self._idx_vis) if self._idx_vis is not None else a
         return self._indptr_np
 
     def _has_long_rows(self):
@@ -220,7 +227,18 @@ class GCXS(SparseArray):
         row_size, col_size = prod(reordered_shape[:axisptr]), prod(reordered_shape[axisptr:])
         check_linear_range(x.shape)
         data = x._data_dev()
-        idt = idx_dtype or x._idx_dtype()
+        # index dtype (compressed.py:52-61): the caller's, else the COO's unless it cannot hold max(rows, cols, nnz)
+        need = max(row_size, col_size, x.nnz)
+        if idx_dtype is not None:
+            idt = np.dtype(idx_dtype)
+            if not can_store(idt, need):
+                raise ValueError(f"cannot store array with the compressed shape {(row_size, col_size)} and nnz "
+                                 f"{x.nnz} with dtype {idt}.")
+        else:
+            idt = np.dtype(x._idx_dtype())
+            if not can_store(idt, need):
+                idt = np.dtype(np.min_scalar_type(need))
+        vis, idt = idt, D.device_index_dtype(idt)
         if axis_order == list(range(x.ndim)):
             keys = x.sorted_keys()
         else:
@@ -235,7 +253,9 @@ class GCXS(SparseArray):
                 keys, perm = Kn.sort_keys(keys, key_bits(x.size))
                 data = Kn.gather(data, perm)
         _, indices, indptr = Kn.csr_from_keys(keys, row_size, col_size, idt)
-        return cls._from_device(data, indices, indptr, x.shape, compressed_axes, x.fill_value)
+        out = cls._from_device(data, indices, indptr, x.shape, compressed_axes, x.fill_value)
+        out._idx_vis = vis if vis != idt else None
+        return out
 
     def tocoo(self):
         """compressed.py:425-460: rows from indptr, then undo the axis reordering (COO rebuild + sort)."""

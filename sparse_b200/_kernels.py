@@ -42,10 +42,10 @@ def _i32arr(vals):
 
 
 def _scalar_bytes(value, dtype) -> ctypes.Array:
-    """8-byte host buffer holding `value` as `dtype` (for fill values / scalars)."""
+    """16-byte host buffer holding `value` as `dtype` (for fill values / scalars; complex128 is the widest)."""
     a = np.zeros(1, dtype=np.dtype(dtype))
     a[0] = value
-    buf = (ctypes.c_uint8 * 8)()
+    buf = (ctypes.c_uint8 * 16)()
     ctypes.memmove(buf, a.ctypes.data, a.itemsize)
     return buf
 
@@ -374,7 +374,7 @@ def cast(x, dtype):
     if not x.is_contiguous():
         x = x.contiguous()
     out = t.empty(x.shape, dtype=D.torch_dtype(dst), device=x.device)
-    _lib.check(_lib.load().b2s_cast(i32(D.dtype_code(src)), i32(D.dtype_code(dst)), vp(D.ptr(x)), i64(x.numel()),
+    _lib.check(_lib.load().b2s_cast(i32(D.cast_code(src)), i32(D.cast_code(dst)), vp(D.ptr(x)), i64(x.numel()),
                                    vp(D.ptr(out)), _sp()))
     return out
 

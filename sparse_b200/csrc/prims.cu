@@ -17,6 +17,12 @@
 
 namespace b2s {
 
+// 16-byte element (complex128) for the element-size generic movers: moved as one 128-bit word, compared bitwise
+struct alignas(16) U128 {
+    uint64_t lo, hi;
+    __host__ __device__ bool operator!=(const U128 &o) const { return lo != o.lo || hi != o.hi; }
+};
+
 constexpr int kMaxDims = 16;
 struct DimPack {
     int64_t stride[kMaxDims];  // multiplier of each *input* row (0 for dropped rows)
@@ -411,7 +417,9 @@ int b2s_gather(int elem_bytes, const void *in_dev, const int64_t *perm_dev, int6
     cudaStream_t s = (cudaStream_t)stream;
     switch (elem_bytes) {
         case 1: gather_kernel<uint8_t><<<grid_for(n), 256, 0, s>>>((const uint8_t *)in_dev, perm_dev, n, (uint8_t *)out_dev); break;
+        case 2: gather_kernel<uint16_t><<<grid_for(n), 256, 0, s>>>((const uint16_t *)in_dev, perm_dev, n, (uint16_t *)out_dev); break;
         case 4: gather_kernel<uint32_t><<<grid_for(n), 256, 0, s>>>((const uint32_t *)in_dev, perm_dev, n, (uint32_t *)out_dev); break;
+        case 16: gather_kernel<U128><<<grid_for(n), 256, 0, s>>>((const U128 *)in_dev, perm_dev, n, (U128 *)out_dev); break;
         case 8: gather_kernel<uint64_t><<<grid_for(n), 256, 0, s>>>((const uint64_t *)in_dev, perm_dev, n, (uint64_t *)out_dev); break;
         default: set_error("gather: elem_bytes %d", elem_bytes); return B2S_ERR_UNSUPPORTED;
     }
@@ -432,7 +440,9 @@ int b2s_flag_not_fill(int elem_bytes, const void *data_dev, int64_t n, const voi
     cudaStream_t s = (cudaStream_t)stream;
     switch (elem_bytes) {
         case 1: { uint8_t f; memcpy(&f, fill_host, 1); flag_not_fill_kernel<uint8_t><<<grid_for(n), 256, 0, s>>>((const uint8_t *)data_dev, n, f, flags_out_dev); break; }
+        case 2: { uint16_t f; memcpy(&f, fill_host, 2); flag_not_fill_kernel<uint16_t><<<grid_for(n), 256, 0, s>>>((const uint16_t *)data_dev, n, f, flags_out_dev); break; }
         case 4: { uint32_t f; memcpy(&f, fill_host, 4); flag_not_fill_kernel<uint32_t><<<grid_for(n), 256, 0, s>>>((const uint32_t *)data_dev, n, f, flags_out_dev); break; }
+        case 16: { U128 f; memcpy(&f, fill_host, 16); flag_not_fill_kernel<U128><<<grid_for(n), 256, 0, s>>>((const U128 *)data_dev, n, f, flags_out_dev); break; }
         case 8: { uint64_t f; memcpy(&f, fill_host, 8); flag_not_fill_kernel<uint64_t><<<grid_for(n), 256, 0, s>>>((const uint64_t *)data_dev, n, f, flags_out_dev); break; }
         default: set_error("flag_not_fill: elem_bytes %d", elem_bytes); return B2S_ERR_UNSUPPORTED;
     }
@@ -483,7 +493,9 @@ int b2s_compact(int elem_bytes, const void *in_dev, const uint8_t *flags_dev, co
     cudaStream_t s = (cudaStream_t)stream;
     switch (elem_bytes) {
         case 1: compact_kernel<uint8_t><<<grid_for(n), 256, 0, s>>>((const uint8_t *)in_dev, flags_dev, pos_dev, n, (uint8_t *)out_dev); break;
+        case 2: compact_kernel<uint16_t><<<grid_for(n), 256, 0, s>>>((const uint16_t *)in_dev, flags_dev, pos_dev, n, (uint16_t *)out_dev); break;
         case 4: compact_kernel<uint32_t><<<grid_for(n), 256, 0, s>>>((const uint32_t *)in_dev, flags_dev, pos_dev, n, (uint32_t *)out_dev); break;
+        case 16: compact_kernel<U128><<<grid_for(n), 256, 0, s>>>((const U128 *)in_dev, flags_dev, pos_dev, n, (U128 *)out_dev); break;
         case 8: compact_kernel<uint64_t><<<grid_for(n), 256, 0, s>>>((const uint64_t *)in_dev, flags_dev, pos_dev, n, (uint64_t *)out_dev); break;
         default: set_error("compact: elem_bytes %d", elem_bytes); return B2S_ERR_UNSUPPORTED;
     }
@@ -495,7 +507,9 @@ int b2s_compact_rows(int elem_bytes, int nrows, const void *in_dev, int64_t in_s
                      const int64_t *pos_dev, int64_t n, void *out_dev, int64_t out_stride, void *stream) {
     if (n == 0 || nrows == 0) return B2S_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (elem_bytes == 4)
+    if (elem_bytes == 2)
+        compact_rows_kernel<uint16_t><<<grid_for(n), 256, 0, s>>>(nrows, (const uint16_t *)in_dev, in_stride, flags_dev, pos_dev, n, (uint16_t *)out_dev, out_stride);
+    else if (elem_bytes == 4)
         compact_rows_kernel<uint32_t><<<grid_for(n), 256, 0, s>>>(nrows, (const uint32_t *)in_dev, in_stride, flags_dev, pos_dev, n, (uint32_t *)out_dev, out_stride);
     else if (elem_bytes == 8)
         compact_rows_kernel<uint64_t><<<grid_for(n), 256, 0, s>>>(nrows, (const uint64_t *)in_dev, in_stride, flags_dev, pos_dev, n, (uint64_t *)out_dev, out_stride);
@@ -587,6 +601,12 @@ int b2s_cast(int src_dtype, int dst_dtype, const void *in_dev, int64_t n, void *
             case B2S_I32: B2S_C(S, int32_t); break;                         \
             case B2S_I64: B2S_C(S, int64_t); break;                         \
             case B2S_BOOL: B2S_C(S, bool); break;                           \
+            case B2S_I8: B2S_C(S, int8_t); break;                           \
+            case B2S_I16: B2S_C(S, int16_t); break;                         \
+            case B2S_U8: B2S_C(S, uint8_t); break;                          \
+            case B2S_U16: B2S_C(S, uint16_t); break;                        \
+            case B2S_U32: B2S_C(S, uint32_t); break;                        \
+            case B2S_U64: B2S_C(S, uint64_t); break;                        \
             default: set_error("cast: dst dtype %d", dst_dtype); return B2S_ERR_UNSUPPORTED; \
         }                                                                   \
         B2S_CHECK_LAUNCH();                                                 \
@@ -597,6 +617,13 @@ int b2s_cast(int src_dtype, int dst_dtype, const void *in_dev, int64_t n, void *
     B2S_ROW(B2S_I32, int32_t)
     B2S_ROW(B2S_I64, int64_t)
     B2S_ROW(B2S_BOOL, bool)
+    // storage-only integer widths: the cast is their way into (and out of) the compute dtype matrix
+    B2S_ROW(B2S_I8, int8_t)
+    B2S_ROW(B2S_I16, int16_t)
+    B2S_ROW(B2S_U8, uint8_t)
+    B2S_ROW(B2S_U16, uint16_t)
+    B2S_ROW(B2S_U32, uint32_t)
+    B2S_ROW(B2S_U64, uint64_t)
 #undef B2S_ROW
 #undef B2S_C
     set_error("cast: src dtype %d", src_dtype);
@@ -608,7 +635,9 @@ int b2s_scatter(int elem_bytes, const void *data_dev, const int64_t *keys_dev, i
     cudaStream_t s = (cudaStream_t)stream;
     switch (elem_bytes) {
         case 1: scatter_kernel<uint8_t><<<grid_for(n), 256, 0, s>>>((const uint8_t *)data_dev, keys_dev, n, (uint8_t *)out_dev); break;
+        case 2: scatter_kernel<uint16_t><<<grid_for(n), 256, 0, s>>>((const uint16_t *)data_dev, keys_dev, n, (uint16_t *)out_dev); break;
         case 4: scatter_kernel<uint32_t><<<grid_for(n), 256, 0, s>>>((const uint32_t *)data_dev, keys_dev, n, (uint32_t *)out_dev); break;
+        case 16: scatter_kernel<U128><<<grid_for(n), 256, 0, s>>>((const U128 *)data_dev, keys_dev, n, (U128 *)out_dev); break;
         case 8: scatter_kernel<uint64_t><<<grid_for(n), 256, 0, s>>>((const uint64_t *)data_dev, keys_dev, n, (uint64_t *)out_dev); break;
         default: set_error("scatter: elem_bytes %d", elem_bytes); return B2S_ERR_UNSUPPORTED;
     }
@@ -621,7 +650,9 @@ int b2s_fill(int elem_bytes, void *out_dev, int64_t n, const void *value_host, v
     cudaStream_t s = (cudaStream_t)stream;
     switch (elem_bytes) {
         case 1: { uint8_t v; memcpy(&v, value_host, 1); fill_kernel<uint8_t><<<grid_for(n), 256, 0, s>>>((uint8_t *)out_dev, n, v); break; }
+        case 2: { uint16_t v; memcpy(&v, value_host, 2); fill_kernel<uint16_t><<<grid_for(n), 256, 0, s>>>((uint16_t *)out_dev, n, v); break; }
         case 4: { uint32_t v; memcpy(&v, value_host, 4); fill_kernel<uint32_t><<<grid_for(n), 256, 0, s>>>((uint32_t *)out_dev, n, v); break; }
+        case 16: { U128 v; memcpy(&v, value_host, 16); fill_kernel<U128><<<grid_for(n), 256, 0, s>>>((U128 *)out_dev, n, v); break; }
         case 8: { uint64_t v; memcpy(&v, value_host, 8); fill_kernel<uint64_t><<<grid_for(n), 256, 0, s>>>((uint64_t *)out_dev, n, v); break; }
         default: set_error("fill: elem_bytes %d", elem_bytes); return B2S_ERR_UNSUPPORTED;
     }
@@ -639,7 +670,9 @@ int b2s_transpose_dense(int elem_bytes, const void *in_dev, int64_t rows, int64_
     dim3 block(32, 8);
     switch (elem_bytes) {
         case 1: transpose_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t *)in_dev, rows, cols, ld_in, (uint8_t *)out_dev, ld_out); break;
+        case 2: transpose_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t *)in_dev, rows, cols, ld_in, (uint16_t *)out_dev, ld_out); break;
         case 4: transpose_kernel<uint32_t><<<grid, block, 0, s>>>((const uint32_t *)in_dev, rows, cols, ld_in, (uint32_t *)out_dev, ld_out); break;
+        case 16: transpose_kernel<U128><<<grid, block, 0, s>>>((const U128 *)in_dev, rows, cols, ld_in, (U128 *)out_dev, ld_out); break;
         case 8: transpose_kernel<uint64_t><<<grid, block, 0, s>>>((const uint64_t *)in_dev, rows, cols, ld_in, (uint64_t *)out_dev, ld_out); break;
         default: set_error("transpose: elem_bytes %d", elem_bytes); return B2S_ERR_UNSUPPORTED;
     }

@@ -40,15 +40,15 @@ def n(x):
 
 def T(a):
     a = np.ascontiguousarray(a)
-    if a.dtype.kind == "u" and a.itemsize > 1:
-        a = a.astype(np.int64)
     return torch.from_numpy(a.copy())
 
 
 def bits_ne(a, fill):
     a = np.ascontiguousarray(a)
     f = np.array([fill], dtype=a.dtype)
-    w = {1: np.uint8, 4: np.uint32, 8: np.uint64}[a.itemsize]
+    if a.itemsize == 16:
+        return (a.view(np.uint64).reshape(-1, 2) != f.view(np.uint64)).any(axis=1)
+    w = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[a.itemsize]
     return a.view(w) != f.view(w)[0]
 
 
