@@ -50,7 +50,8 @@ def _bitor_raw(a, b):
 _BINARY = {
     np.add: 0, np.subtract: 1, np.multiply: 2, np.true_divide: 3, np.maximum: 4, np.minimum: 5, np.fmax: 6,
     np.fmin: 7, np.power: 8, np.floor_divide: 9, np.remainder: 10, np.bitwise_and: 11, np.bitwise_or: 12,
-    np.bitwise_xor: 13, nan_replace: 14, _sel_x: 15, _sel_y: 16, _bitor_raw: 17, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
+    np.bitwise_xor: 13, nan_replace: 14, _sel_x: 15, _sel_y: 16, _bitor_raw: 17, np.left_shift: 18,
+    np.right_shift: 19, np.greater: 32, np.greater_equal: 33, np.less: 34, np.less_equal: 35, np.equal: 36,
     np.not_equal: 37, np.logical_and: 38, np.logical_or: 39, np.logical_xor: 40,
 }
 _UNARY = {

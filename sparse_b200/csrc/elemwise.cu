@@ -28,6 +28,8 @@ enum BinOp {
     OP_SEL_X = 15,   // a != 0 ? b : +0
     OP_SEL_Y = 16,   // a != 0 ? +0 : b
     OP_BITOR_RAW = 17,
+    // integer shifts with NumPy's out-of-range rule: a count outside [0, bits) gives 0 (or -1 for a negative a >> n)
+    OP_LSHIFT = 18, OP_RSHIFT = 19,
     // predicates (bool output)
     OP_GT = 32, OP_GE = 33, OP_LT = 34, OP_LE = 35, OP_EQ = 36, OP_NE = 37, OP_LAND = 38, OP_LOR = 39, OP_LXOR = 40
 };
@@ -133,6 +135,14 @@ __device__ __forceinline__ T bin_apply(int op, T a, T b) {
             case OP_BAND: return a & b;
             case OP_BOR: return a | b;
             case OP_BXOR: return a ^ b;
+            case OP_LSHIFT: {
+                using U = typename std::make_unsigned<T>::type;
+                return ((U)b < (U)(8 * sizeof(T))) ? (T)((U)a << (U)b) : T(0);
+            }
+            case OP_RSHIFT: {
+                using U = typename std::make_unsigned<T>::type;
+                return ((U)b < (U)(8 * sizeof(T))) ? (T)(a >> b) : (a < 0 ? T(-1) : T(0));
+            }
             case OP_NANREPLACE: return a;
             default: return T(0);
         }

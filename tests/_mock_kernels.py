@@ -23,6 +23,7 @@ _BIN = {0: np.add, 1: np.subtract, 2: np.multiply, 3: np.true_divide, 4: np.maxi
         15: lambda a, b: np.where(a != 0, b, np.asarray(b).dtype.type(0)),
         16: lambda a, b: np.where(a != 0, np.asarray(b).dtype.type(0), b),
         17: lambda a, b: (np.asarray(a).view(f"u{np.asarray(a).dtype.itemsize}") | np.asarray(b).view(f"u{np.asarray(b).dtype.itemsize}")).view(np.asarray(a).dtype),
+        18: np.left_shift, 19: np.right_shift,
         32: np.greater, 33: np.greater_equal, 34: np.less, 35: np.less_equal, 36: np.equal,
         37: np.not_equal, 38: np.logical_and, 39: np.logical_or, 40: np.logical_xor}
 _UN = {0: np.negative, 1: np.absolute, 2: np.sqrt, 3: np.square, 4: np.sign, 5: np.exp, 6: np.expm1, 7: np.log,

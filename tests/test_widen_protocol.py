@@ -161,3 +161,23 @@ def test_csr_csc_classes(sp):
         assert np.array_equal(cls.from_numpy(d).todense(), d)
     full = sp.full((10, 20), fill_value=1.0, format="csr")
     assert full.mT.shape == (20, 10) and full.mT.fill_value == 1.0
+
+
+def test_integer_shifts(sp):
+    """tests/test_elemwise.py:534-640 upstream (bitshift binary / scalar / in-place)."""
+    rng = np.random.default_rng(0)
+    x = (sp.random((4, 5), density=0.5, random_state=rng) * 100).astype(np.int64)
+    y = (sp.random((4, 5), density=0.5, random_state=rng) * 10).astype(np.int64)
+    d, e = x.todense(), y.todense()
+    assert np.array_equal((x << y).todense(), d << e)
+    assert np.array_equal((x >> y).todense(), d >> e)
+    assert np.array_equal((x << 3).todense(), d << 3) and np.array_equal((x >> 1).todense(), d >> 1)
+    big = sp.COO.from_numpy(np.array([1, -8, 5, 0], dtype=np.int64))
+    cnt = sp.COO.from_numpy(np.array([70, 65, 63, 2], dtype=np.int64))  # counts >= 64: NumPy gives 0 / -1
+    with np.errstate(all="ignore"):
+        assert np.array_equal((big << cnt).todense(), big.todense() << cnt.todense())
+        assert np.array_equal((big >> cnt).todense(), big.todense() >> cnt.todense())
+    x <<= y
+    assert np.array_equal(x.todense(), d << e)
+    with pytest.raises(TypeError):
+        x << 1.5
