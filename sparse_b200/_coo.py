@@ -408,7 +408,12 @@ class COO(SparseArray):
         if self.dtype == dtype:
             return COO._from_device(self._coords, data.clone(), self.shape, fill,
                                     keys=self.sorted_keys() if self._coords is None else self._keys)
-        vals = Kn.cast(data, dtype)
+        if self.dtype.kind == "c" or dtype.kind == "c":
+            from ._complex import cast_values
+
+            vals = cast_values(data, self.dtype, dtype)
+        else:
+            vals = Kn.cast(data, dtype)
         if self.nnz and not np.can_cast(self.dtype, dtype, casting="safe"):
             flags = Kn.flag_not_fill(vals, fill)
             pos, total = Kn.scan_flags(flags)

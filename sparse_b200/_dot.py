@@ -320,6 +320,10 @@ def _spgemm_csr(a, b, out_shape, dtr, *, wide=False):
 
 def _dot(a, b, return_type=None):
     """Format dispatch of _common.py:339-503 (2-D operands)."""
+    from . import _complex as C
+
+    if (C.is_complex(a) or C.is_complex(b)) and not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray)):
+        return C.dot_complex(_dot, a, b, return_type)  # four real products on the planes
     out_shape = (a.shape[0], b.shape[1])
     if builtins.all(isinstance(arr, SparseArray) for arr in [a, b]) and builtins.any(
             isinstance(arr, GCXS) for arr in [a, b]):

@@ -10,6 +10,7 @@ TypeError -- there is no CPU fallback.
 """
 from __future__ import annotations
 
+from builtins import any as builtins_any
 from itertools import zip_longest
 
 import numpy as np
@@ -235,6 +236,20 @@ class _Elemwise:
             if self.dtype is not None:
                 res = res.astype(self.dtype)
             return COO.from_numpy(res) if res.ndim == 0 else res
+        from . import _complex as C
+
+        if isinstance(self.func, np.ufunc) and builtins_any(C.is_complex(a) for a in self.args) \
+                or (self.dtype is not None and np.dtype(self.dtype).kind == "c"):
+            out = C.elemwise_complex(self.func, self.args)
+            if out is NotImplemented:
+                raise TypeError(f"sparse_b200: {getattr(self.func, '__name__', self.func)} on complex operands is "
+                                "outside the CUDA op set (add, subtract, multiply, divide, negative, conjugate, "
+                                "absolute, square, equal, not_equal, isnan, isinf, isfinite)")
+            if isinstance(out, SparseArray):
+                if self.dtype is not None and np.dtype(self.dtype) != out.dtype:
+                    out = out.astype(self.dtype)
+                return out.asformat(self.out_type, **self.out_kwargs)
+            return out
         if self.dtype is not None and isinstance(self.func, np.ufunc):
             # ufunc(..., dtype=T) (what `out=` turns into, _sparse_array.py:344) selects the T loop: array operands
             # are cast to T BEFORE the operation.  Predicates (bool result whatever the input) keep their operands.

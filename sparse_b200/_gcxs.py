@@ -362,7 +362,12 @@ class GCXS(SparseArray):
         if not np.can_cast(self.dtype, dtype, casting=casting):
             raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
         data, indices, indptr = self._dev()
-        out = GCXS._from_device(Kn.cast(data, dtype) if dtype != self.dtype else data.clone(), indices, indptr,
+        if dtype != self.dtype and (self.dtype.kind == "c" or dtype.kind == "c"):
+            from ._complex import cast_values
+
+            data = cast_values(data, self.dtype, dtype)
+        out = GCXS._from_device(Kn.cast(data, dtype) if dtype != D.np_dtype(data) else
+                                (data.clone() if dtype == self.dtype else data), indices, indptr,
                                 self.shape, self.compressed_axes, np.asarray(self.fill_value).astype(dtype)[()])
         if dtype != self.dtype and not np.can_cast(self.dtype, dtype, casting="safe"):
             out._prune()

@@ -24,6 +24,11 @@ _RED_DTYPES = (np.dtype("float32"), np.dtype("float64"), np.dtype("int32"), np.d
 def reduce_impl(x, method, axis=(0,), keepdims=False, **kwargs):
     from ._gcxs import GCXS
 
+    if x.dtype.kind == "c":
+        from ._complex import reduce_complex
+
+        ax = normalize_axis(axis, x.ndim)
+        return reduce_complex(x, method, ax, keepdims, **{k: v for k, v in kwargs.items() if v is not None})
     if method not in _RED:
         raise TypeError(f"sparse_b200: reduction with {getattr(method, '__name__', method)!r} is not in the CUDA op set "
                         f"({', '.join(sorted(m.__name__ for m in _RED))}); there is no CPU fallback.")

@@ -318,12 +318,21 @@ class SparseArray(NDArrayOperatorsMixin):
     # ---- misc -----------------------------------------------------------------------------------------
     @property
     def real(self):
-        return self
+        """numpy.real: the array itself for real dtypes, the pruned real plane for complex ones."""
+        if self.dtype.kind != "c":
+            return self
+        from ._complex import planes
+
+        return np.positive(planes(self)[0])  # the unary pass drops the zeros stored in the plane
 
     @property
     def imag(self):
-        """Real dtypes: an all-zero array of the same dtype (numpy.imag)."""
-        return np.multiply(self, self.dtype.type(0)) if self._zero_fill() else np.subtract(self, self)
+        """numpy.imag: all zeros (same dtype) for real dtypes, the pruned imaginary plane for complex ones."""
+        if self.dtype.kind != "c":
+            return np.multiply(self, self.dtype.type(0)) if self._zero_fill() else np.subtract(self, self)
+        from ._complex import planes
+
+        return np.positive(planes(self)[1])
 
     def __complex__(self):
         return self._to_scalar(complex)

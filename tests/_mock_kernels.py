@@ -201,6 +201,7 @@ def scatter(data, keys, out):
 def cast(x, dtype):
     if D.np_dtype(x) == np.dtype(dtype):
         return x
+    D.cast_code(D.np_dtype(x)), D.cast_code(dtype)  # same TypeError as the real wrapper for dtypes b2s_cast lacks
     with np.errstate(all="ignore"):
         return T(n(x).astype(dtype))
 

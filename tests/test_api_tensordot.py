@@ -51,6 +51,7 @@ def test_errors(sp):
         sp.tensordot(x, y, axes=1)
     with pytest.raises(TypeError):
         sp.matmul(x, 3)
-    z = sp.COO(np.array([[0], [1]]), np.array([1 + 2j]), shape=(4, 2), has_duplicates=False, sorted=True)
+    z = sp.COO(np.array([[0], [1]]), np.array([1.5], dtype=np.float16), shape=(4, 2), has_duplicates=False,
+               sorted=True)  # float16 is storage-only: no arithmetic, no silent upcast
     with pytest.raises(TypeError, match="dtype"):
         sp.tensordot(x, z, axes=1)
