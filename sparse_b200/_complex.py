@@ -110,9 +110,7 @@ def combine(re, im, cdtype=None):
 
     if not isinstance(re, SparseArray) and not isinstance(im, SparseArray):
         if D.is_device_tensor(re) or D.is_device_tensor(im):
-            t = D.torch()
             shape = re.shape if D.is_device_tensor(re) else im.shape
-            dev = re.device if D.is_device_tensor(re) else im.device
             rdt = D.np_dtype(re if D.is_device_tensor(re) else im)
             if not D.is_device_tensor(re):
                 re = Kn.full(int(np.prod(shape)), re, rdt).reshape(shape)
@@ -188,12 +186,8 @@ def cast_values(data, src, dst):
 # ---------------------------------------------------------------------------------------------------------------
 # element-wise
 # ---------------------------------------------------------------------------------------------------------------
-def _z(p):
-    """Imaginary plane of a real operand: None stands for an exact zero."""
-    return p is not None
-
-
 def _add(x, y):
+    """x + y on planes; None stands for the exactly-zero imaginary plane of a real operand."""
     if x is None:
         return y
     if y is None:

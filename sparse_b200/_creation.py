@@ -177,8 +177,6 @@ def isnan(x, /):
 
 def isposinf(x, out=None):
     """_coo/common.py:937-961."""
-    from ._elemwise import elemwise
-
     res = np.logical_and(np.isinf(x), np.greater(x, 0))
     if out is not None:
         out._make_shallow_copy_of(res)

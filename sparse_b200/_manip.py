@@ -15,7 +15,6 @@ new key order differs from the stored one.  Nothing here touches values on the h
 from __future__ import annotations
 
 import builtins
-import operator
 from collections.abc import Iterable
 
 import numpy as np

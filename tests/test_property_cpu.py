@@ -290,3 +290,88 @@ def test_gcxs_views_match_numpy(data):
     tgt = data.draw(st.sampled_from([shape, (2,) + shape, tuple(3 if e == 1 else e for e in shape)]))
     assert np.array_equal(x.broadcast_to(tgt).todense(), np.broadcast_to(d, tgt))
     assert np.array_equal(g.astype(np.float32).todense(), d.astype(np.float32))
+
+
+# ---- array manipulation (sparse_b200/_manip.py): random shapes, axes, fill values --------------------------------------
+def _check(got, want):
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.array_equal(got.todense(), want)
+    c = got.asformat("coo")
+    # stored entries = everything that differs BITWISE from the fill value (a product -3 * 0 leaves a stored -0.0,
+    # as upstream's `equivalent` does)
+    same = (want == c.fill_value) & (np.signbit(want) == np.signbit(c.fill_value))
+    assert c.nnz == int(np.sum(~same))
+    if c.ndim and c.nnz:
+        assert np.all(np.diff(np.ravel_multi_index(tuple(c.coords), c.shape)) > 0)
+
+
+@SET
+@given(st.data())
+def test_concatenate_stack_match_numpy(data):
+    sp = _sp()
+    shape = data.draw(shapes)
+    fill = data.draw(st.sampled_from([0.0, 2.0]))
+    n = data.draw(st.integers(1, 3))
+    axis = data.draw(st.integers(-len(shape), len(shape) - 1))
+    parts, dense = [], []
+    for i in range(n):
+        s = list(shape)
+        s[axis] = data.draw(st.integers(0, 4))
+        a, d = _rand(tuple(s), data.draw(st.integers(0, 99)), data.draw(st.sampled_from([0.0, 0.4, 1.0])), fill)
+        parts.append(a if data.draw(st.booleans()) or a.ndim < 2 else sp.GCXS(a))
+        dense.append(d)
+    _check(sp.concatenate(parts, axis=axis), np.concatenate(dense, axis=axis))
+    same = [_rand(shape, data.draw(st.integers(0, 99)), 0.5, fill) for _ in range(n)]
+    sax = data.draw(st.integers(-len(shape) - 1, len(shape)))
+    _check(sp.stack([a for a, _ in same], axis=sax), np.stack([d for _, d in same], axis=sax))
+
+
+@SET
+@given(st.data())
+def test_roll_flip_pad_match_numpy(data):
+    sp = _sp()
+    shape = data.draw(shapes)
+    a, d = _rand(shape, data.draw(st.integers(0, 99)), data.draw(st.sampled_from([0.0, 0.5, 1.0])),
+                 data.draw(st.sampled_from([0.0, -1.0])))
+    axis = data.draw(st.one_of(st.none(), st.integers(-len(shape), len(shape) - 1)))
+    shift = data.draw(st.integers(-7, 7))
+    _check(sp.roll(a, shift, axis), np.roll(d, shift, axis))
+    _check(sp.flip(a, axis=axis), np.flip(d, axis=axis))
+    pw = [(data.draw(st.integers(0, 2)), data.draw(st.integers(0, 2))) for _ in shape]
+    _check(sp.pad(a, pw, constant_values=a.fill_value), np.pad(d, pw, constant_values=a.fill_value))
+
+
+@SET
+@given(st.data())
+def test_diagonal_take_match_numpy(data):
+    sp = _sp()
+    shape = data.draw(st.lists(st.integers(1, 5), min_size=2, max_size=4).map(tuple))
+    a, d = _rand(shape, data.draw(st.integers(0, 99)), data.draw(st.sampled_from([0.3, 1.0])))
+    a1 = data.draw(st.integers(0, len(shape) - 1))
+    a2 = data.draw(st.integers(0, len(shape) - 1).filter(lambda v: v != a1))
+    k = data.draw(st.integers(-4, 4))
+    _check(sp.diagonal(a, k, a1, a2), np.diagonal(d, k, a1, a2))
+    _check(sp.triu(a, k), np.triu(d, k))
+    _check(sp.tril(a, k), np.tril(d, k))
+    ax = data.draw(st.integers(0, len(shape) - 1))
+    idx = data.draw(st.lists(st.integers(-shape[ax], shape[ax] - 1), min_size=0, max_size=6))
+    _check(sp.take(a, idx, axis=ax), np.take(d, np.asarray(idx, dtype=np.int64), axis=ax))
+    index = tuple(np.asarray(idx, dtype=np.int64) if p == ax else
+                  data.draw(st.sampled_from([slice(None), slice(None, None, -1), slice(1, None)])) for p in range(len(shape)))
+    _check(a[index], d[index])
+
+
+@SET
+@given(st.data())
+def test_kron_tile_repeat_match_numpy(data):
+    sp = _sp()
+    sa = data.draw(st.lists(st.integers(1, 3), min_size=1, max_size=3).map(tuple))
+    sb = data.draw(st.lists(st.integers(1, 3), min_size=1, max_size=3).map(tuple))
+    a, da = _rand(sa, data.draw(st.integers(0, 99)), 0.5)
+    b, db = _rand(sb, data.draw(st.integers(0, 99)), 0.5)
+    _check(sp.kron(a, b), np.kron(da, db))
+    reps = tuple(data.draw(st.integers(1, 3)) for _ in range(data.draw(st.integers(1, 4))))
+    _check(sp.tile(a, reps), np.tile(da, reps))
+    ax = data.draw(st.one_of(st.none(), st.integers(0, len(sa) - 1)))
+    r = data.draw(st.integers(1, 3))
+    _check(sp.repeat(a, r, axis=ax), np.repeat(da, r, axis=ax))
