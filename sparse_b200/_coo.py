@@ -119,6 +119,13 @@ class COO(SparseArray):
                 raise ValueError("Shape specified by `shape` doesn't match the shape of `coords`; "
                                  f"len(shape)={len(shape)} != coords.shape[0]={ndim_c}")
         check_linear_range(self.shape)
+        from . import _settings
+
+        if _settings.WARN_ON_TOO_DENSE and self.nbytes >= self.size * self._dtype.itemsize:
+            import warnings
+
+            warnings.warn("Attempting to create a sparse array that takes no less memory than than an equivalent "
+                          "dense array. You may want to use a dense array here instead.", RuntimeWarning, stacklevel=1)
         if (not sorted) or has_duplicates or prune:
             self._canonicalise(check_sort=not sorted, sum_dups=has_duplicates, prune=prune)
 
@@ -147,6 +154,38 @@ class COO(SparseArray):
         self._idx_vis = None
         self._dtype = D.np_dtype(data)
         self.fill_value = self._dtype.type(0 if fill_value is None else fill_value)
+        return self
+
+    @classmethod
+    def from_iter(cls, x, shape=None, fill_value=None, dtype=None):
+        """COO from `{(i, j): v}`, `[((i, j), v), ...]`, `(data, (row, col))` or an iterator of the second form
+        (_coo/core.py:469-560): host-side parsing of the input into coordinate / value arrays, then the constructor."""
+        from collections.abc import Sized
+
+        if isinstance(x, dict):
+            x = list(x.items())
+        if not isinstance(x, Sized):
+            x = list(x)
+        if len(x) != 2 and not all(len(item) == 2 for item in x):
+            raise ValueError("Invalid iterable to convert to COO.")
+        if not x:
+            ndim = 0 if shape is None else len(shape)
+            coords = np.empty((ndim, 0), dtype=np.intp)
+            data = np.empty((0,), dtype=dtype)
+            shape = () if shape is None else shape
+        elif not isinstance(x[0][0], Iterable):
+            coords = np.stack([np.asarray(c) for c in x[1]], axis=0)
+            data = np.asarray(x[0], dtype=dtype)
+        else:
+            coords = np.array([item[0] for item in x]).T
+            data = np.array([item[1] for item in x], dtype=dtype)
+        if not (coords.ndim == 2 and data.ndim == 1 and np.issubdtype(coords.dtype, np.integer)
+                and np.all(coords >= 0)):
+            raise ValueError("Invalid iterable to convert to COO.")
+        return cls(coords, data, shape=shape, fill_value=fill_value)
+
+    def enable_caching(self):
+        """Upstream caches transposes / reshapes on request; here they are O(1) or one device pass: a no-op."""
         return self
 
     @classmethod
@@ -473,7 +512,11 @@ class COO(SparseArray):
             return COO(np.zeros((len(shape), 0), dtype=np.intp), self._data_np[:0], shape=shape, has_duplicates=False,
                        sorted=True, fill_value=self.fill_value)
         # only the (lazy) coordinates change; keys and data are shared
-        return COO._from_device(None, self._data_dev(), shape, self.fill_value, keys=self.sorted_keys())
+        out = COO._from_device(None, self._data_dev(), shape, self.fill_value, keys=self.sorted_keys())
+        if self._idx_vis is not None:  # upstream keeps the index dtype, widened when the new extents need it
+            out._idx_vis = self._idx_vis if can_store(self._idx_vis, max(shape) if shape else 0) \
+                else np.dtype(np.min_scalar_type(max(shape)))
+        return out
 
     def _permute_reshape(self, axes, new_shape):
         """transpose(axes) followed by reshape(new_shape) in one pass: linearise with permuted strides,
@@ -582,8 +625,12 @@ def as_coo(x, shape=None, fill_value=None, idx_dtype=None):
         if idx_dtype is not None and np.ndim(x) and not can_store(idx_dtype, max(np.shape(x))):
             raise ValueError(f"cannot cast array with shape {np.shape(x)} to dtype {idx_dtype}.")
         return COO.from_numpy(np.asarray(x), fill_value=fill_value, idx_dtype=idx_dtype)
-    if isinstance(x, (list, tuple)) and not (len(x) and isinstance(x[0], (list, tuple)) and len(x[0]) == 2
-                                               and isinstance(x[0][0], (list, tuple))):
-        return COO.from_numpy(np.asarray(x), fill_value=fill_value, idx_dtype=idx_dtype)
+    if isinstance(x, Iterable) and not isinstance(x, (str, bytes)):
+        try:
+            return COO.from_iter(x, shape=shape, fill_value=fill_value)
+        except (ValueError, TypeError, IndexError):
+            if isinstance(x, (list, tuple)):
+                return COO.from_numpy(np.asarray(x), fill_value=fill_value, idx_dtype=idx_dtype)
+            raise
     raise NotImplementedError(f"Format not supported for conversion. Supplied type is {type(x)}, "
                               "see help(sparse.as_coo) for supported formats.")

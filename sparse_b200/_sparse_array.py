@@ -54,9 +54,9 @@ class SparseArray(NDArrayOperatorsMixin):
 
     def __array__(self, *args, **kwargs):
         """No silent densification (_sparse_array.py:270-280): opt in with SPARSE_AUTO_DENSIFY=1 or call todense()."""
-        import os
+        from . import _settings
 
-        if os.environ.get("SPARSE_AUTO_DENSIFY", "0") not in ("1", "true", "True"):
+        if not _settings.AUTO_DENSIFY:
             raise RuntimeError("Cannot convert a sparse array to dense automatically. To manually densify, use the "
                                "todense method.")
         return np.asarray(self.todense(), *args, **kwargs)

@@ -84,7 +84,9 @@ _module("sparse.numba_backend._compressed.compressed", GCXS=GCXS, CSR=_m.CSR, CS
 nb._compressed = _cmp
 _compressed = _cmp
 numba_backend = nb
-_module("sparse.numba_backend._settings", NEP18_ENABLED=True)
+from sparse_b200 import _settings as _settings_mod
+sys.modules["sparse.numba_backend._settings"] = _settings_mod
+nb._settings = _settings_mod
 nb.DOK = DOK
 _module("sparse.numba_backend._dok", DOK=DOK)
 _module("sparse.numba_backend._sparse_array", SparseArray=_m.SparseArray)
