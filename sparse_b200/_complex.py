@@ -165,6 +165,14 @@ def combine(re, im, cdtype=None):
     return GCXS.from_coo(out, ca) if was_gcxs and out.ndim else out
 
 
+def segment_sum(data, heads, pos, total):
+    """Sum of every run of equal keys (COO._sum_duplicates) for any value dtype: complex runs are summed per plane."""
+    if not data.is_complex():
+        return Kn.segment_sum(data, heads, pos, total)
+    re, im = _deinterleave(data)
+    return _interleave(Kn.segment_sum(re, heads, pos, total), Kn.segment_sum(im, heads, pos, total))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # real <-> complex casts (astype)
 # ---------------------------------------------------------------------------------------------------------------

@@ -18,6 +18,15 @@ from ._sparse_array import SparseArray
 from ._utils import _zero_of_dtype, c_strides, can_store, check_linear_range, key_bits, normalize_axis, prod
 
 
+def _segment_sum(data, heads, pos, total):
+    """Kn.segment_sum for the compute dtypes, per plane for complex values (sparse_b200/_complex.py)."""
+    if data.is_complex():
+        from ._complex import segment_sum
+
+        return segment_sum(data, heads, pos, total)
+    return Kn.segment_sum(data, heads, pos, total)
+
+
 def _is_scipy_sparse(x):
     mod = type(x).__module__
     return mod.startswith("scipy.sparse") and hasattr(x, "tocoo")
@@ -334,7 +343,7 @@ class COO(SparseArray):
         if sum_dups and dups:
             heads = Kn.flag_heads(keys)
             pos, total = Kn.scan_flags(heads)
-            data = Kn.segment_sum(data, heads, pos, total)
+            data = _segment_sum(data, heads, pos, total)
             keys = Kn.compact(keys, heads, pos, total)
             changed = True
         if prune:

@@ -123,6 +123,15 @@ def _parse_einsum_input(operands):
     return lhs, rhs, list(operands)
 
 
+def _segment_sum(data, heads, pos, total):
+    """Kn.segment_sum for the compute dtypes, per plane for complex values (sparse_b200/_complex.py)."""
+    if data.is_complex():
+        from ._complex import segment_sum
+
+        return segment_sum(data, heads, pos, total)
+    return Kn.segment_sum(data, heads, pos, total)
+
+
 def _sum_all(data):
     """0-D COO holding the sum of a device vector (full contraction)."""
     n = int(data.shape[0])
@@ -181,7 +190,7 @@ def _einsum_single(lhs, rhs, operand):
         if dups:  # axes summed away / traced: COO(..., has_duplicates=True) of the reference
             heads = Kn.flag_heads(keys)
             pos, total = Kn.scan_flags(heads)
-            data = Kn.segment_sum(data, heads, pos, total)
+            data = _segment_sum(data, heads, pos, total)
             keys = Kn.compact(keys, heads, pos, total)
         out = COO._from_device(None, data, new_shape, None, keys=keys)
     return GCXS.from_coo(out) if was_gcxs else out

@@ -458,6 +458,85 @@ _NAMES = [k for k, v in list(globals().items()) if callable(v) and not k.startsw
           and k not in ("n", "T", "bits_ne", "install", "uninstall")]
 
 
+# wrappers whose REAL counterpart passes a b2s_dtype code for its value tensors: the mock applies the same dtype
+# matrix (D.dtype_code raises TypeError for anything else), so storage-only dtypes cannot slip through on CPU only
+_CODED = {"spmm_csr_dense", "segment_sum", "spgemm", "spmm_csr_dense_flagged", "dense_to_csr", "ew_merge_fused",
+          "ew_map", "ew_dense", "reduce_fused", "sddmm", "mttkrp"}
+
+
+def _strict(name, fn):
+    import functools
+
+    @functools.wraps(fn)
+    def checked(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.dtype not in (torch.int32, torch.int64, torch.uint8) \
+                    and not (a.dtype == torch.bool and name in ("dense_to_csr",)):
+                D.dtype_code(D.np_dtype(a))
+        return fn(*args, **kwargs)
+
+    return checked
+
+
+_IDX = (torch.int32, torch.int64)
+
+
+def _need_idx(t, what):
+    if isinstance(t, torch.Tensor) and t.dtype not in _IDX:
+        raise TypeError(f"mock: {what} must be int32 / int64 on the device (the kernels take idx_bytes 4 or 8), "
+                        f"got {t.dtype}")
+
+
+def _need_i64(t, what):
+    if isinstance(t, torch.Tensor) and t.dtype != torch.int64:
+        raise TypeError(f"mock: {what} must be int64, got {t.dtype}")
+
+
+def _need_np_idx(dt, what):
+    if np.dtype(dt) not in (np.dtype(np.int32), np.dtype(np.int64)):
+        raise TypeError(f"mock: {what} must be int32 / int64, got {np.dtype(dt)}")
+
+
+# the argument contracts of the real wrappers (sparse_b200/_kernels.py) that NumPy would silently accept
+_CONTRACTS = {
+    "linearize": lambda a, k: _need_idx(a[0], "coords"),
+    "diag_flags": lambda a, k: _need_idx(a[0], "coords"),
+    "unravel": lambda a, k: (_need_i64(a[0], "keys"), _need_np_idx(a[2] if len(a) > 2 else k.get("idx_dtype", np.int64), "idx_dtype")),
+    "slice_keys": lambda a, k: _need_i64(a[0], "keys"),
+    "keys_flags": lambda a, k: _need_i64(a[0], "keys"),
+    "sort_keys": lambda a, k: _need_i64(a[0], "keys"),
+    "flag_heads": lambda a, k: _need_i64(a[0], "keys"),
+    "gather": lambda a, k: _need_i64(a[1], "perm"),
+    "gather_rows": lambda a, k: _need_i64(a[1], "perm"),
+    "scatter": lambda a, k: _need_i64(a[1], "keys"),
+    "compact_rows": lambda a, k: _need_idx(a[0], "coordinate rows"),
+    "csr_from_keys": lambda a, k: (_need_i64(a[0], "keys"), _need_np_idx(a[3] if len(a) > 3 else k.get("idx_dtype", np.int64), "idx_dtype")),
+    "rows_from_indptr": lambda a, k: (_need_idx(a[0], "indptr"), _need_np_idx(a[2] if len(a) > 2 else k.get("idx_dtype", np.int64), "idx_dtype")),
+    "indptr_from_sorted": lambda a, k: _need_np_idx(a[2] if len(a) > 2 else k.get("idx_dtype", np.int64), "idx_dtype"),
+    "indptr_remap": lambda a, k: _need_idx(a[0], "indptr"),
+    "spmm_csr_dense": lambda a, k: (_need_idx(a[1], "indices"), _need_idx(a[2], "indptr")),
+    "spmm_csr_dense_flagged": lambda a, k: (_need_idx(a[1], "indices"), _need_idx(a[2], "indptr")),
+    "spgemm": lambda a, k: [_need_idx(a[i], "index array") for i in (0, 1, 3, 4)],
+    "ew_merge_fused": lambda a, k: (_need_i64(a[1], "keys_a"), _need_i64(a[4], "keys_b")),
+    "ew_dense": lambda a, k: _need_i64(a[2], "keys"),
+    "ew_expand": lambda a, k: _need_idx(a[0], "coords"),
+    "reduce_fused": lambda a, k: _need_i64(a[1], "keys"),
+}
+
+
+def _contract(name, fn):
+    import functools
+
+    check = _CONTRACTS[name]
+
+    @functools.wraps(fn)
+    def checked(*args, **kwargs):
+        check(args, kwargs)
+        return fn(*args, **kwargs)
+
+    return checked
+
+
 def install():
     """Route sparse_b200 through the NumPy mock (CPU torch tensors)."""
     if _ORIG:
@@ -465,7 +544,10 @@ def install():
     D._TEST_CPU = True
     for name in _NAMES:
         _ORIG[name] = getattr(Kn, name)
-        setattr(Kn, name, globals()[name])
+        fn = globals()[name]
+        if name in _CONTRACTS:
+            fn = _contract(name, fn)
+        setattr(Kn, name, _strict(name, fn) if name in _CODED else fn)
 
 
 def uninstall():
