@@ -163,6 +163,8 @@ def device_index_dtype(dt) -> np.dtype:
 def upload_index(arr):
     """Host index array (coords / indices / indptr) -> device int32 / int64 tensor."""
     a = np.asarray(arr)
+    if a.size == 0 and a.dtype.kind not in "iub":
+        a = a.astype(np.int64)  # np.asarray([]) is float64
     if a.dtype.kind not in "iub":
         raise ValueError(f"index arrays must be integers, got {a.dtype}")
     return upload(a, device_index_dtype(a.dtype))
