@@ -318,19 +318,6 @@ def reduce_complex(x, method, axis, keepdims, **kwargs):
 # ---------------------------------------------------------------------------------------------------------------
 # 2-D products
 # ---------------------------------------------------------------------------------------------------------------
-def _dense_binary(op_code, x, y):
-    """Element-wise op of two equal-shape dense device tensors through the COO (x) dense gather kernel with identity
-    keys (the `_dense_result` pattern of _elemwise.py)."""
-    shape = tuple(int(s) for s in x.shape)
-    n = int(np.prod(shape)) if shape else 1
-    keys = Kn.iota(n)
-    from ._utils import c_strides
-
-    _, vals, _ = Kn.ew_dense(op_code, False, keys, x.contiguous().reshape(-1), 1, y.contiguous().reshape(-1),
-                             shape if shape else (1,), c_strides(shape) if shape else [1], 0, D.np_dtype(x))
-    return vals.reshape(shape)
-
-
 def dot_complex(dot2d, a, b, return_type):
     """2-D product with at least one complex operand, on top of the real `_dot` dispatch (`dot2d`)."""
     from ._dot import _dense_dtype, _dot_dtype, _is_dense
@@ -356,8 +343,10 @@ def dot_complex(dot2d, a, b, return_type):
             return p if D.is_device_tensor(p) else D.upload(np.ascontiguousarray(p))
 
         rr, ii, ri, ir = dev(rr), dev(ii), dev(ri), dev(ir)
-        re = rr if ii is None else _dense_binary(1, rr, ii)      # subtract
-        im = ri if ir is None else (ir if ri is None else _dense_binary(0, ri, ir))  # add
+        from ._elemwise import dense_binary
+
+        re = rr if ii is None else dense_binary(np.subtract, rr, ii)
+        im = ri if ir is None else (ir if ri is None else dense_binary(np.add, ri, ir))
         if im is None:
             im = Kn.full(int(re.numel()), 0, rdt).reshape(re.shape)
         out = _interleave(re.contiguous(), im.contiguous())

@@ -238,8 +238,10 @@ def _product(parts):
     acc = parts[0]
     for nxt in parts[1:]:
         if not isinstance(acc, SparseArray) and not isinstance(nxt, SparseArray):
-            acc = (acc if D.is_device_tensor(acc) else D.upload(np.ascontiguousarray(acc))) * (
-                nxt if D.is_device_tensor(nxt) else D.upload(np.ascontiguousarray(nxt)))
+            from ._elemwise import dense_binary
+
+            acc = dense_binary(np.multiply, acc if D.is_device_tensor(acc) else D.upload(np.ascontiguousarray(acc)),
+                               nxt if D.is_device_tensor(nxt) else D.upload(np.ascontiguousarray(nxt)))
         else:
             acc = elemwise(np.multiply, acc, nxt)
     return acc

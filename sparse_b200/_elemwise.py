@@ -183,6 +183,24 @@ def _dense_strides_over(shape, dshape):
     return out
 
 
+def dense_binary(func, x, y):
+    """Element-wise `func` of two dense DEVICE tensors (broadcast against each other) on the element-wise kernel: the
+    COO (x) dense gather with identity keys, i.e. the `_dense_result` pattern below.  Keeps dense (x) dense steps of
+    einsum / complex products off torch's arithmetic."""
+    t = D.torch()
+    shape = tuple(int(s) for s in t.broadcast_shapes(tuple(x.shape), tuple(y.shape)))
+    dt = np.result_type(D.np_dtype(x), D.np_dtype(y))
+    _check_compute_dtype(dt, func)
+    xb = Kn.cast(x, dt).broadcast_to(shape).contiguous().reshape(-1)
+    yb = Kn.cast(y, dt).broadcast_to(shape).contiguous().reshape(-1)
+    n = int(xb.shape[0])
+    if n == 0:
+        return xb.reshape(shape)
+    _, vals, _ = Kn.ew_dense(_BINARY[func], False, Kn.iota(n), xb, 1, yb, shape if shape else (1,),
+                             c_strides(shape) if shape else [1], 0, dt)
+    return vals.reshape(shape)
+
+
 class _Elemwise:
     def __init__(self, func, *args, **kwargs):
         from ._gcxs import GCXS
