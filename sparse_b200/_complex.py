@@ -9,7 +9,8 @@ stored as complex64 / complex128 (the structural kernels are element-size generi
 
 each real product / element-wise step being the existing device path.  Planes of a sparse operand share its
 coordinates (zeros stay stored in a plane); results of different planes can differ in structure, so `combine` aligns
-the two on their UNION with two passes of the merge kernel whose prune test is disabled by an impossible fill value,
+the two on their UNION with two passes of the merge kernel (raw-bit OR with +0: exact) whose prune test is disabled by
+an impossible fill value,
 interleaves the aligned values (a strided copy) and finally prunes the entries equal to the complex fill value.
 
 Values differ from the reference's complex multiply-accumulate only by rounding (sum of products taken per plane):
@@ -146,12 +147,14 @@ def combine(re, im, cdtype=None):
     if kr is ki:
         keys, vr, vi = kr, dr, di
     else:
-        # align both planes on the union: x + 0 keeps x, and the impossible fill value switches the prune test off
+        # align both planes on the union: OR of the raw bit patterns with +0 keeps every value bit for bit (-0.0, NaN
+        # payloads; op 17 of the merge kernel), and the impossible fill value switches the prune test off
         weird = _weird_nan(rdt)
+        bitor = 17
         zr, zi = Kn.full(int(kr.shape[0]), 0, rdt), Kn.full(int(ki.shape[0]), 0, rdt)
-        _, vr, keys = Kn.ew_merge_fused(0, kr, dr, 1, ki, zi, 1, re.fill_value, rdt.type(0), weird, rdt, shape,
+        _, vr, keys = Kn.ew_merge_fused(bitor, kr, dr, 1, ki, zi, 1, re.fill_value, rdt.type(0), weird, rdt, shape,
                                         want_coords=False)
-        _, vi, keys2 = Kn.ew_merge_fused(0, kr, zr, 1, ki, di, 1, rdt.type(0), im.fill_value, weird, rdt, shape,
+        _, vi, keys2 = Kn.ew_merge_fused(bitor, kr, zr, 1, ki, di, 1, rdt.type(0), im.fill_value, weird, rdt, shape,
                                          want_coords=False)
         assert int(keys.shape[0]) == int(keys2.shape[0])
     cdata = _interleave(vr, vi)
@@ -318,9 +321,58 @@ def reduce_complex(x, method, axis, keepdims, **kwargs):
 # ---------------------------------------------------------------------------------------------------------------
 # 2-D products
 # ---------------------------------------------------------------------------------------------------------------
+def _spgemm_complex_gcxs(a, b, dtr, rdt, return_type):
+    """GCXS @ GCXS with complex operands, in the reference's layout (`_dot_csr_csr`, _common.py:639-717: columns of a
+    row in reverse first-touch order, then `prune=True`).  The structure of a Gustavson product depends on the index
+    arrays only, and the planes of an operand share them: the (up to) four real products are run WITHOUT pruning, so
+    their outputs are aligned entry for entry; values are combined on the aligned arrays and only then are the entries
+    equal to the complex zero dropped -- exactly where upstream drops them."""
+    from ._dot import _csr_arrays, _wrap_gcxs
+    from ._elemwise import dense_binary
+    from ._gcxs import GCXS
+
+    out_shape = (a.shape[0], b.shape[1])
+    a = a.asformat("gcxs")
+    b = b.asformat("gcxs", compressed_axes=a.compressed_axes)
+    if a.nbytes > b.nbytes:
+        b = b.change_compressed_axes(a.compressed_axes)
+    else:
+        a = a.change_compressed_axes(b.compressed_axes)
+    if a.compressed_axes == (0,):
+        A, B, ca = a, b, (0,)
+    else:  # csc @ csc: a @ b = (b.T @ a.T).T on the same arrays (_common.py:362-373)
+        A, B, ca = b._2d_transpose(), a._2d_transpose(), (1,)
+    (Ar, Ai), (Br, Bi) = planes(A, rdt), planes(B, rdt)
+    M, K = A._compressed_shape
+    n_col = B._compressed_shape[1]
+
+    def product(x, y):
+        if x is None or y is None:
+            return None
+        xd, xi, xp = _csr_arrays(x, rdt)
+        yd, yi, yp = _csr_arrays(y, rdt)
+        if xi.dtype != yi.dtype:
+            xi, xp, yi, yp = [Kn.cast(t, np.int64) for t in (xi, xp, yi, yp)]
+        indptr, indices, _, data, _ = Kn.spgemm(xp, xi, xd, yp, yi, yd, M, K, n_col, sorted_order=False, prune=False)
+        return data, indices, indptr
+
+    rr, ii, ri, ir = product(Ar, Br), product(Ai, Bi), product(Ar, Bi), product(Ai, Br)
+    _, indices, indptr = rr
+    re = rr[0] if ii is None else dense_binary(np.subtract, rr[0], ii[0])
+    im = ri[0] if ir is None else (ir[0] if ri is None else dense_binary(np.add, ri[0], ir[0]))
+    if im is None:
+        im = Kn.full(int(re.shape[0]), 0, rdt)
+    g = GCXS._from_device(_interleave(re, im), indices, indptr, out_shape, ca)
+    g._prune()
+    if return_type == np.ndarray:
+        return g.todense()
+    return g.tocoo() if return_type == COO else g
+
+
 def dot_complex(dot2d, a, b, return_type):
     """2-D product with at least one complex operand, on top of the real `_dot` dispatch (`dot2d`)."""
     from ._dot import _dense_dtype, _dot_dtype, _is_dense
+    from ._gcxs import GCXS
 
     adt = _dense_dtype(a) if _is_dense(a) else a.dtype
     bdt = _dense_dtype(b) if _is_dense(b) else b.dtype
@@ -328,6 +380,8 @@ def dot_complex(dot2d, a, b, return_type):
     rdt = plane_dtype(dtr)
     ar, ai = planes(a, rdt)
     br, bi = planes(b, rdt)
+    if isinstance(a, SparseArray) and isinstance(b, SparseArray) and (isinstance(a, GCXS) or isinstance(b, GCXS)):
+        return _spgemm_complex_gcxs(a, b, dtr, rdt, return_type)
     dense_in = _is_dense(a) or _is_dense(b)
     dense_out = (dense_in and return_type is None) or return_type == np.ndarray
     # real products; dense operands are device tensors here, so dense results stay on the device

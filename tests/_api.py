@@ -60,7 +60,7 @@ def check_values(got, want, exact=True, rtol=0.0, atol=0.0, what="data"):
     assert got.shape == want.shape, (what, got.shape, want.shape)
     assert got.dtype == want.dtype, (what, got.dtype, want.dtype)
     if exact or got.dtype.kind not in "fc":
-        if got.dtype.kind == "f":
+        if got.dtype.kind in "fc":
             assert same_bits(got, want), f"{what}: not bit-identical (max abs diff {np.nanmax(np.abs(got - want)) if got.size else 0})"
         else:
             assert np.array_equal(got, want), what
@@ -81,7 +81,7 @@ def check_result(sp, got, case, prefix="out_", exact=True, rtol=0.0, atol=0.0):
     assert tuple(got.shape) == shape, (got.shape, shape)
     fill_w = w["fill"][()]
     assert got.fill_value.dtype == fill_w.dtype, (got.fill_value.dtype, fill_w.dtype)
-    if exact or fill_w.dtype.kind != "f":
+    if exact or fill_w.dtype.kind not in "fc":
         assert same_bits(np.asarray(got.fill_value), np.asarray(fill_w)), (got.fill_value, fill_w)
     else:
         assert np.allclose(got.fill_value, fill_w, rtol=rtol, atol=atol, equal_nan=True)

@@ -711,8 +711,50 @@ def gen_examples():
     bk.save()
 
 
+def gen_complex():
+    """Complex operands through the public API (tests/test_dot.py:303-335, tests/test_coo.py:1318-1332 upstream):
+    matmul over formats / return types, element-wise arithmetic, sum."""
+    bk = Book("complex_api")
+    rng = np.random.default_rng(21)
+
+    def crand(shape, dt, density=0.5):
+        re = sparse.random(shape, density=density, random_state=rng)
+        im = sparse.random(shape, density=density, random_state=rng)
+        return (re + im * 1j).astype(dt)
+
+    fmts = [("coo", "coo"), ("coo", "gcxs"), ("gcxs", "coo"), ("gcxs", "gcxs"), ("coo", "dense"), ("dense", "coo"),
+            ("gcxs", "dense"), ("dense", "gcxs")]
+    for dt1, dt2 in (("complex128", "complex128"), ("complex64", "complex64"), ("complex64", "complex128"),
+                     ("complex128", "float64"), ("float32", "complex64")):
+        for sa, sb in (((6, 7), (7, 5)), ((7,), (7, 5)), ((6, 7), (7,)), ((3, 4, 5), (5, 6))):
+            a = crand(sa, dt1) if dt1.startswith("c") else rand_sparse(rng, sa, 0.5, dt1)
+            b = crand(sb, dt2) if dt2.startswith("c") else rand_sparse(rng, sb, 0.5, dt2)
+            for fa, fb in fmts:
+                xa = a.todense() if fa == "dense" else a.asformat(fa)
+                xb = b.todense() if fb == "dense" else b.asformat(fb)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    r = sparse.matmul(xa, xb)
+                bk.add({"op": "matmul", "dt1": dt1, "dt2": dt2, "fa": fa, "fb": fb}, **enc("a_", a), **enc("b_", b),
+                       **enc("out_", r))
+    for dt in ("complex128", "complex64"):
+        a, b = crand((4, 5, 3), dt), crand((4, 5, 3), dt)
+        y = rand_sparse(rng, (5, 1), 0.6, "float64" if dt == "complex128" else "float32")
+        for name, f in (("add", lambda u, v: u + v), ("subtract", lambda u, v: u - v), ("multiply", lambda u, v: u * v)):
+            bk.add({"op": name, "dtype": dt, "kind": "cc"}, **enc("a_", a), **enc("b_", b), **enc("out_", f(a, b)))
+            bk.add({"op": name, "dtype": dt, "kind": "cr"}, **enc("a_", a), **enc("b_", y), **enc("out_", f(a, y)))
+        bk.add({"op": "scale", "dtype": dt}, **enc("a_", a), **enc("out_", a * (2 - 3j)))
+        bk.add({"op": "conj", "dtype": dt}, **enc("a_", a), **enc("out_", a.conj()))
+        bk.add({"op": "real", "dtype": dt}, **enc("a_", a), **enc("out_", a.real))
+        bk.add({"op": "imag", "dtype": dt}, **enc("a_", a), **enc("out_", a.imag))
+        bk.add({"op": "abs", "dtype": dt}, **enc("a_", a), **enc("out_", abs(a)))
+        for axis in (None, 0, (1, 2)):
+            bk.add({"op": "sum", "dtype": dt, "axis": axis}, **enc("a_", a), **enc("out_", a.sum(axis=axis)))
+    bk.save()
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dot", "tensordot", "elemwise", "reduce", "nanreduce", "einsum", "io", "indexing", "nary", "formats", "examples"]
+    which = sys.argv[1:] or ["dot", "tensordot", "elemwise", "reduce", "nanreduce", "einsum", "io", "indexing", "nary", "formats", "examples", "complex"]
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         if "dot" in which:
@@ -737,3 +779,5 @@ if __name__ == "__main__":
             gen_formats()
         if "examples" in which:
             gen_examples()
+        if "complex" in which:
+            gen_complex()

@@ -144,3 +144,46 @@ def test_index_dtype_is_a_host_view(sp):
         sp.COO.from_numpy(np.arange(300), idx_dtype=np.int8)
     with pytest.raises(ValueError):
         sp.GCXS.from_coo(sp.random((25, 25, 25), density=0.01, random_state=2), idx_dtype=np.int8)
+
+
+# ---- against the REFERENCE itself: golden outputs generated by tests/golden/make_golden.py::gen_complex ---------------
+from _api import check_result, dec  # noqa: E402
+from _golden import load  # noqa: E402
+
+GOLD = load("complex_api")
+
+
+def _gid(i, c):
+    return "-".join(str(v) for v in [i, c["op"], c.get("dt1", c.get("dtype")), c.get("dt2", ""), c.get("fa", ""),
+                                     c.get("fb", ""), c.get("kind", ""), c.get("axis", "")] if v != "")
+
+
+@pytest.mark.parametrize("c", GOLD, ids=[_gid(i, c) for i, c in enumerate(GOLD)])
+def test_complex_golden(sp, c):
+    """Result type, shape, fill value and COORDINATES exactly as the reference returns them; values to 2e-6 (complex64)
+    / 1e-12 (complex128) -- the per-plane sums round differently from numba's complex multiply-accumulate."""
+    op = c["op"]
+    c64 = "complex64" in (c.get("dt1"), c.get("dt2"), c.get("dtype")) and "complex128" not in (c.get("dt1"), c.get("dt2"))
+    f32 = c64 or "float32" in (c.get("dt1"), c.get("dt2"))
+    tol = dict(rtol=5e-6, atol=2e-6) if f32 else dict(rtol=1e-12, atol=1e-13)
+    a = dec(sp, c, "a_", c.get("fa", "coo"))
+    if op == "matmul":
+        got = sp.matmul(a, dec(sp, c, "b_", c["fb"]))
+    elif op in ("add", "subtract", "multiply"):
+        b = dec(sp, c, "b_")
+        got = {"add": np.add, "subtract": np.subtract, "multiply": np.multiply}[op](a, b)
+    elif op == "scale":
+        got = a * (2 - 3j)
+    elif op == "conj":
+        got = a.conj()
+    elif op == "real":
+        got = a.real
+    elif op == "imag":
+        got = a.imag
+    elif op == "abs":
+        got = abs(a)
+    else:
+        axis = c["axis"]
+        got = a.sum(axis=tuple(axis) if isinstance(axis, list) else axis)
+    exact = op in ("conj", "real", "imag")
+    check_result(sp, got, c, exact=exact, **({} if exact else tol))
