@@ -8,7 +8,8 @@ _compressed/indexing.py:14-174.  The reference narrows the sorted coordinate row
 sort only when a negative step reverses an axis).  ONE one-dimensional advanced index (integer list / array or
 boolean mask, _coo/indexing.py:136-172) is served by `_manip.take_axis` after the basic part of the index: a lookup
 table over the axis extent is scattered on the device and every surviving entry gathers its slot from it.  Several
-advanced indices in one subscript are not on the CUDA path and raise.
+1-D advanced indices of one length are taken together: their axes are made adjacent, merged into one virtual axis by a
+reshape, and the raveled index list is taken along it.
 """
 from __future__ import annotations
 
@@ -61,53 +62,81 @@ def _normalize(index, shape):
 
 
 def _split_advanced(index, shape):
-    """(index with the advanced entry replaced by a full slice, its position in the RESULT, integer list) or None."""
+    """(index with every advanced entry replaced by a full slice, their positions in the RESULT of that basic index,
+    their integer lists) or None.  Several 1-D advanced indices must have the same length; they are taken together
+    (`x[[0, 1], [0, 2]]` picks (0, 0) and (1, 2)), like `_compute_multi_axis_multi_mask` (_coo/indexing.py:292-349)."""
     adv = [k for k, i in enumerate(index)
            if isinstance(i, (list, np.ndarray)) or (D.is_device_tensor(i) and not isinstance(i, (bool, np.bool_)))]
     if not adv:
         return None
-    if len(adv) > 1:
-        raise NotImplementedError("sparse_b200: more than one advanced (integer-array / boolean-mask) index in a "
-                                  "subscript is not on the CUDA path")
-    k = adv[0]
-    arr = D.download(index[k]) if D.is_device_tensor(index[k]) else np.asarray(index[k])
-    if arr.ndim != 1:
-        raise IndexError("Only one-dimensional iterable indices supported.")
-    # the axis of x the advanced index addresses: entries before it that consume an axis (Ellipsis expands)
     n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
-    axis = 0
-    for i in index[:k]:
-        if i is Ellipsis:
-            axis += len(shape) - n_real
-        elif i is not None:
-            axis += 1
-    if axis >= len(shape):
-        raise IndexError(f"too many indices for array: array is {len(shape)}-dimensional")
-    extent = shape[axis]
-    if arr.size == 0:
+    basic, positions, arrays = list(index), [], []
+    for k in adv:
+        arr = D.download(index[k]) if D.is_device_tensor(index[k]) else np.asarray(index[k])
+        if arr.ndim != 1:
+            raise IndexError("Only one-dimensional iterable indices supported.")
+        # the axis of x the advanced index addresses: entries before it that consume an axis (Ellipsis expands)
+        axis = 0
+        for i in index[:k]:
+            if i is Ellipsis:
+                axis += len(shape) - n_real
+            elif i is not None:
+                axis += 1
+        if axis >= len(shape):
+            raise IndexError(f"too many indices for array: array is {len(shape)}-dimensional")
+        extent = shape[axis]
+        if arr.size == 0:
+            arr = arr.astype(np.int64)
+        if arr.dtype == np.bool_:
+            if len(arr) != extent:
+                raise IndexError(f"boolean index did not match indexed array; dimension is {extent:d} "
+                                 f"but corresponding boolean dimension is {len(arr):d}")
+            arr = np.flatnonzero(arr)
+        elif arr.dtype.kind not in "iu":
+            raise IndexError("only integers, slices (`:`), ellipsis (`...`), numpy.newaxis (`None`) and integer or "
+                             "boolean arrays are valid indices")
         arr = arr.astype(np.int64)
-    if arr.dtype == np.bool_:
-        if len(arr) != extent:
-            raise IndexError(f"boolean index did not match indexed array; dimension is {extent:d} "
-                             f"but corresponding boolean dimension is {len(arr):d}")
-        arr = np.flatnonzero(arr)
-    elif arr.dtype.kind not in "iu":
-        raise IndexError("only integers, slices (`:`), ellipsis (`...`), numpy.newaxis (`None`) and integer or "
-                         "boolean arrays are valid indices")
-    arr = arr.astype(np.int64)
-    if arr.size and (arr.min() < -extent or arr.max() >= extent):
-        bad = arr[(arr < -extent) | (arr >= extent)][0]
-        raise IndexError(f"index {bad} is out of bounds for axis {axis} with size {extent}")
-    arr = np.where(arr < 0, arr + extent, arr)
-    basic = index[:k] + (slice(None),) + index[k + 1:]
-    # position of that axis in the result of the basic part: integers before it drop out, None adds one
-    pos = 0
-    for i in index[:k]:
-        if i is Ellipsis:
-            pos += len(shape) - n_real
-        elif i is None or isinstance(i, slice):
-            pos += 1
-    return basic, pos, arr
+        if arr.size and (arr.min() < -extent or arr.max() >= extent):
+            bad = arr[(arr < -extent) | (arr >= extent)][0]
+            raise IndexError(f"index {bad} is out of bounds for axis {axis} with size {extent}")
+        arrays.append(np.where(arr < 0, arr + extent, arr))
+        basic[k] = slice(None)
+        # position of that axis in the result of the basic part: integers before it drop out, None adds one
+        pos = 0
+        for i in index[:k]:
+            if i is Ellipsis:
+                pos += len(shape) - n_real
+            elif i is None or isinstance(i, (slice, list, np.ndarray)) or D.is_device_tensor(i):
+                pos += 1
+        positions.append(pos)
+    if len({len(a) for a in arrays}) != 1:
+        raise IndexError("shape mismatch: indexing arrays could not be broadcast together. Ensure all indexing arrays "
+                         "are of the same length.")
+    return tuple(basic), positions, arrays
+
+
+def _take_advanced(y, positions, arrays):
+    """Apply the advanced indices to `y` (the result of the basic part, advanced axes still in place)."""
+    from ._manip import take_axis
+
+    if len(positions) == 1:
+        return take_axis(y, arrays[0], positions[0])
+    # several advanced axes: make them adjacent at the first one's position, merge them into ONE virtual axis
+    # (C order), and take the raveled index list along it
+    first = positions[0]
+    rest = [d for d in range(y.ndim) if d not in positions]
+    order = [d for d in rest if d < first] + list(positions) + [d for d in rest if d > first]
+    extents = tuple(y.shape[d] for d in positions)
+    merged = int(np.prod(extents, dtype=np.int64)) if extents else 1
+    if merged > (1 << 28):
+        raise NotImplementedError("sparse_b200: the advanced axes span more than 2^28 positions; index them one at a "
+                                  "time")
+    z = y.transpose(order) if order != list(range(y.ndim)) else y
+    lead = tuple(y.shape[d] for d in rest if d < first)
+    tail = tuple(y.shape[d] for d in rest if d > first)
+    z = z.reshape(lead + (merged,) + tail)
+    combined = np.ravel_multi_index(tuple(arrays), extents) if len(arrays[0]) else np.empty(0, dtype=np.int64)
+    return take_axis(z, combined, len(lead))
 
 
 def coo_getitem(x, index):
@@ -120,11 +149,8 @@ def coo_getitem(x, index):
         index = (index,)
     split = _split_advanced(index, x.shape)
     if split is not None:
-        from ._manip import take_axis
-
-        basic, pos, arr = split
-        y = coo_getitem(x, basic)
-        return take_axis(y, arr, pos)
+        basic, positions, arrays = split
+        return _take_advanced(coo_getitem(x, basic), positions, arrays)
     last_ellipsis = len(index) > 0 and index[-1] is Ellipsis
     items = _normalize(index, x.shape)
     if len(index) != 0 and all(it[0] == "slice" and it[1:] == (0, 1, ext) for it, ext in zip(items, x.shape)) \
@@ -192,6 +218,9 @@ def gcxs_getitem(x, index):
         r = coo_getitem(x.tocoo(), index)
         return GCXS.from_coo(r) if hasattr(r, "nnz") else r
     split = _split_advanced(index, x.shape)
+    if split is not None and len(split[1]) > 1:  # several advanced axes merge into one: default compression
+        r = coo_getitem(x.tocoo(), index)
+        return GCXS.from_coo(r) if hasattr(r, "nnz") else r
     layout_index = split[0] if split is not None else index  # an advanced index keeps its axis, like a slice
     items = _normalize(layout_index, x.shape)
     if split is None and len(index) != 0 and len(items) == x.ndim \

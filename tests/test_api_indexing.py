@@ -44,8 +44,10 @@ def test_indexing_errors(sp):
     for bad in ((Ellipsis, Ellipsis), (1, 1, 1, 1), (slice(None),) * 4, 5, (0, 3), -3, (0, 0, -5), 1.5):
         with pytest.raises(IndexError):
             x[bad]
-    with pytest.raises(NotImplementedError):
-        x[[0, 1], [1, 2]]  # several advanced indices in one subscript are not on the CUDA path
+    with pytest.raises(IndexError):
+        x[[0, 1], [1, 2, 0]]  # advanced indices of different lengths
+    with pytest.raises(IndexError):
+        x[[[0, 1]]]  # only one-dimensional advanced indices
     with pytest.raises(IndexError):
         x[np.array([True, False, True])]  # boolean mask of the wrong length
     with pytest.raises(IndexError):
