@@ -454,15 +454,14 @@ class COO(SparseArray):
         data = self._data_dev()
         fill = np.asarray(self.fill_value).astype(dtype)[()]
         if self.dtype == dtype:
-            return COO._from_device(self._coords, data.clone(), self.shape, fill,
-                                    keys=self.sorted_keys() if self._coords is None else self._keys)
-        if self.dtype.kind == "c" or dtype.kind == "c":
+            vals = data.clone()
+        elif self.dtype.kind == "c" or dtype.kind == "c":
             from ._complex import cast_values
 
             vals = cast_values(data, self.dtype, dtype)
         else:
             vals = Kn.cast(data, dtype)
-        if self.nnz and not np.can_cast(self.dtype, dtype, casting="safe"):
+        if self.nnz:  # always: upstream's elemwise-based astype also drops fill values that were stored explicitly
             flags = Kn.flag_not_fill(vals, fill)
             pos, total = Kn.scan_flags(flags)
             if total != self.nnz:

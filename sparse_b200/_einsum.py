@@ -204,6 +204,8 @@ def einsum(*operands, **kwargs):
     if kwargs:
         raise TypeError(f"sparse_b200.einsum: unsupported keyword arguments {sorted(kwargs)}")
     if not any(isinstance(o, SparseArray) for o in operands):
+        if all(isinstance(o, np.ndarray) for o in operands):
+            return np.einsum(f"{lhs}->{rhs}", *operands, **({"dtype": dtype} if dtype is not None else {}))
         raise ValueError(f"None of the args is sparse: {operands}")
     if dtype is not None:
         operands = [o.astype(dtype) if hasattr(o, "astype") else o.to(D.torch_dtype(dtype)) for o in operands]

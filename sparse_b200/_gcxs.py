@@ -369,8 +369,7 @@ class GCXS(SparseArray):
         out = GCXS._from_device(Kn.cast(data, dtype) if dtype != D.np_dtype(data) else
                                 (data.clone() if dtype == self.dtype else data), indices, indptr,
                                 self.shape, self.compressed_axes, np.asarray(self.fill_value).astype(dtype)[()])
-        if dtype != self.dtype and not np.can_cast(self.dtype, dtype, casting="safe"):
-            out._prune()
+        out._prune()  # always: upstream's elemwise-based astype also drops fill values that were stored explicitly
         return out
 
     def change_compressed_axes(self, new_compressed_axes):

@@ -88,9 +88,15 @@ def _join(parts_keys, parts_data, shape, dtype, fill_value):
 
 
 def _wrap_like(arrays, out, axis, compressed_axes=None):
-    """All-GCXS input gives GCXS output compressed along `axis` unless told otherwise (_compressed/common.py)."""
+    """All-GCXS input gives GCXS output compressed along `axis` unless told otherwise (_compressed/common.py).  A
+    narrow index dtype shared by the inputs is kept (and widened by the usual rule when the result outgrows it)."""
     from ._gcxs import GCXS
 
+    vis = {getattr(a, "_idx_vis", None) for a in arrays}
+    if len(vis) == 1 and None not in vis and out.ndim:
+        (v,) = vis
+        out._idx_vis = v if np.can_cast(np.min_scalar_type(max(out.shape)), v) else np.dtype(
+            np.min_scalar_type(max(out.shape)))
     if builtins.all(isinstance(a, GCXS) for a in arrays):
         if out.ndim < 2:
             return GCXS.from_coo(out)
