@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _device as D
 from . import _kernels as Kn
 from ._coo import COO
 from ._sparse_array import _reduce_super_ufunc
@@ -53,8 +52,8 @@ def reduce_impl(x, method, axis=(0,), keepdims=False, **kwargs):
             shape[ax] = 1
         out = out.reshape(tuple(shape))
     if out.ndim == 0:
-        # 0-D result per the Array API: the element becomes the fill value (nnz = 0)
-        return COO.from_numpy(out.todense()) if not was_gcxs or True else out
+        # 0-D result per the Array API: a COO whose single element is its fill value (nnz = 0), for GCXS input too
+        return COO.from_numpy(out.todense())
     if was_gcxs:
         return GCXS.from_coo(out, None if out.ndim == 1 else (int(np.argmin(out.shape)),))
     return out
