@@ -153,6 +153,8 @@ int b2s_keys_flags(const int64_t *keys_dev, int64_t n, int *unsorted_host, int *
  * _coo/core.py:1315): keys_out = sorted keys, perm_out = source positions. */
 int b2s_sort_keys(const int64_t *keys_in_dev, int64_t n, int key_bits, int64_t *keys_out_dev, int64_t *perm_out_dev,
                   void *stream);
+/* Element movers (gather, compact, scatter, fill, flag_not_fill, transpose_dense): elem_bytes = 1, 2, 4, 8 or 16 -- they
+ * move and compare raw bits, so every value dtype a container can hold passes through them (complex128 = 16 bytes). */
 int b2s_gather(int elem_bytes, const void *in_dev, const int64_t *perm_dev, int64_t n, void *out_dev, void *stream);
 int b2s_flag_heads(const int64_t *keys_dev, int64_t n, uint8_t *flags_out_dev, void *stream);
 /* keep-flags of COO._prune / GCXS._prune: bits(data[i]) != bits(fill) (`equivalent`, _utils.py:448-452). */
@@ -225,6 +227,8 @@ int b2s_indptr_remap(int idx_bytes, const void *old_indptr_dev, int64_t nrows, c
 
 /* ---- broadcasting element-wise coiteration (K5, elemwise.cu) ------------------------------ */
 /* Operator codes: binary 0..13 value ops (add sub mul div maximum minimum fmax fmin pow floordiv mod band bor bxor),
+ * 14 nan_replace, 15 / 16 the two selections of a three-operand where, 17 OR of the raw bit patterns, 18 left_shift and
+ * 19 right_shift (integers; a count outside [0, bits) gives 0, or -1 for a negative value shifted right, as NumPy),
  * 32..40 predicates (gt ge lt le eq ne land lor lxor); unary 0..31 value ops, 64..68 predicates (see elemwise.cu). */
 /* Replaces _Elemwise._match_coo + _match_arrays + _get_func_coords_data (_umath.py:656-751, 53-92, 576-654) for two
  * COO operands: merge-path union of two sorted key streams, each optionally expanded virtually by a trailing
