@@ -7,6 +7,7 @@ Host code is Python; every data-path step is a hand-written CUDA kernel in ``lib
 thin C ABI (``include/sparse_b200.h``) via ctypes.  There is no CPU fallback: without the library or a CUDA device
 operations raise.
 """
+from ._argreduce import argmax, argmin
 from ._coo import COO, as_coo
 from ._creation import (abs, argwhere, asarray, asnumpy, astype, can_cast, diff, empty, empty_like, equal, eye,
                         full, full_like, imag, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
@@ -70,4 +71,4 @@ __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "ten
            "expand_dims", "flip", "roll", "triu", "tril", "diagonal", "diagonalize", "pad", "repeat", "tile", "outer",
            "kron", "take", "clip", "eye", "full", "full_like", "zeros", "zeros_like", "ones", "ones_like", "empty",
            "empty_like", "asnumpy", "can_cast", "result_type", "std", "var", "abs", "reshape", "astype", "equal",
-           "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]
+           "argmax", "argmin", "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]
