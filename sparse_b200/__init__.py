@@ -22,6 +22,7 @@ from ._manip import (concatenate, diagonal, diagonalize, expand_dims, flip, kron
                      pad, permute_dims, repeat, roll, squeeze, stack, swapaxes, take, tile, tril, triu, unstack)
 from ._nanreduce import nanmax, nanmean, nanmin, nanprod, nanreduce, nansum
 from ._random import random
+from ._sorting import sort, unique_counts, unique_values
 from ._sparse_array import SparseArray
 
 __version__ = "0.1.0"
@@ -71,4 +72,4 @@ __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "ten
            "expand_dims", "flip", "roll", "triu", "tril", "diagonal", "diagonalize", "pad", "repeat", "tile", "outer",
            "kron", "take", "clip", "eye", "full", "full_like", "zeros", "zeros_like", "ones", "ones_like", "empty",
            "empty_like", "asnumpy", "can_cast", "result_type", "std", "var", "abs", "reshape", "astype", "equal",
-           "argmax", "argmin", "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]
+           "argmax", "argmin", "sort", "unique_values", "unique_counts", "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]

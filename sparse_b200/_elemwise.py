@@ -196,8 +196,10 @@ def dense_binary(func, x, y):
     n = int(xb.shape[0])
     if n == 0:
         return xb.reshape(shape)
-    _, vals, _ = Kn.ew_dense(_BINARY[func], False, Kn.iota(n), xb, 1, yb, shape if shape else (1,),
-                             c_strides(shape) if shape else [1], 0, dt)
+    code = _BINARY[func]
+    out_dt = np.dtype(np.bool_) if code >= 32 else dt  # predicates write bool, value ops the operand dtype
+    _, vals, _ = Kn.ew_dense(code, False, Kn.iota(n), xb, 1, yb, shape if shape else (1,),
+                             c_strides(shape) if shape else [1], False if code >= 32 else 0, out_dt)
     return vals.reshape(shape)
 
 

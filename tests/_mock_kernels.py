@@ -121,8 +121,13 @@ def keys_flags(keys):
 
 
 def sort_keys(keys, key_bits=64):
+    """Like b2s_sort_keys: stable, UNSIGNED order over the low `key_bits` bits (a negative int64 sorts after every
+    non-negative one)."""
     k = n(keys)
-    perm = np.argsort(k, kind="stable")
+    ku = np.ascontiguousarray(k).view(np.uint64)
+    if 0 < key_bits < 64:
+        ku = ku & np.uint64((1 << key_bits) - 1)
+    perm = np.argsort(ku, kind="stable")
     return T(k[perm]), T(perm.astype(np.int64))
 
 
