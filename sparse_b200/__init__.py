@@ -10,7 +10,7 @@ operations raise.
 from ._argreduce import argmax, argmin
 from ._coo import COO, as_coo
 from ._creation import (abs, argwhere, asarray, asnumpy, astype, can_cast, diff, empty, empty_like, equal, eye,
-                        full, full_like, imag, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
+                        full, full_like, imag, interp, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
                         reshape, result_type, round, std, var, vecdot, zeros, zeros_like)
 from ._dot import dot, matmul, tensordot
 from ._einsum import einsum
@@ -72,4 +72,4 @@ __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "ten
            "expand_dims", "flip", "roll", "triu", "tril", "diagonal", "diagonalize", "pad", "repeat", "tile", "outer",
            "kron", "take", "clip", "eye", "full", "full_like", "zeros", "zeros_like", "ones", "ones_like", "empty",
            "empty_like", "asnumpy", "can_cast", "result_type", "std", "var", "abs", "reshape", "astype", "equal",
-           "argmax", "argmin", "sort", "unique_values", "unique_counts", "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]
+           "argmax", "argmin", "interp", "sort", "unique_values", "unique_counts", "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]

@@ -240,3 +240,75 @@ def diff(x, axis=-1, n=1, prepend=None, append=None):
     for _ in range(n):
         x = x[lead + (slice(1, None),)] - x[lead + (slice(None, -1),)]
     return x
+
+
+def interp(x, xp, fp, left=None, right=None, period=None):
+    """One-dimensional piecewise-linear interpolation of the stored values and of the fill value (_common.py:3267-3349);
+    the result is pruned against the new fill value.
+
+    `np.interp` is not a ufunc, so upstream runs it with NumPy on the host data array.  Here every segment [xp[j], xp[j+1])
+    is applied with element-wise device passes in NumPy's own operation order -- `slope * (v - xp[j]) + fp[j]`, multiply
+    then add, slope computed once on the host in double like `np.interp` does -- selected by the two comparisons and
+    merged with raw-bit ORs, so the values are bit-identical to `np.interp` for real `fp`."""
+    from . import _device as D
+    from . import _kernels as Kn
+    from ._elemwise import _BINARY, _UNARY, _bitor_raw, dense_binary
+    from ._elemwise import _sel_x as _sel_x_op
+    from ._gcxs import GCXS
+
+    if isinstance(xp, SparseArray):
+        xp = xp.todense()
+    if isinstance(fp, SparseArray):
+        fp = fp.todense()
+    if not isinstance(x, SparseArray):
+        return np.interp(x, xp, fp, left=left, right=right, period=period)
+    if period is not None:
+        raise NotImplementedError("sparse_b200.interp: `period` is not on the CUDA path")
+    xp, fp = np.asarray(xp, dtype=np.float64), np.asarray(fp)
+    if np.iscomplexobj(fp):
+        raise TypeError("sparse_b200.interp: complex `fp` is outside the CUDA op set")
+    fp = fp.astype(np.float64)
+    if xp.ndim != 1 or fp.ndim != 1 or len(xp) != len(fp) or len(xp) == 0:
+        raise ValueError("fp and xp are not of the same length." if xp.ndim == 1 and fp.ndim == 1
+                         else "Data points must be 1-D sequences")
+    was_gcxs = isinstance(x, GCXS)
+    c = x.asformat("coo")
+    new_fill = np.float64(np.interp(np.float64(c.fill_value), xp, fp, left=left, right=right))
+    if c.nnz == 0:
+        out = COO(np.zeros((c.ndim, 0), dtype=np.intp), np.empty(0, dtype=np.float64), shape=c.shape,
+                  has_duplicates=False, sorted=True, fill_value=new_fill)
+        return GCXS.from_coo(out, x.compressed_axes) if was_gcxs and out.ndim > 1 else out
+    v = Kn.cast(c._data_dev(), np.float64)
+    lo = np.float64(fp[0] if left is None else left)
+    hi = np.float64(fp[-1] if right is None else right)
+
+    def pick(flag_bool, values):
+        """values where the flag is set, +0 elsewhere (device op `_sel_x`)."""
+        return dense_binary(_sel_x_op, Kn.cast(flag_bool, np.float64), values)
+
+    def cmp(op, scalar):
+        return Kn.ew_map(_BINARY[op], 0, v, np.float64(scalar), False, np.bool_)[0]
+
+    n = int(v.shape[0])
+    acc = pick(cmp(np.less, xp[0]), Kn.full(n, lo, np.float64))
+    acc = dense_binary(_bitor_raw, acc, pick(cmp(np.greater, xp[-1]), Kn.full(n, hi, np.float64)))
+    acc = dense_binary(_bitor_raw, acc, pick(cmp(np.equal, xp[-1]), Kn.full(n, fp[-1], np.float64)))
+    for j in range(len(xp) - 1):
+        inside = dense_binary(np.logical_and, Kn.cast(cmp(np.greater_equal, xp[j]), np.int32),
+                              Kn.cast(cmp(np.less, xp[j + 1]), np.int32))
+        with np.errstate(all="ignore"):
+            slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j])
+        seg, _ = Kn.ew_map(_BINARY[np.subtract], 0, v, np.float64(xp[j]), 0, np.float64)
+        seg, _ = Kn.ew_map(_BINARY[np.multiply], 0, seg, np.float64(slope), 0, np.float64)
+        seg, _ = Kn.ew_map(_BINARY[np.add], 0, seg, np.float64(fp[j]), 0, np.float64)
+        acc = dense_binary(_bitor_raw, acc, pick(inside, seg))
+    # NaN inputs stay NaN (no comparison selects them): v + 0 where v is NaN
+    is_nan, _ = Kn.ew_map(_UNARY[np.isnan], 2, v, None, False, np.bool_)
+    acc = dense_binary(_bitor_raw, acc, pick(is_nan, v))
+    keys = c.sorted_keys()
+    flags = Kn.flag_not_fill(acc, new_fill)
+    pos, total = Kn.scan_flags(flags)
+    if total != n:
+        acc, keys = Kn.compact(acc, flags, pos, total), Kn.compact(keys, flags, pos, total)
+    out = COO._from_device(None, acc, c.shape, new_fill, keys=keys)
+    return GCXS.from_coo(out, x.compressed_axes) if was_gcxs and out.ndim > 1 else out

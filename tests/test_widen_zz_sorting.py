@@ -70,3 +70,26 @@ def test_sort_errors_and_bool(sp):
         sp.unique_values(np.ones(3))
     with pytest.raises(ValueError):
         sp.unique_counts(np.ones(3))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_interp_is_bit_identical_to_numpy(sp, seed):
+    """tests/test_coo.py:2171-2213 upstream (`TestInterp`) and random tables: values, fill value and pruning."""
+    rng = np.random.default_rng(seed)
+    x = sp.random((6, 7, 3), density=float(rng.choice([0.0, 0.4, 1.0])), random_state=rng,
+                  fill_value=float(rng.choice([0, 0.3, -2]))) * 4 - 1.5
+    k = int(rng.integers(1, 6))
+    xp = np.sort(rng.choice(np.arange(-4, 8) / 2.0, size=k, replace=False))
+    fp = rng.standard_normal(k)
+    for kw in ({}, {"left": -7.0}, {"right": 9.5}):
+        for arr in (x, x.asformat("gcxs")):
+            got = sp.interp(arr, xp, fp, **kw)
+            want = np.interp(x.todense(), xp, fp, **kw)
+            assert type(got) is type(arr) and got.fill_value == np.interp(x.fill_value, xp, fp, **kw)
+            assert np.array_equal(got.todense().view(np.uint64), want.view(np.uint64))
+            assert got.nnz == int(np.sum(want != got.fill_value))
+    y = sp.random((10, 10, 10), random_state=seed)
+    got = np.interp(y, sp.COO.from_numpy(np.array([-1, 0, 1])), [3, 2, 0])  # __array_function__, sparse table
+    assert got.fill_value == 2 and np.array_equal(got.todense(), np.interp(y.todense(), [-1, 0, 1], [3, 2, 0]))
+    with pytest.raises(TypeError):
+        sp.interp(y, [-1, 0, 1], np.array([3, 2, 0]) + 1j)
