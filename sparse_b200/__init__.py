@@ -7,9 +7,31 @@ Host code is Python; every data-path step is a hand-written CUDA kernel in ``lib
 thin C ABI (``include/sparse_b200.h``) via ctypes.  There is no CPU fallback: without the library or a CUDA device
 operations raise.
 """
+# the ufuncs / dtypes / constants of the Array-API namespace are NumPy's own objects: calling one on a sparse array goes
+# through __array_ufunc__ to the device element-wise path (or raises TypeError if it is not in the CUDA op set)
+from numpy import (add, bitwise_and, bitwise_not, bitwise_or, bitwise_xor, ceil, complex64, complex128, conj,  # noqa: F401
+                   copysign, cos, cosh, divide, e, exp, expm1, finfo, float16, float32, float64, floor, floor_divide,
+                   greater, greater_equal, hypot, iinfo, inf, int8, int16, int32, int64, isfinite, less, less_equal,
+                   log, log1p, log2, log10, logaddexp, logical_and, logical_not, logical_or, logical_xor, maximum,
+                   minimum, multiply, nan, negative, newaxis, nextafter, not_equal, pi, positive, reciprocal,
+                   remainder, sign, signbit, sin, sinh, sqrt, square, subtract, tan, tanh, trunc, uint8, uint16,
+                   uint32, uint64)
+from numpy import arccos as acos  # noqa: F401
+from numpy import arccosh as acosh  # noqa: F401
+from numpy import arcsin as asin  # noqa: F401
+from numpy import arcsinh as asinh  # noqa: F401
+from numpy import arctan as atan  # noqa: F401
+from numpy import arctan2 as atan2  # noqa: F401
+from numpy import arctanh as atanh  # noqa: F401
+from numpy import bool_ as bool  # noqa: F401
+from numpy import invert as bitwise_invert  # noqa: F401
+from numpy import left_shift as bitwise_left_shift  # noqa: F401
+from numpy import power as pow  # noqa: F401
+from numpy import right_shift as bitwise_right_shift  # noqa: F401
+
 from ._argreduce import argmax, argmin
 from ._coo import COO, as_coo
-from ._creation import (abs, argwhere, asarray, asnumpy, astype, can_cast, diff, empty, empty_like, equal, eye,
+from ._creation import (abs, argwhere, asCOO, asarray, asnumpy, astype, broadcast_arrays, broadcast_shapes, can_cast, diff, empty, empty_like, equal, eye,
                         full, full_like, imag, interp, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
                         reshape, result_type, round, std, var, vecdot, zeros, zeros_like)
 from ._dot import dot, matmul, tensordot
@@ -72,4 +94,15 @@ __all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "ten
            "expand_dims", "flip", "roll", "triu", "tril", "diagonal", "diagonalize", "pad", "repeat", "tile", "outer",
            "kron", "take", "clip", "eye", "full", "full_like", "zeros", "zeros_like", "ones", "ones_like", "empty",
            "empty_like", "asnumpy", "can_cast", "result_type", "std", "var", "abs", "reshape", "astype", "equal",
-           "argmax", "argmin", "interp", "sort", "unique_values", "unique_counts", "round", "isinf", "isnan", "isposinf", "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff"]
+           "argmax", "argmin", "interp", "sort", "unique_values", "unique_counts", "round", "isinf", "isnan", "isposinf",
+           "isneginf", "nonzero", "argwhere", "imag", "real", "vecdot", "diff", "asCOO", "broadcast_arrays",
+           "broadcast_shapes",
+           # NumPy's ufuncs, dtypes and constants under the Array-API names (sparse/numba_backend/__init__.py upstream)
+           "acos", "acosh", "add", "asin", "asinh", "atan", "atan2", "atanh", "bitwise_and", "bitwise_invert",
+           "bitwise_left_shift", "bitwise_not", "bitwise_or", "bitwise_right_shift", "bitwise_xor", "bool", "ceil",
+           "complex128", "complex64", "conj", "copysign", "cos", "cosh", "divide", "e", "exp", "expm1", "finfo", "float16",
+           "float32", "float64", "floor", "floor_divide", "greater", "greater_equal", "hypot", "iinfo", "inf", "int16",
+           "int32", "int64", "int8", "isfinite", "less", "less_equal", "log", "log10", "log1p", "log2", "logaddexp",
+           "logical_and", "logical_not", "logical_or", "logical_xor", "maximum", "minimum", "multiply", "nan", "negative",
+           "newaxis", "nextafter", "not_equal", "pi", "positive", "pow", "reciprocal", "remainder", "sign", "signbit",
+           "sin", "sinh", "sqrt", "square", "subtract", "tan", "tanh", "trunc", "uint16", "uint32", "uint64", "uint8"]

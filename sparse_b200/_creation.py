@@ -312,3 +312,28 @@ def interp(x, xp, fp, left=None, right=None, period=None):
         acc, keys = Kn.compact(acc, flags, pos, total), Kn.compact(keys, flags, pos, total)
     out = COO._from_device(None, acc, c.shape, new_fill, keys=keys)
     return GCXS.from_coo(out, x.compressed_axes) if was_gcxs and out.ndim > 1 else out
+
+
+def asCOO(x, name="asCOO", check=True):
+    """COO of `x`; a dense input is refused when `check` is set (_coo/common.py:21-53)."""
+    from ._coo import _is_scipy_sparse
+
+    if check and not (isinstance(x, SparseArray) or _is_scipy_sparse(x)):
+        raise ValueError(f"Performing this operation would produce a dense result: {name}")
+    return x if isinstance(x, COO) else COO(x)
+
+
+def broadcast_shapes(*shapes):
+    """numpy.broadcast_shapes (_coo/common.py:1599-1617)."""
+    return np.broadcast_shapes(*shapes)
+
+
+def broadcast_arrays(*arrays):
+    """Every array broadcast to the common shape (_common.py:2835-2869); dense inputs become COO."""
+    shape = np.broadcast_shapes(*[a.shape for a in arrays])
+    out = []
+    for a in arrays:
+        if isinstance(a, (np.generic, np.ndarray)):
+            a = COO.from_numpy(np.asarray(a))
+        out.append(a.broadcast_to(shape))
+    return tuple(out)
