@@ -470,7 +470,22 @@ def where(condition, x=None, y=None):
     if cdt != np.bool_:
         c = c != 0  # truth value first: a narrowing cast could flush a tiny non-zero to zero
     c = c.astype(work) if hasattr(c, "astype") else work.type(bool(c))
-    out = elemwise(_bitor_raw, elemwise(_sel_x, c, as_t(x)), elemwise(_sel_y, c, as_t(y)))
+    def step(func, a, b):
+        """One binary pass; two DENSE operands (np.where(dense, dense, sparse)) meet on the device kernel directly."""
+        if isinstance(a, SparseArray) or isinstance(b, SparseArray):
+            return elemwise(func, a, b)
+
+        def dev(v):
+            if D.is_device_tensor(v):
+                return v
+            v = np.asarray(v, dtype=work)
+            return D.upload(np.ascontiguousarray(v)) if v.ndim else Kn.full(1, v[()], work)
+
+        return dense_binary(func, dev(a), dev(b))
+
+    out = step(_bitor_raw, step(_sel_x, c, as_t(x)), step(_sel_y, c, as_t(y)))
+    if D.is_device_tensor(out):  # every step was dense (only reachable through the np.where dispatch)
+        out = D.download(out)
     return out.astype(np.bool_) if T == np.bool_ else out
 
 

@@ -75,6 +75,9 @@ class SparseArray(NDArrayOperatorsMixin):
         sparse_func = getattr(module, name, None)
         if sparse_func is None or sparse_func is func:
             sparse_func = getattr(type(self), name, None)
+        if (sparse_func is None or not callable(sparse_func)) and len(args) == 1 and not kwargs and args[0] is self \
+                and name in ("shape", "ndim", "size"):
+            return getattr(self, name)  # np.shape / np.ndim / np.size: plain attributes (_sparse_array.py:300-304)
         if sparse_func is None or not callable(sparse_func):
             return NotImplemented
         return sparse_func(*args, **kwargs)

@@ -42,12 +42,11 @@ from sparse_b200 import _coo as _coo_mod, _gcxs as _gcxs_mod
 
 
 class _OutOfScope(type):
-    """Placeholder for reference types that are outside the hot path (DOK ...): any use skips the test."""
+    """Placeholder for reference types that are outside the hot path (DOK ...): constructing one gives a stub whose
+    every use raises NotImplementedError("dok ..."), which the conftest below turns into a skip."""
 
     def __call__(cls, *a, **k):
-        import pytest
-
-        pytest.skip(f"{cls.__name__} is outside the hot path (DESIGN.md s0)")
+        return type.__call__(cls)
 
     def __getattr__(cls, name):
         if name.startswith("__"):
@@ -56,7 +55,15 @@ class _OutOfScope(type):
 
 
 class DOK(metaclass=_OutOfScope):
-    pass
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        raise NotImplementedError("dok is outside the hot path (DESIGN.md s0)")
+
+    def __array_function__(self, *a, **k):
+        raise NotImplementedError("dok is outside the hot path (DESIGN.md s0)")
+
+    __array_ufunc__ = None
 
 
 def __getattr__(name):
