@@ -6,6 +6,8 @@ SPARSE_WARN_ON_TOO_DENSE=1  warn when a COO takes no less memory than the equiva
 """
 import os
 
+import numpy as np
+
 
 def _flag(name: str) -> bool:
     value = os.environ.get(name, "").strip().lower()
@@ -15,3 +17,4 @@ def _flag(name: str) -> bool:
 AUTO_DENSIFY = _flag("SPARSE_AUTO_DENSIFY")
 WARN_ON_TOO_DENSE = _flag("SPARSE_WARN_ON_TOO_DENSE")
 NEP18_ENABLED = True  # __array_function__ dispatch is always on in the NumPy versions this package supports
+IS_NUMPY2 = np.lib.NumpyVersion(np.__version__) >= "2.0.0a1"
