@@ -34,6 +34,7 @@ from ._coo import COO, as_coo
 from ._creation import (abs, argwhere, asCOO, asarray, asnumpy, astype, broadcast_arrays, broadcast_shapes, can_cast, diff, empty, empty_like, equal, eye,
                         full, full_like, imag, interp, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
                         reshape, result_type, round, std, var, vecdot, zeros, zeros_like)
+from ._dok import DOK
 from ._dot import dot, matmul, tensordot
 from ._einsum import einsum
 from ._elemwise import broadcast_to, elemwise, where
@@ -86,11 +87,11 @@ def all(x, /, *, axis=None, keepdims=False):
     return x.all(axis=axis, keepdims=keepdims)
 
 
-__all__ = ["COO", "GCXS", "CSR", "CSC", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
+__all__ = ["COO", "DOK", "GCXS", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
            "elemwise", "broadcast_to", "where", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
            "einsum", "save_npz", "load_npz", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce",
            # array manipulation and creation next to the hot path (widened per SURVEY.md s8f)
-           "concatenate", "concat", "unstack", "moveaxis", "swapaxes", "permute_dims", "matrix_transpose", "squeeze",
+           "concatenate", "concat", "unstack", "moveaxis", "permute_dims", "matrix_transpose", "squeeze",
            "expand_dims", "flip", "roll", "triu", "tril", "diagonal", "diagonalize", "pad", "repeat", "tile", "outer",
            "kron", "take", "clip", "eye", "full", "full_like", "zeros", "zeros_like", "ones", "ones_like", "empty",
            "empty_like", "asnumpy", "can_cast", "result_type", "std", "var", "abs", "reshape", "astype", "equal",

@@ -390,8 +390,15 @@ class COO(SparseArray):
         """_coo/core.py:asformat -- "coo" / "gcxs" / "csr" / "csc" / "dense" (names or classes)."""
         from ._gcxs import CSC, CSR, GCXS
 
+        from ._dok import DOK
+
         if isinstance(format, str):
-            format = {"coo": COO, "gcxs": GCXS, "csr": CSR, "csc": CSC, "dense": np.ndarray}.get(format, format)
+            format = {"coo": COO, "gcxs": GCXS, "csr": CSR, "csc": CSC, "dok": DOK, "dense": np.ndarray}.get(format,
+                                                                                                              format)
+        if isinstance(format, type) and issubclass(format, DOK):
+            if kwargs:
+                raise ValueError(f"Extra kwargs found: {kwargs}")
+            return DOK.from_coo(self)
         if isinstance(format, type) and issubclass(format, (CSR, CSC)):
             if kwargs:
                 raise ValueError(f"Extra kwargs found: {kwargs}")

@@ -93,9 +93,11 @@ def asarray(obj, /, *, dtype=None, format=None, copy=False, device=None, **kwarg
     from ._gcxs import CSC, CSR, GCXS
 
     _check_device(device)
-    if format not in {None, "coo", "gcxs", "csc", "csr"}:
+    from ._dok import DOK
+
+    if format not in {None, "coo", "dok", "gcxs", "csc", "csr"}:
         raise ValueError(f"{format} format not supported.")
-    classes = {"coo": COO, "gcxs": GCXS, "csc": CSC, "csr": CSR}
+    classes = {"coo": COO, "dok": DOK, "gcxs": GCXS, "csc": CSC, "csr": CSR}
     if isinstance(obj, SparseArray):
         if copy:
             obj = obj.copy()
@@ -271,6 +273,10 @@ def interp(x, xp, fp, left=None, right=None, period=None):
     if xp.ndim != 1 or fp.ndim != 1 or len(xp) != len(fp) or len(xp) == 0:
         raise ValueError("fp and xp are not of the same length." if xp.ndim == 1 and fp.ndim == 1
                          else "Data points must be 1-D sequences")
+    from ._dok import DOK
+
+    if isinstance(x, DOK):
+        return DOK.from_coo(interp(x.to_coo(), xp, fp, left=left, right=right))
     was_gcxs = isinstance(x, GCXS)
     c = x.asformat("coo")
     new_fill = np.float64(np.interp(np.float64(c.fill_value), xp, fp, left=left, right=right))

@@ -95,6 +95,11 @@ def tensordot(a, b, axes=2, *, return_type=None):
         a = GCXS.from_scipy_sparse(a)
     if _is_scipy_sparse(b):
         b = GCXS.from_scipy_sparse(b)
+    # any other SparseArray (the DOK builder) computes as COO (_common.py:132-135: `asformat` to a supported type)
+    if isinstance(a, SparseArray) and not isinstance(a, (COO, GCXS)):
+        a = a.asformat("coo")
+    if isinstance(b, SparseArray) and not isinstance(b, (COO, GCXS)):
+        b = b.asformat("coo")
     try:
         iter(axes)
     except TypeError:
@@ -209,6 +214,10 @@ def matmul(a, b):
     check_zero_fill_value(a, b)
     if not hasattr(a, "ndim") or not hasattr(b, "ndim"):
         raise TypeError(f"Cannot perform dot product on types {type(a)}, {type(b)}")
+    if isinstance(a, SparseArray) and not isinstance(a, (COO, GCXS)):
+        a = a.asformat("coo")
+    if isinstance(b, SparseArray) and not isinstance(b, (COO, GCXS)):
+        b = b.asformat("coo")
     if _check_nan(a) or _check_nan(b):
         warnings.warn("Nan will not be propagated in matrix multiplication", RuntimeWarning, stacklevel=1)
 

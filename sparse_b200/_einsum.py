@@ -207,6 +207,14 @@ def einsum(*operands, **kwargs):
         if all(isinstance(o, np.ndarray) for o in operands):
             return np.einsum(f"{lhs}->{rhs}", *operands, **({"dtype": dtype} if dtype is not None else {}))
         raise ValueError(f"None of the args is sparse: {operands}")
+    from ._dok import DOK
+
+    sparse_ops = [o for o in operands if isinstance(o, SparseArray)]
+    if any(isinstance(o, DOK) for o in sparse_ops):  # the DOK builder computes as COO; all-DOK input gives DOK back
+        all_dok = all(isinstance(o, DOK) for o in sparse_ops)
+        out = einsum(f"{lhs}->{rhs}", *[o.to_coo() if isinstance(o, DOK) else o for o in operands],
+                     **({"dtype": dtype} if dtype is not None else {}))
+        return DOK.from_coo(out.asformat("coo")) if all_dok and isinstance(out, SparseArray) else out
     if dtype is not None:
         operands = [o.astype(dtype) if hasattr(o, "astype") else o.to(D.torch_dtype(dtype)) for o in operands]
     if len(operands) == 1:

@@ -212,7 +212,11 @@ class _Elemwise:
         if len(sparse_args) == 0:
             raise ValueError(f"None of the args is sparse: {args}")
         out_kwargs = {}
-        if all(isinstance(arg, GCXS) for arg in sparse_args):
+        from ._dok import DOK
+
+        if all(isinstance(arg, DOK) for arg in sparse_args):
+            out_type = DOK  # _umath.py:417-418: DOK operands only -> DOK result
+        elif all(isinstance(arg, GCXS) for arg in sparse_args):
             out_type = GCXS
             if len({arg.compressed_axes for arg in sparse_args}) == 1:
                 out_kwargs["compressed_axes"] = sparse_args[0].compressed_axes

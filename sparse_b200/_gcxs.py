@@ -333,8 +333,15 @@ class GCXS(SparseArray):
 
     def asformat(self, format, **kwargs):
         """compressed.py:asformat -- "gcxs" / "csr" / "csc" / "coo" / "dense" (names or classes)."""
+        from ._dok import DOK
+
         if isinstance(format, str):
-            format = {"gcxs": GCXS, "csr": CSR, "csc": CSC, "coo": COO, "dense": np.ndarray}.get(format, format)
+            format = {"gcxs": GCXS, "csr": CSR, "csc": CSC, "coo": COO, "dok": DOK, "dense": np.ndarray}.get(format,
+                                                                                                              format)
+        if isinstance(format, type) and issubclass(format, DOK):
+            if kwargs:
+                raise ValueError(f"Extra kwargs found: {kwargs}")
+            return DOK.from_coo(self.tocoo())
         if isinstance(format, type) and issubclass(format, (CSR, CSC)):
             if kwargs:
                 raise ValueError(f"Extra kwargs found: {kwargs}")

@@ -41,29 +41,7 @@ from sparse_b200 import sum, max, min, prod, mean, any, all, random, COO, GCXS  
 from sparse_b200 import _coo as _coo_mod, _gcxs as _gcxs_mod
 
 
-class _OutOfScope(type):
-    """Placeholder for reference types that are outside the hot path (DOK ...): constructing one gives a stub whose
-    every use raises NotImplementedError("dok ..."), which the conftest below turns into a skip."""
-
-    def __call__(cls, *a, **k):
-        return type.__call__(cls)
-
-    def __getattr__(cls, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return cls
-
-
-class DOK(metaclass=_OutOfScope):
-    def __getattr__(self, name):
-        if name.startswith("__") and name.endswith("__"):
-            raise AttributeError(name)
-        raise NotImplementedError("dok is outside the hot path (DESIGN.md s0)")
-
-    def __array_function__(self, *a, **k):
-        raise NotImplementedError("dok is outside the hot path (DESIGN.md s0)")
-
-    __array_ufunc__ = None
+DOK = _m.DOK
 
 
 def __getattr__(name):
@@ -124,12 +102,7 @@ def main(argv):
     os.makedirs(tdir)
     with open(os.path.join(tdir, "conftest.py"), "w") as f:
         f.write("import pytest\n\n\n@pytest.fixture(scope='session')\ndef rng():\n"
-                "    from sparse.numba_backend._utils import default_rng\n    return default_rng\n\n\n"
-                "@pytest.hookimpl(hookwrapper=True)\ndef pytest_runtest_call(item):\n"
-                "    # a DOK parametrisation (outside the hot path, DESIGN.md s0) is a skip, not a gap\n"
-                "    outcome = yield\n    exc = outcome.excinfo\n"
-                "    if exc and issubclass(exc[0], NotImplementedError) and 'dok' in str(exc[1]).lower():\n"
-                "        outcome.force_exception(pytest.skip.Exception('DOK is outside the hot path'))\n")
+                "    from sparse.numba_backend._utils import default_rng\n    return default_rng\n")
     files, rest, patches = [], [], []
     it = iter(argv)
     for a in it:
