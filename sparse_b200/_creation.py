@@ -18,10 +18,14 @@ from ._sparse_array import SparseArray
 from ._utils import check_zero_fill_value, normalize_axis
 
 
-def _check_device(device):
-    if device not in (None, "cpu", "cuda") and not str(device).startswith("cuda"):
-        raise ValueError(f'Device not understood. Only "cuda" (and, for compatibility, "cpu") is allowed, '
-                         f"but received: {device}")
+def _check_device(device, method=False):
+    """Arrays live on the CUDA device; `"cpu"` is accepted so that Array-API code written against upstream (which only
+    knows `"cpu"`, _common.py:33-41, _sparse_array.py:55-57) keeps running."""
+    if device in (None, "cpu", "cuda") or str(device).startswith("cuda"):
+        return
+    if method:
+        raise ValueError(f"Only `device='cuda'` (or 'cpu', for compatibility) is supported. Got {device!r}.")
+    raise ValueError(f"Device must be `'cuda'`, `'cpu'` (accepted for compatibility) or `None`. Got {device!r}.")
 
 
 def full(shape, fill_value, dtype=None, format="coo", order="C", *, device=None, **kwargs):

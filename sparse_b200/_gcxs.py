@@ -142,7 +142,7 @@ class GCXS(SparseArray):
         """Move the arrays to HBM now (they stay resident); returns self."""
         from ._creation import _check_device
 
-        _check_device(device)
+        _check_device(device, method=True)
         self._dev()
         return self
 
