@@ -172,6 +172,8 @@ class COO(SparseArray):
         from collections.abc import Sized
 
         if isinstance(x, dict):
+            if shape is None:
+                raise TypeError("`shape` must be given when converting a dictionary to COO.")
             x = list(x.items())
         if not isinstance(x, Sized):
             x = list(x)

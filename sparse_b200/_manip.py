@@ -225,7 +225,7 @@ def squeeze(x, /, axis=None):
         axis = (axis,)
     for d in axis:
         if not isinstance(d, (int, np.integer)):
-            raise IndexError(f"Invalid axis index: {d}. Axis index must be an integer.")
+            raise ValueError(f"Invalid axis parameter: `{d}`.")
     axis = tuple(int(d) + x.ndim if d < 0 else int(d) for d in axis)
     for d in axis:
         if not 0 <= d < x.ndim:
@@ -267,16 +267,28 @@ def roll(a, shift, axis=None):
     a = a if isinstance(a, SparseArray) else as_coo(a)
     if axis is None:
         return roll(a.reshape((-1,)), shift, 0).reshape(a.shape)
+    if np.ndim(shift) > 1 or np.ndim(axis) > 1:
+        raise ValueError("'shift' and 'axis' must be integers or 1D sequences.")
+    if isinstance(shift, Iterable) and not isinstance(axis, Iterable):
+        raise ValueError("If 'shift' is a 1D sequence, 'axis' must have equal length.")
     if not isinstance(shift, Iterable):
         shift = (shift,)
     if not isinstance(axis, Iterable):
         axis = (axis,)
-    shift, axis = tuple(shift), tuple(axis)
+    shift, axis = tuple(int(v) for v in shift), tuple(axis)
     if len(shift) == 1 and len(axis) > 1:
         shift = shift * len(axis)
     if len(shift) != len(axis):
         raise ValueError("If 'shift' is a 1D sequence, 'axis' must have equal length.")
     axis = normalize_axis(axis, a.ndim)
+    # upstream adds the shift to the coordinate rows in their own dtype (_coo/common.py:788-806): a shift that a narrow
+    # or unsigned index dtype cannot hold is refused here as well
+    idt = np.dtype(_as_coo(a)._idx_dtype()) if isinstance(a, SparseArray) else np.dtype(np.intp)
+    from ._utils import can_store
+
+    if not can_store(idt, max(max(a.shape), max(abs(v) for v in shift))) or (idt.kind == "u" and min(shift) < 0):
+        raise ValueError(f"cannot roll with coords.dtype {idt} and shift {shift}. Try casting coords to a larger "
+                         "signed dtype.")
     out = a
     for sh, ax in zip(shift, axis):
         n = out.shape[ax]
