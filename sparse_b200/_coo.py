@@ -195,6 +195,19 @@ class COO(SparseArray):
             raise ValueError("Invalid iterable to convert to COO.")
         return cls(coords, data, shape=shape, fill_value=fill_value)
 
+    # ---- pickling: the state is the host mirror (device tensors are re-created lazily on the receiving side) --------
+    def __getstate__(self):
+        return {"coords": self.coords, "data": self.data, "shape": self.shape, "fill_value": self.fill_value}
+
+    def __setstate__(self, state):
+        self.__init__(state["coords"], state["data"], shape=state["shape"], has_duplicates=False, sorted=True,
+                      fill_value=state["fill_value"])
+
+    def __sizeof__(self):
+        return self.nbytes
+
+    _cache = None  # upstream's opt-in transpose / reshape cache: those operations are O(1) or one device pass here
+
     def enable_caching(self):
         """Upstream caches transposes / reshapes on request; here they are O(1) or one device pass: a no-op."""
         return self

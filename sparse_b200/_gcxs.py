@@ -79,6 +79,18 @@ class GCXS(SparseArray):
         self._compressed_axes = o._compressed_axes
         self.fill_value = o.fill_value
 
+    # ---- pickling: the state is the host mirror -----------------------------------------------------------------------
+    def __getstate__(self):
+        return {"data": self.data, "indices": self.indices, "indptr": self.indptr, "shape": self.shape,
+                "compressed_axes": self.compressed_axes, "fill_value": self.fill_value, "cls": type(self).__name__}
+
+    def __setstate__(self, state):
+        GCXS.__init__(self, (state["data"], state["indices"], state["indptr"]), shape=state["shape"],
+                      compressed_axes=state["compressed_axes"], fill_value=state["fill_value"])
+
+    def __sizeof__(self):
+        return self.nbytes
+
     def _make_shallow_copy_of(self, other):
         """`out=` target of a ufunc (compressed.py:_make_shallow_copy_of)."""
         self._adopt(other if isinstance(other, GCXS) else GCXS.from_coo(other.asformat("coo"), self.compressed_axes))

@@ -199,3 +199,18 @@ def test_where_with_dense_operands_and_array_properties(sp):
     with pytest.raises(ValueError):
         sp.asCOO(x)
     assert np.array_equal(sp.add(y, y).todense(), x + x) and sp.float32 is np.float32  # namespace re-exports
+
+
+def test_pickle_round_trip(sp):
+    """The pickled state is the host mirror (coordinates / indices and values); device arrays are rebuilt lazily."""
+    import pickle
+    import sys
+
+    x = sp.random((5, 6, 3), density=0.4, random_state=0, fill_value=1.5)
+    for a in (x, x.asformat("gcxs"), sp.CSR(x[0]), sp.DOK(x)):
+        b = pickle.loads(pickle.dumps(a))
+        assert type(b) is type(a) and b.fill_value == a.fill_value and np.array_equal(b.todense(), a.todense())
+        if hasattr(a, "compressed_axes"):
+            assert a.compressed_axes == b.compressed_axes
+    assert np.array_equal((pickle.loads(pickle.dumps(x)) + x).todense(), 2 * x.todense())
+    assert 400 < sys.getsizeof(sp.COO.from_numpy(np.eye(100))) < np.eye(100).nbytes / 10
