@@ -24,6 +24,10 @@ def _segment_sum(data, heads, pos, total):
         from ._complex import segment_sum
 
         return segment_sum(data, heads, pos, total)
+    dt = D.np_dtype(data)
+    if dt not in D._CODES and dt.kind in "iu":
+        # storage-only integer widths: sum in int64, cast back (two's-complement wrap = NumPy's reduceat in that dtype)
+        return Kn.cast(Kn.segment_sum(Kn.cast(data, np.int64), heads, pos, total), dt)
     return Kn.segment_sum(data, heads, pos, total)
 
 
@@ -435,9 +439,7 @@ class COO(SparseArray):
         from ._utils import check_fill_value
 
         check_fill_value(self, accept_fv=accept_fv)
-        if self.ndim != 2:
-            raise ValueError("Can only convert a 2-dimensional array to a Scipy sparse matrix.")
-        result = scipy.sparse.coo_array((self.data, self.coords), shape=self.shape)
+        result = scipy.sparse.coo_array((self.data, tuple(self.coords)), shape=self.shape)  # n-D with SciPy >= 1.13
         result.has_canonical_format = True
         return result
 

@@ -80,8 +80,10 @@ def test_scipy_round_trips(sp):
 
 def test_scipy_export_checks(sp):
     x = sp.random((3, 4, 5), density=0.5, random_state=1)
+    nd = x.to_scipy_sparse()  # n-D coo_array (SciPy >= 1.13), like upstream (_coo/core.py:1166-1198)
+    assert nd.shape == (3, 4, 5) and nd.nnz == x.nnz
     with pytest.raises(ValueError):
-        x.to_scipy_sparse()
+        x.tocsr()
     y = sp.random((3, 4), density=0.5, random_state=1, fill_value=1.0)
     with pytest.raises(ValueError):
         y.to_scipy_sparse()
