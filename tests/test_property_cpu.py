@@ -375,3 +375,24 @@ def test_kron_tile_repeat_match_numpy(data):
     ax = data.draw(st.one_of(st.none(), st.integers(0, len(sa) - 1)))
     r = data.draw(st.integers(1, 3))
     _check(sp.repeat(a, r, axis=ax), np.repeat(da, r, axis=ax))
+
+
+@SET
+@given(st.data())
+def test_argreduce_sort_unique_match_numpy(data):
+    sp = _sp()
+    shape = data.draw(shapes)
+    fill = data.draw(st.sampled_from([0.0, 2.0, -1.0]))
+    a, d = _rand(shape, data.draw(st.integers(0, 99)), data.draw(st.sampled_from([0.0, 0.3, 0.8, 1.0])), fill)
+    axis = data.draw(st.one_of(st.none(), st.integers(-len(shape), len(shape) - 1)))
+    keepdims = data.draw(st.booleans())
+    assert np.array_equal(sp.argmax(a, axis=axis, keepdims=keepdims).todense(), np.argmax(d, axis=axis, keepdims=keepdims))
+    assert np.array_equal(sp.argmin(a, axis=axis, keepdims=keepdims).todense(), np.argmin(d, axis=axis, keepdims=keepdims))
+    ax = data.draw(st.integers(-len(shape), len(shape) - 1))
+    desc = data.draw(st.booleans())
+    want = np.sort(d, axis=ax)
+    _check(sp.sort(a, axis=ax, descending=desc), np.flip(want, axis=ax) if desc else want)
+    vals, counts = np.unique(d, return_counts=True)
+    got = sp.unique_counts(a)
+    assert np.array_equal(got.values, vals) and np.array_equal(got.counts, counts)
+    assert np.array_equal(sp.unique_values(a), vals)
