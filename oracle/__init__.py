@@ -9,9 +9,10 @@ imports it; the product has no CPU fallback.
 * ``dot_oracle.c`` (compiled to ``liboracle.so``): the numba kernels of
   ``sparse/numba_backend/_common.py:543-1158`` plus ``_match_arrays``
   (``_umath.py:53-92``) and ``_calc_counts_invidx`` (``_coo/core.py:1601-1628``).
-* ``oracle.elemwise`` / ``oracle.reduce`` / ``oracle.containers``: numpy
-  restatements of the NumPy-level glue (``_umath.py``, ``_sparse_array.py:372-437``,
-  ``_coo/core.py``, ``_compressed/compressed.py``).
+* the NumPy-level glue around those kernels (``_umath.py``, ``_sparse_array.py:372-437``,
+  ``_coo/core.py``, ``_compressed/compressed.py``) is not restated here: for it the
+  checker is the reference itself, through the golden input / output fixtures of
+  ``tests/golden/`` (2500+ cases written by ``tests/golden/make_golden.py``).
 
 Parity status: PINNED against golden vectors generated from the reference
 itself (``tests/golden/make_golden.py``), checked in ``tests/test_oracle_golden.py``.
