@@ -97,6 +97,14 @@ def _op_code(func, table, what):
         ) from None
 
 
+# narrow / unsigned integer dtypes are storage-only on the device; their arithmetic is exact in a wider signed type and
+# the C narrowing cast wraps exactly like NumPy's arithmetic in the narrow type (two's complement, modulo 2**bits)
+_WIDE_FOR = {np.dtype("int8"): np.dtype("int32"), np.dtype("int16"): np.dtype("int32"),
+             np.dtype("uint8"): np.dtype("int32"), np.dtype("uint16"): np.dtype("int32"),
+             np.dtype("uint32"): np.dtype("int64")}
+_NOT_VIA_WIDE = (np.power, np.left_shift, np.right_shift, np.true_divide)
+
+
 def _check_compute_dtype(dt, func):
     if np.dtype(dt) not in _COMPUTE_DTYPES:
         raise TypeError(f"sparse_b200: {getattr(func, '__name__', func)} on dtype {dt} is outside the CUDA dtype matrix "
@@ -327,6 +335,8 @@ class _Elemwise:
             func = np.positive  # conj of a real array is the array itself
         op = _op_code(func, _UNARY, "unary")
         out_dt, T = _resolve(func, _stand_in(a))
+        if T in _WIDE_FOR and func not in _NOT_VIA_WIDE:
+            return self._via_wide(func, T, out_dt)
         _check_compute_dtype(T, func)
         with np.errstate(all="ignore"):
             fill = np.asarray(func(a.fill_value)).astype(out_dt)[()]
@@ -336,6 +346,27 @@ class _Elemwise:
                        has_duplicates=False, sorted=True, fill_value=fill)
         vals, flags = Kn.ew_map(op, 2, Kn.cast(data, T), None, fill, out_dt)
         return self._keep(a, vals, flags, fill)
+
+    def _via_wide(self, func, T, out_dt):
+        """Narrow / unsigned integer operands: compute in the wider signed type, then cast back (the cast prunes the
+        entries that wrap around to the fill value)."""
+        W = _WIDE_FOR[T]
+
+        def widen(v):
+            if isinstance(v, COO):
+                return v.astype(W) if v.dtype != W else v
+            if isinstance(v, np.ndarray) and v.ndim > 0:
+                return v.astype(W)
+            if D.is_device_tensor(v):
+                return Kn.cast(v, W)
+            return W.type(v)
+
+        out = _Elemwise(func, *[widen(a) for a in self.args]).get_result()
+        if out_dt == np.bool_ or not hasattr(out, "astype"):
+            return out
+        if isinstance(out, np.ndarray):
+            return out.astype(out_dt)
+        return out.asformat("coo").astype(out_dt)
 
     def _keep(self, a, vals, flags, fill):
         pos, total = Kn.scan_flags(flags)
@@ -358,6 +389,8 @@ class _Elemwise:
             func = _BOOL_BITWISE[func]
         op = _op_code(func, _BINARY, "binary")
         out_dt, T = _resolve(func, la, lb)
+        if T in _WIDE_FOR and func not in _NOT_VIA_WIDE:
+            return self._via_wide(func, T, out_dt)
         _check_compute_dtype(T, func)
         if op < 32 and out_dt == np.bool_:
             raise TypeError(f"sparse_b200: {func.__name__} with boolean output is outside the CUDA dtype matrix")

@@ -114,8 +114,8 @@ def test_complex_casts_and_structure(sp):
 
 @pytest.mark.parametrize("dt", [np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64, np.float16])
 def test_storage_only_dtypes(sp, dt):
-    """Narrow / unsigned values keep their dtype (no silent upcast); structure ops move them, `astype` brings them
-    into the compute matrix, arithmetic on them raises."""
+    """Narrow / unsigned values keep their dtype (no silent upcast) and every structural operation moves them.  uint64
+    and float16 are storage-only (arithmetic raises; `astype` is the way into the compute matrix)."""
     a = np.array([[1, 0, 3], [0, 0, 2]], dtype=dt)
     x = sp.COO(a)
     assert x.dtype == dt and np.array_equal(x.todense(), a)
@@ -123,12 +123,38 @@ def test_storage_only_dtypes(sp, dt):
     g = sp.GCXS(x)
     assert g.dtype == dt and np.array_equal(g.todense(), a)
     assert np.array_equal(sp.concatenate([x, x]).todense(), np.concatenate([a, a]))
-    with pytest.raises(TypeError):
-        x + x
+    if np.dtype(dt) in (np.uint64, np.float16):
+        with pytest.raises(TypeError):
+            x + x
     if np.dtype(dt) != np.float16:
         y = x.astype(np.int64)
         assert np.array_equal((y + y).todense(), a.astype(np.int64) * 2)
         assert np.array_equal(y.astype(dt).todense(), a)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.int8, np.int16, np.uint16, np.uint32])
+def test_narrow_integer_arithmetic_wraps_like_numpy(sp, dt):
+    """int8 ... uint32 compute in a wider signed type and are cast back: NumPy's modular arithmetic, result dtype kept,
+    entries that wrap around to the fill value pruned."""
+    rng = np.random.default_rng(7)
+    info = np.iinfo(dt)
+    a = rng.integers(info.min, int(info.max) + 1, size=(5, 6)).astype(dt)
+    b = rng.integers(info.min, int(info.max) + 1, size=(5, 6)).astype(dt)
+    a[rng.random((5, 6)) < 0.5] = 0
+    b[rng.random((5, 6)) < 0.5] = 0
+    x, y = sp.COO.from_numpy(a), sp.COO.from_numpy(b)
+    with np.errstate(all="ignore"):
+        for f in (np.add, np.subtract, np.multiply, np.maximum, np.minimum, np.bitwise_and, np.bitwise_or,
+                  np.bitwise_xor, np.greater, np.equal, np.floor_divide, np.remainder):
+            got, want = f(x, y), f(a, b)
+            assert got.dtype == want.dtype and np.array_equal(got.todense(), want), f.__name__
+            assert got.nnz == int(np.sum(want != got.fill_value)), f.__name__
+        for f in (np.negative, np.abs, np.square, np.invert):
+            got, want = f(x), f(a)
+            assert got.dtype == want.dtype and np.array_equal(got.todense(), want), f.__name__
+        assert np.array_equal((x + dt(3)).todense(), a + dt(3)) and (x * 2).dtype == (a * 2).dtype
+        assert np.array_equal((x * 2).todense(), a * 2) and np.array_equal(_dense(x + b), a + b)
+        assert np.array_equal((x.asformat("gcxs") - y.asformat("gcxs")).todense(), a - b)
 
 
 def test_index_dtype_is_a_host_view(sp):
