@@ -175,19 +175,6 @@ def test_one_advanced_index(sp, xy, index):
     assert_eq(g, d[index])
 
 
-MULTI = [([0, 1],) * 2, ([0, 1], [0, 2]), ([0, 1], [0, 2], [3, 1]), ([1, 1, 0], [2, 2, 0]), (slice(None), [0, 2], [1, 1]),
-         (1, [0, 2], [1, 1]), ([1, 0], [2, 1], None), (Ellipsis, [0, 1], [3, 0]), ([0, 1], slice(None), [0, 3]),
-         ([], [])]
-
-
-@pytest.mark.parametrize("index", MULTI, ids=[str(i).replace(" ", "") for i in MULTI])
-def test_several_advanced_indices(sp, xy, index):
-    """tests/test_coo.py:456-457 upstream and more: 1-D advanced indices of one length are taken together."""
-    x, _, d, _ = xy
-    assert_eq(x[index], d[index])
-    assert_eq(sp.GCXS(x)[index], d[index])
-
-
 def test_take(sp, xy):
     x, _, d, _ = xy
     assert_eq(sp.take(x, [2, 0, 2], axis=1), np.take(d, [2, 0, 2], axis=1))

@@ -181,36 +181,3 @@ def test_integer_shifts(sp):
     assert np.array_equal(x.todense(), d << e)
     with pytest.raises(TypeError):
         x << 1.5
-
-
-def test_where_with_dense_operands_and_array_properties(sp):
-    """tests/test_array_function.py:59-80 upstream: np.where over every mix of dense / sparse operands; np.shape & co."""
-    y = sp.random((7, 6), density=0.4, random_state=0)
-    x = y.todense()
-    want = np.where(x.astype(bool), x, x)
-    for order in [(0, 0, 1), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)]:
-        a, b, c = [(x, y)[i] for i in order]
-        got = np.where(a.astype(bool), b, c)
-        assert np.array_equal(got.todense() if hasattr(got, "todense") else got, want), order
-    assert np.shape(y) == (7, 6) and np.ndim(y) == 2 and np.size(y) == 42
-    assert sp.asCOO(y) is y and sp.broadcast_shapes((3, 1), (1, 4)) == (3, 4)
-    p, q = sp.broadcast_arrays(y[:1], np.ones((7, 1)))
-    assert p.shape == q.shape == (7, 6) and np.array_equal(p.todense(), np.broadcast_to(x[:1], (7, 6)))
-    with pytest.raises(ValueError):
-        sp.asCOO(x)
-    assert np.array_equal(sp.add(y, y).todense(), x + x) and sp.float32 is np.float32  # namespace re-exports
-
-
-def test_pickle_round_trip(sp):
-    """The pickled state is the host mirror (coordinates / indices and values); device arrays are rebuilt lazily."""
-    import pickle
-    import sys
-
-    x = sp.random((5, 6, 3), density=0.4, random_state=0, fill_value=1.5)
-    for a in (x, x.asformat("gcxs"), sp.CSR(x[0]), sp.DOK(x)):
-        b = pickle.loads(pickle.dumps(a))
-        assert type(b) is type(a) and b.fill_value == a.fill_value and np.array_equal(b.todense(), a.todense())
-        if hasattr(a, "compressed_axes"):
-            assert a.compressed_axes == b.compressed_axes
-    assert np.array_equal((pickle.loads(pickle.dumps(x)) + x).todense(), 2 * x.todense())
-    assert 400 < sys.getsizeof(sp.COO.from_numpy(np.eye(100))) < np.eye(100).nbytes / 10

@@ -132,31 +132,6 @@ def test_storage_only_dtypes(sp, dt):
         assert np.array_equal(y.astype(dt).todense(), a)
 
 
-@pytest.mark.parametrize("dt", [np.uint8, np.int8, np.int16, np.uint16, np.uint32])
-def test_narrow_integer_arithmetic_wraps_like_numpy(sp, dt):
-    """int8 ... uint32 compute in a wider signed type and are cast back: NumPy's modular arithmetic, result dtype kept,
-    entries that wrap around to the fill value pruned."""
-    rng = np.random.default_rng(7)
-    info = np.iinfo(dt)
-    a = rng.integers(info.min, int(info.max) + 1, size=(5, 6)).astype(dt)
-    b = rng.integers(info.min, int(info.max) + 1, size=(5, 6)).astype(dt)
-    a[rng.random((5, 6)) < 0.5] = 0
-    b[rng.random((5, 6)) < 0.5] = 0
-    x, y = sp.COO.from_numpy(a), sp.COO.from_numpy(b)
-    with np.errstate(all="ignore"):
-        for f in (np.add, np.subtract, np.multiply, np.maximum, np.minimum, np.bitwise_and, np.bitwise_or,
-                  np.bitwise_xor, np.greater, np.equal, np.floor_divide, np.remainder):
-            got, want = f(x, y), f(a, b)
-            assert got.dtype == want.dtype and np.array_equal(got.todense(), want), f.__name__
-            assert got.nnz == int(np.sum(want != got.fill_value)), f.__name__
-        for f in (np.negative, np.abs, np.square, np.invert):
-            got, want = f(x), f(a)
-            assert got.dtype == want.dtype and np.array_equal(got.todense(), want), f.__name__
-        assert np.array_equal((x + dt(3)).todense(), a + dt(3)) and (x * 2).dtype == (a * 2).dtype
-        assert np.array_equal((x * 2).todense(), a * 2) and np.array_equal(_dense(x + b), a + b)
-        assert np.array_equal((x.asformat("gcxs") - y.asformat("gcxs")).todense(), a - b)
-
-
 def test_index_dtype_is_a_host_view(sp):
     """tests/test_compressed.py:397-405 upstream (`test_upcast`): uint8 coordinates, uint16 once they overflow."""
     a = sp.random((50, 50, 50), density=0.1, format="coo", idx_dtype=np.uint8, random_state=1)
@@ -170,46 +145,3 @@ def test_index_dtype_is_a_host_view(sp):
         sp.COO.from_numpy(np.arange(300), idx_dtype=np.int8)
     with pytest.raises(ValueError):
         sp.GCXS.from_coo(sp.random((25, 25, 25), density=0.01, random_state=2), idx_dtype=np.int8)
-
-
-# ---- against the REFERENCE itself: golden outputs generated by tests/golden/make_golden.py::gen_complex ---------------
-from _api import check_result, dec  # noqa: E402
-from _golden import load  # noqa: E402
-
-GOLD = load("complex_api")
-
-
-def _gid(i, c):
-    return "-".join(str(v) for v in [i, c["op"], c.get("dt1", c.get("dtype")), c.get("dt2", ""), c.get("fa", ""),
-                                     c.get("fb", ""), c.get("kind", ""), c.get("axis", "")] if v != "")
-
-
-@pytest.mark.parametrize("c", GOLD, ids=[_gid(i, c) for i, c in enumerate(GOLD)])
-def test_complex_golden(sp, c):
-    """Result type, shape, fill value and COORDINATES exactly as the reference returns them; values to 2e-6 (complex64)
-    / 1e-12 (complex128) -- the per-plane sums round differently from numba's complex multiply-accumulate."""
-    op = c["op"]
-    c64 = "complex64" in (c.get("dt1"), c.get("dt2"), c.get("dtype")) and "complex128" not in (c.get("dt1"), c.get("dt2"))
-    f32 = c64 or "float32" in (c.get("dt1"), c.get("dt2"))
-    tol = dict(rtol=5e-6, atol=2e-6) if f32 else dict(rtol=1e-12, atol=1e-13)
-    a = dec(sp, c, "a_", c.get("fa", "coo"))
-    if op == "matmul":
-        got = sp.matmul(a, dec(sp, c, "b_", c["fb"]))
-    elif op in ("add", "subtract", "multiply"):
-        b = dec(sp, c, "b_")
-        got = {"add": np.add, "subtract": np.subtract, "multiply": np.multiply}[op](a, b)
-    elif op == "scale":
-        got = a * (2 - 3j)
-    elif op == "conj":
-        got = a.conj()
-    elif op == "real":
-        got = a.real
-    elif op == "imag":
-        got = a.imag
-    elif op == "abs":
-        got = abs(a)
-    else:
-        axis = c["axis"]
-        got = a.sum(axis=tuple(axis) if isinstance(axis, list) else axis)
-    exact = op in ("conj", "real", "imag")
-    check_result(sp, got, c, exact=exact, **({} if exact else tol))
