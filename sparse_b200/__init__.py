@@ -30,6 +30,7 @@ from numpy import power as pow  # noqa: F401
 from numpy import right_shift as bitwise_right_shift  # noqa: F401
 
 from ._argreduce import argmax, argmin
+from ._settings import IS_NUMPY2 as _IS_NUMPY2
 from ._coo import COO, as_coo
 from ._creation import (abs, argwhere, asCOO, asarray, asnumpy, astype, broadcast_arrays, broadcast_shapes, can_cast, diff, empty, empty_like, equal, eye,
                         full, full_like, imag, interp, isinf, isnan, isneginf, isposinf, nonzero, ones, ones_like, real,
@@ -49,6 +50,8 @@ from ._sorting import sort, unique_counts, unique_values
 from ._sparse_array import SparseArray
 
 __version__ = "0.1.0"
+# `__all__` below is exactly upstream's namespace (tests/test_namespace.py there); the fused example kernels `sddmm` and
+# `mttkrp`, the 2-D classes `CSR` / `CSC` and a few helpers are importable attributes outside of it.
 
 
 def clip(a, min=None, max=None, out=None):
@@ -88,7 +91,7 @@ def all(x, /, *, axis=None, keepdims=False):
 
 
 __all__ = ["COO", "DOK", "GCXS", "SparseArray", "as_coo", "asarray", "tensordot", "matmul", "dot", "stack",
-           "elemwise", "broadcast_to", "where", "sddmm", "mttkrp", "random", "sum", "max", "min", "prod", "mean", "any", "all",
+           "elemwise", "broadcast_to", "where", "random", "sum", "max", "min", "prod", "mean", "any", "all",
            "einsum", "save_npz", "load_npz", "nansum", "nanprod", "nanmean", "nanmax", "nanmin", "nanreduce",
            # array manipulation and creation next to the hot path (widened per SURVEY.md s8f)
            "concatenate", "concat", "unstack", "moveaxis", "permute_dims", "matrix_transpose", "squeeze",
@@ -107,3 +110,8 @@ __all__ = ["COO", "DOK", "GCXS", "SparseArray", "as_coo", "asarray", "tensordot"
            "logical_and", "logical_not", "logical_or", "logical_xor", "maximum", "minimum", "multiply", "nan", "negative",
            "newaxis", "nextafter", "not_equal", "pi", "positive", "pow", "reciprocal", "remainder", "sign", "signbit",
            "sin", "sinh", "sqrt", "square", "subtract", "tan", "tanh", "trunc", "uint16", "uint32", "uint64", "uint8"]
+
+if _IS_NUMPY2:  # numpy.isdtype exists from NumPy 2.0 on (upstream adds it to the namespace under the same condition)
+    from numpy import isdtype  # noqa: E402,F401
+
+    __all__.append("isdtype")
