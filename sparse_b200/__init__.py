@@ -115,3 +115,5 @@ if _IS_NUMPY2:  # numpy.isdtype exists from NumPy 2.0 on (upstream adds it to th
     from numpy import isdtype  # noqa: E402,F401
 
     __all__.append("isdtype")
+
+__all__ = sorted(__all__)
