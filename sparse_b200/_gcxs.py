@@ -297,6 +297,11 @@ class GCXS(SparseArray):
         return COO._from_device(None, data, self.shape, self.fill_value, keys=keys)  # coordinates derived lazily
 
     @classmethod
+    def from_iter(cls, x, shape=None, compressed_axes=None, fill_value=None, idx_dtype=None):
+        """compressed.py:221-227: through COO.from_iter."""
+        return cls.from_coo(COO.from_iter(x, shape, fill_value), compressed_axes, idx_dtype)
+
+    @classmethod
     def from_numpy(cls, x, compressed_axes=None, fill_value=None, idx_dtype=None):
         return cls.from_coo(COO.from_numpy(x, fill_value=fill_value, idx_dtype=idx_dtype), compressed_axes)
 

@@ -273,6 +273,17 @@ class SparseArray(NDArrayOperatorsMixin):
     def conj(self):
         return np.conj(self)
 
+    def maybe_densify(self, max_size=1000, min_density=0.25):
+        """Dense array if the array is small or dense enough, else ValueError (_coo/core.py:1393-1448)."""
+        if self.size > max_size and self.density < min_density:
+            raise ValueError("Operation would require converting large sparse array to dense")
+        return self.todense()
+
+    def todok(self):
+        from ._dok import DOK
+
+        return DOK.from_coo(self.asformat("coo"))
+
     # ---- structure (thin forwards to _manip; `COO.flatten/swapaxes/squeeze/nonzero`, _coo/core.py) ----------
     def flatten(self, order="C"):
         if order not in {"C", None}:
