@@ -144,6 +144,9 @@ def coo_getitem(x, index):
     from ._coo import COO
 
     if isinstance(index, str):
+        if x.dtype.names is None:
+            raise IndexError("only integers, slices (`:`), ellipsis (`...`), numpy.newaxis (`None`) and integer or "
+                             "boolean arrays are valid indices")
         raise NotImplementedError("sparse_b200: structured dtypes are outside the CUDA dtype matrix")
     if not isinstance(index, tuple):
         index = (index,)

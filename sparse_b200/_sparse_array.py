@@ -41,7 +41,7 @@ class SparseArray(NDArrayOperatorsMixin):
 
     @property
     def density(self):
-        return self.nnz / self.size if self.size else 0.0
+        return self.nnz / self.size if self.size else float("nan")  # 0 / 0 like upstream's NumPy division
 
     @property
     def device(self):
@@ -66,6 +66,26 @@ class SparseArray(NDArrayOperatorsMixin):
                 f"fill_value={self.fill_value}>")
 
     __str__ = __repr__
+
+    def _repr_html_(self):
+        """Jupyter summary table (same rows as upstream's `html_table`, _utils.py:472-504)."""
+        def size(n):
+            for unit, lim in (("", 2**10), ("K", 2**20), ("M", 2**30), ("G", 2**40), ("T", 2**50)):
+                if n < lim:
+                    return str(n) if not unit else f"{n / (lim >> 10):.1f}{unit}"
+            return f"{n / 2**50:.1f}P"
+
+        density = self.nnz / self.size if self.size else float("nan")
+        rows = [("Format", type(self).__name__.lower()), ("Data Type", self.dtype), ("Shape", self.shape),
+                ("nnz", self.nnz), ("Density", density), ("Read-only", not hasattr(self, "__setitem__"))]
+        if hasattr(self, "nbytes"):
+            dense = self.size * np.dtype(self.dtype).itemsize
+            rows += [("Size", size(self.nbytes)), ("Storage ratio", f"{self.nbytes / dense if dense else float('nan'):.2f}")]
+        if type(self).__name__ == "GCXS":
+            rows.append(("Compressed Axes", self.compressed_axes))
+        cells = "".join(f'<tr><th style="text-align: left">{h}</th><td style="text-align: left">{v}</td></tr>'
+                        for h, v in rows)
+        return f"<table><tbody>{cells}</tbody></table>"
 
     # ---- NumPy protocols ---------------------------------------------------------------------------
     def __array_function__(self, func, types, args, kwargs):
