@@ -46,6 +46,7 @@ class COO(SparseArray):
         self._coords = None  # device [ndim, nnz]
         self._data = None    # device [nnz]
         self._keys = None    # device sorted linear keys (cache)
+        self._cache = {} if cache else None  # opt-in result cache of transpose / reshape / tocsr / tocsc
         self._idx_vis = None  # index dtype shown to the caller when it is not the device one (int32 / int64)
 
         if isinstance(coords, COO):
@@ -205,16 +206,34 @@ class COO(SparseArray):
 
     def __setstate__(self, state):
         self.__init__(state["coords"], state["data"], shape=state["shape"], has_duplicates=False, sorted=True,
-                      fill_value=state["fill_value"])
+                      fill_value=state["fill_value"])  # the cache is not part of the state
 
     def __sizeof__(self):
         return self.nbytes
 
-    _cache = None  # upstream's opt-in transpose / reshape cache: those operations are O(1) or one device pass here
+    _cache = None
 
     def enable_caching(self):
-        """Upstream caches transposes / reshapes on request; here they are O(1) or one device pass: a no-op."""
+        """Opt-in result cache (_coo/core.py:`cache=True`): repeated `transpose` / `reshape` / `tocsr` / `tocsc` calls
+        with the same arguments hand back the same object; the three most recent results per method are kept."""
+        if self._cache is None:
+            self._cache = {}
         return self
+
+    def _cached(self, name, key, compute):
+        if self._cache is None:
+            return compute()
+        import collections
+
+        bucket = self._cache.setdefault(name, collections.deque(maxlen=3))
+        for k, v in bucket:
+            if k == key:
+                return v
+        v = compute()
+        if isinstance(v, COO) and v is not self and v._cache is None:
+            v._cache = {}  # results of a caching array cache as well (chains like x.reshape(..).T.tocsr())
+        bucket.append((key, v))
+        return v
 
     @classmethod
     def from_numpy(cls, x, fill_value=None, idx_dtype=None):
@@ -403,7 +422,21 @@ class COO(SparseArray):
         return self
 
     def copy(self, deep=True):
-        return COO(self)
+        """Shallow: the same arrays; deep: clones (device tensors and host mirrors alike).  The cache is not copied."""
+        out = COO.__new__(COO)
+        out._copy_from(self)
+        out._cache = None
+        if deep:
+            for name in ("_coords", "_data", "_keys"):
+                v = getattr(self, name)
+                setattr(out, name, v.clone() if v is not None else None)
+            for name in ("_coords_np", "_data_np"):
+                v = getattr(self, name)
+                setattr(out, name, v.copy() if v is not None else None)
+        else:
+            out.coords, out.data  # materialise the host mirrors once so that both objects hand out the same arrays
+            self._coords_np, self._data_np = out._coords_np, out._data_np
+        return out
 
     def asformat(self, format, **kwargs):
         """_coo/core.py:asformat -- "coo" / "gcxs" / "csr" / "csc" / "dense" (names or classes)."""
@@ -452,8 +485,11 @@ class COO(SparseArray):
         check_zero_fill_value(self)
         if self.ndim != 2:
             raise ValueError("This array must be two-dimensional for this conversion to work.")
-        g = self.asformat("gcxs", compressed_axes=(0,))
-        return scipy.sparse.csr_array((g.data, g.indices, g.indptr), shape=self.shape)
+        def build():
+            g = self.asformat("gcxs", compressed_axes=(0,))
+            return scipy.sparse.csr_array((g.data, g.indices, g.indptr), shape=self.shape)
+
+        return self._cached("tocsr", (), build)
 
     def tocsc(self):
         import scipy.sparse
@@ -463,8 +499,11 @@ class COO(SparseArray):
         check_zero_fill_value(self)
         if self.ndim != 2:
             raise ValueError("This array must be two-dimensional for this conversion to work.")
-        g = self.asformat("gcxs", compressed_axes=(1,))
-        return scipy.sparse.csc_array((g.data, g.indices, g.indptr), shape=self.shape)
+        def build():
+            g = self.asformat("gcxs", compressed_axes=(1,))
+            return scipy.sparse.csc_array((g.data, g.indices, g.indptr), shape=self.shape)
+
+        return self._cached("tocsc", (), build)
 
     def astype(self, dtype, casting="unsafe", copy=True):
         """Cast of the stored values and the fill value.  Upstream routes this through `elemwise`
@@ -512,7 +551,8 @@ class COO(SparseArray):
             raise ValueError("axes don't match array")
         if axes == tuple(range(self.ndim)):
             return self
-        return self._permute_reshape(axes, tuple(self.shape[a] for a in axes))
+        return self._cached("transpose", axes,
+                            lambda: self._permute_reshape(axes, tuple(self.shape[a] for a in axes)))
 
     @property
     def T(self):
@@ -538,6 +578,9 @@ class COO(SparseArray):
             raise ValueError(f"cannot reshape array of size {self.size} into shape {shape}")
         if self.shape == shape:
             return self
+        return self._cached("reshape", shape, lambda: self._reshape(shape))
+
+    def _reshape(self, shape):
         check_linear_range(shape)
         # linear index is invariant under a C-order reshape: only the coordinates are re-derived
         if self.nnz == 0 and self._data is None:
