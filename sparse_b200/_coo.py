@@ -433,8 +433,8 @@ class COO(SparseArray):
             for name in ("_coords_np", "_data_np"):
                 v = getattr(self, name)
                 setattr(out, name, v.copy() if v is not None else None)
-        else:
-            out.coords, out.data  # materialise the host mirrors once so that both objects hand out the same arrays
+        elif self.nbytes <= (64 << 20):
+            out.coords, out.data  # small arrays: materialise the host mirrors once, both objects hand out the same arrays
             self._coords_np, self._data_np = out._coords_np, out._data_np
         return out
 
