@@ -333,6 +333,25 @@ def _dot(a, b, return_type=None):
 
     if (C.is_complex(a) or C.is_complex(b)) and not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray)):
         return C.dot_complex(_dot, a, b, return_type)  # four real products on the planes
+    from ._elemwise import _WIDE_FOR
+
+    dts = [_dense_dtype(x) if _is_dense(x) else x.dtype for x in (a, b)]
+    dtr = _dot_dtype(*dts)
+    if dtr in _WIDE_FOR and not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray)):
+        # narrow / unsigned integer products: exact in the wider signed type, cast back = NumPy's modular arithmetic
+        W = _WIDE_FOR[dtr]
+        host_in = not builtins.any(D.is_device_tensor(x) for x in (a, b))
+
+        def widen(x):
+            if isinstance(x, SparseArray):
+                return x.astype(W) if x.dtype != W else x
+            return Kn.cast(D.upload(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x, W)
+
+        out = _dot(widen(a), widen(b), return_type)
+        if isinstance(out, SparseArray):
+            return out.astype(dtr)
+        out = Kn.cast(out if D.is_device_tensor(out) else D.upload(np.ascontiguousarray(out)), dtr)
+        return D.download(out) if host_in else out
     out_shape = (a.shape[0], b.shape[1])
     if builtins.all(isinstance(arr, SparseArray) for arr in [a, b]) and builtins.any(
             isinstance(arr, GCXS) for arr in [a, b]):

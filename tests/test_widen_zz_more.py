@@ -37,6 +37,13 @@ def test_narrow_integer_arithmetic_wraps_like_numpy(sp, dt):
         assert np.array_equal((x + dt(3)).todense(), a + dt(3)) and (x * 2).dtype == (a * 2).dtype
         assert np.array_equal((x * 2).todense(), a * 2) and np.array_equal(_dense(x + b), a + b)
         assert np.array_equal((x.asformat("gcxs") - y.asformat("gcxs")).todense(), a - b)
+        want = a @ b.T  # products: exact in the wide type, wrapped by the cast back
+        for fa in ("coo", "gcxs", "dense"):
+            for fb in ("coo", "gcxs", "dense"):
+                if fa == fb == "dense":
+                    continue
+                got = (a if fa == "dense" else x.asformat(fa)) @ (b.T if fb == "dense" else y.T.asformat(fb))
+                assert _dense(got).dtype == want.dtype and np.array_equal(_dense(got), want), (fa, fb)
 
 
 
