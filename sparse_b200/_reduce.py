@@ -67,6 +67,11 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
     # result dtype by NumPy's own rules (e.g. add.reduce(int32) -> int64; logical_* -> bool)
     with np.errstate(all="ignore"):
         res_dt = method.reduce(np.zeros(1, dtype=x.dtype), **kwargs).dtype
+    narrow_back = None
+    if res_dt not in _RED_DTYPES and res_dt.kind in "iu":
+        # narrow / unsigned integer results (uint8 max, the uint64 NumPy sums unsigned values into): reduced in int64,
+        # cast back at the end (modular like NumPy's own arithmetic in that dtype)
+        narrow_back, res_dt = res_dt, np.dtype(np.int64)
     if res_dt not in _RED_DTYPES:
         raise TypeError(f"sparse_b200: reduction dtype {res_dt} is outside the CUDA dtype matrix")
     work_dt = res_dt
@@ -82,8 +87,9 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
         with np.errstate(all="ignore"):
             result_fill = np.asarray(super_ufunc(fill_w, ncols)).astype(work_dt)[()]
     if x.nnz == 0:
-        return COO(np.zeros((len(neg_axis), 0), dtype=np.intp), np.empty(0, dtype=work_dt), shape=kept_shape,
-                   has_duplicates=False, sorted=True, fill_value=result_fill)
+        out_dt = narrow_back or work_dt
+        return COO(np.zeros((len(neg_axis), 0), dtype=np.intp), np.empty(0, dtype=out_dt), shape=kept_shape,
+                   has_duplicates=False, sorted=True, fill_value=np.asarray(result_fill).astype(out_dt)[()])
     # kept axes first; keys over (kept..., reduced...) so that group id = key // ncols (sort only if not already so)
     keys, data = x._permuted_keys(neg_axis + tuple(axis))
     data = Kn.cast(data, work_dt)
@@ -95,4 +101,5 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
         pos, total = Kn.scan_flags(flags)
         vals = Kn.compact(vals, flags, pos, total)
         gids = Kn.compact(gids, flags, pos, total)
-    return COO._from_device(None, vals, kept_shape, result_fill, keys=gids)  # coordinates are derived lazily
+    out = COO._from_device(None, vals, kept_shape, result_fill, keys=gids)  # coordinates are derived lazily
+    return out.astype(narrow_back) if narrow_back is not None else out

@@ -37,6 +37,10 @@ def test_narrow_integer_arithmetic_wraps_like_numpy(sp, dt):
         assert np.array_equal((x + dt(3)).todense(), a + dt(3)) and (x * 2).dtype == (a * 2).dtype
         assert np.array_equal((x * 2).todense(), a * 2) and np.array_equal(_dense(x + b), a + b)
         assert np.array_equal((x.asformat("gcxs") - y.asformat("gcxs")).todense(), a - b)
+        for axis in (None, 0, 1):  # reductions: NumPy's result dtype (uint64 for unsigned sums), modular like NumPy
+            for name in ("sum", "max", "min", "prod", "any"):
+                got, ref = getattr(x, name)(axis=axis), getattr(a, name)(axis=axis)
+                assert got.dtype == np.asarray(ref).dtype and np.array_equal(got.todense(), ref), (name, axis)
         want = a @ b.T  # products: exact in the wide type, wrapped by the cast back
         for fa in ("coo", "gcxs", "dense"):
             for fb in ("coo", "gcxs", "dense"):
