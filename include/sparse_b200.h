@@ -279,6 +279,21 @@ int b2s_mttkrp(int dtype, int idx_bytes, int64_t I_, int64_t J, const void *indp
                const void *l_dev, const void *vals_dev, const void *d_dev, int64_t ldd, const void *c_dev, int64_t ldc,
                void *out_dev, int64_t ldo, void *stream);
 
+/* ---- copy-engine exchange of a row-sharded dense operand (peer.cu; SURVEY.md s8(e), no reference counterpart: the
+ * reference is single-process) ------------------------------------------------------------------------------------
+ * b2s_peer_alloc: cudaMalloc'ed (IPC-exportable) device buffer; b2s_peer_export writes its 64-byte CUDA IPC handle;
+ * b2s_peer_open maps a peer process's buffer (peer access enabled lazily); b2s_peer_gather copies every rank's shard
+ * (shards_dev[r], r = 0..world-1, entry `rank` = the local shard) to dst_full_dev + r*shard_bytes with
+ * cudaMemcpyAsync -- DMA over NVLink, no kernel, no SM taken from the product kernel it overlaps -- round-robin over
+ * `streams`, starting at rank+1. */
+int b2s_peer_alloc(void **dev_ptr, int64_t nbytes);
+int b2s_peer_free(void *dev_ptr);
+int b2s_peer_export(void *dev_ptr, void *handle64);
+int b2s_peer_open(const void *handle64, void **dev_ptr);
+int b2s_peer_close(void *dev_ptr);
+int b2s_peer_gather(void *dst_full_dev, const void *const *shards_dev, int world, int rank, int64_t shard_bytes,
+                    void *const *streams, int n_streams);
+
 #ifdef __cplusplus
 }
 #endif

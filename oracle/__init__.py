@@ -81,6 +81,12 @@ def max_threads() -> int:
     return int(lib().orc_max_threads())
 
 
+def set_threads(n: int) -> int:
+    """Fix the OpenMP thread count of the row-parallel kernels; returns the count now in effect."""
+    lib().orc_set_threads(ctypes.c_int(int(n)))
+    return max_threads()
+
+
 def _i64(x):
     return np.ascontiguousarray(x, dtype=np.int64)
 

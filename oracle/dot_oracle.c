@@ -42,6 +42,16 @@ int orc_max_threads(void) {
 #endif
 }
 
+/* fix the number of OpenMP threads of the row-parallel loops (bench.py's "all cores" figure must not depend on the
+ * launcher's OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_threads(int n) {
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ */
 /* _csr_csr_count_nnz, _common.py:543-570                              */
 /* Number of structural entries of A*B (marker array per output row).  */

@@ -155,6 +155,9 @@ class COO(SparseArray):
     def _make_shallow_copy_of(self, other):
         """`out=` target of a ufunc (_coo/core.py:_make_shallow_copy_of): adopt the result's arrays."""
         self._copy_from(other.asformat("coo") if not isinstance(other, COO) else other)
+        # results cached for the OLD contents (enable_caching) are stale now; upstream replaces __dict__, i.e. takes
+        # the result's cache (None)
+        self._cache = None
 
     @classmethod
     def _from_device(cls, coords, data, shape, fill_value=None, keys=None):

@@ -81,6 +81,172 @@ def all_gather_varlen(x, group=None):
     return [b[:s] for b, s in zip(bufs, sizes)]
 
 
+class _RawDeviceBuffer:
+    """`__cuda_array_interface__` holder for a cudaMalloc'ed / IPC-mapped pointer (torch.as_tensor wraps it, no copy)."""
+
+    def __init__(self, ptr: int, shape, np_dtype):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": np.dtype(np_dtype).str,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class PeerGather:
+    """All-gather of equal row shards of a dense operand by COPY ENGINES over NVLink (csrc/peer.cu).
+
+    Every rank owns an IPC-exported shard buffer (`.shard`, a torch view the caller fills) and `n_buffers` full-size
+    receive buffers; `gather(slot)` pulls all world shards into buffer `slot` with cudaMemcpyAsync on side streams --
+    DMA, no kernel -- so the exchange takes no SM and no issue slot from the DRAM-bound product kernel it overlaps
+    (an SM-based NCCL all-gather slows K1 by 5.6 % at N = 8, profiles/r01).  Ordering inside a rank is by events
+    (`gather` waits for `release(slot)`, consumers call `acquire(slot)`); ordering ACROSS ranks (a peer's shard must be
+    complete before it is pulled) is the caller's: `publish()` = local synchronise + barrier after writing `.shard`.
+    """
+
+    def __init__(self, shard_rows: int, ncols: int, dtype, group=None, n_buffers: int = 2, n_streams: int = 2):
+        import ctypes
+
+        from . import _lib
+
+        dist = _dist()
+        t = D.torch()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dtype = np.dtype(dtype)
+        self.shard_rows, self.ncols = int(shard_rows), int(ncols)
+        self.shard_bytes = self.shard_rows * self.ncols * self.dtype.itemsize
+        self._lib = lib = _lib.load()
+        dev = t.device("cuda", t.cuda.current_device())
+        p = ctypes.c_void_p()
+        _lib.check(lib.b2s_peer_alloc(ctypes.byref(p), _lib.i64(self.shard_bytes)), "b2s_peer_alloc")
+        self._own = int(p.value)
+        h = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.b2s_peer_export(_lib.vp(self._own), h), "b2s_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(h), group=group)
+        self._ptrs, self._opened = [], []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                self._ptrs.append(self._own)
+                continue
+            q = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(hb)
+            _lib.check(lib.b2s_peer_open(buf, ctypes.byref(q)), f"b2s_peer_open(rank {r})")
+            self._ptrs.append(int(q.value))
+            self._opened.append(int(q.value))
+        self._ptr_arr = (ctypes.c_void_p * self.world)(*self._ptrs)
+        self.shard = t.as_tensor(_RawDeviceBuffer(self._own, (self.shard_rows, self.ncols), self.dtype), device=dev)
+        self.buffers = [t.empty((self.shard_rows * self.world, self.ncols), dtype=self.shard.dtype, device=dev)
+                        for _ in range(n_buffers)]
+        self.streams = [t.cuda.Stream(device=dev) for _ in range(n_streams)]
+        self._stream_arr = (ctypes.c_void_p * n_streams)(*[s.cuda_stream for s in self.streams])
+        self._done = [[t.cuda.Event() for _ in self.streams] for _ in range(n_buffers)]
+        self._released = [t.cuda.Event() for _ in range(n_buffers)]
+        for e in self._released:
+            e.record()
+
+    def publish(self):
+        """The local shard is final: make it visible to the peers (device sync + barrier)."""
+        D.torch().cuda.synchronize()
+        _dist().barrier(group=self.group)
+
+    def gather(self, slot: int):
+        """Start pulling every rank's shard into buffers[slot] (returns immediately; copy engines do the work)."""
+        from . import _lib
+
+        for s in self.streams:
+            s.wait_event(self._released[slot])
+        _lib.check(self._lib.b2s_peer_gather(_lib.vp(D.ptr(self.buffers[slot])), self._ptr_arr, _lib.i32(self.world),
+                                             _lib.i32(self.rank), _lib.i64(self.shard_bytes), self._stream_arr,
+                                             _lib.i32(len(self.streams))), "b2s_peer_gather")
+        for s, e in zip(self.streams, self._done[slot]):
+            e.record(s)
+
+    def acquire(self, slot: int, stream=None):
+        """Make `stream` (default: current) wait until buffers[slot] holds the gathered operand; returns it."""
+        stream = stream or D.torch().cuda.current_stream()
+        for e in self._done[slot]:
+            stream.wait_event(e)
+        return self.buffers[slot]
+
+    def release(self, slot: int, stream=None):
+        """The consumer launched on `stream` is the last reader of buffers[slot]; the next gather(slot) waits for it."""
+        self._released[slot].record(stream or D.torch().cuda.current_stream())
+
+    def close(self):
+        D.torch().cuda.synchronize()
+        _dist().barrier(group=self.group)  # nobody is still pulling from the buffer freed below
+        for q in self._opened:
+            self._lib.b2s_peer_close(ctypes_vp(q))
+        self._opened = []
+        if self._own:
+            self.shard = None
+            self._lib.b2s_peer_free(ctypes_vp(self._own))
+            self._own = 0
+
+
+def ctypes_vp(x):
+    import ctypes
+
+    return ctypes.c_void_p(int(x))
+
+
+def gpu_numa_cpus(device_index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs; None when it cannot be determined)."""
+    import os
+
+    try:
+        t = D.torch()
+        bus = t.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.4
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            import subprocess
+
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                                  str(device_index)], capture_output=True, text=True, timeout=10).stdout.strip()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = []
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(device_index: int, local_rank: int = 0, local_world: int = 1):
+    """Pin this process (and every thread it starts afterwards: the library's host thread pool, pinned-staging
+    first-touch) to its GPU's NUMA node, split evenly between the ranks whose GPUs share that node.  Host staging of
+    the host-buffer product is memory-bound; with 8 ranks and no affinity the ranks of GPUs 4-7 stage through the
+    other socket.  Returns a description (dict) or None when the topology is not visible."""
+    import os
+
+    got = gpu_numa_cpus(device_index)
+    if got is None:
+        return None
+    node, cpus = got
+    # ranks that share the node: assume local ranks map to device indices 0..local_world-1
+    sharers = [r for r in range(local_world) if (gpu_numa_cpus(r) or (None,))[0] == node] or [local_rank]
+    k = sharers.index(local_rank) if local_rank in sharers else 0
+    per = max(1, len(cpus) // len(sharers))
+    mine = cpus[k * per:(k + 1) * per] or cpus
+    try:
+        os.sched_setaffinity(0, mine)
+    except Exception:
+        return None
+    return {"numa_node": node, "cpus": len(mine), "first_cpu": mine[0], "ranks_on_node": len(sharers)}
+
+
 def tensordot_rowblock(a_local, b_shard, group=None, out=None):
     """Local block of ``A @ B`` (dense result rows owned by this rank).
 

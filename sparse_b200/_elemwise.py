@@ -454,6 +454,8 @@ class _Elemwise:
 
     def _dense_result(self, sp, dense, swap, op, T, out_dt):
         """func(sparse.todense(), ndarray) when the fill value is not constant (_umath.py:463-465)."""
+        if tuple(sp.shape) != tuple(self.shape):  # a sparse row / column / scalar against a dense array
+            sp = broadcast_to(sp.asformat("coo"), self.shape)
         full = Kn.cast(sp.todense_device().reshape(-1), T)
         keys = Kn.iota(int(full.shape[0]))
         _, vals, _ = Kn.ew_dense(op, swap, keys, full, 1, dense, self.shape,

@@ -502,15 +502,30 @@ def kron(a, b):
     check_zero_fill_value(*(x for x in (a, b) if isinstance(x, SparseArray)))
     if np.isscalar(a) or np.isscalar(b) or getattr(a, "ndim", 1) == 0 or getattr(b, "ndim", 1) == 0:
         return a * b
-    a = _as_coo(a) if isinstance(a, SparseArray) else np.asarray(a)
-    b = _as_coo(b) if isinstance(b, SparseArray) else np.asarray(b)
+    a, b = _as_coo(a), _as_coo(b)  # a dense operand contributes its non-zero entries (as_coo prunes)
     nd = max(a.ndim, b.ndim)
     a = a.reshape((1,) * (nd - a.ndim) + tuple(a.shape))
     b = b.reshape((1,) * (nd - b.ndim) + tuple(b.shape))
-    a_wide = a.reshape(tuple(v for s in a.shape for v in (s, 1)))
-    b_wide = b.reshape(tuple(v for s in b.shape for v in (1, s)))
-    res = a_wide * b_wide
-    return res.reshape(tuple(sa * sb for sa, sb in zip(a.shape, b.shape)))
+    out_shape = tuple(sa * sb for sa, sb in zip(a.shape, b.shape))
+    from ._elemwise import _BINARY, dense_binary
+
+    dtr = np.result_type(a.dtype, b.dtype)
+    na, nb = a.nnz, b.nnz
+    if na == 0 or nb == 0:
+        return _empty(out_shape, dtr, dtr.type(0))
+    # stored x stored only, like upstream (a broadcast product would also store negative * fill = -0.0):
+    # pair (p, q) -> coordinate a_coords[:, p] * b.shape + b_coords[:, q], value a.data[p] * b.data[q]
+    t = D.torch()
+    pair = Kn.iota(na * nb)
+    ia, _ = Kn.ew_map(_BINARY[np.floor_divide], 0, pair, np.int64(nb), 0, np.int64)
+    ib, _ = Kn.ew_map(_BINARY[np.remainder], 0, pair, np.int64(nb), 0, np.int64)
+    ka = Kn.gather(_rekey(a, [sb * st for sb, st in zip(b.shape, c_strides(out_shape))]), ia)
+    kb = Kn.gather(_rekey(b, c_strides(out_shape)), ib)
+    keys = dense_binary(np.add, ka, kb)
+    data = dense_binary(np.multiply, Kn.cast(Kn.gather(a._data_dev(), ia), dtr),
+                        Kn.cast(Kn.gather(b._data_dev(), ib), dtr))
+    del t
+    return _sorted_result(keys, data, out_shape, dtr.type(0))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -8,9 +8,7 @@ as the plain reductions (csrc/reduce_fused.cu; `fmax` / `fmin` are reduction ops
 """
 from __future__ import annotations
 
-import operator
 import warnings
-from functools import reduce as _functools_reduce
 
 import numpy as np
 
@@ -76,27 +74,24 @@ def nanprod(x, axis=None, keepdims=False, dtype=None, out=None):
 
 
 def nanmean(x, axis=None, keepdims=False, dtype=None, out=None):
-    """_coo/common.py:364-415: nansum / (slice size - NaN count), NumPy's dtype rules for the division."""
+    """Mean over the non-NaN elements of every slice (_coo/common.py:364-415 upstream): the NaN-free sum divided by
+    the number of valid elements, with NumPy's dtype rules for the division; integer input has no NaNs."""
     assert out is None
     x = _as_coo(x, "nanmean")
-    if not np.issubdtype(x.dtype, np.floating):
+    if x.dtype.kind != "f":
         return x.mean(axis=axis, keepdims=keepdims, dtype=dtype)
-    mask = np.isnan(x)
-    x2 = _replace_nan(x, 0)
-    nancount = mask.sum(axis=axis, dtype="i8", keepdims=keepdims)
-    if axis is None:
-        axis = tuple(range(x.ndim))
-    elif not isinstance(axis, tuple):
-        axis = (axis,)
-    den = _functools_reduce(operator.mul, (x.shape[i] for i in axis), 1)
-    den = den - nancount
-    if (den == 0).any():
+    red = tuple(range(x.ndim)) if axis is None else (axis if isinstance(axis, tuple) else (axis,))
+    slice_size = 1
+    for a in red:
+        slice_size *= x.shape[a]
+    valid = slice_size - np.isnan(x).sum(axis=axis, dtype=np.int64, keepdims=keepdims)  # per-slice count (sparse)
+    if (valid == 0).any():
         warnings.warn("Mean of empty slice", RuntimeWarning, stacklevel=1)
-    num = np.sum(x2, axis=axis, dtype=dtype, keepdims=keepdims)
+    total = _replace_nan(x, 0).sum(axis=red, dtype=dtype, keepdims=keepdims)
     with np.errstate(invalid="ignore", divide="ignore"):
-        if num.ndim:
-            return np.true_divide(num, den, casting="unsafe")
-        return (num / den).astype(dtype if dtype is not None else x.dtype)
+        if total.ndim:
+            return np.true_divide(total, valid, casting="unsafe")
+        return (total / valid).astype(x.dtype if dtype is None else dtype)
 
 
 def _nan_extreme(x, method, name, axis, keepdims, dtype):

@@ -59,6 +59,9 @@ def reduce_impl(x, method, axis=(0,), keepdims=False, **kwargs):
     return out
 
 
+_SIGN64 = np.int64(-(2**63))
+
+
 def _reduce_coo(x, method, axis, super_ufunc, kwargs):
     op = _RED[method]
     neg_axis = tuple(ax for ax in range(x.ndim) if ax not in set(axis))
@@ -77,6 +80,11 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
     work_dt = res_dt
     kept_shape = tuple(x.shape[d] for d in neg_axis)
     fill_in = x.fill_value
+    # uint64 through int64 is modular-correct for add / multiply only; the ORDER-based reductions see values >= 2**63
+    # as negative.  x ^ 2**63 maps the unsigned order onto the signed one: flip before, flip back after.
+    flip = narrow_back == np.dtype(np.uint64) and op in (2, 3)
+    if flip:
+        fill_in = np.asarray(fill_in, dtype=np.uint64).view(np.int64)[()] ^ _SIGN64
     if op in (4, 5):  # logical reductions work on truth values
         fill_w = np.bool_(bool(fill_in))
         work_dt = np.dtype(np.bool_)
@@ -88,11 +96,17 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
             result_fill = np.asarray(super_ufunc(fill_w, ncols)).astype(work_dt)[()]
     if x.nnz == 0:
         out_dt = narrow_back or work_dt
+        if flip:
+            result_fill = np.int64(result_fill) ^ _SIGN64
         return COO(np.zeros((len(neg_axis), 0), dtype=np.intp), np.empty(0, dtype=out_dt), shape=kept_shape,
                    has_duplicates=False, sorted=True, fill_value=np.asarray(result_fill).astype(out_dt)[()])
     # kept axes first; keys over (kept..., reduced...) so that group id = key // ncols (sort only if not already so)
     keys, data = x._permuted_keys(neg_axis + tuple(axis))
     data = Kn.cast(data, work_dt)
+    if flip:
+        from ._elemwise import _BINARY
+
+        data, _ = Kn.ew_map(_BINARY[np.bitwise_xor], 0, data, _SIGN64, 0, np.int64)
     # one fused segmented-scan pass pair: values with the fill-value contribution applied, group ids (= linear index
     # over the kept axes) and their coordinates (_grouped_reduce + _sparse_array.py:405-422 + _reduce_return)
     _, gids, vals, n_eq = Kn.reduce_fused(op, keys, data, ncols, fill_w, result_fill, kept_shape, want_coords=False)
@@ -101,5 +115,8 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
         pos, total = Kn.scan_flags(flags)
         vals = Kn.compact(vals, flags, pos, total)
         gids = Kn.compact(gids, flags, pos, total)
+    if flip:
+        vals, _ = Kn.ew_map(_BINARY[np.bitwise_xor], 0, vals, _SIGN64, 0, np.int64)
+        result_fill = np.int64(result_fill) ^ _SIGN64
     out = COO._from_device(None, vals, kept_shape, result_fill, keys=gids)  # coordinates are derived lazily
     return out.astype(narrow_back) if narrow_back is not None else out

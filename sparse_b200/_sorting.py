@@ -148,7 +148,7 @@ def sort(x, /, *, axis=-1, descending=False, stable=False):
         ds_cmp, fill_c = ds, T.type(fill)
     with np.errstate(all="ignore"):
         after, _ = Kn.ew_map(_BINARY[np.less if descending else np.greater], 0, ds_cmp, fill_c, False, np.bool_)
-        if T.kind == "f":
+        if T.kind == "f" and not descending:  # NaNs sort last ascending (after the fills), FIRST descending
             from ._elemwise import _UNARY
 
             nan_e, _ = Kn.ew_map(_UNARY[np.isnan], 2, ds, None, False, np.bool_)

@@ -18,53 +18,58 @@ def _zero_of_dtype(dtype):
 
 
 def equivalent(x, y, /, loose=False):
-    """`equivalent`, _utils.py:406-452 -- for host scalars (fill values) only."""
-    x = np.asarray(x)
-    y = np.asarray(y)
-    dt = np.result_type(x.dtype, y.dtype)
-    if not any(np.issubdtype(dt, t) for t in [np.floating, np.complexfloating]):
+    """Equality in the sense the reference prunes by (_utils.py:406-452 upstream): integers and booleans compare by
+    value; floating-point and complex values compare by BIT PATTERN, so +0.0 and -0.0 differ and a NaN equals the
+    identical NaN.  `loose=True` is ordinary equality that also lets any NaN equal any NaN.  Fill values are host
+    scalars, but arrays broadcast as usual."""
+    x, y = np.asarray(x), np.asarray(y)
+    common = np.result_type(x.dtype, y.dtype)
+    if common.kind not in "fc":
         return x == y
     if loose:
-        return (x == y) | ((x != x) & (y != y))
-    if x.size == 0 or y.size == 0:
-        return np.empty(np.broadcast_shapes(x.shape, y.shape), dtype=np.bool_)
-    x, y = np.broadcast_arrays(x[..., None], y[..., None])
-    return (x.astype(dt).view(np.uint8) == y.astype(dt).view(np.uint8)).all(axis=-1)
+        return (x == y) | (np.isnan(x) & np.isnan(y))
+    xb, yb = np.broadcast_arrays(x.astype(common), y.astype(common))
+    raw = [np.ascontiguousarray(v).reshape(-1).view(np.uint8).reshape(-1, common.itemsize) for v in (xb, yb)]
+    return (raw[0] == raw[1]).all(axis=1).reshape(xb.shape)[()]
 
 
 def check_zero_fill_value(*args, loose=True):
-    """_utils.py:562-596: tensordot / matmul / dot require zero fill values."""
-    for i, arg in enumerate(args):
-        if getattr(arg, "size", 1) == 0:
+    """tensordot / matmul / dot / kron are only defined for zero fill values (_utils.py:562-596 upstream; same
+    message).  Operands without a fill value (ndarrays) and empty operands pass."""
+    for position, operand in enumerate(args):
+        fv = getattr(operand, "fill_value", None)
+        if fv is None or getattr(operand, "size", 1) == 0:
             continue
-        if hasattr(arg, "fill_value") and not equivalent(arg.fill_value, _zero_of_dtype(arg.dtype), loose=loose):
+        if not equivalent(fv, _zero_of_dtype(operand.dtype), loose=loose):
             raise ValueError(
-                f"This operation requires zero fill values, but argument {i:d} had a fill value of {arg.fill_value!s}."
+                f"This operation requires zero fill values, but argument {position:d} had a fill value of {fv!s}."
             )
 
 
 def check_fill_value(x, /, *, accept_fv=None):
-    """_utils.py:531-560: raise unless the fill value is one of `accept_fv` (default: zero only)."""
-    if accept_fv is None:
-        accept_fv = [0]
-    if not isinstance(accept_fv, Iterable):
-        accept_fv = [accept_fv]
-    if not any(equivalent(fv, x.fill_value, loose=True) for fv in accept_fv):
-        raise ValueError(f"{x.fill_value=} but should be in {accept_fv}.")
+    """Raise unless x's fill value is (loosely) one of `accept_fv` -- a scalar or a collection, default zero
+    (_utils.py:531-560 upstream; same message)."""
+    allowed = [0] if accept_fv is None else (list(accept_fv) if isinstance(accept_fv, Iterable) else [accept_fv])
+    for fv in allowed:
+        if equivalent(fv, x.fill_value, loose=True):
+            return
+    raise ValueError(f"{x.fill_value=} but should be in {allowed}.")
 
 
 def normalize_axis(axis, ndim):
-    """_utils.py:normalize_axis."""
+    """None stays None; an integer becomes its non-negative form; a collection is normalised item by item
+    (`normalize_axis` upstream; ValueError with upstream's wording for anything else)."""
     if axis is None:
         return None
-    if isinstance(axis, (int, np.integer)):
-        axis = int(axis)
-        if axis < -ndim or axis >= ndim:
-            raise ValueError(f"Invalid axis index {axis} for ndim={ndim}")
-        return axis % ndim if ndim else axis
-    if isinstance(axis, Iterable):
+    if isinstance(axis, Iterable) and not isinstance(axis, (str, bytes)):
         return tuple(normalize_axis(a, ndim) for a in axis)
-    raise ValueError(f"axis {axis} not understood")
+    try:
+        a = operator.index(axis)
+    except TypeError:
+        raise ValueError(f"axis {axis} not understood") from None
+    if not -ndim <= a < ndim:
+        raise ValueError(f"Invalid axis index {a} for ndim={ndim}")
+    return a + ndim if a < 0 else a
 
 
 def can_store(dtype, scalar) -> bool:
@@ -77,21 +82,23 @@ def can_store(dtype, scalar) -> bool:
 
 
 def check_compressed_axes(ndim, compressed_axes):
-    """_utils.py:check_compressed_axes."""
+    """Validate GCXS `compressed_axes` against an ndim (or a shape): a collection of distinct in-range integers that
+    leaves at least one axis uncompressed (`check_compressed_axes` upstream; same messages)."""
     if compressed_axes is None:
         return
-    if isinstance(ndim, Iterable):
-        ndim = len(ndim)
+    nd = len(ndim) if isinstance(ndim, Iterable) else ndim
     if not isinstance(compressed_axes, Iterable):
         raise ValueError("compressed_axes must be an iterable")
-    if len(compressed_axes) == ndim:
-        raise ValueError("cannot compress all axes")
-    if len(set(compressed_axes)) != len(compressed_axes):
-        raise ValueError("axes must be unique")
-    if not all(isinstance(a, (int, np.integer)) for a in compressed_axes):
-        raise ValueError("axes must be integers")
-    if min(compressed_axes) < 0 or max(compressed_axes) >= ndim:
-        raise ValueError("axis out of range")
+    axes = list(compressed_axes)
+    rules = (
+        (lambda: len(axes) == nd, "cannot compress all axes"),
+        (lambda: len(set(axes)) != len(axes), "axes must be unique"),
+        (lambda: any(not isinstance(a, (int, np.integer)) for a in axes), "axes must be integers"),
+        (lambda: min(axes) < 0 or max(axes) >= nd, "axis out of range"),
+    )
+    for broken, message in rules:
+        if broken():
+            raise ValueError(message)
 
 
 def c_strides(shape):

@@ -46,7 +46,9 @@ __global__ void dense_flags_kernel(const T *__restrict__ x, int64_t n, int mode,
         bool keep;
         if (mode == 0) keep = (v != T(0));
         else {
-            if constexpr (sizeof(T) == 4) {
+            if constexpr (sizeof(T) == 1) {
+                keep = v != T(0);
+            } else if constexpr (sizeof(T) == 4) {
                 uint32_t u;
                 memcpy(&u, &v, 4);
                 keep = u != 0u;
@@ -180,6 +182,7 @@ int b2s_dense_to_csr_begin(int dtype, int64_t M, int64_t N, const void *x_dev, c
             case B2S_F64: dense_flags_kernel<double><<<grid_n(n), 256, 0, s>>>((const double *)x_dev, n, mode, pl->flags); break;
             case B2S_I32: dense_flags_kernel<int32_t><<<grid_n(n), 256, 0, s>>>((const int32_t *)x_dev, n, mode, pl->flags); break;
             case B2S_I64: dense_flags_kernel<int64_t><<<grid_n(n), 256, 0, s>>>((const int64_t *)x_dev, n, mode, pl->flags); break;
+            case B2S_BOOL: dense_flags_kernel<uint8_t><<<grid_n(n), 256, 0, s>>>((const uint8_t *)x_dev, n, mode, pl->flags); break;
             default: set_error("dense_to_csr: dtype %d", dtype); return B2S_ERR_UNSUPPORTED;
         }
         B2S_CHECK_LAUNCH();
@@ -219,6 +222,7 @@ int b2s_dense_to_csr_finish(void *plan, int64_t *rows_out_or_null_dev, int64_t *
             case B2S_F64: B2S_DF(double); break;
             case B2S_I32: B2S_DF(int32_t); break;
             case B2S_I64: B2S_DF(int64_t); break;
+            case B2S_BOOL: B2S_DF(uint8_t); break;
             default: rc = B2S_ERR_UNSUPPORTED;
         }
 #undef B2S_DF

@@ -17,7 +17,14 @@ def test_reference_arm_json_line():
                 "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "GNNZ/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    cb = line["cpu_baseline"]
+    if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "sparse", "__init__.py")):
+        # the reference itself (numba, single-threaded by construction) + the labelled all-cores port figure
+        assert cb["kind"] == "reference" and cb["cores"] == 1 and "numba" in cb and cb["value"] == line["value"]
+        assert cb["all_cores_port"]["kind"] == "port" and cb["all_cores_port"]["cores"] >= 1
+    else:  # baseline/_ref not installed (tools/make_ref.sh): the C port stands in and says so
+        assert cb["kind"] == "port" and cb["cores"] >= 1 and "baseline/_ref missing" in cb["sample"]
+    assert "same arrays" in cb["sample"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
 
 

@@ -369,7 +369,9 @@ def test_kron_tile_repeat_match_numpy(data):
     sb = data.draw(st.lists(st.integers(1, 3), min_size=1, max_size=3).map(tuple))
     a, da = _rand(sa, data.draw(st.integers(0, 99)), 0.5)
     b, db = _rand(sb, data.draw(st.integers(0, 99)), 0.5)
-    _check(sp.kron(a, b), np.kron(da, db))
+    k = sp.kron(a, b)  # stored x stored only, as upstream (_coo/common.py:67-129): no -0.0 from negative * fill
+    assert k.shape == np.kron(da, db).shape and np.array_equal(k.todense(), np.kron(da, db))
+    assert k.nnz == a.nnz * b.nnz and not np.signbit(k.todense()[np.kron(da, db) == 0]).any()
     reps = tuple(data.draw(st.integers(1, 3)) for _ in range(data.draw(st.integers(1, 4))))
     _check(sp.tile(a, reps), np.tile(da, reps))
     ax = data.draw(st.one_of(st.none(), st.integers(0, len(sa) - 1)))

@@ -7,7 +7,7 @@
 #       --master-addr 127.0.0.1 --master-port 29511 tools/bench_multi.py > gpurun_out/multi_2.log 2>&1'
 set -u
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x -n 4 -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/gpu_tests.log
 tail -5 gpurun_out/gpu_tests.log
 timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
