@@ -64,6 +64,76 @@ def test_c3_full_size_broadcast_add_and_multiply():
     assert np.array_equal(m0.data, want_max)
 
 
+def test_c3_full_size_matches_the_reference_digests():
+    """C3 against the REFERENCE ITSELF at full size: tests/golden/fullsize_digests.json holds, for the seeded inputs of
+    tests/golden/fullsize_inputs.py, nnz and SHA-256 (coordinates + value bit patterns) of the reference's add /
+    multiply / maximum results in float64 and float32, and coordinates digest + sampled values of its reductions."""
+    import json
+    import os
+    import sys
+
+    sp = _sp()
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    import fullsize_inputs as FI
+
+    with open(os.path.join(gdir, "fullsize_digests.json")) as f:
+        want = json.load(f)["cases"]
+    for dt in (np.float64, np.float32):
+        (ca, da), (cb, db) = FI.c3_inputs(dt)
+        name = np.dtype(dt).name
+        a = sp.COO(ca, da, shape=FI.C3_SHAPE_A, has_duplicates=False, sorted=True)
+        b = sp.COO(cb, db, shape=FI.C3_SHAPE_B, has_duplicates=False, sorted=True)
+        w = want[f"c3_inputs_{name}"]
+        assert (a.nnz, b.nnz) == (w["a_nnz"], w["b_nnz"]) and FI.coo_digest(a.coords, a.data) == w["a"]
+        for f in (np.add, np.multiply, np.maximum):
+            r = f(a, b)
+            w = want[f"c3_{f.__name__}_{name}"]
+            assert isinstance(r, sp.COO) and r.dtype == dt and r.nnz == w["nnz"], (f.__name__, name, r.nnz)
+            assert FI.coo_digest(r.coords, r.data) == w["sha256"], (f.__name__, name)
+        if dt == np.float64:
+            for axis in ((3,), (0, 1), (0,)):
+                for red in ("sum", "max"):
+                    r = getattr(a, red)(axis=axis)
+                    w = want[f"c3_{red}_axis{''.join(map(str, axis))}_float64"]
+                    assert r.nnz == w["nnz"] and FI.digest(np.asarray(r.coords, dtype=np.int64)) == w["coords_sha256"]
+                    got = r.data[:: w["sample_step"]]
+                    assert np.allclose(got, w["values_sample"], rtol=1e-12, atol=0), (red, axis)
+                    assert np.isclose(float(np.sum(r.data)), w["total"], rtol=1e-11)
+
+
+def test_c2_full_size_sampled_rows_bit_exact():
+    """C2 at the configured size (1e6 x 1e6, nnz 1e8, N = 128, fp32): 12 000 rows of the product -- a contiguous block
+    and a random sample -- are bit-identical to the oracle's _dot_csr_ndarray on the same arrays."""
+    import torch
+
+    import bench
+    from sparse_b200 import _kernels as Kn
+
+    _sp()
+    dev = torch.device("cuda", 0)
+    M = K = 1_000_000
+    N = 128
+    vals, cols, indptr, B = bench.make_workload(torch, M, K, 100_000_000, N, 77, dev)
+    C = Kn.spmm_csr_dense(vals, cols, indptr, B, M, K, N)
+    ip = indptr.cpu().numpy().astype(np.int64)
+    Bh = B.cpu().numpy()
+    rng = np.random.default_rng(5)
+    rows = np.unique(np.concatenate([np.arange(499_000, 503_000), rng.choice(M, 8000, replace=False)]))
+    seg = [np.arange(ip[r], ip[r + 1]) for r in rows]
+    sel = np.concatenate(seg)
+    sub_ptr = np.zeros(len(rows) + 1, np.int64)
+    np.cumsum([len(s) for s in seg], out=sub_ptr[1:])
+    sel_t = torch.from_numpy(sel).to(dev)
+    want = oracle.dot_csr_ndarray((len(rows), N), vals[sel_t].cpu().numpy(), cols[sel_t].cpu().numpy().astype(np.int64),
+                                  sub_ptr, Bh)
+    got = C[torch.from_numpy(rows).to(dev)].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # linearity in a power of two holds exactly over the whole product (size-independent property)
+    C2 = Kn.spmm_csr_dense(vals * 2.0, cols, indptr, B, M, K, N)
+    assert torch.equal(C2, C * 2.0)
+
+
 def test_c5_full_size_spgemm_bit_exact():
     """C5: (1e6 x 1e6, density 1e-5)^2 -- indptr/indices/data identical to the oracle of _dot_csr_csr
     (reverse-first-touch column order included)."""
@@ -83,15 +153,19 @@ def test_c5_full_size_spgemm_bit_exact():
     assert np.array_equal(got.data.view(np.uint32), d[keep].view(np.uint32))
 
 
-def test_c4_sddmm_large_properties():
-    """C4-shaped SDDMM (1e6 x 1e6 mask, K = 256, fp32; nnz reduced to 2e7 to keep the test short):
-    exact linearity in a power of two, coordinates preserved, sampled entries vs a float64 restatement."""
+def test_c4_sddmm_full_size_properties():
+    """C4 at the configured size (1e6 x 1e6 mask, nnz 1e8, K = 256, fp32): exact linearity in a power of two,
+    coordinates preserved, sampled entries vs a float64 restatement."""
     sp = _sp()
     import torch
 
+    import bench
+
     rng = np.random.default_rng(4)
     n, K = 1_000_000, 256
-    s = sp.random((n, n), nnz=20_000_000, random_state=rng).astype(np.float32)
+    vals, cols, indptr, _ = bench.make_workload(torch, n, n, 100_000_000, 1, 21, torch.device("cuda", 0))
+    s = sp.GCXS((vals, cols, indptr), shape=(n, n), compressed_axes=(0,)).tocoo()
+    del vals, cols, indptr
     g = torch.Generator(device="cuda").manual_seed(5)
     a = torch.rand((n, K), generator=g, device="cuda", dtype=torch.float32)
     b = torch.rand((K, n), generator=g, device="cuda", dtype=torch.float32)
