@@ -119,10 +119,10 @@ __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
 }
 
 // One tile of the SINGLE-pass segmented reduction.
-// Loads and stores go through shared memory so that global accesses are fully coalesced: the tile's 2048 (key, value)
-// pairs are loaded with unit stride, each thread then reads its 8 consecutive pairs from a padded layout
-// (index e + e/8: 2-way instead of 16-way bank conflicts), and the finished runs of the tile -- which occupy one
-// contiguous range of output slots -- are staged in the same buffers and written out with unit stride.
+// Every thread owns RD_ITEMS consecutive (key, value) pairs and reads them straight from global memory with 16-byte
+// vector loads (a warp covers one contiguous 2-4 KB range; the four loads of a thread hit the same L1 lines), so the
+// inputs never pass through shared memory.  The finished runs of the tile -- which occupy one contiguous range of
+// output slots -- are staged in shared memory and written out with unit stride.
 // The carry-in of a tile (the run still open at its first element + the number of run heads before it) comes from a
 // decoupled look-back over the tile descriptors of its predecessors (Merrill & Garland): tiles are taken in TICKET
 // order, every tile publishes its own aggregate before it waits for anything and only ever waits on smaller tickets
@@ -130,9 +130,6 @@ __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
 // (aggregate / inclusive prefix), so its look-back needs no fences; the carry-in RUN only ever needs the predecessors'
 // aggregates back to the nearest tile that contains a head (usually the immediate predecessor), which are published
 // (payload, __threadfence, status) before that tile waits for anything.
-constexpr int RD_PAD = RD_TILE + RD_TILE / 8 + 8;
-__device__ __forceinline__ int rd_pad(int e) { return e + (e >> 3); }
-
 enum : uint64_t { RD_AGG = 1ull << 62, RD_PREFIX = 2ull << 62, RD_VALUE = (1ull << 62) - 1 };
 template <typename T>
 struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entries each)
@@ -141,15 +138,32 @@ struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entr
     int64_t *run_meta;   // ... and (count << 1) | "the tile contains a head"; valid once heads[] is non-zero
 };
 
-// IS_ADD: the operator is known at compile time for sums (the common case): no per-element switch
-template <typename T, bool IS_ADD>
+// RD_ITEMS consecutive elements of p[] starting at element `first` (a multiple of RD_ITEMS): 16-byte loads when the
+// array is 16-byte aligned (VEC), element loads otherwise
+template <typename E, bool VEC>
+__device__ __forceinline__ void load_items(const E *__restrict__ p, int64_t first, E (&out)[RD_ITEMS]) {
+    if constexpr (VEC && (RD_ITEMS * sizeof(E)) % 16 == 0) {
+        constexpr int NV = (int)(RD_ITEMS * sizeof(E) / 16);
+        const uint4 *src = reinterpret_cast<const uint4 *>(p + first);
+        uint4 tmp[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tmp[q] = __ldg(src + q);
+        memcpy(out, tmp, sizeof(out));
+    } else {
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) out[i] = p[first + i];
+    }
+}
+
+// OP >= 0: the operator is a compile-time constant (no per-element switch); OP = -1: runtime operator
+template <typename T, int OP, bool VEC>
 __global__ void __launch_bounds__(RD_THREADS, 4)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
                    FastDiv fcols, int op_rt, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
                    T result_fill, int64_t *__restrict__ out_gid, T *__restrict__ out_val,
                    unsigned long long *__restrict__ counters /* [0] results equal to result_fill, [1] groups */) {
-    __shared__ int64_t sk[RD_PAD];
-    __shared__ T sv[RD_PAD];
+    __shared__ int64_t sk[RD_TILE + 1];
+    __shared__ T sv[RD_TILE + 1];
     __shared__ int s_flag[RD_THREADS / 32];
     __shared__ T s_val[RD_THREADS / 32];
     __shared__ int64_t s_cnt[RD_THREADS / 32];
@@ -157,7 +171,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     __shared__ int64_t s_tile, s_hexcl, s_ccnt;
     __shared__ int s_cflag;
     __shared__ T s_cval;
-    const int op = IS_ADD ? (int)RF_ADD : op_rt;
+    const int op = OP >= 0 ? OP : op_rt;
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
     __syncthreads();
     const int64_t tile = s_tile;
@@ -165,38 +179,35 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     const int64_t base = tile_base + (int64_t)threadIdx.x * RD_ITEMS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    // coalesced tile load: slot e holds element tile_base + e (group id, value); slot -1 / RD_TILE = neighbours
-#pragma unroll
-    for (int i = 0; i < RD_ITEMS; ++i) {
-        const int e = threadIdx.x + i * RD_THREADS;
-        const int64_t p = tile_base + e;
-        int64_t gk = -1;
-        T vv = T(0);
-        if (p < n) {
-            gk = (int64_t)fcols.div((uint64_t)keys[p]);
-            vv = vals[p];
-        }
-        sk[rd_pad(e)] = gk;
-        sv[rd_pad(e)] = vv;
-    }
-    __shared__ int64_t s_edge[2];
-    if (threadIdx.x == 0) {
-        s_edge[0] = (tile_base > 0) ? (int64_t)fcols.div((uint64_t)keys[tile_base - 1]) : -1;
-        s_edge[1] = (tile_base + RD_TILE < n) ? (int64_t)fcols.div((uint64_t)keys[tile_base + RD_TILE]) : -1;
-    }
-    __syncthreads();
-
     int64_t g[RD_ITEMS];
     T v[RD_ITEMS];
+    if (base + RD_ITEMS <= n) {
+        load_items<int64_t, VEC>(keys, base, g);
+        load_items<T, VEC>(vals, base, v);
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) g[i] = (int64_t)fcols.div((uint64_t)g[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) {
+            const int64_t p = base + i;
+            g[i] = -1;
+            v[i] = T(0);
+            if (p < n) {
+                g[i] = (int64_t)fcols.div((uint64_t)keys[p]);
+                v[i] = vals[p];
+            }
+        }
+    }
+    // group ids of the neighbours: the previous thread's last element, the next thread's first one
+    int64_t gprev = __shfl_up_sync(0xffffffffu, g[RD_ITEMS - 1], 1);
+    int64_t gnext_thread = __shfl_down_sync(0xffffffffu, g[0], 1);
+    if (lane == 0) gprev = base > 0 && base - 1 < n ? (int64_t)fcols.div((uint64_t)keys[base - 1]) : -1;
+    if (lane == 31) gnext_thread = base + RD_ITEMS < n ? (int64_t)fcols.div((uint64_t)keys[base + RD_ITEMS]) : -1;
+
     bool head[RD_ITEMS];
-    const int e0 = threadIdx.x * RD_ITEMS;
-    const int64_t gprev = (threadIdx.x == 0) ? s_edge[0] : sk[rd_pad(e0 - 1)];
-    const int64_t gnext_thread = (threadIdx.x == RD_THREADS - 1) ? s_edge[1] : sk[rd_pad(e0 + RD_ITEMS)];
 #pragma unroll
     for (int i = 0; i < RD_ITEMS; ++i) {
         const int64_t p = base + i;
-        g[i] = sk[rd_pad(e0 + i)];
-        v[i] = sv[rd_pad(e0 + i)];
         head[i] = (p < n) && ((p == 0) || (g[i] != (i == 0 ? gprev : g[i - 1])));
     }
     // thread summary: run still open at the end of the thread's range
@@ -237,7 +248,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         s_cnt[w] = incl.cnt;
         s_heads[w] = hincl;
     }
-    __syncthreads();  // (also: every thread has copied its inputs out of sk / sv)
+    __syncthreads();
     Run<T> wcarry;  // warps before this one, no carry-in yet
     wcarry.flag = 0;
     wcarry.val = T(0);
@@ -265,8 +276,8 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         __threadfence();
         *(volatile uint64_t *)&desc.heads[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (uint64_t)tile_heads;
     }
-    // the staging buffers alias the input buffers: mark every slot empty
-    for (int i = threadIdx.x; i < RD_TILE + 1; i += RD_THREADS) sk[i] = -1;
+    // output staging: the tile finishes at most tile_heads + 1 runs; mark those slots empty
+    for (int i = threadIdx.x; i < tile_heads + 1; i += RD_THREADS) sk[i] = -1;
     if (w == 0) {
         Run<T> excl;
         excl.flag = 0;
@@ -387,7 +398,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
             const bool last = (p == n - 1) ||
                               ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1]) : (g[i] != gnext_thread));
             if (last) {
-                const int loc = (int)(hcount - 1 - slot0);  // 0 .. RD_TILE
+                const int loc = (int)(hcount - 1 - slot0);  // 0 .. tile_heads
                 sk[loc] = g[i];
                 sv[loc] = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
             }
@@ -395,7 +406,7 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     }
     __syncthreads();
     int eq = 0;
-    for (int l = threadIdx.x; l < RD_TILE + 1; l += RD_THREADS) {
+    for (int l = threadIdx.x; l < tile_heads + 1; l += RD_THREADS) {
         const int64_t gid = sk[l];
         if (gid >= 0) {
             const int64_t idx = slot0 + l;
@@ -440,16 +451,27 @@ static int rd_single_t(const int64_t *keys, const void *vals, int64_t n, int64_t
     T fill, rfill;
     memcpy(&fill, fill_host, sizeof(T));
     memcpy(&rfill, result_fill_host, sizeof(T));
-    if (op == RF_ADD)
-        reduce_tile_kernel<T, true><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
-                                                                       make_fastdiv((uint64_t)ncols), op, d, ticket,
-                                                                       fill, apply_fix, rfill, gid_out, (T *)vals_out,
-                                                                       counters);
-    else
-        reduce_tile_kernel<T, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
-                                                                        make_fastdiv((uint64_t)ncols), op, d, ticket,
-                                                                        fill, apply_fix, rfill, gid_out,
-                                                                        (T *)vals_out, counters);
+    const bool vec = (((uintptr_t)keys | (uintptr_t)vals) & 15) == 0;
+    const FastDiv fd = make_fastdiv((uint64_t)ncols);
+#define B2S_RD(OPC)                                                                                                   \
+    do {                                                                                                              \
+        if (vec)                                                                                                      \
+            reduce_tile_kernel<T, OPC, true><<<(unsigned)nt, RD_THREADS, 0, s>>>(                                     \
+                keys, (const T *)vals, n, ncols, fd, op, d, ticket, fill, apply_fix, rfill, gid_out, (T *)vals_out,   \
+                counters);                                                                                            \
+        else                                                                                                          \
+            reduce_tile_kernel<T, OPC, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(                                    \
+                keys, (const T *)vals, n, ncols, fd, op, d, ticket, fill, apply_fix, rfill, gid_out, (T *)vals_out,   \
+                counters);                                                                                            \
+    } while (0)
+    switch (op) {  // the common operators are compile-time constants of their own instantiation
+        case RF_ADD: B2S_RD(RF_ADD); break;
+        case RF_MAX: B2S_RD(RF_MAX); break;
+        case RF_MIN: B2S_RD(RF_MIN); break;
+        case RF_MUL: B2S_RD(RF_MUL); break;
+        default: B2S_RD(-1); break;
+    }
+#undef B2S_RD
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }

@@ -10,17 +10,21 @@
 //
 // Replaces _csr_csr_count_nnz (:543-570), _dot_csr_csr (:639-717), _dot_coo_coo (:907-976).
 //
-// Structure (one numeric pass, no separate symbolic pass):
-//   1. row_products: P_i = sum over A-row entries of the B-row lengths; U_i = min(P_i, n_col) bounds nnz_i.
-//   2. rows are binned by P_i: warp-per-row with a shared-memory hash of 128 or 512 slots (P_i <= 64 / 256),
-//      CTA-per-row with a global-memory hash for longer rows.
-//   3. numeric kernels stage the row's products in visiting order, insert them in that order
-//      (__match_any_sync groups equal columns inside a 32-chunk so adds stay sequential), remember each
-//      column's first-touch sequence number, and write (col, sum) at offset ub_off[i] + rank, where rank comes
-//      from a bitmap over sequence numbers (REF) or a counting rank over columns (SORTED).
-//   4. finish: per-row compaction from the upper-bound layout to the final CSR/COO arrays, optionally
-//      dropping values bitwise equal to +0 (the prune=True of _common.py:374-379) and reversing rows in the
-//      all-dense case.
+// Structure (ONE pass over the products, final arrays written directly -- no symbolic pass, no upper-bound layout,
+// no compaction pass, no scan kernels):
+//   1. products: P_i = sum over A-row entries of the B-row lengths (8 lanes per row), U_i = min(P_i, n_col);
+//      sum U_i bounds the output size (the caller allocates that much and trims), rows with P_i > 256 are listed.
+//   2. (rare) long rows: CTA-per-row kernel with a global-memory hash, results parked in a side buffer.
+//   3. ordered kernel: rows are taken in ROW ORDER, WARPS consecutive rows per tile, tiles in ticket order.  A warp
+//      builds its row in a shared-memory hash table sized for the row (32 .. 512 slots, load <= 1/2): the products are
+//      generated 32 at a time in the reference's visiting order, equal columns inside a chunk are grouped by
+//      __match_any_sync so their adds stay sequential, slots are claimed WITHOUT atomics (store, __syncwarp, re-read:
+//      the table belongs to one warp), and the n-th first touch records its slot in ord[n] -- so the row comes out
+//      in REVERSE first-touch order (REF; exactly the reference's intrusive linked list) or ranked by column
+//      (SORTED) straight from shared memory.  The tile's row counts are scanned, the tile's offset comes from a
+//      DECOUPLED LOOK-BACK over the preceding tiles' (status | count) words, and every warp writes its row -- pruned of
+//      +0 if asked (the prune=True of _common.py:374-379) -- coalesced at its final position, together with indptr.
+//   4. (tiny matrices only) the row reversal of a completely dense result (:709-714), in place.
 #include <cub/cub.cuh>
 #include <type_traits>
 
@@ -76,12 +80,15 @@ __device__ __forceinline__ T narrow_sum(W s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1. products per row
+// 1. products per row, output bound, list of long rows
 // ---------------------------------------------------------------------------------------------
+// counters: [0] sum of U over all rows, [1] number of long rows, [2] sum of U over long rows, [3] max P of a long row
 template <typename I>
-__global__ void row_products_kernel(int64_t M, int64_t n_col, const I *__restrict__ a_indptr,
-                                    const I *__restrict__ a_indices, const I *__restrict__ b_indptr,
-                                    int64_t *__restrict__ P, int64_t *__restrict__ U) {
+__global__ void __launch_bounds__(256)
+spgemm_products_kernel(int64_t M, int64_t n_col, int64_t pmax_short, const I *__restrict__ a_indptr,
+                       const I *__restrict__ a_indices, const I *__restrict__ b_indptr, int64_t *__restrict__ P,
+                       int64_t *__restrict__ long_rows, int64_t *__restrict__ side_off,
+                       unsigned long long *__restrict__ counters) {
     // 8 lanes per row: A rows are short in the common case
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gid >> 3;
@@ -97,207 +104,347 @@ __global__ void row_products_kernel(int64_t M, int64_t n_col, const I *__restric
     acc += __shfl_xor_sync(FULL, acc, 1);
     acc += __shfl_xor_sync(FULL, acc, 2);
     acc += __shfl_xor_sync(FULL, acc, 4);
+    int64_t u = 0;
     if (row < M && sub == 0) {
         P[row] = acc;
-        U[row] = acc < n_col ? acc : n_col;
+        u = acc < n_col ? acc : n_col;
+        if (acc > pmax_short) {
+            const unsigned long long at = atomicAdd(counters + 1, 1ull);
+            long_rows[at] = row;
+            side_off[row] = (int64_t)atomicAdd(counters + 2, (unsigned long long)u);
+            atomicMax(counters + 3, (unsigned long long)acc);
+        }
+    }
+    // one atomic per CTA for the output bound
+    __shared__ int64_t s_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(FULL, u, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        if (t) atomicAdd(counters + 0, (unsigned long long)t);
     }
 }
 
-// classify rows into bins (atomic append; order inside a bin is irrelevant).  lists = 4 arrays of M entries.
-__global__ void bin_rows_kernel(int64_t M, const int64_t *__restrict__ P, int64_t t0, int64_t t1, int64_t t2,
-                                int64_t *__restrict__ lists, unsigned long long *__restrict__ counts,
-                                unsigned long long *__restrict__ maxP) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= M) return;
-    const int64_t p = P[row];
-    if (p == 0) return;
-    const int bin = p <= t0 ? 0 : (p <= t1 ? 1 : (p <= t2 ? 2 : 3));
-    lists[(int64_t)bin * M + atomicAdd(counts + bin, 1ull)] = row;
-    if (bin == 3) atomicMax(maxP, (unsigned long long)p);
-}
+// ---------------------------------------------------------------------------------------------
+// 3. ordered single-pass numeric kernel (see the header comment)
+// ---------------------------------------------------------------------------------------------
+#define SG_AGG (1ull << 62)
+#define SG_PREFIX (2ull << 62)
+#define SG_VAL ((1ull << 62) - 1)
 
-// ---------------------------------------------------------------------------------------------
-// 3a. warp-per-row numeric kernel, shared-memory hash of H slots (rows with P <= H/2)
-// ---------------------------------------------------------------------------------------------
-template <typename T, typename W, typename I, int H, int WARPS, bool SORTED>
+template <typename T, typename W, typename I, int HMAX, int WARPS>
+struct OrderedSmem {
+    static constexpr int PMAX = HMAX / 2;
+    // per-warp carve-up (bytes), 16-byte aligned pieces
+    static constexpr size_t key_b = ((size_t)HMAX * sizeof(I) + 15) & ~(size_t)15;
+    static constexpr size_t sum_b = ((size_t)HMAX * sizeof(W) + 15) & ~(size_t)15;
+    static constexpr size_t ord_b = ((size_t)PMAX * 2 + 15) & ~(size_t)15;
+    static constexpr size_t off_b = 36 * 4;                 // exclusive product offsets of the A chunk (+ total)
+    static constexpr size_t bs_b = 32 * 8;                  // B row starts
+    static constexpr size_t av_b = ((size_t)32 * sizeof(T) + 15) & ~(size_t)15;
+    static constexpr size_t per_warp = key_b + sum_b + ord_b + off_b + bs_b + av_b;
+    static constexpr size_t total = per_warp * WARPS;
+};
+
+template <typename T, typename W, typename I, int HMAX, int WARPS, bool SORTED>
 __global__ void __launch_bounds__(WARPS * 32)
-spgemm_warp_kernel(const int64_t *__restrict__ rows, int64_t n_rows, const I *__restrict__ a_indptr,
-                   const I *__restrict__ a_indices, const T *__restrict__ a_data, const I *__restrict__ b_indptr,
-                   const I *__restrict__ b_indices, const T *__restrict__ b_data,
-                   const int64_t *__restrict__ ub_off, int64_t *__restrict__ tmp_idx, T *__restrict__ tmp_val,
-                   int64_t *__restrict__ row_nnz, int64_t *__restrict__ row_nz) {
-    constexpr int PMAX = H / 2;
-    constexpr int WORDS = (PMAX + 31) / 32;
-    static_assert(WORDS <= 32, "bitmap must fit one word per lane");
+spgemm_ordered_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restrict__ a_indices,
+                      const T *__restrict__ a_data, const I *__restrict__ b_indptr, const I *__restrict__ b_indices,
+                      const T *__restrict__ b_data, const int64_t *__restrict__ Pv,
+                      const int64_t *__restrict__ side_off, const int64_t *__restrict__ side_idx,
+                      const T *__restrict__ side_val, const int64_t *__restrict__ long_nnz,
+                      const int64_t *__restrict__ long_nz, int prune, uint64_t *__restrict__ status,
+                      unsigned int *__restrict__ ticket, int64_t *__restrict__ out_ptr, int64_t *__restrict__ out_idx,
+                      int64_t *__restrict__ out_rows, T *__restrict__ out_val, unsigned long long *__restrict__ totals) {
+    using L = OrderedSmem<T, W, I, HMAX, WARPS>;
+    constexpr int PMAX = L::PMAX;
     constexpr I EMPTY = Empty<I>::value;
-    __shared__ I st_key[WARPS][PMAX];
-    __shared__ T st_val[WARPS][PMAX];
-    __shared__ I tb_key[WARPS][H];
-    __shared__ int tb_seq[WARPS][H];
-    __shared__ W tb_sum[WARPS][H];
-    __shared__ int s_off[WARPS][32];
-    __shared__ int64_t s_bs[WARPS][32];
-    __shared__ T s_av[WARPS][32];
-    __shared__ unsigned s_bits[WARPS][32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int64_t s_excl[WARPS];
+    __shared__ int64_t s_prefix;
+    __shared__ int64_t s_tile;
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
-    const int64_t warps_total = (int64_t)gridDim.x * WARPS;
-    for (int64_t ri = (int64_t)blockIdx.x * WARPS + w; ri < n_rows; ri += warps_total) {
-        const int64_t row = rows[ri];
-        for (int s = lane; s < H; s += 32) tb_key[w][s] = EMPTY;
-        s_bits[w][lane] = 0u;
-        __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned char *mine = smem_raw + (size_t)w * L::per_warp;
+    I *key = reinterpret_cast<I *>(mine);
+    W *sum = reinterpret_cast<W *>(mine + L::key_b);
+    uint16_t *ord = reinterpret_cast<uint16_t *>(mine + L::key_b + L::sum_b);
+    int *s_off = reinterpret_cast<int *>(mine + L::key_b + L::sum_b + L::ord_b);
+    int64_t *s_bs = reinterpret_cast<int64_t *>(mine + L::key_b + L::sum_b + L::ord_b + L::off_b);
+    T *s_av = reinterpret_cast<T *>(mine + L::key_b + L::sum_b + L::ord_b + L::off_b + L::bs_b);
 
-        // ---- stage 1: expand the row's products, in visiting order, into shared memory ----------
-        const int64_t as = (int64_t)a_indptr[row], ae = (int64_t)a_indptr[row + 1];
-        int P = 0;
-        for (int64_t ab = as; ab < ae; ab += 32) {
-            const bool live = ab + lane < ae;
-            I j = 0;
-            T av = T(0);
-            int64_t bs = 0;
-            int len = 0;
-            if (live) {
-                j = a_indices[ab + lane];
-                av = a_data[ab + lane];
-                bs = (int64_t)b_indptr[j];
-                len = (int)((int64_t)b_indptr[j + 1] - bs);
-            }
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            s_off[w][lane] = incl - len;
-            s_bs[w][lane] = bs;
-            s_av[w][lane] = av;
-            __syncwarp();
-            for (int t = lane; t < total; t += 32) {
-                int lo = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
-                    if (s_off[w][lo + step] <= t) lo += step;
-                const int q = t - s_off[w][lo];
-                const int64_t src = s_bs[w][lo] + q;
-                st_key[w][P + t] = b_indices[src];
-                st_val[w][P + t] = mul_rn(s_av[w][lo], b_data[src]);
-            }
-            P += total;
-            __syncwarp();
-        }
+    const int64_t n_tiles = (M + WARPS - 1) / WARPS;
+    unsigned long long my_struct = 0;  // structural entries of the rows this warp handled (lane 0 counts)
 
-        // ---- stage 2: insert in visiting order; equal columns inside a chunk stay sequential -----
-        int distinct = 0;
-        for (int c = 0; c < P; c += 32) {
-            const int t = c + lane;
-            const bool active = t < P;
-            const unsigned amask = __ballot_sync(FULL, active);
-            bool isnew = false;
-            if (active) {
-                const I k = st_key[w][t];
-                const T p = st_val[w][t];
-                const unsigned grp = __match_any_sync(amask, k);
-                const int leader = __ffs(grp) - 1;
-                const int gsz = __popc(grp);
-                const bool lead = lane == leader;
-                int slot = 0;
-                if (lead) {
-                    unsigned h = hash_col<I>(k) & (H - 1);
-                    while (true) {
-                        const I cur = tb_key[w][h];
-                        if (cur == k) break;
-                        if (cur == EMPTY) {
-                            const I old = cas_key(&tb_key[w][h], EMPTY, k);
-                            if (old == EMPTY) {
-                                isnew = true;
-                                break;
-                            }
-                            if (old == k) break;
+    while (true) {
+        __syncthreads();  // everybody is done with the previous tile's shared state
+        if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const int64_t row = tile * WARPS + w;
+        const int64_t P = row < M ? Pv[row] : 0;
+        const bool is_long = P > PMAX;
+        int distinct = 0;  // structural entries of a short row
+        int64_t cnt = 0;   // entries this row contributes to the output
+
+        if (P > 0 && !is_long) {
+            int H = 32;
+            while (H < 2 * (int)P) H <<= 1;
+            const unsigned mask = (unsigned)(H - 1);
+            for (int s = lane; s < H; s += 32) key[s] = EMPTY;
+            __syncwarp();
+            const int64_t as = (int64_t)a_indptr[row], ae = (int64_t)a_indptr[row + 1];
+            for (int64_t ab = as; ab < ae; ab += 32) {
+                // ---- the A chunk: B row extents and their exclusive offsets -------------------------------
+                const bool live = ab + lane < ae;
+                T av = T(0);
+                int64_t bs = 0;
+                int len = 0;
+                if (live) {
+                    const I j = a_indices[ab + lane];
+                    av = a_data[ab + lane];
+                    bs = (int64_t)b_indptr[j];
+                    len = (int)((int64_t)b_indptr[j + 1] - bs);
+                }
+                int incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                s_off[lane] = incl - len;
+                s_bs[lane] = bs;
+                s_av[lane] = av;
+                __syncwarp();
+                // ---- its products, 32 at a time, in visiting order ----------------------------------------
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    const bool active = t < total;
+                    I k = EMPTY;
+                    T p = T(0);
+                    if (active) {
+                        int lo = 0;
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1)
+                            if (s_off[lo + step] <= t) lo += step;
+                        const int64_t src = s_bs[lo] + (t - s_off[lo]);
+                        k = b_indices[src];
+                        p = mul_rn(s_av[lo], b_data[src]);
+                    }
+                    const unsigned amask = __ballot_sync(FULL, active);
+                    unsigned grp = 0;
+                    if (active) grp = __match_any_sync(amask, k);
+                    const bool lead = active && (lane == __ffs(grp) - 1);
+                    const int gsz = __popc(grp);
+                    // claim / find the slot -- no atomics: the table belongs to this warp; a lane that sees an empty
+                    // slot stores its key, everybody synchronises, and the lane whose key is there owns the slot
+                    unsigned h = hash_col<I>(k) & mask;
+                    bool pending = lead, isnew = false;
+                    while (__any_sync(FULL, pending)) {
+                        I cur = EMPTY;
+                        if (pending) cur = key[h];
+                        const bool empty = pending && cur == EMPTY;
+                        __syncwarp();
+                        if (empty) key[h] = k;
+                        __syncwarp();
+                        if (empty) {
+                            cur = key[h];
+                            isnew = cur == k;
                         }
-                        h = (h + 1) & (H - 1);
+                        if (pending) {
+                            if (cur == k) pending = false;
+                            else h = (h + 1) & mask;
+                        }
                     }
-                    slot = (int)h;
-                    if (isnew) {
-                        tb_seq[w][slot] = t;
-                        tb_sum[w][slot] = W(0);
-                        atomicOr(&s_bits[w][t >> 5], 1u << (t & 31));
+                    // the n-th first touch of the row remembers its slot: ord[n] = slot
+                    const unsigned newmask = __ballot_sync(FULL, isnew);
+                    if (isnew) ord[distinct + __popc(newmask & lt)] = (uint16_t)h;
+                    distinct += __popc(newmask);
+                    // accumulate: adds to one column stay in visiting order (lane order inside the chunk)
+                    if (!__any_sync(FULL, lead && gsz > 1)) {
+                        if (lead) {
+                            const W s0 = isnew ? W(0) : sum[h];
+                            sum[h] = add_rn(s0, (W)p);
+                        }
+                    } else {
+                        const int maxg = __reduce_max_sync(FULL, lead ? gsz : 0);
+                        W s0 = (lead && !isnew) ? sum[h] : W(0);
+                        for (int r = 0; r < maxg; ++r) {
+                            const bool take = lead && r < gsz;
+                            const int src = take ? (int)__fns(grp, 0, r + 1) : lane;
+                            const T v = __shfl_sync(FULL, p, src);
+                            if (take) s0 = add_rn(s0, (W)v);
+                        }
+                        if (lead) sum[h] = s0;
                     }
+                    __syncwarp();
                 }
-                const int maxg = __reduce_max_sync(amask, gsz);
-                W s = lead ? tb_sum[w][slot] : W(0);
-                for (int r = 0; r < maxg; ++r) {
-                    const bool take = lead && r < gsz;
-                    const int src = take ? (int)__fns(grp, 0, r + 1) : lane;
-                    const T v = __shfl_sync(amask, p, src);
-                    if (take) s = add_rn(s, (W)v);
-                }
-                if (lead) tb_sum[w][slot] = s;
+                __syncwarp();
             }
-            distinct += __popc(__ballot_sync(FULL, isnew));
-            __syncwarp();
-        }
-
-        // ---- stage 3: order the row and write it at its upper-bound offset -----------------------
-        const int64_t ub = ub_off[row];
-        int nz = 0;
-        if constexpr (!SORTED) {
-            // rank = number of first touches with a larger sequence number (reverse first-touch order)
-            const unsigned word = s_bits[w][lane];
-            int suf = (lane < WORDS) ? __popc(word) : 0;  // inclusive suffix count over words >= lane
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_down_sync(FULL, suf, o);
-                if (lane + o < 32) suf += v;
-            }
-            s_off[w][lane] = suf;
-            __syncwarp();
-            for (int s = lane; s < H; s += 32) {
-                const I k = tb_key[w][s];
-                if (k != EMPTY) {
-                    const int t = tb_seq[w][s];
-                    const int wd = t >> 5;
-                    const int above = (wd + 1 < 32 ? s_off[w][wd + 1] : 0) + __popc((s_bits[w][wd] >> (t & 31)) >> 1);
-                    const T v = narrow_sum<T, W>(tb_sum[w][s]);
-                    tmp_idx[ub + above] = (int64_t)k;
-                    tmp_val[ub + above] = v;
+            cnt = distinct;
+            if (prune) {  // entries that survive prune=True: everything but +0
+                int nz = 0;
+                for (int i = lane; i < distinct; i += 32) {
+                    const T v = narrow_sum<T, W>(sum[ord[i]]);
                     nz += is_pos_zero_bits(v) ? 0 : 1;
                 }
+                cnt = __reduce_add_sync(FULL, nz);
             }
-        } else {
-            // compact the table into the (now free) staging area, then counting rank by column
-            int base = 0;
-            for (int s0 = 0; s0 < H; s0 += 32) {
-                const int s = s0 + lane;
-                const I k = tb_key[w][s];
-                const bool occ = k != EMPTY;
-                const unsigned m = __ballot_sync(FULL, occ);
-                if (occ) {
-                    const int dst = base + __popc(m & ((1u << lane) - 1));
-                    st_key[w][dst] = k;
-                    st_val[w][dst] = narrow_sum<T, W>(tb_sum[w][s]);
+            if (lane == 0) my_struct += (unsigned long long)distinct;
+        } else if (is_long) {
+            cnt = prune ? long_nz[row] : long_nnz[row];
+            if (lane == 0) my_struct += (unsigned long long)long_nnz[row];
+        }
+
+        // ---- the tile's offset: scan of the WARPS row counts + decoupled look-back over the earlier tiles ----
+        if (lane == 0) s_excl[w] = cnt;  // holds the count until warp 0 scans it
+        __syncthreads();
+        if (w == 0) {
+            int64_t c = lane < WARPS ? s_excl[lane] : 0;
+            int64_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int64_t tile_total = __shfl_sync(FULL, incl, 31);
+            if (lane < WARPS) s_excl[lane] = incl - c;
+            if (lane == 0)
+                *(volatile uint64_t *)&status[tile] = (tile == 0 ? SG_PREFIX : SG_AGG) | (uint64_t)tile_total;
+            int64_t excl = 0;
+            if (tile > 0) {
+                int64_t look = tile - 1;  // lane 0 looks at the nearest predecessor
+                while (true) {
+                    const int64_t idx = look - lane;
+                    uint64_t sv = idx >= 0 ? *(volatile uint64_t *)&status[idx] : SG_PREFIX;
+                    while (__any_sync(FULL, (sv >> 62) == 0)) {
+                        if ((sv >> 62) == 0) sv = *(volatile uint64_t *)&status[idx];
+                    }
+                    const unsigned pm = __ballot_sync(FULL, (sv >> 62) == 2);
+                    const int first = pm ? __ffs(pm) - 1 : 31;  // nearest tile that already knows its prefix
+                    int64_t v = lane <= first ? (int64_t)(sv & SG_VAL) : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                    excl += v;
+                    if (pm) break;
+                    look -= 32;
+                }
+                if (lane == 0) *(volatile uint64_t *)&status[tile] = SG_PREFIX | (uint64_t)(excl + tile_total);
+            }
+            if (lane == 0) {
+                s_prefix = excl;
+                if (tile == n_tiles - 1) {
+                    out_ptr[M] = excl + tile_total;
+                    totals[1] = (unsigned long long)(excl + tile_total);
+                }
+            }
+        }
+        __syncthreads();
+        if (row >= M) continue;
+        const int64_t off = s_prefix + s_excl[w];
+        if (lane == 0) out_ptr[row] = off;
+
+        // ---- write the row at its final position ----------------------------------------------------------------
+        if (is_long) {
+            const int64_t src = side_off[row];
+            const int64_t n = long_nnz[row];
+            int64_t base = 0;
+            for (int64_t c0 = 0; c0 < n; c0 += 32) {
+                const int64_t q = c0 + lane;
+                int64_t k = 0;
+                T v = T(0);
+                bool keep = false;
+                if (q < n) {
+                    k = side_idx[src + q];
+                    v = side_val[src + q];
+                    keep = !prune || !is_pos_zero_bits(v);
+                }
+                const unsigned m = __ballot_sync(FULL, keep);
+                if (keep) {
+                    const int64_t o = off + base + __popc(m & lt);
+                    out_idx[o] = k;
+                    out_val[o] = v;
+                    if (out_rows) out_rows[o] = row;
                 }
                 base += __popc(m);
             }
-            __syncwarp();
-            for (int e = lane; e < distinct; e += 32) {
-                const I k = st_key[w][e];
-                int rank = 0;
-                for (int f = 0; f < distinct; ++f) rank += (st_key[w][f] < k) ? 1 : 0;
-                const T v = st_val[w][e];
-                tmp_idx[ub + rank] = (int64_t)k;
-                tmp_val[ub + rank] = v;
-                nz += is_pos_zero_bits(v) ? 0 : 1;
+        } else if (distinct > 0) {
+            if constexpr (!SORTED) {
+                int base = 0;
+                for (int i0 = 0; i0 < distinct; i0 += 32) {
+                    const int i = i0 + lane;
+                    I k = 0;
+                    T v = T(0);
+                    bool keep = false;
+                    if (i < distinct) {
+                        const int slot = ord[distinct - 1 - i];  // reverse first-touch order
+                        k = key[slot];
+                        v = narrow_sum<T, W>(sum[slot]);
+                        keep = !prune || !is_pos_zero_bits(v);
+                    }
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) {
+                        const int64_t o = off + base + __popc(m & lt);
+                        out_idx[o] = (int64_t)k;
+                        out_val[o] = v;
+                        if (out_rows) out_rows[o] = row;
+                    }
+                    base += __popc(m);
+                }
+            } else {
+                // ascending columns: rank by counting among the kept entries (pruned ones are struck out of ord)
+                if (prune) {
+                    for (int i = lane; i < distinct; i += 32) {
+                        const T v = narrow_sum<T, W>(sum[ord[i]]);
+                        if (is_pos_zero_bits(v)) ord[i] = 0xFFFFu;
+                    }
+                    __syncwarp();
+                }
+                for (int e = lane; e < distinct; e += 32) {
+                    const unsigned slot = ord[e];
+                    if (slot == 0xFFFFu) continue;
+                    const I k = key[slot];
+                    int rank = 0;
+                    for (int f = 0; f < distinct; ++f) {
+                        const unsigned sf = ord[f];
+                        rank += (sf != 0xFFFFu && key[sf] < k) ? 1 : 0;
+                    }
+                    const int64_t o = off + rank;
+                    out_idx[o] = (int64_t)k;
+                    out_val[o] = narrow_sum<T, W>(sum[slot]);
+                    if (out_rows) out_rows[o] = row;
+                }
             }
         }
-        nz = __reduce_add_sync(FULL, nz);
-        if (lane == 0) {
-            row_nnz[row] = distinct;
-            row_nz[row] = nz;
+    }
+    if (lane == 0 && my_struct) atomicAdd(totals + 0, my_struct);
+}
+
+// completely dense result: the reference re-reverses every row (_common.py:709-714).  In place, warp per row.
+template <typename T>
+__global__ void spgemm_reverse_rows_kernel(int64_t M, const int64_t *__restrict__ ptr, int64_t *__restrict__ idx,
+                                           T *__restrict__ val) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < M; row += nwarps) {
+        const int64_t s = ptr[row], n = ptr[row + 1] - s;
+        for (int64_t i = lane; i < n / 2; i += 32) {
+            const int64_t a = s + i, b = s + n - 1 - i;
+            const int64_t ka = idx[a], kb = idx[b];
+            const T va = val[a], vb = val[b];
+            idx[a] = kb;
+            idx[b] = ka;
+            val[a] = vb;
+            val[b] = va;
         }
-        __syncwarp();
     }
 }
 
@@ -522,52 +669,6 @@ spgemm_block_kernel(const int64_t *__restrict__ rows, int64_t n_rows, int64_t n_
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// 4. finish: compaction from the upper-bound layout (+ optional prune, row reversal, COO rows,
-//    per-row ascending sort for long rows in SORTED mode)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void spgemm_finish_kernel(int64_t M, const int64_t *__restrict__ ub_off,
-                                     const int64_t *__restrict__ row_nnz, const int64_t *__restrict__ out_ptr,
-                                     const int64_t *__restrict__ tmp_idx, const T *__restrict__ tmp_val, int prune,
-                                     int reverse, int64_t *__restrict__ out_idx, int64_t *__restrict__ out_rows,
-                                     T *__restrict__ out_val) {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = warp; row < M; row += nwarps) {
-        const int64_t n = row_nnz[row];
-        if (n == 0) continue;
-        const int64_t src = ub_off[row];
-        int64_t dst = out_ptr[row];
-        for (int64_t c = 0; c < n; c += 32) {
-            const int64_t p = c + lane;
-            bool keep = false;
-            int64_t k = 0;
-            T v = T(0);
-            if (p < n) {
-                const int64_t q = reverse ? (n - 1 - p) : p;
-                k = tmp_idx[src + q];
-                v = tmp_val[src + q];
-                keep = !prune || !is_pos_zero_bits(v);
-            }
-            const unsigned m = __ballot_sync(FULL, keep);
-            if (keep) {
-                const int64_t o = dst + __popc(m & ((1u << lane) - 1));
-                out_idx[o] = k;
-                out_val[o] = v;
-                if (out_rows) out_rows[o] = row;
-            }
-            dst += __popc(m);
-        }
-    }
-}
-
-__global__ void zero_i64_kernel(int64_t *p, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = 0;
-}
-
 // per-row ascending sort of (idx, val) segments for rows that went through the block kernel in SORTED mode
 // (rare, long rows): one CTA per row, odd-even transposition over global memory is too slow, so use a
 // bitonic-free approach: rank by counting inside the CTA (O(n^2 / threads)); rows here have n <= n_col.
@@ -597,103 +698,86 @@ __global__ void sort_long_rows_kernel(const int64_t *__restrict__ rows, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// plan object kept between begin and finish
+// plan object kept between begin and run
 // ---------------------------------------------------------------------------------------------
 struct SpgemmPlan {
-    int dtype;
-    int sorted;
+    int dtype, idx_bytes, sorted, wide;
     int64_t M, n_col;
-    int64_t nnz_struct, nnz_pruned, ub_total;
-    int64_t *P, *U, *ub_off, *row_nnz, *row_nz;  // [M] (+1 for offsets)
-    int64_t *tmp_idx;
-    void *tmp_val;
+    int64_t ub_total, n_long, side_total, long_pmax;
+    const void *a_indptr, *a_indices, *a_data, *b_indptr, *b_indices, *b_data;
+    int64_t *P, *long_rows, *side_off;          // [M]
+    unsigned long long *counters;               // [4] (spgemm_products_kernel) + [2] totals of the ordered kernel
     cudaStream_t stream;
 };
 
-static int64_t g_t0 = 64, g_t1 = 128, g_t2 = 256;  // bin thresholds on products per row (tests may lower them)
+// rows with more products than this go through the CTA-per-row kernel (tests may lower it to exercise that path)
+static int64_t g_pmax_short = 256;
 
-static int exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t s) {
-    if (n == 0) return B2S_OK;
-    size_t tmp_bytes = 0;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, s));
-    void *tmp = nullptr;
-    int rc = scratch_alloc(&tmp, tmp_bytes, s);
-    if (rc) return rc;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, s));
-    count_launch(2);
-    return scratch_free(tmp, s);
+template <typename T, typename W, typename I>
+static int spgemm_products(SpgemmPlan *pl) {
+    cudaStream_t s = pl->stream;
+    const int64_t M = pl->M;
+    B2S_CUDA(cudaMemsetAsync(pl->counters, 0, 6 * 8, s));
+    const int64_t threads = M * 8;
+    spgemm_products_kernel<I><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+        M, pl->n_col, g_pmax_short, (const I *)pl->a_indptr, (const I *)pl->a_indices, (const I *)pl->b_indptr, pl->P,
+        pl->long_rows, pl->side_off, pl->counters);
+    B2S_CHECK_LAUNCH();
+    unsigned long long hc[4];
+    B2S_CUDA(cudaMemcpyAsync(hc, pl->counters, 32, cudaMemcpyDeviceToHost, s));
+    B2S_CUDA(cudaStreamSynchronize(s));
+    pl->ub_total = (int64_t)hc[0];
+    pl->n_long = (int64_t)hc[1];
+    pl->side_total = (int64_t)hc[2];
+    pl->long_pmax = (int64_t)hc[3];
+    return B2S_OK;
+}
+
+template <typename T, typename W, typename I, int HMAX, int WARPS>
+static int launch_ordered(SpgemmPlan *pl, int prune, const int64_t *side_idx, const T *side_val,
+                          const int64_t *long_nnz, const int64_t *long_nz, uint64_t *status, unsigned int *ticket,
+                          int64_t *out_ptr, int64_t *out_idx, int64_t *out_rows, T *out_val) {
+    using L = OrderedSmem<T, W, I, HMAX, WARPS>;
+    cudaStream_t s = pl->stream;
+    auto kern_r = spgemm_ordered_kernel<T, W, I, HMAX, WARPS, false>;
+    auto kern_s = spgemm_ordered_kernel<T, W, I, HMAX, WARPS, true>;
+    auto kern = pl->sorted ? kern_s : kern_r;
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    int occ = 1;
+    B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, L::total));
+    if (occ < 1) occ = 1;
+    const int64_t n_tiles = (pl->M + WARPS - 1) / WARPS;
+    int64_t blocks = (int64_t)num_sms() * occ;
+    if (blocks > n_tiles) blocks = n_tiles;
+    kern<<<(unsigned)blocks, WARPS * 32, L::total, s>>>(
+        pl->M, (const I *)pl->a_indptr, (const I *)pl->a_indices, (const T *)pl->a_data, (const I *)pl->b_indptr,
+        (const I *)pl->b_indices, (const T *)pl->b_data, pl->P, pl->side_off, side_idx, side_val, long_nnz, long_nz,
+        prune, status, ticket, out_ptr, out_idx, out_rows, out_val, pl->counters + 4);
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
 }
 
 template <typename T, typename W, typename I>
-static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_indices, const void *a_data,
-                          const void *b_indptr, const void *b_indices, const void *b_data) {
+static int spgemm_run_t(SpgemmPlan *pl, int prune, int64_t *indptr_out, int64_t *indices_out, int64_t *rows_out,
+                        void *data_out, int64_t *nnz_struct_out, int64_t *nnz_out) {
     cudaStream_t s = pl->stream;
     const int64_t M = pl->M;
-    const I *ap = (const I *)a_indptr, *ai = (const I *)a_indices, *bp = (const I *)b_indptr,
-            *bi = (const I *)b_indices;
-    const T *ad = (const T *)a_data, *bd = (const T *)b_data;
+    const I *ap = (const I *)pl->a_indptr, *ai = (const I *)pl->a_indices, *bp = (const I *)pl->b_indptr,
+            *bi = (const I *)pl->b_indices;
+    const T *ad = (const T *)pl->a_data, *bd = (const T *)pl->b_data;
     int rc;
-    // 1. products per row and upper bounds
-    {
-        const int64_t threads = M * 8;
-        row_products_kernel<I><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(M, pl->n_col, ap, ai, bp, pl->P, pl->U);
-        B2S_CHECK_LAUNCH();
-    }
-    if ((rc = exclusive_scan_i64(pl->U, pl->ub_off, M + 1, s))) return rc;  // U[M] = 0 sentinel
-    B2S_CUDA(cudaMemcpyAsync(&pl->ub_total, pl->ub_off + M, 8, cudaMemcpyDeviceToHost, s));
-    // 2. bins
-    int64_t *lists = nullptr;
-    unsigned long long *counts = nullptr;
-    if ((rc = scratch_alloc((void **)&lists, (size_t)M * 4 * 8, s))) return rc;
-    if ((rc = scratch_alloc((void **)&counts, 5 * 8, s))) return rc;
-    B2S_CUDA(cudaMemsetAsync(counts, 0, 40, s));
-    bin_rows_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, pl->P, g_t0, g_t1, g_t2, lists, counts, counts + 4);
-    B2S_CHECK_LAUNCH();
-    unsigned long long hc[5];
-    B2S_CUDA(cudaMemcpyAsync(hc, counts, 40, cudaMemcpyDeviceToHost, s));
-    B2S_CUDA(cudaStreamSynchronize(s));
-    // upper-bound output buffers
-    if ((rc = scratch_alloc((void **)&pl->tmp_idx, (size_t)pl->ub_total * 8, s))) return rc;
-    if ((rc = scratch_alloc((void **)&pl->tmp_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
-    zero_i64_kernel<<<(unsigned)((M + 255) / 256 > 2048 ? 2048 : (M + 255) / 256), 256, 0, s>>>(pl->row_nnz, M + 1);
-    zero_i64_kernel<<<(unsigned)((M + 255) / 256 > 2048 ? 2048 : (M + 255) / 256), 256, 0, s>>>(pl->row_nz, M + 1);
-    count_launch(2);
-    const int sms = num_sms();
-    // 3a. warp-per-row bins: persistent grids sized by the occupancy the shared-memory footprint allows
-#define B2S_WARP_BIN(BIN, H, WARPS)                                                                                  \
-    if (hc[BIN]) {                                                                                                   \
-        auto kern_s = spgemm_warp_kernel<T, W, I, H, WARPS, true>;                                                   \
-        auto kern_r = spgemm_warp_kernel<T, W, I, H, WARPS, false>;                                                  \
-        int occ = 1;                                                                                                 \
-        if (pl->sorted) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_s, WARPS * 32, 0);                  \
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_r, WARPS * 32, 0);                             \
-        if (occ < 1) occ = 1;                                                                                        \
-        int64_t blocks = ((int64_t)hc[BIN] + WARPS - 1) / WARPS;                                                     \
-        if (blocks > (int64_t)sms * occ) blocks = (int64_t)sms * occ;                                                \
-        const int64_t *lst = lists + (int64_t)BIN * M;                                                               \
-        if (pl->sorted)                                                                                              \
-            kern_s<<<(unsigned)blocks, WARPS * 32, 0, s>>>(lst, (int64_t)hc[BIN], ap, ai, ad, bp, bi, bd, pl->ub_off, \
-                                                           pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);   \
-        else                                                                                                         \
-            kern_r<<<(unsigned)blocks, WARPS * 32, 0, s>>>(lst, (int64_t)hc[BIN], ap, ai, ad, bp, bi, bd, pl->ub_off, \
-                                                           pl->tmp_idx, (T *)pl->tmp_val, pl->row_nnz, pl->row_nz);   \
-        B2S_CHECK_LAUNCH();                                                                                          \
-    }
-    constexpr bool kWide = (sizeof(W) + sizeof(I)) > 8;  // keeps static shared memory under 48 KB
-    B2S_WARP_BIN(0, 128, 8)
-    if constexpr (kWide) {
-        B2S_WARP_BIN(1, 256, 4)
-        B2S_WARP_BIN(2, 512, 2)
-    } else {
-        B2S_WARP_BIN(1, 256, 8)
-        B2S_WARP_BIN(2, 512, 4)
-    }
-#undef B2S_WARP_BIN
-    // 3b. long rows
-    if (hc[3]) {
+    // 2. long rows (rare): CTA per row, global-memory hash, parked in a side buffer in their final order
+    int64_t *side_idx = nullptr, *long_nnz = nullptr, *long_nz = nullptr;
+    T *side_val = nullptr;
+    if (pl->n_long) {
         constexpr int WARPS = 8;
         constexpr int TILE = 2048;
-        const int64_t Pmax = (int64_t)hc[4];
+        if ((rc = scratch_alloc((void **)&side_idx, (size_t)pl->side_total * 8, s))) return rc;
+        if ((rc = scratch_alloc((void **)&side_val, (size_t)pl->side_total * sizeof(T), s))) return rc;
+        if ((rc = scratch_alloc((void **)&long_nnz, (size_t)(M + 1) * 8, s))) return rc;  // indexed by row; only the
+        if ((rc = scratch_alloc((void **)&long_nz, (size_t)(M + 1) * 8, s))) return rc;   // long rows' entries are used
+        const int sms = num_sms();
+        const int64_t Pmax = pl->long_pmax;
         const int64_t cap = Pmax < pl->n_col ? Pmax : pl->n_col;
         int64_t Hmax = 64;
         while (Hmax < 2 * cap) Hmax <<= 1;
@@ -701,89 +785,71 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
         size_t per_cta = (((size_t)Hmax * sizeof(I) + 15) & ~(size_t)15) + (size_t)Hmax * 8 + (size_t)Hmax * 8 +
                          ((nwords_max * 4 + 15) & ~(size_t)15) + nwords_max * 8 + 64;
         per_cta = (per_cta + 255) & ~(size_t)255;
-        int64_t ctas = (int64_t)hc[3] < (int64_t)sms * 2 ? (int64_t)hc[3] : (int64_t)sms * 2;
+        int64_t ctas = pl->n_long < (int64_t)sms * 2 ? pl->n_long : (int64_t)sms * 2;
         const size_t budget = (size_t)8 << 30;
         while (ctas > 1 && (size_t)ctas * per_cta > budget) ctas /= 2;
         unsigned char *scratch = nullptr;
         if ((rc = scratch_alloc((void **)&scratch, (size_t)ctas * per_cta, s))) return rc;
         spgemm_block_kernel<T, W, I, WARPS, TILE><<<(unsigned)ctas, WARPS * 32, 0, s>>>(
-            lists + 3 * M, (int64_t)hc[3], pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off, pl->tmp_idx,
-            (T *)pl->tmp_val, pl->row_nnz, pl->row_nz, scratch, per_cta, Hmax, Pmax);
+            pl->long_rows, pl->n_long, pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->side_off, side_idx, side_val,
+            long_nnz, long_nz, scratch, per_cta, Hmax, Pmax);
         B2S_CHECK_LAUNCH();
         if (pl->sorted) {
             int64_t *sc_idx = nullptr;
             T *sc_val = nullptr;
-            if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->ub_total * 8, s))) return rc;
-            if ((rc = scratch_alloc((void **)&sc_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
-            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(lists + 3 * M, (int64_t)hc[3], pl->ub_off, pl->row_nnz,
-                                                                   pl->tmp_idx, (T *)pl->tmp_val, sc_idx, sc_val);
+            if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->side_total * 8, s))) return rc;
+            if ((rc = scratch_alloc((void **)&sc_val, (size_t)pl->side_total * sizeof(T), s))) return rc;
+            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(pl->long_rows, pl->n_long, pl->side_off, long_nnz,
+                                                                   side_idx, side_val, sc_idx, sc_val);
             B2S_CHECK_LAUNCH();
             scratch_free(sc_idx, s);
             scratch_free(sc_val, s);
         }
         scratch_free(scratch, s);
     }
-    scratch_free(lists, s);
-    scratch_free(counts, s);
-    // totals: structural nnz and pruned nnz
-    int64_t *red = nullptr;
-    if ((rc = scratch_alloc((void **)&red, 16, s))) return rc;
-    {
-        size_t tb = 0;
-        B2S_CUDA(cub::DeviceReduce::Sum(nullptr, tb, pl->row_nnz, red, (int)M, s));
-        void *tmp = nullptr;
-        if ((rc = scratch_alloc(&tmp, tb, s))) return rc;
-        B2S_CUDA(cub::DeviceReduce::Sum(tmp, tb, pl->row_nnz, red, (int)M, s));
-        B2S_CUDA(cub::DeviceReduce::Sum(tmp, tb, pl->row_nz, red + 1, (int)M, s));
-        count_launch(2);
-        scratch_free(tmp, s);
-    }
-    int64_t h[2];
-    B2S_CUDA(cudaMemcpyAsync(h, red, 16, cudaMemcpyDeviceToHost, s));
-    B2S_CUDA(cudaStreamSynchronize(s));
-    scratch_free(red, s);
-    pl->nnz_struct = h[0];
-    pl->nnz_pruned = h[1];
-    return B2S_OK;
-}
-
-template <typename T>
-static int spgemm_finish_t(SpgemmPlan *pl, int prune, int64_t *indptr_out, int64_t *indices_out, int64_t *rows_out,
-                           void *data_out) {
-    cudaStream_t s = pl->stream;
-    const int64_t M = pl->M;
-    int rc;
-    const int64_t *cnt = prune ? pl->row_nz : pl->row_nnz;
-    // exclusive scan of the per-row counts -> indptr (M+1 entries; cnt[M] == 0 sentinel)
+    // 3. ordered single pass: final indptr / indices / data (/ COO rows)
+    int64_t *own_ptr = nullptr;
     int64_t *ptr = indptr_out;
-    int64_t *own = nullptr;
     if (!ptr) {
-        if ((rc = scratch_alloc((void **)&own, (size_t)(M + 1) * 8, s))) return rc;
-        ptr = own;
+        if ((rc = scratch_alloc((void **)&own_ptr, (size_t)(M + 1) * 8, s))) return rc;
+        ptr = own_ptr;
     }
-    if ((rc = exclusive_scan_i64(cnt, ptr, M + 1, s))) return rc;
-    const int reverse = (!pl->sorted && pl->n_col > 0 && pl->nnz_struct == pl->M * pl->n_col) ? 1 : 0;
-    if (pl->nnz_struct > 0) {
+    constexpr int WARPS_O = 8;
+    const int64_t n_tiles = (M + WARPS_O - 1) / WARPS_O;
+    unsigned char *look = nullptr;
+    if ((rc = scratch_alloc((void **)&look, 16 + (size_t)n_tiles * 8, s))) return rc;
+    B2S_CUDA(cudaMemsetAsync(look, 0, 16 + (size_t)n_tiles * 8, s));  // ticket and every status word start at 0
+    rc = launch_ordered<T, W, I, 512, WARPS_O>(pl, prune, side_idx, side_val, long_nnz, long_nz,
+                                               (uint64_t *)(look + 16), (unsigned int *)look, ptr, indices_out, rows_out,
+                                               (T *)data_out);
+    if (rc) return rc;
+    unsigned long long tot[2];
+    B2S_CUDA(cudaMemcpyAsync(tot, pl->counters + 4, 16, cudaMemcpyDeviceToHost, s));
+    B2S_CUDA(cudaStreamSynchronize(s));
+    scratch_free(look, s);
+    if (side_idx) scratch_free(side_idx, s);
+    if (side_val) scratch_free(side_val, s);
+    if (long_nnz) scratch_free(long_nnz, s);
+    if (long_nz) scratch_free(long_nz, s);
+    *nnz_struct_out = (int64_t)tot[0];
+    *nnz_out = (int64_t)tot[1];
+    // 4. the completely dense result comes out with every row reversed (_common.py:709-714)
+    if (!pl->sorted && pl->n_col > 0 && (int64_t)tot[0] == M * pl->n_col && tot[1] > 0) {
         int64_t blocks = (M * 32 + 255) / 256;
         if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
-        spgemm_finish_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(M, pl->ub_off, pl->row_nnz, ptr, pl->tmp_idx,
-                                                                (const T *)pl->tmp_val, prune, reverse, indices_out,
-                                                                rows_out, (T *)data_out);
+        spgemm_reverse_rows_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(M, ptr, indices_out, (T *)data_out);
         B2S_CHECK_LAUNCH();
     }
-    if (own) scratch_free(own, s);
+    if (own_ptr) scratch_free(own_ptr, s);
     return B2S_OK;
 }
 
 static void plan_free(SpgemmPlan *pl) {
     cudaStream_t s = pl->stream;
     scratch_free(pl->P, s);
-    scratch_free(pl->U, s);
-    scratch_free(pl->ub_off, s);
-    scratch_free(pl->row_nnz, s);
-    scratch_free(pl->row_nz, s);
-    scratch_free(pl->tmp_idx, s);
-    scratch_free(pl->tmp_val, s);
+    scratch_free(pl->long_rows, s);
+    scratch_free(pl->side_off, s);
+    scratch_free(pl->counters, s);
     delete pl;
 }
 
@@ -794,87 +860,87 @@ using namespace b2s;
 extern "C" {
 
 int b2s_spgemm_set_thresholds(int64_t t0, int64_t t1) {
-    g_t0 = (t0 >= 1 && t0 <= 64) ? t0 : 64;
-    g_t2 = (t1 >= g_t0 && t1 <= 256) ? t1 : 256;
-    g_t1 = g_t2 < 128 ? g_t2 : (g_t0 > 128 ? g_t0 : 128);
-    if (g_t1 > g_t2) g_t1 = g_t2;
+    // historical two-threshold form: the larger one is the product count above which a row takes the CTA-per-row path
+    (void)t0;
+    g_pmax_short = (t1 >= 1 && t1 <= 256) ? t1 : 256;
     return B2S_OK;
 }
 
 int b2s_spgemm_begin(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t n_col, const void *a_indptr_dev,
                      const void *a_indices_dev, const void *a_data_dev, const void *b_indptr_dev,
                      const void *b_indices_dev, const void *b_data_dev, int sorted_order, int wide_accumulate,
-                     void **plan_out,
-                     int64_t *nnz_struct_out, int64_t *nnz_pruned_out, void *stream) {
-    B2S_REQUIRE(plan_out && nnz_struct_out && nnz_pruned_out, B2S_ERR_INVALID, "spgemm_begin: NULL output");
+                     void **plan_out, int64_t *capacity_out, void *stream) {
+    B2S_REQUIRE(plan_out && capacity_out, B2S_ERR_INVALID, "spgemm_begin: NULL output");
     B2S_REQUIRE(M >= 0 && K >= 0 && n_col >= 0, B2S_ERR_INVALID, "spgemm_begin: negative dimension");
     B2S_REQUIRE(idx_bytes == 4 || idx_bytes == 8, B2S_ERR_INVALID, "spgemm_begin: idx_bytes");
-    B2S_REQUIRE(M + 1 < 2147483647LL, B2S_ERR_OVERFLOW, "spgemm_begin: M too large for the device scan");
+    B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F64 || dtype == B2S_I32 || dtype == B2S_I64, B2S_ERR_UNSUPPORTED,
+                "spgemm: dtype %d", dtype);
     cudaStream_t s = (cudaStream_t)stream;
     SpgemmPlan *pl = new SpgemmPlan();
     memset(pl, 0, sizeof(*pl));
     pl->dtype = dtype;
+    pl->idx_bytes = idx_bytes;
     pl->sorted = sorted_order ? 1 : 0;
-    const bool wide = wide_accumulate != 0;
+    pl->wide = wide_accumulate ? 1 : 0;
     pl->M = M;
     pl->n_col = n_col;
     pl->stream = s;
+    pl->a_indptr = a_indptr_dev;
+    pl->a_indices = a_indices_dev;
+    pl->a_data = a_data_dev;
+    pl->b_indptr = b_indptr_dev;
+    pl->b_indices = b_indices_dev;
+    pl->b_data = b_data_dev;
     int rc = B2S_OK;
     const size_t mb = (size_t)(M + 1) * 8;
-    if ((rc = scratch_alloc((void **)&pl->P, mb, s)) || (rc = scratch_alloc((void **)&pl->U, mb, s)) ||
-        (rc = scratch_alloc((void **)&pl->ub_off, mb, s)) || (rc = scratch_alloc((void **)&pl->row_nnz, mb, s)) ||
-        (rc = scratch_alloc((void **)&pl->row_nz, mb, s))) {
+    if ((rc = scratch_alloc((void **)&pl->P, mb, s)) || (rc = scratch_alloc((void **)&pl->long_rows, mb, s)) ||
+        (rc = scratch_alloc((void **)&pl->side_off, mb, s)) || (rc = scratch_alloc((void **)&pl->counters, 64, s))) {
         plan_free(pl);
         return rc;
     }
-    cudaMemsetAsync(pl->P, 0, mb, s);
-    cudaMemsetAsync(pl->U, 0, mb, s);
     if (M > 0) {
-#define B2S_NUM(T, I)                                                                                         \
-    rc = wide ? spgemm_numeric<T, double, I>(pl, a_indptr_dev, a_indices_dev, a_data_dev, b_indptr_dev,        \
-                                             b_indices_dev, b_data_dev)                                       \
-              : spgemm_numeric<T, T, I>(pl, a_indptr_dev, a_indices_dev, a_data_dev, b_indptr_dev,             \
-                                        b_indices_dev, b_data_dev)
-        if (idx_bytes == 4) {
-            switch (dtype) {
-                case B2S_F32: B2S_NUM(float, int32_t); break;
-                case B2S_F64: B2S_NUM(double, int32_t); break;
-                case B2S_I32: B2S_NUM(int32_t, int32_t); break;
-                case B2S_I64: B2S_NUM(int64_t, int32_t); break;
-                default: set_error("spgemm: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
-            }
-        } else {
-            switch (dtype) {
-                case B2S_F32: B2S_NUM(float, int64_t); break;
-                case B2S_F64: B2S_NUM(double, int64_t); break;
-                case B2S_I32: B2S_NUM(int32_t, int64_t); break;
-                case B2S_I64: B2S_NUM(int64_t, int64_t); break;
-                default: set_error("spgemm: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
-            }
-        }
-#undef B2S_NUM
+        rc = idx_bytes == 4 ? spgemm_products<float, float, int32_t>(pl) : spgemm_products<float, float, int64_t>(pl);
     }
     if (rc != B2S_OK) {
         plan_free(pl);
         return rc;
     }
     *plan_out = pl;
-    *nnz_struct_out = pl->nnz_struct;
-    *nnz_pruned_out = pl->nnz_pruned;
+    *capacity_out = pl->ub_total;
     return B2S_OK;
 }
 
-int b2s_spgemm_finish(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev,
-                      int64_t *rows_out_dev, void *data_out_dev) {
-    B2S_REQUIRE(plan != nullptr, B2S_ERR_INVALID, "spgemm_finish: NULL plan");
+int b2s_spgemm_run(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev, int64_t *rows_out_dev,
+                   void *data_out_dev, int64_t *nnz_struct_out, int64_t *nnz_out) {
+    B2S_REQUIRE(plan != nullptr && nnz_struct_out && nnz_out, B2S_ERR_INVALID, "spgemm_run: NULL argument");
     SpgemmPlan *pl = (SpgemmPlan *)plan;
-    int rc;
-    switch (pl->dtype) {
-        case B2S_F32: rc = spgemm_finish_t<float>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
-        case B2S_F64: rc = spgemm_finish_t<double>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
-        case B2S_I32: rc = spgemm_finish_t<int32_t>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
-        case B2S_I64: rc = spgemm_finish_t<int64_t>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
-        default: rc = B2S_ERR_UNSUPPORTED;
+    int rc = B2S_OK;
+    *nnz_struct_out = 0;
+    *nnz_out = 0;
+    if (pl->M > 0) {
+#define B2S_RUN(T, I)                                                                                             \
+    rc = pl->wide ? spgemm_run_t<T, double, I>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev,           \
+                                               data_out_dev, nnz_struct_out, nnz_out)                             \
+                  : spgemm_run_t<T, T, I>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev,  \
+                                          nnz_struct_out, nnz_out)
+        if (pl->idx_bytes == 4) {
+            switch (pl->dtype) {
+                case B2S_F32: B2S_RUN(float, int32_t); break;
+                case B2S_F64: B2S_RUN(double, int32_t); break;
+                case B2S_I32: B2S_RUN(int32_t, int32_t); break;
+                default: B2S_RUN(int64_t, int32_t); break;
+            }
+        } else {
+            switch (pl->dtype) {
+                case B2S_F32: B2S_RUN(float, int64_t); break;
+                case B2S_F64: B2S_RUN(double, int64_t); break;
+                case B2S_I32: B2S_RUN(int32_t, int64_t); break;
+                default: B2S_RUN(int64_t, int64_t); break;
+            }
+        }
+#undef B2S_RUN
+    } else if (indptr_out_dev) {
+        cudaMemsetAsync(indptr_out_dev, 0, 8, pl->stream);
     }
     plan_free(pl);
     return rc;

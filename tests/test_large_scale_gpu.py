@@ -171,13 +171,16 @@ def test_c4_sddmm_full_size_properties():
     b = torch.rand((K, n), generator=g, device="cuda", dtype=torch.float32)
     r1 = sp.sddmm(s, a, b)
     r2 = sp.sddmm(s * np.float32(2.0), a, b)
-    assert r1.nnz == s.nnz and np.array_equal(r1.coords, s.coords)
+    # uniform[0,1) float32 values hit exactly 0.0 a few times in 1e8 draws: those products are +0 and are pruned,
+    # like upstream's `s * (a @ b)`
+    nz = s.data != 0
+    assert r1.nnz == int(nz.sum()) and np.array_equal(r1.coords, s.coords[:, nz])
     assert np.array_equal(r2.data, r1.data * np.float32(2.0))
-    sel = rng.choice(s.nnz, 2000, replace=False)
-    ii, jj = s.coords[0, sel], s.coords[1, sel]
+    sel = rng.choice(r1.nnz, 2000, replace=False)
+    ii, jj = r1.coords[0, sel], r1.coords[1, sel]
     ah = a[torch.from_numpy(ii).cuda()].double().cpu().numpy()
     bh = b[:, torch.from_numpy(jj).cuda()].double().cpu().numpy().T
-    want = s.data[sel].astype(np.float64) * np.einsum("nk,nk->n", ah, bh)
+    want = s.data[nz][sel].astype(np.float64) * np.einsum("nk,nk->n", ah, bh)
     assert np.allclose(r1.data[sel], want, rtol=2e-5, atol=0)
 
 

@@ -3,6 +3,10 @@
 # reference arm.  Usage: gpurun --timeout 1500 -- 'bash tools/gpu_call.sh'
 set -u
 mkdir -p gpurun_out
+# new kernels first, under a short timeout (a hang must not eat the call)
+timeout 300 python -m pytest tests/test_spgemm_gpu.py tests/test_large_scale_gpu.py -m gpu -x -q -p no:cacheprovider > gpurun_out/gpu_tests_new.log 2>&1
+echo "pytest(new) rc=$?" >> gpurun_out/gpu_tests_new.log
+tail -15 gpurun_out/gpu_tests_new.log
 timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/gpu_tests.log
 tail -4 gpurun_out/gpu_tests.log
