@@ -192,13 +192,10 @@ int b2s_any_nan(int dtype, const void *data_dev, int64_t n, int *result_host, vo
 /*
  * Replaces _dot_csr_csr_type(dt1,dt2)(out_shape, a_data, b_data, a_indices, b_indices, a_indptr, b_indptr)
  * (_common.py:639-717, called at :359-373) and _dot_coo_coo (:907-976, called at :459-461).
- * begin(): counts the products per row (the operand arrays must stay alive until run()) and returns in
- * *capacity_out an upper bound of the result's stored entries, sum_i min(products_i, n_col) -- the count pass of the
- * reference (_csr_csr_count_nnz, :543-570) gives the exact number; here the caller allocates `capacity` entries and
- * run() reports how many were written, so the products are generated ONCE.  run(): single pass in row order (decoupled
- * look-back for the row offsets) into caller buffers indptr[M+1] or NULL, indices[capacity], rows[capacity] or NULL
- * (COO output), data[capacity]; prune = 1 drops sums bitwise equal to +0 (the prune=True of :374-379); returns the
- * structural nnz and the number of entries written, and frees the plan.
+ * begin(): runs the whole numeric product (one pass over the products, warp per row, shared-memory hash) into an
+ * upper-bound layout and returns the structural nnz and the nnz after dropping sums bitwise equal to +0 -- the count
+ * pass of the reference (_csr_csr_count_nnz, :543-570) is not a separate pass here.  finish(): compacts into
+ * caller-allocated outputs (indptr[M+1] or NULL, indices[nnz], rows[nnz] or NULL, data[nnz]) and frees the plan.
  * sorted_order = 0: reverse-first-touch column order per row, bit-identical to the reference's linked list
  * (incl. the all-dense row flip); 1: ascending columns (canonical COO order).
  * wide_accumulate = 1: float64 accumulator and "skip if sum == 0" of _dot_csc_ndarray_sparse (:835, :852).
@@ -206,9 +203,9 @@ int b2s_any_nan(int dtype, const void *data_dev, int64_t n, int *result_host, vo
 int b2s_spgemm_begin(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t n_col, const void *a_indptr_dev,
                      const void *a_indices_dev, const void *a_data_dev, const void *b_indptr_dev,
                      const void *b_indices_dev, const void *b_data_dev, int sorted_order, int wide_accumulate,
-                     void **plan_out, int64_t *capacity_out, void *stream);
-int b2s_spgemm_run(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev, int64_t *rows_out_dev,
-                   void *data_out_dev, int64_t *nnz_struct_out, int64_t *nnz_out);
+                     void **plan_out, int64_t *nnz_struct_out, int64_t *nnz_pruned_out, void *stream);
+int b2s_spgemm_finish(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev,
+                      int64_t *rows_out_dev, void *data_out_dev);
 int b2s_spgemm_abort(void *plan);
 /* test hook: rows with more than t1 (<= 256) products take the CTA-per-row path */
 int b2s_spgemm_set_thresholds(int64_t t0, int64_t t1);

@@ -428,35 +428,23 @@ def spgemm(a_indptr, a_indices, a_data, b_indptr, b_indices, b_data, M, K, n_col
     idt = a_indptr.dtype
     assert a_indices.dtype == idt and b_indptr.dtype == idt and b_indices.dtype == idt
     plan = ctypes.c_void_p(0)
-    cap = ctypes.c_int64(0)
+    n_struct, n_pruned = ctypes.c_int64(0), ctypes.c_int64(0)
     rc = lib.b2s_spgemm_begin(i32(D.dtype_code(dt)), i32(_idx_bytes(a_indptr)), i64(M), i64(K), i64(n_col),
                               vp(D.ptr(a_indptr)), vp(D.ptr(a_indices)), vp(D.ptr(a_data)), vp(D.ptr(b_indptr)),
                               vp(D.ptr(b_indices)), vp(D.ptr(b_data)), i32(1 if sorted_order else 0),
-                              i32(1 if wide else 0), ctypes.byref(plan), ctypes.byref(cap), _sp())
+                              i32(1 if wide else 0), ctypes.byref(plan), ctypes.byref(n_struct),
+                              ctypes.byref(n_pruned), _sp())
     _lib.check(rc, "b2s_spgemm_begin")
-    # outputs are allocated for the upper bound sum_i min(products_i, n_col) and trimmed to what the single pass wrote
-    capacity = int(cap.value)
+    nnz = int(n_pruned.value) if prune else int(n_struct.value)
     dev = a_data.device
-    indices = t.empty(capacity, dtype=t.int64, device=dev)
-    data = t.empty(capacity, dtype=a_data.dtype, device=dev)
+    indices = t.empty(nnz, dtype=t.int64, device=dev)
+    data = t.empty(nnz, dtype=a_data.dtype, device=dev)
     indptr = t.empty(M + 1, dtype=t.int64, device=dev) if want_indptr else None
-    rows = t.empty(capacity, dtype=t.int64, device=dev) if want_rows else None
-    n_struct, n_out = ctypes.c_int64(0), ctypes.c_int64(0)
-    rc = lib.b2s_spgemm_run(plan, i32(1 if prune else 0), vp(D.ptr(indptr) if want_indptr else 0),
-                            vp(D.ptr(indices)), vp(D.ptr(rows) if want_rows else 0), vp(D.ptr(data)),
-                            ctypes.byref(n_struct), ctypes.byref(n_out))
-    _lib.check(rc, "b2s_spgemm_run")
-    nnz = int(n_out.value)
-    if M == 0 and want_indptr:
-        indptr.zero_()
-
-    def trim(x):
-        if x is None or nnz == capacity:
-            return x
-        # a view keeps the whole allocation alive: copy when more than 1/8 of it would be dead weight
-        return x[:nnz].clone() if (capacity - nnz) * 8 > capacity else x[:nnz]
-
-    return indptr, trim(indices), trim(rows), trim(data), int(n_struct.value)
+    rows = t.empty(nnz, dtype=t.int64, device=dev) if want_rows else None
+    rc = lib.b2s_spgemm_finish(plan, i32(1 if prune else 0), vp(D.ptr(indptr) if want_indptr else 0),
+                               vp(D.ptr(indices)), vp(D.ptr(rows) if want_rows else 0), vp(D.ptr(data)))
+    _lib.check(rc, "b2s_spgemm_finish")
+    return indptr, indices, rows, data, int(n_struct.value)
 
 
 def spgemm_set_thresholds(t0=64, t1=256):

@@ -87,34 +87,31 @@ __device__ __forceinline__ T fill_fix(int op, T v, int64_t count, int64_t ncols,
     return nf != 0 ? red_apply<T>(op, v, fill) : v;
 }
 
+// State of the run that is open at some position of the sorted stream: its value so far and the GLOBAL position of its
+// head (-1: no head inside the scanned range, the run started earlier).  Runs are contiguous ranges of the sorted
+// stream, so the number of elements of a finished run -- needed by the fill-value contribution -- is simply
+// (last position - head position + 1): nothing is counted.
 template <typename T>
-struct Run {  // state of the run that is open at some position
-    int flag;     // 1 if a head lies at or before this position (within the scanned range)
+struct Run {
     T val;
-    int64_t cnt;
+    int64_t hp;
 };
 
 template <typename T>
 __device__ __forceinline__ Run<T> run_combine(int op, const Run<T> &a, const Run<T> &b) {
     // b comes after a
     Run<T> r;
-    r.flag = a.flag | b.flag;
-    if (b.flag) {
-        r.val = b.val;
-        r.cnt = b.cnt;
-    } else {
-        r.val = (a.cnt == 0) ? b.val : ((b.cnt == 0) ? a.val : red_apply<T>(op, a.val, b.val));
-        r.cnt = a.cnt + b.cnt;
-    }
+    r.hp = a.hp > b.hp ? a.hp : b.hp;
+    const T both = red_apply<T>(op, a.val, b.val);
+    r.val = b.hp >= 0 ? b.val : both;
     return r;
 }
 
 template <typename T>
 __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
     Run<T> r;
-    r.flag = __shfl_up_sync(0xffffffffu, x.flag, o);
     r.val = __shfl_up_sync(0xffffffffu, x.val, o);
-    r.cnt = __shfl_up_sync(0xffffffffu, x.cnt, o);
+    r.hp = __shfl_up_sync(0xffffffffu, x.hp, o);
     return r;
 }
 
@@ -164,12 +161,10 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                    unsigned long long *__restrict__ counters /* [0] results equal to result_fill, [1] groups */) {
     __shared__ int64_t sk[RD_TILE + 1];
     __shared__ T sv[RD_TILE + 1];
-    __shared__ int s_flag[RD_THREADS / 32];
     __shared__ T s_val[RD_THREADS / 32];
     __shared__ int64_t s_cnt[RD_THREADS / 32];
     __shared__ int s_heads[RD_THREADS / 32];
     __shared__ int64_t s_tile, s_hexcl, s_ccnt;
-    __shared__ int s_cflag;
     __shared__ T s_cval;
     const int op = OP >= 0 ? OP : op_rt;
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
@@ -181,12 +176,14 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
 
     int64_t g[RD_ITEMS];
     T v[RD_ITEMS];
+    unsigned vm = 0xFFu;  // valid items
     if (base + RD_ITEMS <= n) {
         load_items<int64_t, VEC>(keys, base, g);
         load_items<T, VEC>(vals, base, v);
 #pragma unroll
         for (int i = 0; i < RD_ITEMS; ++i) g[i] = (int64_t)fcols.div((uint64_t)g[i]);
     } else {
+        vm = 0;
 #pragma unroll
         for (int i = 0; i < RD_ITEMS; ++i) {
             const int64_t p = base + i;
@@ -195,40 +192,33 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
             if (p < n) {
                 g[i] = (int64_t)fcols.div((uint64_t)keys[p]);
                 v[i] = vals[p];
+                vm |= 1u << i;
             }
         }
     }
     // group ids of the neighbours: the previous thread's last element, the next thread's first one
     int64_t gprev = __shfl_up_sync(0xffffffffu, g[RD_ITEMS - 1], 1);
-    int64_t gnext_thread = __shfl_down_sync(0xffffffffu, g[0], 1);
-    if (lane == 0) gprev = base > 0 && base - 1 < n ? (int64_t)fcols.div((uint64_t)keys[base - 1]) : -1;
-    if (lane == 31) gnext_thread = base + RD_ITEMS < n ? (int64_t)fcols.div((uint64_t)keys[base + RD_ITEMS]) : -1;
-
-    bool head[RD_ITEMS];
+    int64_t gnext = __shfl_down_sync(0xffffffffu, g[0], 1);
+    if (lane == 0) gprev = (base > 0 && base - 1 < n) ? (int64_t)fcols.div((uint64_t)keys[base - 1]) : -2;
+    if (lane == 31) gnext = base + RD_ITEMS < n ? (int64_t)fcols.div((uint64_t)keys[base + RD_ITEMS]) : -2;
+    // head mask (an element past the end counts as a head: it closes the last real run and is never emitted) and
+    // "last element of its run" mask
+    unsigned hm = (g[0] != gprev) ? 1u : 0u;
 #pragma unroll
-    for (int i = 0; i < RD_ITEMS; ++i) {
-        const int64_t p = base + i;
-        head[i] = (p < n) && ((p == 0) || (g[i] != (i == 0 ? gprev : g[i - 1])));
-    }
-    // thread summary: run still open at the end of the thread's range
+    for (int i = 1; i < RD_ITEMS; ++i) hm |= (g[i] != g[i - 1]) ? (1u << i) : 0u;
+    hm |= ~vm & 0xFFu;
+    const unsigned lastm = ((hm >> 1) | ((g[RD_ITEMS - 1] != gnext) ? (1u << (RD_ITEMS - 1)) : 0u)) & vm;
+    const int nheads = __popc(hm & vm);
+    // thread summary: the run still open at the end of the thread's range (branch-free)
     Run<T> mine;
-    mine.flag = 0;
-    mine.val = T(0);
-    mine.cnt = 0;
-    int nheads = 0;
+    mine.val = v[0];
+    mine.hp = (hm & 1u) ? base : -1;
 #pragma unroll
-    for (int i = 0; i < RD_ITEMS; ++i) {
-        if (base + i < n) {
-            if (head[i]) {
-                mine.flag = 1;
-                mine.val = v[i];
-                mine.cnt = 1;
-                ++nheads;
-            } else {
-                mine.val = mine.cnt == 0 ? v[i] : red_apply<T>(op, mine.val, v[i]);
-                mine.cnt += 1;
-            }
-        }
+    for (int i = 1; i < RD_ITEMS; ++i) {
+        const bool h = (hm >> i) & 1u;
+        const T both = red_apply<T>(op, mine.val, v[i]);
+        mine.val = h ? v[i] : both;
+        mine.hp = h ? base + i : mine.hp;
     }
     // block-level inclusive segmented scan of the thread summaries (+ plain scan of head counts)
     Run<T> incl = mine;
@@ -243,46 +233,46 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         }
     }
     if (lane == 31) {
-        s_flag[w] = incl.flag;
         s_val[w] = incl.val;
-        s_cnt[w] = incl.cnt;
+        s_cnt[w] = incl.hp;
         s_heads[w] = hincl;
     }
     __syncthreads();
-    Run<T> wcarry;  // warps before this one, no carry-in yet
-    wcarry.flag = 0;
+    Run<T> wcarry;  // warps before this one (no tile carry-in yet); warp 0: nothing, replaced by the carry below
     wcarry.val = T(0);
-    wcarry.cnt = 0;
+    wcarry.hp = -1;
     Run<T> tile_agg = wcarry;
     int hbefore_local = 0, tile_heads = 0;
+    bool have_w = false, have_t = false;
 #pragma unroll
     for (int q = 0; q < RD_THREADS / 32; ++q) {
         Run<T> wq;
-        wq.flag = s_flag[q];
         wq.val = s_val[q];
-        wq.cnt = s_cnt[q];
+        wq.hp = s_cnt[q];
         if (q < w) {
-            wcarry = run_combine<T>(op, wcarry, wq);
+            wcarry = have_w ? run_combine<T>(op, wcarry, wq) : wq;
+            have_w = true;
             hbefore_local += s_heads[q];
         }
-        tile_agg = run_combine<T>(op, tile_agg, wq);
+        tile_agg = have_t ? run_combine<T>(op, tile_agg, wq) : wq;
+        have_t = true;
         tile_heads += s_heads[q];
     }
     // publish the aggregate (tile 0: already the inclusive prefix) before waiting for anybody: run payload first,
-    // then the status word that makes it visible
+    // then the status word that makes it visible.  run_meta = head position + 1 (0: the tile contains no head)
     if (threadIdx.x == 0) {
         *(volatile T *)&desc.run_val[tile] = tile_agg.val;
-        *(volatile int64_t *)&desc.run_meta[tile] = (tile_agg.cnt << 1) | (int64_t)tile_agg.flag;
+        *(volatile int64_t *)&desc.run_meta[tile] = tile_agg.hp + 1;
         __threadfence();
         *(volatile uint64_t *)&desc.heads[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (uint64_t)tile_heads;
     }
     // output staging: the tile finishes at most tile_heads + 1 runs; mark those slots empty
     for (int i = threadIdx.x; i < tile_heads + 1; i += RD_THREADS) sk[i] = -1;
     if (w == 0) {
-        Run<T> excl;
-        excl.flag = 0;
+        Run<T> excl;  // the run open at the first element of the tile
         excl.val = T(0);
-        excl.cnt = 0;
+        excl.hp = -1;
+        bool have_excl = false;
         int64_t hexcl = 0;
         if (tile != 0) {
             int64_t p = tile - 1;  // lane 0 looks at the nearest predecessor
@@ -297,31 +287,34 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                 }
                 __threadfence();
                 const int64_t meta = idx >= 0 ? *(volatile int64_t *)&desc.run_meta[idx] : 1;  // before tile 0: a head
-                const unsigned fm = __ballot_sync(0xffffffffu, (meta & 1) != 0);
+                const unsigned fm = __ballot_sync(0xffffffffu, meta != 0);
                 const int firstf = fm ? __ffs(fm) - 1 : 31;
+                // ordered reduction over lanes 0 .. firstf (lane + o holds an EARLIER tile: it goes on the left);
+                // lanes past firstf and tiles before tile 0 do not take part
+                const bool part = lane <= firstf && idx >= 0;
                 Run<T> x;
-                x.flag = 0;
-                x.val = T(0);
-                x.cnt = 0;
-                if (lane <= firstf && idx >= 0) {
-                    x.flag = (int)(meta & 1);
-                    x.cnt = meta >> 1;
-                    x.val = *(volatile T *)&desc.run_val[idx];
-                }
-                // ordered reduction: lane + o holds an EARLIER tile, so it goes on the left
+                x.val = part ? *(volatile T *)&desc.run_val[idx] : T(0);
+                x.hp = part ? meta - 1 : -1;
+                int have = part ? 1 : 0;
                 const int steps = firstf == 0 ? 0 : 32;
                 for (int o = 1; o < steps; o <<= 1) {
                     Run<T> other;
-                    other.flag = __shfl_down_sync(0xffffffffu, x.flag, o);
                     other.val = __shfl_down_sync(0xffffffffu, x.val, o);
-                    other.cnt = __shfl_down_sync(0xffffffffu, x.cnt, o);
-                    if (lane + o < 32) x = run_combine<T>(op, other, x);
+                    other.hp = __shfl_down_sync(0xffffffffu, x.hp, o);
+                    const int oh = __shfl_down_sync(0xffffffffu, have, o);
+                    if (lane + o < 32 && oh) {
+                        x = have ? run_combine<T>(op, other, x) : other;
+                        have = 1;
+                    }
                 }
                 Run<T> win;
-                win.flag = __shfl_sync(0xffffffffu, x.flag, 0);
                 win.val = __shfl_sync(0xffffffffu, x.val, 0);
-                win.cnt = __shfl_sync(0xffffffffu, x.cnt, 0);
-                excl = run_combine<T>(op, win, excl);  // this window lies before everything gathered so far
+                win.hp = __shfl_sync(0xffffffffu, x.hp, 0);
+                const int winh = __shfl_sync(0xffffffffu, have, 0);
+                if (winh) {  // this window lies before everything gathered so far
+                    excl = have_excl ? run_combine<T>(op, win, excl) : win;
+                    have_excl = true;
+                }
                 if (fm) break;
                 q -= 32;
             }
@@ -359,49 +352,39 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         }
         if (lane == 0) {
             s_hexcl = hexcl;
-            s_cflag = excl.flag;
             s_cval = excl.val;
-            s_ccnt = excl.cnt;
+            s_ccnt = excl.hp;
             if (tile == (int64_t)gridDim.x - 1) counters[1] = (unsigned long long)(hexcl + tile_heads);
         }
     }
     __syncthreads();
-    Run<T> carry;
-    carry.flag = s_cflag;
-    carry.val = s_cval;
-    carry.cnt = s_ccnt;
-    carry = run_combine<T>(op, carry, wcarry);
-    const int64_t hbefore = s_hexcl + hbefore_local;
-    const int64_t slot0 = s_hexcl - 1;  // output slot of a run that started before this tile
-    Run<T> prev = run_shfl_up(incl, 1);
-    int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
-    Run<T> st = carry;
-    int64_t hcount = hbefore;  // heads strictly before this thread's first element
+    // the run open in front of this thread: tile carry-in, then the warps before, then the lanes before.  The first
+    // element of the stream is a head, so an operand that does not exist (tile 0, warp 0, lane 0) is never used.
+    Run<T> st;
+    st.val = s_cval;
+    st.hp = s_ccnt;
+    if (w > 0) st = tile == 0 ? wcarry : run_combine<T>(op, st, wcarry);
+    const Run<T> prev = run_shfl_up(incl, 1);
+    const int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
+    int64_t hcount = s_hexcl + hbefore_local;  // heads strictly before this thread's first element
     if (lane > 0) {
-        st = run_combine<T>(op, carry, prev);
+        st = (tile == 0 && w == 0) ? prev : run_combine<T>(op, st, prev);
         hcount += hprev;
     }
+    const int64_t slot0 = s_hexcl - 1;  // output slot of a run that started before this tile
     T rv = st.val;
-    int64_t rc = st.cnt;
+    int64_t rhp = st.hp;
 #pragma unroll
     for (int i = 0; i < RD_ITEMS; ++i) {
-        const int64_t p = base + i;
-        if (p < n) {
-            if (head[i]) {
-                rv = v[i];
-                rc = 1;
-                ++hcount;
-            } else {
-                rv = rc == 0 ? v[i] : red_apply<T>(op, rv, v[i]);
-                rc += 1;
-            }
-            const bool last = (p == n - 1) ||
-                              ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1]) : (g[i] != gnext_thread));
-            if (last) {
-                const int loc = (int)(hcount - 1 - slot0);  // 0 .. tile_heads
-                sk[loc] = g[i];
-                sv[loc] = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
-            }
+        const bool h = (hm >> i) & 1u;
+        const T both = red_apply<T>(op, rv, v[i]);
+        rv = h ? v[i] : both;
+        rhp = h ? base + i : rhp;
+        hcount += (hm & vm) >> i & 1u;
+        if ((lastm >> i) & 1u) {
+            const int loc = (int)(hcount - 1 - slot0);  // 0 .. tile_heads
+            sk[loc] = g[i];
+            sv[loc] = apply_fix ? fill_fix<T>(op, rv, base + i - rhp + 1, ncols, fill) : rv;
         }
     }
     __syncthreads();

@@ -10,21 +10,22 @@
 //
 // Replaces _csr_csr_count_nnz (:543-570), _dot_csr_csr (:639-717), _dot_coo_coo (:907-976).
 //
-// Structure (ONE pass over the products, final arrays written directly -- no symbolic pass, no upper-bound layout,
-// no compaction pass, no scan kernels):
-//   1. products: P_i = sum over A-row entries of the B-row lengths (8 lanes per row), U_i = min(P_i, n_col);
-//      sum U_i bounds the output size (the caller allocates that much and trims), rows with P_i > 256 are listed.
-//   2. (rare) long rows: CTA-per-row kernel with a global-memory hash, results parked in a side buffer.
-//   3. ordered kernel: rows are taken in ROW ORDER, WARPS consecutive rows per tile, tiles in ticket order.  A warp
-//      builds its row in a shared-memory hash table sized for the row (32 .. 512 slots, load <= 1/2): the products are
-//      generated 32 at a time in the reference's visiting order, equal columns inside a chunk are grouped by
-//      __match_any_sync so their adds stay sequential, slots are claimed WITHOUT atomics (store, __syncwarp, re-read:
-//      the table belongs to one warp), and the n-th first touch records its slot in ord[n] -- so the row comes out
-//      in REVERSE first-touch order (REF; exactly the reference's intrusive linked list) or ranked by column
-//      (SORTED) straight from shared memory.  The tile's row counts are scanned, the tile's offset comes from a
-//      DECOUPLED LOOK-BACK over the preceding tiles' (status | count) words, and every warp writes its row -- pruned of
-//      +0 if asked (the prune=True of _common.py:374-379) -- coalesced at its final position, together with indptr.
-//   4. (tiny matrices only) the row reversal of a completely dense result (:709-714), in place.
+// Structure (one numeric pass, no separate symbolic pass):
+//   1. products: P_i = sum over A-row entries of the B-row lengths (8 lanes per row), U_i = min(P_i, n_col) bounds
+//      nnz_i; an exclusive scan of U gives every row its place in an upper-bound layout; rows with P_i > 256 are listed.
+//   2. (rare) long rows: CTA-per-row kernel with a global-memory hash.
+//   3. row kernel: one warp = one row at a time (rows dealt out four at a time by a ticket), software-pipelined three
+//      rows deep: the ticket, the A row and the B row extents of the following rows are loaded while the current row
+//      is multiplied, and all B entries of a row are fetched in one round trip before the inserts start.  The row is
+//      built in a shared-memory hash table sized for it (64 .. 512 slots, load <= 1/2): products are inserted 32 at a
+//      time in the reference's visiting order, equal columns inside a chunk are grouped by __match_any_sync so their
+//      adds stay sequential, slots are claimed WITHOUT atomics (store, __syncwarp, re-read: the table belongs to one
+//      warp), and the n-th first touch records its slot in ord[n] -- so the row is written in REVERSE first-touch
+//      order (REF; exactly the reference's intrusive linked list) or ranked by column (SORTED), coalesced, at its
+//      upper-bound offset.
+//   4. finish: scan of the row counts -> indptr; per-row compaction from the upper-bound layout to the final CSR/COO
+//      arrays, optionally dropping values bitwise equal to +0 (the prune=True of _common.py:374-379) and reversing
+//      rows in the all-dense case (:709-714).
 #include <cub/cub.cuh>
 #include <type_traits>
 
@@ -82,12 +83,12 @@ __device__ __forceinline__ T narrow_sum(W s) {
 // ---------------------------------------------------------------------------------------------
 // 1. products per row, output bound, list of long rows
 // ---------------------------------------------------------------------------------------------
-// counters: [0] sum of U over all rows, [1] number of long rows, [2] sum of U over long rows, [3] max P of a long row
+// counters: [0] sum of U over all rows, [1] number of long rows, [3] max P of a long row
 template <typename I>
 __global__ void __launch_bounds__(256)
 spgemm_products_kernel(int64_t M, int64_t n_col, int64_t pmax_short, const I *__restrict__ a_indptr,
                        const I *__restrict__ a_indices, const I *__restrict__ b_indptr, int64_t *__restrict__ P,
-                       int64_t *__restrict__ long_rows, int64_t *__restrict__ side_off,
+                       int64_t *__restrict__ U, int64_t *__restrict__ long_rows,
                        unsigned long long *__restrict__ counters) {
     // 8 lanes per row: A rows are short in the common case
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,10 +109,10 @@ spgemm_products_kernel(int64_t M, int64_t n_col, int64_t pmax_short, const I *__
     if (row < M && sub == 0) {
         P[row] = acc;
         u = acc < n_col ? acc : n_col;
+        U[row] = u;
         if (acc > pmax_short) {
             const unsigned long long at = atomicAdd(counters + 1, 1ull);
             long_rows[at] = row;
-            side_off[row] = (int64_t)atomicAdd(counters + 2, (unsigned long long)u);
             atomicMax(counters + 3, (unsigned long long)acc);
         }
     }
@@ -129,43 +130,39 @@ spgemm_products_kernel(int64_t M, int64_t n_col, int64_t pmax_short, const I *__
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. ordered single-pass numeric kernel (see the header comment)
+// 3. warp-per-row numeric kernel (see the header comment)
 // ---------------------------------------------------------------------------------------------
-#define SG_AGG (1ull << 62)
-#define SG_PREFIX (2ull << 62)
-#define SG_VAL ((1ull << 62) - 1)
-
 template <typename T, typename W, typename I, int HMAX, int WARPS>
 struct OrderedSmem {
     static constexpr int PMAX = HMAX / 2;
-    // per-warp carve-up (bytes), 16-byte aligned pieces
+    // per-warp carve-up (bytes), 16-byte aligned pieces: the hash table (key, sum) and the first-touch order
     static constexpr size_t key_b = ((size_t)HMAX * sizeof(I) + 15) & ~(size_t)15;
     static constexpr size_t sum_b = ((size_t)HMAX * sizeof(W) + 15) & ~(size_t)15;
     static constexpr size_t ord_b = ((size_t)PMAX * 2 + 15) & ~(size_t)15;
-    static constexpr size_t off_b = 36 * 4;                 // exclusive product offsets of the A chunk (+ total)
-    static constexpr size_t bs_b = 32 * 8;                  // B row starts
-    static constexpr size_t av_b = ((size_t)32 * sizeof(T) + 15) & ~(size_t)15;
-    static constexpr size_t per_warp = key_b + sum_b + ord_b + off_b + bs_b + av_b;
+    static constexpr size_t per_warp = key_b + sum_b + ord_b;
     static constexpr size_t total = per_warp * WARPS;
+    // CTAs per SM the shared-memory footprint allows (227 KB per SM, 1 KB reserved per CTA), at most 8
+    static constexpr int ctas_by_smem = (int)((227 * 1024) / (total + 1024));
+    static constexpr int min_ctas = ctas_by_smem < 1 ? 1 : (ctas_by_smem > 8 ? 8 : ctas_by_smem);
 };
 
+// One warp = one row at a time, rows dealt out four at a time by a global ticket.  Three rows ahead of the one being
+// multiplied the warp already holds the row number, two rows ahead the A row (indices, values), one row ahead the B row
+// extents: the dependent loads a_indptr -> a_indices -> b_indptr of a row are issued one row-time before their results
+// are used.
 template <typename T, typename W, typename I, int HMAX, int WARPS, bool SORTED>
-__global__ void __launch_bounds__(WARPS * 32)
-spgemm_ordered_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restrict__ a_indices,
-                      const T *__restrict__ a_data, const I *__restrict__ b_indptr, const I *__restrict__ b_indices,
-                      const T *__restrict__ b_data, const int64_t *__restrict__ Pv,
-                      const int64_t *__restrict__ side_off, const int64_t *__restrict__ side_idx,
-                      const T *__restrict__ side_val, const int64_t *__restrict__ long_nnz,
-                      const int64_t *__restrict__ long_nz, int prune, uint64_t *__restrict__ status,
-                      unsigned int *__restrict__ ticket, int64_t *__restrict__ out_ptr, int64_t *__restrict__ out_idx,
-                      int64_t *__restrict__ out_rows, T *__restrict__ out_val, unsigned long long *__restrict__ totals) {
+__global__ void __launch_bounds__(WARPS * 32, (OrderedSmem<T, W, I, HMAX, WARPS>::min_ctas))
+spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restrict__ a_indices,
+                   const T *__restrict__ a_data, const I *__restrict__ b_indptr, const I *__restrict__ b_indices,
+                   const T *__restrict__ b_data, const int64_t *__restrict__ Pv, const int64_t *__restrict__ ub_off,
+                   int64_t pmax_short, unsigned int *__restrict__ ticket, int64_t *__restrict__ tmp_idx,
+                   T *__restrict__ tmp_val, int64_t *__restrict__ row_nnz, int64_t *__restrict__ row_nz,
+                   unsigned long long *__restrict__ totals /* [0] structural entries, [1] entries != +0 */) {
     using L = OrderedSmem<T, W, I, HMAX, WARPS>;
     constexpr int PMAX = L::PMAX;
+    constexpr int CH = PMAX / 32;  // product chunks a row can have
     constexpr I EMPTY = Empty<I>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int64_t s_excl[WARPS];
-    __shared__ int64_t s_prefix;
-    __shared__ int64_t s_tile;
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -174,277 +171,245 @@ spgemm_ordered_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__rest
     I *key = reinterpret_cast<I *>(mine);
     W *sum = reinterpret_cast<W *>(mine + L::key_b);
     uint16_t *ord = reinterpret_cast<uint16_t *>(mine + L::key_b + L::sum_b);
-    int *s_off = reinterpret_cast<int *>(mine + L::key_b + L::sum_b + L::ord_b);
-    int64_t *s_bs = reinterpret_cast<int64_t *>(mine + L::key_b + L::sum_b + L::ord_b + L::off_b);
-    T *s_av = reinterpret_cast<T *>(mine + L::key_b + L::sum_b + L::ord_b + L::off_b + L::bs_b);
 
-    const int64_t n_tiles = (M + WARPS - 1) / WARPS;
-    unsigned long long my_struct = 0;  // structural entries of the rows this warp handled (lane 0 counts)
+    unsigned long long my_struct = 0, my_nz = 0;  // totals over the rows this warp handled
+    int distinct = 0;                             // structural entries of the row in the table
+
+    // ---- one chunk of <= 32 products (visiting order = lane order) goes into the table ----------------------
+    auto insert = [&](I k, T p, bool active, unsigned mask) {
+        const unsigned amask = __ballot_sync(FULL, active);
+        unsigned grp = 0;
+        if (active) grp = __match_any_sync(amask, k);
+        const bool lead = active && (lane == __ffs(grp) - 1);
+        const int gsz = __popc(grp);
+        // claim / find the slot -- no atomics: the table belongs to this warp; a lane that sees an empty slot stores
+        // its key, everybody synchronises, and the lane whose key is there owns the slot
+        unsigned h = hash_col<I>(k) & mask;
+        bool pending = lead, isnew = false;
+        while (__any_sync(FULL, pending)) {
+            I cur = EMPTY;
+            if (pending) cur = key[h];
+            const bool empty = pending && cur == EMPTY;
+            __syncwarp();
+            if (empty) key[h] = k;
+            __syncwarp();
+            if (empty) {
+                cur = key[h];
+                isnew = cur == k;
+            }
+            if (pending) {
+                if (cur == k) pending = false;
+                else h = (h + 1) & mask;
+            }
+        }
+        // the n-th first touch of the row remembers its slot: ord[n] = slot
+        const unsigned newmask = __ballot_sync(FULL, isnew);
+        if (isnew) ord[distinct + __popc(newmask & lt)] = (uint16_t)h;
+        distinct += __popc(newmask);
+        // accumulate: adds to one column stay in visiting order (lane order inside the chunk)
+        if (!__any_sync(FULL, lead && gsz > 1)) {
+            if (lead) {
+                const W s0 = isnew ? W(0) : sum[h];
+                sum[h] = add_rn(s0, (W)p);
+            }
+        } else {
+            const int maxg = __reduce_max_sync(FULL, lead ? gsz : 0);
+            W s0 = (lead && !isnew) ? sum[h] : W(0);
+            for (int r = 0; r < maxg; ++r) {
+                const bool take = lead && r < gsz;
+                const int src = take ? (int)__fns(grp, 0, r + 1) : lane;
+                const T v = __shfl_sync(FULL, p, src);
+                if (take) s0 = add_rn(s0, (W)v);
+            }
+            if (lead) sum[h] = s0;
+        }
+        __syncwarp();
+    };
+
+    // ---- the products of one A chunk (<= 32 entries; lane l holds entry l: B row start, length, A value) ------------
+    auto multiply_chunk = [&](I bs, int len, T av, unsigned mask) {
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int excl = incl - len;  // lanes past the row's entries hold `total`
+        // all loads of the chunk group first (one round trip to memory), then the inserts
+        I kk[CH];
+        T pp[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            kk[c] = EMPTY;
+            pp[c] = T(0);
+            if (c * 32 < total) {
+                const int t = c * 32 + lane;
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int e = __shfl_sync(FULL, excl, lo + step);
+                    if (e <= t) lo += step;
+                }
+                const I b0 = __shfl_sync(FULL, bs, lo);
+                const T a0 = __shfl_sync(FULL, av, lo);
+                const int e0 = __shfl_sync(FULL, excl, lo);
+                if (t < total) {
+                    const int64_t src = (int64_t)b0 + (t - e0);
+                    kk[c] = b_indices[src];
+                    pp[c] = mul_rn(a0, b_data[src]);
+                }
+            }
+        }
+        // one copy of the insert code (it is long: an unrolled version overflows the instruction cache); the chunk's
+        // registers are picked by predicated moves
+#pragma unroll 1
+        for (int c = 0; c * 32 < total; ++c) {
+            I k = kk[0];
+            T p = pp[0];
+#pragma unroll
+            for (int q = 1; q < CH; ++q)
+                if (c == q) {
+                    k = kk[q];
+                    p = pp[q];
+                }
+            insert(k, p, c * 32 + lane < total, mask);
+        }
+    };
+
+    // ---- row pipeline ---------------------------------------------------------------------------------------------
+    constexpr int ROWS_PER_TICKET = 4;
+    bool exhausted = false;
+    int64_t gen_next = 0, gen_end = 0;
+    auto next_row = [&]() -> int64_t {
+        if (gen_next == gen_end) {
+            if (exhausted) return -1;
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(ticket, 1u);
+            t = __shfl_sync(FULL, t, 0);
+            gen_next = (int64_t)t * ROWS_PER_TICKET;
+            gen_end = gen_next + ROWS_PER_TICKET < M ? gen_next + ROWS_PER_TICKET : M;
+            if (gen_next >= M) {
+                exhausted = true;
+                gen_next = gen_end = 0;
+                return -1;
+            }
+        }
+        return gen_next++;
+    };
+    // stage 3 (ticket + row extent), stage 2 (+ A entries), stage 1 (+ B extents); row < 0 = empty slot
+    int64_t row3 = -1, as3 = 0, ae3 = 0;
+    int64_t row2 = -1, as2 = 0, ae2 = 0;
+    I j2 = 0;
+    T av2 = T(0);
+    int64_t row1 = -1, as1 = 0, ae1 = 0;
+    I bs1 = 0;
+    int len1 = 0;
+    T av1 = T(0);
 
     while (true) {
-        __syncthreads();  // everybody is done with the previous tile's shared state
-        if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= n_tiles) break;
-        const int64_t row = tile * WARPS + w;
-        const int64_t P = row < M ? Pv[row] : 0;
-        const bool is_long = P > PMAX;
-        int distinct = 0;  // structural entries of a short row
-        int64_t cnt = 0;   // entries this row contributes to the output
+        // rotate the pipeline: the loads issued here are consumed one iteration later
+        const int64_t row = row1, as = as1, ae = ae1;
+        const I bs = bs1;
+        const int len = len1;
+        const T av = av1;
+        row1 = row2, as1 = as2, ae1 = ae2, av1 = av2;
+        bs1 = 0, len1 = 0;
+        if (row1 >= 0 && as1 + lane < ae1) {
+            bs1 = b_indptr[j2];
+            len1 = (int)(b_indptr[j2 + 1] - bs1);
+        }
+        row2 = row3, as2 = as3, ae2 = ae3;
+        j2 = 0, av2 = T(0);
+        if (row2 >= 0 && as2 + lane < ae2) {
+            j2 = a_indices[as2 + lane];
+            av2 = a_data[as2 + lane];
+        }
+        row3 = next_row();
+        if (row3 >= 0) {
+            as3 = (int64_t)a_indptr[row3];
+            ae3 = (int64_t)a_indptr[row3 + 1];
+        }
+        if (row < 0) {
+            if (row1 < 0 && row2 < 0 && row3 < 0) break;
+            continue;
+        }
 
-        if (P > 0 && !is_long) {
-            int H = 32;
-            while (H < 2 * (int)P) H <<= 1;
+        // ---- multiply row `row` -------------------------------------------------------------------------------------
+        const bool one_chunk = ae - as <= 32;
+        int64_t P;
+        if (one_chunk) {
+            int tot = len;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+            P = tot;
+        } else {
+            P = Pv[row];
+        }
+        if (P == 0) {
+            if (lane == 0) row_nnz[row] = 0, row_nz[row] = 0;
+            continue;
+        }
+        if (P > pmax_short) continue;  // long row: the CTA-per-row kernel owns it (and its counts)
+        distinct = 0;
+        {
+            int H = 64;
+            while (H < 4 * (int)P && H < HMAX) H <<= 1;  // load <= 1/4 when the table has room, <= 1/2 always
             const unsigned mask = (unsigned)(H - 1);
             for (int s = lane; s < H; s += 32) key[s] = EMPTY;
             __syncwarp();
-            const int64_t as = (int64_t)a_indptr[row], ae = (int64_t)a_indptr[row + 1];
-            for (int64_t ab = as; ab < ae; ab += 32) {
-                // ---- the A chunk: B row extents and their exclusive offsets -------------------------------
-                const bool live = ab + lane < ae;
-                T av = T(0);
-                int64_t bs = 0;
-                int len = 0;
-                if (live) {
-                    const I j = a_indices[ab + lane];
-                    av = a_data[ab + lane];
-                    bs = (int64_t)b_indptr[j];
-                    len = (int)((int64_t)b_indptr[j + 1] - bs);
-                }
-                int incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int total = __shfl_sync(FULL, incl, 31);
-                s_off[lane] = incl - len;
-                s_bs[lane] = bs;
-                s_av[lane] = av;
-                __syncwarp();
-                // ---- its products, 32 at a time, in visiting order ----------------------------------------
-                for (int t0 = 0; t0 < total; t0 += 32) {
-                    const int t = t0 + lane;
-                    const bool active = t < total;
-                    I k = EMPTY;
-                    T p = T(0);
-                    if (active) {
-                        int lo = 0;
-#pragma unroll
-                        for (int step = 16; step > 0; step >>= 1)
-                            if (s_off[lo + step] <= t) lo += step;
-                        const int64_t src = s_bs[lo] + (t - s_off[lo]);
-                        k = b_indices[src];
-                        p = mul_rn(s_av[lo], b_data[src]);
-                    }
-                    const unsigned amask = __ballot_sync(FULL, active);
-                    unsigned grp = 0;
-                    if (active) grp = __match_any_sync(amask, k);
-                    const bool lead = active && (lane == __ffs(grp) - 1);
-                    const int gsz = __popc(grp);
-                    // claim / find the slot -- no atomics: the table belongs to this warp; a lane that sees an empty
-                    // slot stores its key, everybody synchronises, and the lane whose key is there owns the slot
-                    unsigned h = hash_col<I>(k) & mask;
-                    bool pending = lead, isnew = false;
-                    while (__any_sync(FULL, pending)) {
-                        I cur = EMPTY;
-                        if (pending) cur = key[h];
-                        const bool empty = pending && cur == EMPTY;
-                        __syncwarp();
-                        if (empty) key[h] = k;
-                        __syncwarp();
-                        if (empty) {
-                            cur = key[h];
-                            isnew = cur == k;
-                        }
-                        if (pending) {
-                            if (cur == k) pending = false;
-                            else h = (h + 1) & mask;
-                        }
-                    }
-                    // the n-th first touch of the row remembers its slot: ord[n] = slot
-                    const unsigned newmask = __ballot_sync(FULL, isnew);
-                    if (isnew) ord[distinct + __popc(newmask & lt)] = (uint16_t)h;
-                    distinct += __popc(newmask);
-                    // accumulate: adds to one column stay in visiting order (lane order inside the chunk)
-                    if (!__any_sync(FULL, lead && gsz > 1)) {
-                        if (lead) {
-                            const W s0 = isnew ? W(0) : sum[h];
-                            sum[h] = add_rn(s0, (W)p);
-                        }
-                    } else {
-                        const int maxg = __reduce_max_sync(FULL, lead ? gsz : 0);
-                        W s0 = (lead && !isnew) ? sum[h] : W(0);
-                        for (int r = 0; r < maxg; ++r) {
-                            const bool take = lead && r < gsz;
-                            const int src = take ? (int)__fns(grp, 0, r + 1) : lane;
-                            const T v = __shfl_sync(FULL, p, src);
-                            if (take) s0 = add_rn(s0, (W)v);
-                        }
-                        if (lead) sum[h] = s0;
-                    }
-                    __syncwarp();
-                }
-                __syncwarp();
-            }
-            cnt = distinct;
-            if (prune) {  // entries that survive prune=True: everything but +0
-                int nz = 0;
-                for (int i = lane; i < distinct; i += 32) {
-                    const T v = narrow_sum<T, W>(sum[ord[i]]);
-                    nz += is_pos_zero_bits(v) ? 0 : 1;
-                }
-                cnt = __reduce_add_sync(FULL, nz);
-            }
-            if (lane == 0) my_struct += (unsigned long long)distinct;
-        } else if (is_long) {
-            cnt = prune ? long_nz[row] : long_nnz[row];
-            if (lane == 0) my_struct += (unsigned long long)long_nnz[row];
-        }
-
-        // ---- the tile's offset: scan of the WARPS row counts + decoupled look-back over the earlier tiles ----
-        if (lane == 0) s_excl[w] = cnt;  // holds the count until warp 0 scans it
-        __syncthreads();
-        if (w == 0) {
-            int64_t c = lane < WARPS ? s_excl[lane] : 0;
-            int64_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int64_t tile_total = __shfl_sync(FULL, incl, 31);
-            if (lane < WARPS) s_excl[lane] = incl - c;
-            if (lane == 0)
-                *(volatile uint64_t *)&status[tile] = (tile == 0 ? SG_PREFIX : SG_AGG) | (uint64_t)tile_total;
-            int64_t excl = 0;
-            if (tile > 0) {
-                int64_t look = tile - 1;  // lane 0 looks at the nearest predecessor
-                while (true) {
-                    const int64_t idx = look - lane;
-                    uint64_t sv = idx >= 0 ? *(volatile uint64_t *)&status[idx] : SG_PREFIX;
-                    while (__any_sync(FULL, (sv >> 62) == 0)) {
-                        if ((sv >> 62) == 0) sv = *(volatile uint64_t *)&status[idx];
-                    }
-                    const unsigned pm = __ballot_sync(FULL, (sv >> 62) == 2);
-                    const int first = pm ? __ffs(pm) - 1 : 31;  // nearest tile that already knows its prefix
-                    int64_t v = lane <= first ? (int64_t)(sv & SG_VAL) : 0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                    excl += v;
-                    if (pm) break;
-                    look -= 32;
-                }
-                if (lane == 0) *(volatile uint64_t *)&status[tile] = SG_PREFIX | (uint64_t)(excl + tile_total);
-            }
-            if (lane == 0) {
-                s_prefix = excl;
-                if (tile == n_tiles - 1) {
-                    out_ptr[M] = excl + tile_total;
-                    totals[1] = (unsigned long long)(excl + tile_total);
-                }
-            }
-        }
-        __syncthreads();
-        if (row >= M) continue;
-        const int64_t off = s_prefix + s_excl[w];
-        if (lane == 0) out_ptr[row] = off;
-
-        // ---- write the row at its final position ----------------------------------------------------------------
-        if (is_long) {
-            const int64_t src = side_off[row];
-            const int64_t n = long_nnz[row];
-            int64_t base = 0;
-            for (int64_t c0 = 0; c0 < n; c0 += 32) {
-                const int64_t q = c0 + lane;
-                int64_t k = 0;
-                T v = T(0);
-                bool keep = false;
-                if (q < n) {
-                    k = side_idx[src + q];
-                    v = side_val[src + q];
-                    keep = !prune || !is_pos_zero_bits(v);
-                }
-                const unsigned m = __ballot_sync(FULL, keep);
-                if (keep) {
-                    const int64_t o = off + base + __popc(m & lt);
-                    out_idx[o] = k;
-                    out_val[o] = v;
-                    if (out_rows) out_rows[o] = row;
-                }
-                base += __popc(m);
-            }
-        } else if (distinct > 0) {
-            if constexpr (!SORTED) {
-                int base = 0;
-                for (int i0 = 0; i0 < distinct; i0 += 32) {
-                    const int i = i0 + lane;
-                    I k = 0;
-                    T v = T(0);
-                    bool keep = false;
-                    if (i < distinct) {
-                        const int slot = ord[distinct - 1 - i];  // reverse first-touch order
-                        k = key[slot];
-                        v = narrow_sum<T, W>(sum[slot]);
-                        keep = !prune || !is_pos_zero_bits(v);
-                    }
-                    const unsigned m = __ballot_sync(FULL, keep);
-                    if (keep) {
-                        const int64_t o = off + base + __popc(m & lt);
-                        out_idx[o] = (int64_t)k;
-                        out_val[o] = v;
-                        if (out_rows) out_rows[o] = row;
-                    }
-                    base += __popc(m);
-                }
+            if (one_chunk) {
+                multiply_chunk(bs, len, av, mask);
             } else {
-                // ascending columns: rank by counting among the kept entries (pruned ones are struck out of ord)
-                if (prune) {
-                    for (int i = lane; i < distinct; i += 32) {
-                        const T v = narrow_sum<T, W>(sum[ord[i]]);
-                        if (is_pos_zero_bits(v)) ord[i] = 0xFFFFu;
+                for (int64_t ab = as; ab < ae; ab += 32) {
+                    I cbs = 0;
+                    int clen = 0;
+                    T cav = T(0);
+                    if (ab + lane < ae) {
+                        const I j = a_indices[ab + lane];
+                        cav = a_data[ab + lane];
+                        cbs = b_indptr[j];
+                        clen = (int)(b_indptr[j + 1] - cbs);
                     }
-                    __syncwarp();
-                }
-                for (int e = lane; e < distinct; e += 32) {
-                    const unsigned slot = ord[e];
-                    if (slot == 0xFFFFu) continue;
-                    const I k = key[slot];
-                    int rank = 0;
-                    for (int f = 0; f < distinct; ++f) {
-                        const unsigned sf = ord[f];
-                        rank += (sf != 0xFFFFu && key[sf] < k) ? 1 : 0;
-                    }
-                    const int64_t o = off + rank;
-                    out_idx[o] = (int64_t)k;
-                    out_val[o] = narrow_sum<T, W>(sum[slot]);
-                    if (out_rows) out_rows[o] = row;
+                    multiply_chunk(cbs, clen, cav, mask);
                 }
             }
         }
-    }
-    if (lane == 0 && my_struct) atomicAdd(totals + 0, my_struct);
-}
-
-// completely dense result: the reference re-reverses every row (_common.py:709-714).  In place, warp per row.
-template <typename T>
-__global__ void spgemm_reverse_rows_kernel(int64_t M, const int64_t *__restrict__ ptr, int64_t *__restrict__ idx,
-                                           T *__restrict__ val) {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = warp; row < M; row += nwarps) {
-        const int64_t s = ptr[row], n = ptr[row + 1] - s;
-        for (int64_t i = lane; i < n / 2; i += 32) {
-            const int64_t a = s + i, b = s + n - 1 - i;
-            const int64_t ka = idx[a], kb = idx[b];
-            const T va = val[a], vb = val[b];
-            idx[a] = kb;
-            idx[b] = ka;
-            val[a] = vb;
-            val[b] = va;
+        // ---- write the row at its upper-bound offset, in its final order ---------------------------------------------
+        const int64_t ub = ub_off[row];
+        int nz = 0;
+        if constexpr (!SORTED) {
+            for (int i = lane; i < distinct; i += 32) {
+                const int slot = ord[distinct - 1 - i];  // reverse first-touch order
+                const T v = narrow_sum<T, W>(sum[slot]);
+                tmp_idx[ub + i] = (int64_t)key[slot];
+                tmp_val[ub + i] = v;
+                nz += is_pos_zero_bits(v) ? 0 : 1;
+            }
+        } else {
+            for (int e = lane; e < distinct; e += 32) {  // ascending columns: rank by counting
+                const int slot = ord[e];
+                const I k = key[slot];
+                int rank = 0;
+                for (int f = 0; f < distinct; ++f) rank += (key[ord[f]] < k) ? 1 : 0;
+                const T v = narrow_sum<T, W>(sum[slot]);
+                tmp_idx[ub + rank] = (int64_t)k;
+                tmp_val[ub + rank] = v;
+                nz += is_pos_zero_bits(v) ? 0 : 1;
+            }
         }
+        nz = __reduce_add_sync(FULL, nz);
+        if (lane == 0) {
+            row_nnz[row] = distinct;
+            row_nz[row] = nz;
+        }
+        my_struct += (unsigned long long)distinct;
+        my_nz += (unsigned long long)nz;
+        __syncwarp();  // the table is reused by the next row
+    }
+    if (lane == 0 && my_struct) {
+        atomicAdd(totals + 0, my_struct);
+        atomicAdd(totals + 1, my_nz);
     }
 }
 
@@ -461,7 +426,7 @@ spgemm_block_kernel(const int64_t *__restrict__ rows, int64_t n_rows, int64_t n_
                     const int64_t *__restrict__ Pv, const int64_t *__restrict__ ub_off,
                     int64_t *__restrict__ tmp_idx, T *__restrict__ tmp_val, int64_t *__restrict__ row_nnz,
                     int64_t *__restrict__ row_nz, unsigned char *__restrict__ scratch, size_t per_cta,
-                    int64_t Hmax, int64_t Pmax) {
+                    int64_t Hmax, int64_t Pmax, unsigned long long *__restrict__ totals) {
     constexpr int THREADS = WARPS * 32;
     constexpr I EMPTY = Empty<I>::value;
     __shared__ I st_key[TILE];
@@ -664,8 +629,50 @@ spgemm_block_kernel(const int64_t *__restrict__ rows, int64_t n_rows, int64_t n_
             for (int i = 0; i < WARPS; ++i) tot += s_red[i];
             row_nnz[row] = distinct;
             row_nz[row] = tot;
+            atomicAdd(totals + 0, (unsigned long long)distinct);
+            atomicAdd(totals + 1, (unsigned long long)tot);
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. finish: compaction from the upper-bound layout (+ optional prune, row reversal, COO rows)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void spgemm_finish_kernel(int64_t M, const int64_t *__restrict__ ub_off,
+                                     const int64_t *__restrict__ row_nnz, const int64_t *__restrict__ out_ptr,
+                                     const int64_t *__restrict__ tmp_idx, const T *__restrict__ tmp_val, int prune,
+                                     int reverse, int64_t *__restrict__ out_idx, int64_t *__restrict__ out_rows,
+                                     T *__restrict__ out_val) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < M; row += nwarps) {
+        const int64_t n = row_nnz[row];
+        if (n == 0) continue;
+        const int64_t src = ub_off[row];
+        int64_t dst = out_ptr[row];
+        for (int64_t c = 0; c < n; c += 32) {
+            const int64_t p = c + lane;
+            bool keep = false;
+            int64_t k = 0;
+            T v = T(0);
+            if (p < n) {
+                const int64_t q = reverse ? (n - 1 - p) : p;
+                k = tmp_idx[src + q];
+                v = tmp_val[src + q];
+                keep = !prune || !is_pos_zero_bits(v);
+            }
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int64_t o = dst + __popc(m & ((1u << lane) - 1));
+                out_idx[o] = k;
+                out_val[o] = v;
+                if (out_rows) out_rows[o] = row;
+            }
+            dst += __popc(m);
+        }
     }
 }
 
@@ -698,86 +705,67 @@ __global__ void sort_long_rows_kernel(const int64_t *__restrict__ rows, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// plan object kept between begin and run
+// plan object kept between begin and finish
 // ---------------------------------------------------------------------------------------------
 struct SpgemmPlan {
-    int dtype, idx_bytes, sorted, wide;
+    int dtype;
+    int sorted;
     int64_t M, n_col;
-    int64_t ub_total, n_long, side_total, long_pmax;
-    const void *a_indptr, *a_indices, *a_data, *b_indptr, *b_indices, *b_data;
-    int64_t *P, *long_rows, *side_off;          // [M]
-    unsigned long long *counters;               // [4] (spgemm_products_kernel) + [2] totals of the ordered kernel
+    int64_t nnz_struct, nnz_pruned, ub_total;
+    int64_t *P, *U, *ub_off, *row_nnz, *row_nz, *long_rows;  // [M] (+1 for offsets)
+    unsigned long long *counters;                            // [4] products kernel, [4..5] totals, [6] ticket
+    int64_t *tmp_idx;
+    void *tmp_val;
     cudaStream_t stream;
 };
 
 // rows with more products than this go through the CTA-per-row kernel (tests may lower it to exercise that path)
 static int64_t g_pmax_short = 256;
 
+static int exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, cudaStream_t s) {
+    if (n == 0) return B2S_OK;
+    size_t tmp_bytes = 0;
+    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, s));
+    void *tmp = nullptr;
+    int rc = scratch_alloc(&tmp, tmp_bytes, s);
+    if (rc) return rc;
+    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, s));
+    count_launch(2);
+    return scratch_free(tmp, s);
+}
+
 template <typename T, typename W, typename I>
-static int spgemm_products(SpgemmPlan *pl) {
+static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_indices, const void *a_data,
+                          const void *b_indptr, const void *b_indices, const void *b_data) {
     cudaStream_t s = pl->stream;
     const int64_t M = pl->M;
-    B2S_CUDA(cudaMemsetAsync(pl->counters, 0, 6 * 8, s));
-    const int64_t threads = M * 8;
-    spgemm_products_kernel<I><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
-        M, pl->n_col, g_pmax_short, (const I *)pl->a_indptr, (const I *)pl->a_indices, (const I *)pl->b_indptr, pl->P,
-        pl->long_rows, pl->side_off, pl->counters);
-    B2S_CHECK_LAUNCH();
+    const I *ap = (const I *)a_indptr, *ai = (const I *)a_indices, *bp = (const I *)b_indptr,
+            *bi = (const I *)b_indices;
+    const T *ad = (const T *)a_data, *bd = (const T *)b_data;
+    int rc;
+    // 1. products per row, upper bounds, long-row list; the scan places every row in the upper-bound layout
+    B2S_CUDA(cudaMemsetAsync(pl->counters, 0, 8 * 8, s));
+    {
+        const int64_t threads = M * 8;
+        spgemm_products_kernel<I><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+            M, pl->n_col, g_pmax_short, ap, ai, bp, pl->P, pl->U, pl->long_rows, pl->counters);
+        B2S_CHECK_LAUNCH();
+    }
+    if ((rc = exclusive_scan_i64(pl->U, pl->ub_off, M + 1, s))) return rc;  // U[M] = 0 sentinel
     unsigned long long hc[4];
     B2S_CUDA(cudaMemcpyAsync(hc, pl->counters, 32, cudaMemcpyDeviceToHost, s));
     B2S_CUDA(cudaStreamSynchronize(s));
     pl->ub_total = (int64_t)hc[0];
-    pl->n_long = (int64_t)hc[1];
-    pl->side_total = (int64_t)hc[2];
-    pl->long_pmax = (int64_t)hc[3];
-    return B2S_OK;
-}
-
-template <typename T, typename W, typename I, int HMAX, int WARPS>
-static int launch_ordered(SpgemmPlan *pl, int prune, const int64_t *side_idx, const T *side_val,
-                          const int64_t *long_nnz, const int64_t *long_nz, uint64_t *status, unsigned int *ticket,
-                          int64_t *out_ptr, int64_t *out_idx, int64_t *out_rows, T *out_val) {
-    using L = OrderedSmem<T, W, I, HMAX, WARPS>;
-    cudaStream_t s = pl->stream;
-    auto kern_r = spgemm_ordered_kernel<T, W, I, HMAX, WARPS, false>;
-    auto kern_s = spgemm_ordered_kernel<T, W, I, HMAX, WARPS, true>;
-    auto kern = pl->sorted ? kern_s : kern_r;
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
-    int occ = 1;
-    B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, L::total));
-    if (occ < 1) occ = 1;
-    const int64_t n_tiles = (pl->M + WARPS - 1) / WARPS;
-    int64_t blocks = (int64_t)num_sms() * occ;
-    if (blocks > n_tiles) blocks = n_tiles;
-    kern<<<(unsigned)blocks, WARPS * 32, L::total, s>>>(
-        pl->M, (const I *)pl->a_indptr, (const I *)pl->a_indices, (const T *)pl->a_data, (const I *)pl->b_indptr,
-        (const I *)pl->b_indices, (const T *)pl->b_data, pl->P, pl->side_off, side_idx, side_val, long_nnz, long_nz,
-        prune, status, ticket, out_ptr, out_idx, out_rows, out_val, pl->counters + 4);
-    B2S_CHECK_LAUNCH();
-    return B2S_OK;
-}
-
-template <typename T, typename W, typename I>
-static int spgemm_run_t(SpgemmPlan *pl, int prune, int64_t *indptr_out, int64_t *indices_out, int64_t *rows_out,
-                        void *data_out, int64_t *nnz_struct_out, int64_t *nnz_out) {
-    cudaStream_t s = pl->stream;
-    const int64_t M = pl->M;
-    const I *ap = (const I *)pl->a_indptr, *ai = (const I *)pl->a_indices, *bp = (const I *)pl->b_indptr,
-            *bi = (const I *)pl->b_indices;
-    const T *ad = (const T *)pl->a_data, *bd = (const T *)pl->b_data;
-    int rc;
-    // 2. long rows (rare): CTA per row, global-memory hash, parked in a side buffer in their final order
-    int64_t *side_idx = nullptr, *long_nnz = nullptr, *long_nz = nullptr;
-    T *side_val = nullptr;
-    if (pl->n_long) {
+    const int64_t n_long = (int64_t)hc[1];
+    if ((rc = scratch_alloc((void **)&pl->tmp_idx, (size_t)pl->ub_total * 8, s))) return rc;
+    if ((rc = scratch_alloc((void **)&pl->tmp_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
+    const int sms = num_sms();
+    unsigned long long *totals = pl->counters + 4;
+    // 2. long rows (rare): CTA per row, global-memory hash
+    if (n_long) {
         constexpr int WARPS = 8;
         constexpr int TILE = 2048;
-        if ((rc = scratch_alloc((void **)&side_idx, (size_t)pl->side_total * 8, s))) return rc;
-        if ((rc = scratch_alloc((void **)&side_val, (size_t)pl->side_total * sizeof(T), s))) return rc;
-        if ((rc = scratch_alloc((void **)&long_nnz, (size_t)(M + 1) * 8, s))) return rc;  // indexed by row; only the
-        if ((rc = scratch_alloc((void **)&long_nz, (size_t)(M + 1) * 8, s))) return rc;   // long rows' entries are used
-        const int sms = num_sms();
-        const int64_t Pmax = pl->long_pmax;
+        const int64_t Pmax = (int64_t)hc[3];
         const int64_t cap = Pmax < pl->n_col ? Pmax : pl->n_col;
         int64_t Hmax = 64;
         while (Hmax < 2 * cap) Hmax <<= 1;
@@ -785,71 +773,95 @@ static int spgemm_run_t(SpgemmPlan *pl, int prune, int64_t *indptr_out, int64_t 
         size_t per_cta = (((size_t)Hmax * sizeof(I) + 15) & ~(size_t)15) + (size_t)Hmax * 8 + (size_t)Hmax * 8 +
                          ((nwords_max * 4 + 15) & ~(size_t)15) + nwords_max * 8 + 64;
         per_cta = (per_cta + 255) & ~(size_t)255;
-        int64_t ctas = pl->n_long < (int64_t)sms * 2 ? pl->n_long : (int64_t)sms * 2;
+        int64_t ctas = n_long < (int64_t)sms * 2 ? n_long : (int64_t)sms * 2;
         const size_t budget = (size_t)8 << 30;
         while (ctas > 1 && (size_t)ctas * per_cta > budget) ctas /= 2;
         unsigned char *scratch = nullptr;
         if ((rc = scratch_alloc((void **)&scratch, (size_t)ctas * per_cta, s))) return rc;
         spgemm_block_kernel<T, W, I, WARPS, TILE><<<(unsigned)ctas, WARPS * 32, 0, s>>>(
-            pl->long_rows, pl->n_long, pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->side_off, side_idx, side_val,
-            long_nnz, long_nz, scratch, per_cta, Hmax, Pmax);
+            pl->long_rows, n_long, pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off, pl->tmp_idx,
+            (T *)pl->tmp_val, pl->row_nnz, pl->row_nz, scratch, per_cta, Hmax, Pmax, totals);
         B2S_CHECK_LAUNCH();
         if (pl->sorted) {
             int64_t *sc_idx = nullptr;
             T *sc_val = nullptr;
-            if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->side_total * 8, s))) return rc;
-            if ((rc = scratch_alloc((void **)&sc_val, (size_t)pl->side_total * sizeof(T), s))) return rc;
-            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(pl->long_rows, pl->n_long, pl->side_off, long_nnz,
-                                                                   side_idx, side_val, sc_idx, sc_val);
+            if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->ub_total * 8, s))) return rc;
+            if ((rc = scratch_alloc((void **)&sc_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
+            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(pl->long_rows, n_long, pl->ub_off, pl->row_nnz,
+                                                                   pl->tmp_idx, (T *)pl->tmp_val, sc_idx, sc_val);
             B2S_CHECK_LAUNCH();
             scratch_free(sc_idx, s);
             scratch_free(sc_val, s);
         }
         scratch_free(scratch, s);
     }
-    // 3. ordered single pass: final indptr / indices / data (/ COO rows)
-    int64_t *own_ptr = nullptr;
-    int64_t *ptr = indptr_out;
-    if (!ptr) {
-        if ((rc = scratch_alloc((void **)&own_ptr, (size_t)(M + 1) * 8, s))) return rc;
-        ptr = own_ptr;
-    }
-    constexpr int WARPS_O = 8;
-    const int64_t n_tiles = (M + WARPS_O - 1) / WARPS_O;
-    unsigned char *look = nullptr;
-    if ((rc = scratch_alloc((void **)&look, 16 + (size_t)n_tiles * 8, s))) return rc;
-    B2S_CUDA(cudaMemsetAsync(look, 0, 16 + (size_t)n_tiles * 8, s));  // ticket and every status word start at 0
-    rc = launch_ordered<T, W, I, 512, WARPS_O>(pl, prune, side_idx, side_val, long_nnz, long_nz,
-                                               (uint64_t *)(look + 16), (unsigned int *)look, ptr, indices_out, rows_out,
-                                               (T *)data_out);
-    if (rc) return rc;
-    unsigned long long tot[2];
-    B2S_CUDA(cudaMemcpyAsync(tot, pl->counters + 4, 16, cudaMemcpyDeviceToHost, s));
-    B2S_CUDA(cudaStreamSynchronize(s));
-    scratch_free(look, s);
-    if (side_idx) scratch_free(side_idx, s);
-    if (side_val) scratch_free(side_val, s);
-    if (long_nnz) scratch_free(long_nnz, s);
-    if (long_nz) scratch_free(long_nz, s);
-    *nnz_struct_out = (int64_t)tot[0];
-    *nnz_out = (int64_t)tot[1];
-    // 4. the completely dense result comes out with every row reversed (_common.py:709-714)
-    if (!pl->sorted && pl->n_col > 0 && (int64_t)tot[0] == M * pl->n_col && tot[1] > 0) {
-        int64_t blocks = (M * 32 + 255) / 256;
-        if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
-        spgemm_reverse_rows_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(M, ptr, indices_out, (T *)data_out);
+    // 3. every other row: warp per row, persistent grid sized by the occupancy the shared-memory footprint allows
+    {
+        constexpr int WARPS = 4;
+        using L = OrderedSmem<T, W, I, 512, WARPS>;
+        auto kern_r = spgemm_rows_kernel<T, W, I, 512, WARPS, false>;
+        auto kern_s = spgemm_rows_kernel<T, W, I, 512, WARPS, true>;
+        auto kern = pl->sorted ? kern_s : kern_r;
+        B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+        int occ = 1;
+        B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, L::total));
+        if (occ < 1) occ = 1;
+        int64_t blocks = (int64_t)sms * occ;
+        const int64_t need = (M + WARPS - 1) / WARPS;
+        if (blocks > need) blocks = need;
+        kern<<<(unsigned)blocks, WARPS * 32, L::total, s>>>(M, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off,
+                                                            g_pmax_short < 256 ? g_pmax_short : (int64_t)256,
+                                                            (unsigned int *)(pl->counters + 6), pl->tmp_idx,
+                                                            (T *)pl->tmp_val, pl->row_nnz, pl->row_nz, totals);
         B2S_CHECK_LAUNCH();
     }
-    if (own_ptr) scratch_free(own_ptr, s);
+    unsigned long long h[2];
+    B2S_CUDA(cudaMemcpyAsync(h, totals, 16, cudaMemcpyDeviceToHost, s));
+    B2S_CUDA(cudaStreamSynchronize(s));
+    pl->nnz_struct = (int64_t)h[0];
+    pl->nnz_pruned = (int64_t)h[1];
+    return B2S_OK;
+}
+
+template <typename T>
+static int spgemm_finish_t(SpgemmPlan *pl, int prune, int64_t *indptr_out, int64_t *indices_out, int64_t *rows_out,
+                           void *data_out) {
+    cudaStream_t s = pl->stream;
+    const int64_t M = pl->M;
+    int rc;
+    const int64_t *cnt = prune ? pl->row_nz : pl->row_nnz;
+    // exclusive scan of the per-row counts -> indptr (M+1 entries; cnt[M] == 0 sentinel)
+    int64_t *ptr = indptr_out;
+    int64_t *own = nullptr;
+    if (!ptr) {
+        if ((rc = scratch_alloc((void **)&own, (size_t)(M + 1) * 8, s))) return rc;
+        ptr = own;
+    }
+    if ((rc = exclusive_scan_i64(cnt, ptr, M + 1, s))) return rc;
+    const int reverse = (!pl->sorted && pl->n_col > 0 && pl->nnz_struct == pl->M * pl->n_col) ? 1 : 0;
+    if (pl->nnz_struct > 0) {
+        int64_t blocks = (M * 32 + 255) / 256;
+        if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+        spgemm_finish_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(M, pl->ub_off, pl->row_nnz, ptr, pl->tmp_idx,
+                                                                (const T *)pl->tmp_val, prune, reverse, indices_out,
+                                                                rows_out, (T *)data_out);
+        B2S_CHECK_LAUNCH();
+    }
+    if (own) scratch_free(own, s);
     return B2S_OK;
 }
 
 static void plan_free(SpgemmPlan *pl) {
     cudaStream_t s = pl->stream;
     scratch_free(pl->P, s);
+    scratch_free(pl->U, s);
+    scratch_free(pl->ub_off, s);
+    scratch_free(pl->row_nnz, s);
+    scratch_free(pl->row_nz, s);
     scratch_free(pl->long_rows, s);
-    scratch_free(pl->side_off, s);
     scratch_free(pl->counters, s);
+    scratch_free(pl->tmp_idx, s);
+    scratch_free(pl->tmp_val, s);
     delete pl;
 }
 
@@ -869,78 +881,79 @@ int b2s_spgemm_set_thresholds(int64_t t0, int64_t t1) {
 int b2s_spgemm_begin(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t n_col, const void *a_indptr_dev,
                      const void *a_indices_dev, const void *a_data_dev, const void *b_indptr_dev,
                      const void *b_indices_dev, const void *b_data_dev, int sorted_order, int wide_accumulate,
-                     void **plan_out, int64_t *capacity_out, void *stream) {
-    B2S_REQUIRE(plan_out && capacity_out, B2S_ERR_INVALID, "spgemm_begin: NULL output");
+                     void **plan_out,
+                     int64_t *nnz_struct_out, int64_t *nnz_pruned_out, void *stream) {
+    B2S_REQUIRE(plan_out && nnz_struct_out && nnz_pruned_out, B2S_ERR_INVALID, "spgemm_begin: NULL output");
     B2S_REQUIRE(M >= 0 && K >= 0 && n_col >= 0, B2S_ERR_INVALID, "spgemm_begin: negative dimension");
     B2S_REQUIRE(idx_bytes == 4 || idx_bytes == 8, B2S_ERR_INVALID, "spgemm_begin: idx_bytes");
-    B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F64 || dtype == B2S_I32 || dtype == B2S_I64, B2S_ERR_UNSUPPORTED,
-                "spgemm: dtype %d", dtype);
+    B2S_REQUIRE(M + 1 < 2147483647LL, B2S_ERR_OVERFLOW, "spgemm_begin: M too large for the device scan");
     cudaStream_t s = (cudaStream_t)stream;
     SpgemmPlan *pl = new SpgemmPlan();
     memset(pl, 0, sizeof(*pl));
     pl->dtype = dtype;
-    pl->idx_bytes = idx_bytes;
     pl->sorted = sorted_order ? 1 : 0;
-    pl->wide = wide_accumulate ? 1 : 0;
+    const bool wide = wide_accumulate != 0;
     pl->M = M;
     pl->n_col = n_col;
     pl->stream = s;
-    pl->a_indptr = a_indptr_dev;
-    pl->a_indices = a_indices_dev;
-    pl->a_data = a_data_dev;
-    pl->b_indptr = b_indptr_dev;
-    pl->b_indices = b_indices_dev;
-    pl->b_data = b_data_dev;
     int rc = B2S_OK;
     const size_t mb = (size_t)(M + 1) * 8;
-    if ((rc = scratch_alloc((void **)&pl->P, mb, s)) || (rc = scratch_alloc((void **)&pl->long_rows, mb, s)) ||
-        (rc = scratch_alloc((void **)&pl->side_off, mb, s)) || (rc = scratch_alloc((void **)&pl->counters, 64, s))) {
+    if ((rc = scratch_alloc((void **)&pl->P, mb, s)) || (rc = scratch_alloc((void **)&pl->U, mb, s)) ||
+        (rc = scratch_alloc((void **)&pl->ub_off, mb, s)) || (rc = scratch_alloc((void **)&pl->row_nnz, mb, s)) ||
+        (rc = scratch_alloc((void **)&pl->row_nz, mb, s)) || (rc = scratch_alloc((void **)&pl->long_rows, mb, s)) ||
+        (rc = scratch_alloc((void **)&pl->counters, 64, s))) {
         plan_free(pl);
         return rc;
     }
+    cudaMemsetAsync(pl->U + M, 0, 8, s);        // sentinel of the scans
+    cudaMemsetAsync(pl->row_nnz + M, 0, 8, s);
+    cudaMemsetAsync(pl->row_nz + M, 0, 8, s);
     if (M > 0) {
-        rc = idx_bytes == 4 ? spgemm_products<float, float, int32_t>(pl) : spgemm_products<float, float, int64_t>(pl);
+#define B2S_NUM(T, I)                                                                                         \
+    rc = wide ? spgemm_numeric<T, double, I>(pl, a_indptr_dev, a_indices_dev, a_data_dev, b_indptr_dev,        \
+                                             b_indices_dev, b_data_dev)                                       \
+              : spgemm_numeric<T, T, I>(pl, a_indptr_dev, a_indices_dev, a_data_dev, b_indptr_dev,             \
+                                        b_indices_dev, b_data_dev)
+        if (idx_bytes == 4) {
+            switch (dtype) {
+                case B2S_F32: B2S_NUM(float, int32_t); break;
+                case B2S_F64: B2S_NUM(double, int32_t); break;
+                case B2S_I32: B2S_NUM(int32_t, int32_t); break;
+                case B2S_I64: B2S_NUM(int64_t, int32_t); break;
+                default: set_error("spgemm: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
+            }
+        } else {
+            switch (dtype) {
+                case B2S_F32: B2S_NUM(float, int64_t); break;
+                case B2S_F64: B2S_NUM(double, int64_t); break;
+                case B2S_I32: B2S_NUM(int32_t, int64_t); break;
+                case B2S_I64: B2S_NUM(int64_t, int64_t); break;
+                default: set_error("spgemm: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
+            }
+        }
+#undef B2S_NUM
     }
     if (rc != B2S_OK) {
         plan_free(pl);
         return rc;
     }
     *plan_out = pl;
-    *capacity_out = pl->ub_total;
+    *nnz_struct_out = pl->nnz_struct;
+    *nnz_pruned_out = pl->nnz_pruned;
     return B2S_OK;
 }
 
-int b2s_spgemm_run(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev, int64_t *rows_out_dev,
-                   void *data_out_dev, int64_t *nnz_struct_out, int64_t *nnz_out) {
-    B2S_REQUIRE(plan != nullptr && nnz_struct_out && nnz_out, B2S_ERR_INVALID, "spgemm_run: NULL argument");
+int b2s_spgemm_finish(void *plan, int prune, int64_t *indptr_out_dev, int64_t *indices_out_dev,
+                      int64_t *rows_out_dev, void *data_out_dev) {
+    B2S_REQUIRE(plan != nullptr, B2S_ERR_INVALID, "spgemm_finish: NULL plan");
     SpgemmPlan *pl = (SpgemmPlan *)plan;
-    int rc = B2S_OK;
-    *nnz_struct_out = 0;
-    *nnz_out = 0;
-    if (pl->M > 0) {
-#define B2S_RUN(T, I)                                                                                             \
-    rc = pl->wide ? spgemm_run_t<T, double, I>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev,           \
-                                               data_out_dev, nnz_struct_out, nnz_out)                             \
-                  : spgemm_run_t<T, T, I>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev,  \
-                                          nnz_struct_out, nnz_out)
-        if (pl->idx_bytes == 4) {
-            switch (pl->dtype) {
-                case B2S_F32: B2S_RUN(float, int32_t); break;
-                case B2S_F64: B2S_RUN(double, int32_t); break;
-                case B2S_I32: B2S_RUN(int32_t, int32_t); break;
-                default: B2S_RUN(int64_t, int32_t); break;
-            }
-        } else {
-            switch (pl->dtype) {
-                case B2S_F32: B2S_RUN(float, int64_t); break;
-                case B2S_F64: B2S_RUN(double, int64_t); break;
-                case B2S_I32: B2S_RUN(int32_t, int64_t); break;
-                default: B2S_RUN(int64_t, int64_t); break;
-            }
-        }
-#undef B2S_RUN
-    } else if (indptr_out_dev) {
-        cudaMemsetAsync(indptr_out_dev, 0, 8, pl->stream);
+    int rc;
+    switch (pl->dtype) {
+        case B2S_F32: rc = spgemm_finish_t<float>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
+        case B2S_F64: rc = spgemm_finish_t<double>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
+        case B2S_I32: rc = spgemm_finish_t<int32_t>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
+        case B2S_I64: rc = spgemm_finish_t<int64_t>(pl, prune, indptr_out_dev, indices_out_dev, rows_out_dev, data_out_dev); break;
+        default: rc = B2S_ERR_UNSUPPORTED;
     }
     plan_free(pl);
     return rc;

@@ -256,7 +256,7 @@ void set_call_skew(int v) { t_skew = v; }
 // spmm_skew.cu
 template <typename T, typename I>
 int skew_begin(int64_t M, int64_t N, const void *ad, const void *ai, const void *ap, const void *b, int64_t ldb,
-               void *out, int64_t ldc, cudaStream_t s, uint8_t **skip_out);
+               void *out, int64_t ldc, cudaStream_t s, uint8_t **skip_out, bool aligned16);
 int skew_end(cudaStream_t s, uint8_t *skip);
 
 template <typename T, typename I, int VEC, int G, int U>
@@ -285,7 +285,7 @@ static int dispatch_g(int64_t M, int64_t N, const void *ad, const void *ai, cons
             // nnz-balanced mode: rows longer than kLongRow go to the column-split kernel on a side stream (they start
             // first and run concurrently with the row-split kernel, which skips them)
             uint8_t *skip = nullptr;
-            int rc = skew_begin<T, I>(M, N, ad, ai, ap, b, ldb, out, ldc, s, &skip);
+            int rc = skew_begin<T, I>(M, N, ad, ai, ap, b, ldb, out, ldc, s, &skip, VEC > 1);
             if (rc) return rc;
             rc = launch_v1<T, I, VEC, 32, 8>(M, N, ad, ai, ap, b, ldb, out, ldc, s, skip);
             const int rc2 = skew_end(s, skip);

@@ -168,10 +168,12 @@ def test_panel_mode_refuses_unsorted_rows():
     assert bits_equal(D.download(got), oracle.dot_csr_ndarray((M, N), a_data, a_indices, a_indptr, b))
 
 
-@pytest.mark.parametrize("dtype,N", [(np.float32, 128), (np.float64, 64), (np.float32, 256), (np.int64, 128)])
+@pytest.mark.parametrize("dtype,N", [(np.float32, 128), (np.float64, 64), (np.float32, 256), (np.int64, 128),
+                                     (np.float32, 132), (np.float64, 72), (np.float32, 129)])
 def test_long_rows_take_the_column_split_kernel(dtype, N):
-    """nnz-balanced mode: rows with more than 4096 entries are computed by the column-split kernel on a side stream;
-    the row-split kernel skips them.  Results must stay bit-identical to the oracle."""
+    """nnz-balanced mode: rows longer than max(512, 4 x mean) are computed by the column-split kernel on a side stream
+    (shared-memory ring of cp.async copies when B's rows are 16-byte aligned -- incl. a zero-filled tail panel --, the
+    register-staged kernel otherwise: N = 129); the row-split kernel skips them.  Bit-identical to the oracle."""
     from sparse_b200 import _device as D
     from sparse_b200 import _kernels as Kn
 

@@ -28,8 +28,7 @@ for clamp in (500, 2000, 4000, 8000, 50000):
     ip32 = indptr.to(torch.int32)
     out = {}
     for skew in (0, 1):
-        lib.b2s_spmm_set_skew(ctypes.c_int(skew))
-        out[skew] = timeit(lambda: Kn.spmm_csr_dense(vals, cols, ip32, B, M, K, 128, out=C), reps=5)
+        out[skew] = timeit(lambda: Kn.spmm_csr_dense(vals, cols, ip32, B, M, K, 128, out=C, long_rows=bool(skew)),
+                           reps=5)
     print(f"clamp {clamp:6d} max_len {int(lens.max().item()):6d} rows>4096 {int((lens > 4096).sum().item()):6d} "
           f"nnz_in_long {int(lens[lens > 4096].sum().item()):9d}  skew_off {out[0]:.3f} ms  skew_on {out[1]:.3f} ms", flush=True)
-lib.b2s_spmm_set_skew(ctypes.c_int(1))
