@@ -189,27 +189,43 @@ def ctypes_vp(x):
     return ctypes.c_void_p(int(x))
 
 
+_numa_note = [""]
+
+
 def gpu_numa_cpus(device_index: int):
     """CPUs of the NUMA node the GPU hangs off (sysfs; None when it cannot be determined)."""
     import os
 
+    bus = None
     try:
+        import subprocess
+
+        # nvidia-smi prints "00000000:1B:00.0" (8-digit PCI domain); CUDA_VISIBLE_DEVICES renumbers devices, so ask
+        # the runtime for the UUID-independent PCI id of the ordinal CUDA uses
         t = D.torch()
-        bus = t.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.4
+        props = t.cuda.get_device_properties(device_index)
+        dom = getattr(props, "pci_domain_id", None)
+        b_ = getattr(props, "pci_bus_id", None)
+        d_ = getattr(props, "pci_device_id", None)
+        if isinstance(b_, int) and isinstance(d_, int):
+            bus = f"{int(dom or 0):04x}:{b_:02x}:{d_:02x}.0"
+        elif isinstance(b_, str):
+            bus = b_
+        if bus is None:
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                                  str(device_index)], capture_output=True, text=True, timeout=10).stdout.strip()
     except Exception:
         bus = None
     try:
-        if bus is None:
-            import subprocess
-
-            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
-                                  str(device_index)], capture_output=True, text=True, timeout=10).stdout.strip()
+        if not bus:
+            return None
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
             bus = bus[4:]
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
+            _numa_note[0] = f"sysfs numa_node of {bus} is {node} (no NUMA topology visible in this container / VM)"
             return None
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             spec = f.read().strip()
@@ -220,7 +236,8 @@ def gpu_numa_cpus(device_index: int):
         allowed = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in allowed]
         return (node, cpus) if cpus else None
-    except Exception:
+    except Exception as e:
+        _numa_note[0] = f"{type(e).__name__}: {e}"
         return None
 
 
@@ -233,7 +250,7 @@ def bind_to_gpu_numa(device_index: int, local_rank: int = 0, local_world: int = 
 
     got = gpu_numa_cpus(device_index)
     if got is None:
-        return None
+        return {"numa_node": None, "note": _numa_note[0] or "GPU PCI id not found"}
     node, cpus = got
     # ranks that share the node: assume local ranks map to device indices 0..local_world-1
     sharers = [r for r in range(local_world) if (gpu_numa_cpus(r) or (None,))[0] == node] or [local_rank]

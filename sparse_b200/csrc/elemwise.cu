@@ -319,31 +319,16 @@ constexpr uint64_t LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull
 __device__ __forceinline__ uint64_t lb_load(const uint64_t *p) { return *(const volatile uint64_t *)p; }
 __device__ __forceinline__ void lb_store(uint64_t *p, uint64_t v) { *(volatile uint64_t *)p = v; }
 
-// Shared memory of one tile, carved from one byte buffer.  Fast path (the tile's keys span < 2^32, which only an
-// extremely sparse key space violates): keys as 32-bit offsets from the tile's smallest key and BOTH operands' values,
-// loaded with unit stride -- the serial per-thread merge then touches shared memory only (4-byte compares, no
-// dependent global gathers).  Fallback: 64-bit keys in shared memory, values gathered from global memory.  The kept
-// (key offset | key, value) pairs are compacted into the same buffer and written out with unit stride.
-template <typename T, typename O>
-struct EwSmem {
-    static constexpr int N = EW_TILE + 2;
-    static constexpr size_t fast = 2 * (size_t)N * 4 + 2 * (((size_t)N * sizeof(T) + 7) & ~(size_t)7);
-    static constexpr size_t slow = 2 * (size_t)N * 8;
-    static constexpr size_t outb = (size_t)EW_TILE * 8 + (size_t)EW_TILE * sizeof(O);
-    static constexpr size_t m1 = fast > slow ? fast : slow;
-    static constexpr size_t bytes = (m1 > outb ? m1 : outb) + 16;
-};
-
 template <typename T, typename O, bool PRED>
-__global__ void __launch_bounds__(EW_THREADS, (sizeof(T) > 4 ? 5 : 6))
+__global__ void __launch_bounds__(EW_THREADS, 6)
 ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restrict__ db, T fill_a, T fill_b,
                       O out_fill, int op, const int64_t *__restrict__ split_a, O *__restrict__ vals_out,
                       int64_t *__restrict__ keys_out, uint64_t *__restrict__ lb_status,
                       unsigned int *__restrict__ lb_ticket, int64_t *__restrict__ total_out) {
-    __shared__ __align__(16) unsigned char s_raw[EwSmem<T, O>::bytes];
+    __shared__ int64_t sa[EW_TILE + 2];
+    __shared__ int64_t sb[EW_TILE + 2];
     __shared__ int s_warp[EW_THREADS / 32];
     __shared__ int64_t s_tile, s_base;
-    constexpr int NS = EW_TILE + 2;
     const int64_t la = A.len(), lb = B.len();
     const int64_t total = la + lb;
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(lb_ticket, 1u);
@@ -354,182 +339,70 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
     const int64_t a0 = split_a[tile], a1 = split_a[tile + 1];
     const int64_t b0 = d0 - a0, b1 = d1 - a1;
     const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+    constexpr int64_t NEG = INT64_MIN, POS = INT64_MAX;
+    // stage both key ranges (+ one sentinel on each side); all global loads of a thread are issued before the first
+    // shared-memory store so that up to 2 x EW_LD of them are in flight per thread
+    constexpr int EW_LD = (EW_TILE + 2 + EW_THREADS - 1) / EW_THREADS;
+    {
+        int64_t ra[EW_LD], rb[EW_LD];
+#pragma unroll
+        for (int k = 0; k < EW_LD; ++k) {
+            const int i = threadIdx.x + k * EW_THREADS;
+            const int64_t pa = a0 - 1 + i, pb = b0 - 1 + i;
+            ra[k] = (i < na + 2) ? ((pa < 0) ? NEG : (pa < la ? A.key(pa) : POS)) : POS;
+            rb[k] = (i < nb + 2) ? ((pb < 0) ? NEG : (pb < lb ? B.key(pb) : POS)) : POS;
+        }
+#pragma unroll
+        for (int k = 0; k < EW_LD; ++k) {
+            const int i = threadIdx.x + k * EW_THREADS;
+            if (i < na + 2) sa[i] = ra[k];
+            if (i < nb + 2) sb[i] = rb[k];
+        }
+    }
+    __syncthreads();
+    const int64_t *ka = sa + 1, *kb = sb + 1;
     const int dloc = threadIdx.x * EW_ITEMS;
     const int dn = (int)(d1 - d0);
-    // the tile's key range (every thread computes the same four broadcast loads)
-    int64_t kmin = INT64_MAX, kmax = INT64_MIN;
-    if (na > 0) {
-        kmin = A.key(a0);
-        kmax = A.key(a1 - 1);
-    }
-    if (nb > 0) {
-        const int64_t f = B.key(b0), l = B.key(b1 - 1);
-        kmin = f < kmin ? f : kmin;
-        kmax = l > kmax ? l : kmax;
-    }
-    const bool fast = (uint64_t)(kmax - kmin) < 0xFFFFFFF0ull;
-    constexpr int EW_LD = (EW_TILE + 2 + EW_THREADS - 1) / EW_THREADS;
-    uint32_t rk32[EW_ITEMS];   // fast path: kept candidates' key offsets
-    int64_t rkey[EW_ITEMS];    // fallback: their keys
+    int64_t rkey[EW_ITEMS];
     O rval[EW_ITEMS];
     unsigned keepmask = 0;
-
-    if (fast) {
-        uint32_t *sa = reinterpret_cast<uint32_t *>(s_raw);
-        uint32_t *sb = sa + NS;
-        T *va_s = reinterpret_cast<T *>(s_raw + 2 * (size_t)NS * 4);
-        T *vb_s = reinterpret_cast<T *>(s_raw + 2 * (size_t)NS * 4 + (((size_t)NS * sizeof(T) + 7) & ~(size_t)7));
-        // offsets are key - kmin + 1, so 0 is "smaller than everything" and 0xFFFFFFFF "larger than everything";
-        // the real neighbours just outside the tile (needed for the equal-key tests at the borders) are clamped
-        auto rel = [&](int64_t k) -> uint32_t {
-            if (k < kmin) return 0u;
-            const uint64_t d = (uint64_t)(k - kmin) + 1ull;
-            return d >= 0xFFFFFFFFull ? 0xFFFFFFFEu : (uint32_t)d;
-        };
-        {
-            uint32_t ra[EW_LD], rb[EW_LD];
-            T xa[EW_LD], xb[EW_LD];
-#pragma unroll
-            for (int k = 0; k < EW_LD; ++k) {
-                const int i = threadIdx.x + k * EW_THREADS;
-                const int64_t pa = a0 - 1 + i, pb = b0 - 1 + i;
-                ra[k] = 0xFFFFFFFFu;
-                rb[k] = 0xFFFFFFFFu;
-                xa[k] = T(0);
-                xb[k] = T(0);
-                if (i < na + 2) {
-                    if (pa < 0) ra[k] = 0u;
-                    else if (pa < la) {
-                        const int64_t q = A.src(pa);
-                        ra[k] = rel(A.R == 1 ? A.keys[pa] : A.keys[q] * A.R + (pa - q * A.R));
-                        xa[k] = da[q];
-                    }
-                }
-                if (i < nb + 2) {
-                    if (pb < 0) rb[k] = 0u;
-                    else if (pb < lb) {
-                        const int64_t q = B.src(pb);
-                        rb[k] = rel(B.R == 1 ? B.keys[pb] : B.keys[q] * B.R + (pb - q * B.R));
-                        xb[k] = db[q];
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < EW_LD; ++k) {
-                const int i = threadIdx.x + k * EW_THREADS;
-                if (i < na + 2) {
-                    sa[i] = ra[k];
-                    va_s[i] = xa[k];
-                }
-                if (i < nb + 2) {
-                    sb[i] = rb[k];
-                    vb_s[i] = xb[k];
-                }
-            }
+    if (dloc < dn) {
+        int lo = dloc > nb ? dloc - nb : 0;
+        int hi = dloc < na ? dloc : na;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ka[mid] <= kb[dloc - 1 - mid]) lo = mid + 1;
+            else hi = mid;
         }
-        __syncthreads();
-        const uint32_t *ka = sa + 1, *kb = sb + 1;
-        const T *xa = va_s + 1, *xb = vb_s + 1;
-        if (dloc < dn) {
-            int lo = dloc > nb ? dloc - nb : 0;
-            int hi = dloc < na ? dloc : na;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (ka[mid] <= kb[dloc - 1 - mid]) lo = mid + 1;
-                else hi = mid;
-            }
-            int i = lo, j = dloc - lo;
+        int i = lo, j = dloc - lo;
 #pragma unroll
-            for (int it = 0; it < EW_ITEMS; ++it) {
-                const int d = dloc + it;
-                rk32[it] = 0;
-                rval[it] = O(0);
-                if (d < dn) {
-                    const bool take_a = (j >= nb) || (i < na && ka[i] <= kb[j]);
-                    uint32_t key;
-                    T va, vb;
-                    bool emit = true;
-                    if (take_a) {
-                        key = ka[i];
-                        va = xa[i];
-                        vb = (kb[j] == key) ? xb[j] : fill_b;
-                        ++i;
-                    } else {
-                        key = kb[j];
-                        emit = (ka[i - 1] != key);
-                        va = fill_a;
-                        vb = xb[j];
-                        ++j;
-                    }
-                    O r;
-                    if constexpr (PRED) r = (O)bin_pred<T>(op, va, vb);
-                    else r = (O)bin_apply<T>(op, va, vb);
-                    rk32[it] = key;
-                    rval[it] = r;
-                    if (emit && bits_differ<O>(r, out_fill)) keepmask |= 1u << it;
+        for (int it = 0; it < EW_ITEMS; ++it) {
+            const int d = dloc + it;
+            rkey[it] = 0;
+            rval[it] = O(0);
+            if (d < dn) {
+                const bool take_a = (j >= nb) || (i < na && ka[i] <= kb[j]);
+                int64_t key;
+                T va, vb;
+                bool emit = true;
+                if (take_a) {
+                    key = ka[i];
+                    va = da[A.src(a0 + i)];
+                    vb = (kb[j] == key) ? db[B.src(b0 + j)] : fill_b;
+                    ++i;
+                } else {
+                    key = kb[j];
+                    emit = (ka[i - 1] != key);
+                    va = fill_a;
+                    vb = db[B.src(b0 + j)];
+                    ++j;
                 }
-            }
-        }
-    } else {
-        int64_t *sa = reinterpret_cast<int64_t *>(s_raw);
-        int64_t *sb = sa + NS;
-        constexpr int64_t NEG = INT64_MIN, POS = INT64_MAX;
-        {
-            int64_t ra[EW_LD], rb[EW_LD];
-#pragma unroll
-            for (int k = 0; k < EW_LD; ++k) {
-                const int i = threadIdx.x + k * EW_THREADS;
-                const int64_t pa = a0 - 1 + i, pb = b0 - 1 + i;
-                ra[k] = (i < na + 2) ? ((pa < 0) ? NEG : (pa < la ? A.key(pa) : POS)) : POS;
-                rb[k] = (i < nb + 2) ? ((pb < 0) ? NEG : (pb < lb ? B.key(pb) : POS)) : POS;
-            }
-#pragma unroll
-            for (int k = 0; k < EW_LD; ++k) {
-                const int i = threadIdx.x + k * EW_THREADS;
-                if (i < na + 2) sa[i] = ra[k];
-                if (i < nb + 2) sb[i] = rb[k];
-            }
-        }
-        __syncthreads();
-        const int64_t *ka = sa + 1, *kb = sb + 1;
-        if (dloc < dn) {
-            int lo = dloc > nb ? dloc - nb : 0;
-            int hi = dloc < na ? dloc : na;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (ka[mid] <= kb[dloc - 1 - mid]) lo = mid + 1;
-                else hi = mid;
-            }
-            int i = lo, j = dloc - lo;
-#pragma unroll
-            for (int it = 0; it < EW_ITEMS; ++it) {
-                const int d = dloc + it;
-                rkey[it] = 0;
-                rval[it] = O(0);
-                if (d < dn) {
-                    const bool take_a = (j >= nb) || (i < na && ka[i] <= kb[j]);
-                    int64_t key;
-                    T va, vb;
-                    bool emit = true;
-                    if (take_a) {
-                        key = ka[i];
-                        va = da[A.src(a0 + i)];
-                        vb = (kb[j] == key) ? db[B.src(b0 + j)] : fill_b;
-                        ++i;
-                    } else {
-                        key = kb[j];
-                        emit = (ka[i - 1] != key);
-                        va = fill_a;
-                        vb = db[B.src(b0 + j)];
-                        ++j;
-                    }
-                    O r;
-                    if constexpr (PRED) r = (O)bin_pred<T>(op, va, vb);
-                    else r = (O)bin_apply<T>(op, va, vb);
-                    rkey[it] = key;
-                    rval[it] = r;
-                    if (emit && bits_differ<O>(r, out_fill)) keepmask |= 1u << it;
-                }
+                O r;
+                if constexpr (PRED) r = (O)bin_pred<T>(op, va, vb);
+                else r = (O)bin_apply<T>(op, va, vb);
+                rkey[it] = key;
+                rval[it] = r;
+                if (emit && bits_differ<O>(r, out_fill)) keepmask |= 1u << it;
             }
         }
     }
@@ -543,7 +416,7 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
         if (lane >= o) incl += v;
     }
     if (lane == 31) s_warp[w] = incl;
-    __syncthreads();  // also: every thread is done reading the staged operands
+    __syncthreads();  // also: every thread is done reading sa / sb
     int woff = 0, tile_total = 0;
 #pragma unroll
     for (int q = 0; q < EW_THREADS / 32; ++q) {
@@ -553,16 +426,14 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
     }
     // publish this tile's count as early as possible: successors can start summing while we compact
     if (threadIdx.x == 0) lb_store(&lb_status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | (uint64_t)tile_total);
-    // compact into shared memory (reusing the staging buffer), then coalesced write-out
-    int64_t *sk = reinterpret_cast<int64_t *>(s_raw);
-    uint32_t *sk32 = reinterpret_cast<uint32_t *>(s_raw);
-    O *sv = reinterpret_cast<O *>(s_raw + (size_t)EW_TILE * 8);
+    // compact into shared memory (reusing the key staging arrays), then coalesced write-out
+    int64_t *sk = sa;
+    O *sv = reinterpret_cast<O *>(sb);
     int pos = woff + incl - mine;
 #pragma unroll
     for (int it = 0; it < EW_ITEMS; ++it) {
         if (keepmask & (1u << it)) {
-            if (fast) sk32[pos] = rk32[it];
-            else sk[pos] = rkey[it];
+            sk[pos] = rkey[it];
             sv[pos] = rval[it];
             ++pos;
         }
@@ -610,10 +481,9 @@ ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__r
     }
     __syncthreads();
     const int64_t base = s_base;
-    const int64_t kbase = kmin - 1;
     for (int t = threadIdx.x; t < tile_total; t += EW_THREADS) {
         vals_out[base + t] = sv[t];
-        keys_out[base + t] = fast ? kbase + (int64_t)sk32[t] : sk[t];
+        keys_out[base + t] = sk[t];
     }
 }
 

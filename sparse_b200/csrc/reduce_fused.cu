@@ -154,7 +154,7 @@ __device__ __forceinline__ void load_items(const E *__restrict__ p, int64_t firs
 
 // OP >= 0: the operator is a compile-time constant (no per-element switch); OP = -1: runtime operator
 template <typename T, int OP, bool VEC>
-__global__ void __launch_bounds__(RD_THREADS, 4)
+__global__ void __launch_bounds__(RD_THREADS, 5)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
                    FastDiv fcols, int op_rt, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
                    T result_fill, int64_t *__restrict__ out_gid, T *__restrict__ out_val,

@@ -41,6 +41,13 @@ __device__ __forceinline__ unsigned hash_col(I k) {
     x *= 0x9E3779B97F4A7C15ull;
     return (unsigned)(x >> 32);
 }
+// cheaper variant for the shared-memory tables (<= 2^12 slots): 32-bit multiplicative (Fibonacci) hashing, upper bits
+template <typename I>
+__device__ __forceinline__ unsigned hash_small(I k) {
+    unsigned x = (unsigned)k;
+    if constexpr (sizeof(I) == 8) x ^= (unsigned)((uint64_t)k >> 32) * 0x85EBCA6Bu;
+    return (x * 0x9E3779B1u) >> 20;
+}
 
 template <typename I>
 struct Empty {
@@ -160,7 +167,6 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
                    unsigned long long *__restrict__ totals /* [0] structural entries, [1] entries != +0 */) {
     using L = OrderedSmem<T, W, I, HMAX, WARPS>;
     constexpr int PMAX = L::PMAX;
-    constexpr int CH = PMAX / 32;  // product chunks a row can have
     constexpr I EMPTY = Empty<I>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -184,7 +190,7 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
         const int gsz = __popc(grp);
         // claim / find the slot -- no atomics: the table belongs to this warp; a lane that sees an empty slot stores
         // its key, everybody synchronises, and the lane whose key is there owns the slot
-        unsigned h = hash_col<I>(k) & mask;
+        unsigned h = hash_small<I>(k) & mask;
         bool pending = lead, isnew = false;
         while (__any_sync(FULL, pending)) {
             I cur = EMPTY;
@@ -236,43 +242,35 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
         }
         const int total = __shfl_sync(FULL, incl, 31);
         const int excl = incl - len;  // lanes past the row's entries hold `total`
-        // all loads of the chunk group first (one round trip to memory), then the inserts
-        I kk[CH];
-        T pp[CH];
+        // software pipeline over the chunks of 32 products: the loads of chunk c + 1 are in flight while chunk c is
+        // inserted (two live (column, product) registers -- no register arrays, no unrolled copies of the insert)
+        auto fetch = [&](int c, I &k, T &p) {
+            k = EMPTY;
+            p = T(0);
+            const int t = c * 32 + lane;
+            int lo = 0;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            kk[c] = EMPTY;
-            pp[c] = T(0);
-            if (c * 32 < total) {
-                const int t = c * 32 + lane;
-                int lo = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const int e = __shfl_sync(FULL, excl, lo + step);
-                    if (e <= t) lo += step;
-                }
-                const I b0 = __shfl_sync(FULL, bs, lo);
-                const T a0 = __shfl_sync(FULL, av, lo);
-                const int e0 = __shfl_sync(FULL, excl, lo);
-                if (t < total) {
-                    const int64_t src = (int64_t)b0 + (t - e0);
-                    kk[c] = b_indices[src];
-                    pp[c] = mul_rn(a0, b_data[src]);
-                }
+            for (int step = 16; step > 0; step >>= 1) {
+                const int e = __shfl_sync(FULL, excl, lo + step);
+                if (e <= t) lo += step;
             }
-        }
-        // one copy of the insert code (it is long: an unrolled version overflows the instruction cache); the chunk's
-        // registers are picked by predicated moves
+            const I b0 = __shfl_sync(FULL, bs, lo);
+            const T a0 = __shfl_sync(FULL, av, lo);
+            const int e0 = __shfl_sync(FULL, excl, lo);
+            if (t < total) {
+                const int64_t src = (int64_t)b0 + (t - e0);
+                k = b_indices[src];
+                p = mul_rn(a0, b_data[src]);
+            }
+        };
+        I kn;
+        T pn;
+        if (total > 0) fetch(0, kn, pn);
 #pragma unroll 1
         for (int c = 0; c * 32 < total; ++c) {
-            I k = kk[0];
-            T p = pp[0];
-#pragma unroll
-            for (int q = 1; q < CH; ++q)
-                if (c == q) {
-                    k = kk[q];
-                    p = pp[q];
-                }
+            const I k = kn;
+            const T p = pn;
+            if ((c + 1) * 32 < total) fetch(c + 1, kn, pn);
             insert(k, p, c * 32 + lane < total, mask);
         }
     };

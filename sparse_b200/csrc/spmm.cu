@@ -126,6 +126,94 @@ spmm_csr_dense_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const 
     if (row_ok && col_ok && !skipped) store_c<T, VEC>(C + row * ldc + col0, acc);
 }
 
+template <typename T, typename I, int VEC, int G, int U>
+__global__ void __launch_bounds__(256)
+spmm_csr_dense_dyn_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const I *__restrict__ a_indices,
+                      const I *__restrict__ a_indptr, const T *__restrict__ B, int64_t ldb, T *__restrict__ C,
+                      int64_t ldc, const uint8_t *__restrict__ skip, unsigned int *__restrict__ row_counter) {
+    static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "G must be a power of two <= 32");
+    static_assert(U <= G && G % U == 0, "U must divide G");
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ROWS_PER_WARP = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (G - 1);
+    static_assert(G == 32, "the dynamic-row variant is warp per row");
+    const int64_t col0 = ((int64_t)blockIdx.y * G + sub) * VEC;
+    const bool col_ok = col0 < N;
+    constexpr unsigned ROWS_PER_TICKET = 2;
+    for (;;) {
+    // rows are dealt out two at a time by a global counter: a warp that drew a long row simply draws fewer rows, so
+    // no CTA sits on one busy warp (skewed matrices: the row-split grid's static 8 rows per CTA idles 7 warps)
+    unsigned first = 0;
+    if (lane == 0) first = atomicAdd(row_counter + blockIdx.y, ROWS_PER_TICKET);
+    first = __shfl_sync(FULL, first, 0);
+    if ((int64_t)first >= M) break;
+    for (unsigned rr = 0; rr < ROWS_PER_TICKET; ++rr) {
+    const int64_t row = (int64_t)first + rr;
+    const bool row_ok = row < M;
+
+    int64_t base = 0, end = 0;
+    // rows marked in `skip` are long rows handled by the column-split kernel (spmm_skew.cu)
+    const bool skipped = skip != nullptr && row_ok && skip[row] != 0;
+    if (row_ok && !skipped) {
+        base = (int64_t)a_indptr[row];
+        end = (int64_t)a_indptr[row + 1];
+    }
+    const uint64_t pol_b = policy_evict_last();
+    const T *bcol = B + col0;
+
+    T acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = T(0);
+
+    // prefetch the first chunk of the row's (index, value) stream
+    I col_n = 0;
+    T val_n = T(0);
+    if (base + sub < end) {
+        col_n = ldg_stream(a_indices + base + sub);
+        val_n = ldg_stream(a_data + base + sub);
+    }
+
+    auto any = [&](bool p) -> bool {
+        if constexpr (G == 32) return p;  // whole warp shares the row: already uniform
+        else return __any_sync(FULL, p);
+    };
+
+    while (any(base < end)) {
+        const I col = col_n;
+        const T val = val_n;
+        int64_t rem = end - base;
+        const int cnt = rem > G ? G : (rem > 0 ? (int)rem : 0);
+        const int64_t nb = base + G;
+        if (nb + sub < end) {  // prefetch the next chunk while this one is consumed
+            col_n = ldg_stream(a_indices + nb + sub);
+            val_n = ldg_stream(a_data + nb + sub);
+        }
+#pragma unroll 1
+        for (int j = 0; j < G; j += U) {
+            if (!any(j < cnt)) break;
+            Pack<T, VEC> bv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const I c = __shfl_sync(FULL, col, j + u, G);
+                if (j + u < cnt && col_ok) bv[u] = load_b<T, VEC>(bcol + (int64_t)c * ldb, pol_b);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const T v = __shfl_sync(FULL, val, j + u, G);
+                if (j + u < cnt) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] = add_rn(acc[k], mul_rn(v, bv[u].v[k]));
+                }
+            }
+        }
+        base = nb;
+    }
+    if (row_ok && col_ok && !skipped) store_c<T, VEC>(C + row * ldc + col0, acc);
+    }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Variant 2: 1-D bulk-TMA gather (cp.async.bulk -> shared-memory ring, mbarrier complete_tx).
 // One warp per row; ring of 32 stages of ROWB bytes per warp; position p of the row's nnz stream
@@ -258,6 +346,7 @@ template <typename T, typename I>
 int skew_begin(int64_t M, int64_t N, const void *ad, const void *ai, const void *ap, const void *b, int64_t ldb,
                void *out, int64_t ldc, cudaStream_t s, uint8_t **skip_out, bool aligned16);
 int skew_end(cudaStream_t s, uint8_t *skip);
+unsigned int *skew_row_counter();  // 64 zero-initialisable counters of the in-flight call (nullptr: unavailable)
 
 template <typename T, typename I, int VEC, int G, int U>
 static int launch_v1(int64_t M, int64_t N, const void *ad, const void *ai, const void *ap, const void *b, int64_t ldb,
@@ -287,7 +376,25 @@ static int dispatch_g(int64_t M, int64_t N, const void *ad, const void *ai, cons
             uint8_t *skip = nullptr;
             int rc = skew_begin<T, I>(M, N, ad, ai, ap, b, ldb, out, ldc, s, &skip, VEC > 1);
             if (rc) return rc;
-            rc = launch_v1<T, I, VEC, 32, 8>(M, N, ad, ai, ap, b, ldb, out, ldc, s, skip);
+            {
+                // the rows that stay row-split are drawn dynamically by persistent warps
+                unsigned int *counter = skew_row_counter();
+                const int64_t gy = (N + (int64_t)32 * VEC - 1) / ((int64_t)32 * VEC);
+                if (counter != nullptr && gy <= 64) {
+                    B2S_CUDA(cudaMemsetAsync(counter, 0, 64 * sizeof(unsigned int), s));
+                    auto kern = spmm_csr_dense_dyn_kernel<T, I, VEC, 32, 8>;
+                    int occ = 1;
+                    B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+                    if (occ < 1) occ = 1;
+                    dim3 grid((unsigned)(num_sms() * occ), (unsigned)gy);
+                    kern<<<grid, 256, 0, s>>>(M, N, (const T *)ad, (const I *)ai, (const I *)ap, (const T *)b, ldb,
+                                              (T *)out, ldc, skip, counter);
+                    B2S_CHECK_LAUNCH();
+                    rc = B2S_OK;
+                } else {
+                    rc = launch_v1<T, I, VEC, 32, 8>(M, N, ad, ai, ap, b, ldb, out, ldc, s, skip);
+                }
+            }
             const int rc2 = skew_end(s, skip);
             return rc ? rc : rc2;
         }

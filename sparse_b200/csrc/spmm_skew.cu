@@ -215,6 +215,8 @@ static SkewState &skew_state() {
 // scratch of the in-flight call (freed in skew_end)
 static thread_local int64_t *t_list = nullptr;
 static thread_local unsigned int *t_count = nullptr;
+static thread_local unsigned int *t_rowctr = nullptr;
+unsigned int *skew_row_counter() { return t_rowctr; }
 
 template <typename T, typename I>
 int skew_begin(int64_t M, int64_t N, const void *ad, const void *ai, const void *ap, const void *b, int64_t ldb,
@@ -227,6 +229,7 @@ int skew_begin(int64_t M, int64_t N, const void *ad, const void *ai, const void 
     if ((rc = scratch_alloc((void **)&skip, (size_t)M, s))) return rc;
     if ((rc = scratch_alloc((void **)&t_list, (size_t)kLongCap * 8, s))) return rc;
     if ((rc = scratch_alloc((void **)&t_count, 4, s))) return rc;
+    if ((rc = scratch_alloc((void **)&t_rowctr, 64 * sizeof(unsigned int), s))) return rc;
     B2S_CUDA(cudaMemsetAsync(t_count, 0, 4, s));
     mark_long_rows_kernel<I><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, (const I *)ap, skip, t_list, t_count);
     B2S_CHECK_LAUNCH();
@@ -263,8 +266,10 @@ int skew_end(cudaStream_t s, uint8_t *skip) {
     scratch_free(skip, s);
     scratch_free(t_list, s);
     scratch_free(t_count, s);
+    scratch_free(t_rowctr, s);
     t_list = nullptr;
     t_count = nullptr;
+    t_rowctr = nullptr;
     return B2S_OK;
 }
 

@@ -22,7 +22,7 @@ import bench  # noqa: E402
 import sparse_b200 as sp  # noqa: E402
 from sparse_b200 import _lib  # noqa: E402
 
-DEV = torch.device("cuda", 0)
+DEV = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
 PEAK, _ = bench.peaks()
 
 

@@ -246,7 +246,10 @@ def main():
     # ---- C3-large: element-wise add and reductions, range-partitioned on the leading axis -----------
     if "c3" in args.which and not tiny:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
-        from bench_configs import rand_coo  # seeded device generator: the same tensors on every rank
+        import bench_configs
+
+        bench_configs.DEV = dev  # its generators default to cuda:0
+        rand_coo = bench_configs.rand_coo  # seeded device generator: the same tensors on every rank
 
         shape_a, shape_b = (512, 512, 512, 64), (512, 512, 512, 1)
         a = rand_coo(shape_a, int(85_899_345 * args.scale), 10)
