@@ -193,11 +193,17 @@ class GCXS(SparseArray):
         return self._indptr_np
 
     def _has_long_rows(self):
-        """Does some compressed row hold more than 4096 entries?  (cached; enables K1's nnz-balanced long-row kernel)"""
+        """Is the row-length distribution skewed -- longest compressed row > max(512, 8 x the mean)?  (cached; one device
+        reduction per matrix.)  Enables K1's nnz-balanced mode: rows are drawn dynamically by persistent warps and rows
+        longer than max(512, 4 x mean) go to the shared-memory-ring kernel (csrc/spmm_skew.cu).  Uniform matrices (the
+        C2 headline: Poisson(100) rows, longest ~150) keep the static row-split grid."""
         if getattr(self, "_long_rows_flag", None) is None:
             _, _, indptr = self._dev()
-            self._long_rows_flag = (self.ndim >= 2 and self.nnz > 4096
-                                    and Kn.csr_max_row_nnz(indptr, self._compressed_shape[0]) > 4096)
+            rows = self._compressed_shape[0]
+            self._long_rows_flag = False
+            if self.ndim >= 2 and self.nnz > 4096 and rows >= 4096:
+                longest = Kn.csr_max_row_nnz(indptr, rows)
+                self._long_rows_flag = longest > max(512, 8 * (self.nnz // max(rows, 1)))
         return self._long_rows_flag
 
     def _rows_sorted(self):

@@ -87,39 +87,42 @@ __device__ __forceinline__ T fill_fix(int op, T v, int64_t count, int64_t ncols,
     return nf != 0 ? red_apply<T>(op, v, fill) : v;
 }
 
-// State of the run that is open at some position of the sorted stream: its value so far and the GLOBAL position of its
-// head (-1: no head inside the scanned range, the run started earlier).  Runs are contiguous ranges of the sorted
-// stream, so the number of elements of a finished run -- needed by the fill-value contribution -- is simply
-// (last position - head position + 1): nothing is counted.
 template <typename T>
-struct Run {
+struct Run {  // state of the run that is open at some position
+    int flag;     // 1 if a head lies at or before this position (within the scanned range)
     T val;
-    int64_t hp;
+    int64_t cnt;
 };
 
 template <typename T>
 __device__ __forceinline__ Run<T> run_combine(int op, const Run<T> &a, const Run<T> &b) {
     // b comes after a
     Run<T> r;
-    r.hp = a.hp > b.hp ? a.hp : b.hp;
-    const T both = red_apply<T>(op, a.val, b.val);
-    r.val = b.hp >= 0 ? b.val : both;
+    r.flag = a.flag | b.flag;
+    if (b.flag) {
+        r.val = b.val;
+        r.cnt = b.cnt;
+    } else {
+        r.val = (a.cnt == 0) ? b.val : ((b.cnt == 0) ? a.val : red_apply<T>(op, a.val, b.val));
+        r.cnt = a.cnt + b.cnt;
+    }
     return r;
 }
 
 template <typename T>
 __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
     Run<T> r;
+    r.flag = __shfl_up_sync(0xffffffffu, x.flag, o);
     r.val = __shfl_up_sync(0xffffffffu, x.val, o);
-    r.hp = __shfl_up_sync(0xffffffffu, x.hp, o);
+    r.cnt = __shfl_up_sync(0xffffffffu, x.cnt, o);
     return r;
 }
 
 // One tile of the SINGLE-pass segmented reduction.
-// Every thread owns RD_ITEMS consecutive (key, value) pairs and reads them straight from global memory with 16-byte
-// vector loads (a warp covers one contiguous 2-4 KB range; the four loads of a thread hit the same L1 lines), so the
-// inputs never pass through shared memory.  The finished runs of the tile -- which occupy one contiguous range of
-// output slots -- are staged in shared memory and written out with unit stride.
+// Loads and stores go through shared memory so that global accesses are fully coalesced: the tile's 2048 (key, value)
+// pairs are loaded with unit stride, each thread then reads its 8 consecutive pairs from a padded layout
+// (index e + e/8: 2-way instead of 16-way bank conflicts), and the finished runs of the tile -- which occupy one
+// contiguous range of output slots -- are staged in the same buffers and written out with unit stride.
 // The carry-in of a tile (the run still open at its first element + the number of run heads before it) comes from a
 // decoupled look-back over the tile descriptors of its predecessors (Merrill & Garland): tiles are taken in TICKET
 // order, every tile publishes its own aggregate before it waits for anything and only ever waits on smaller tickets
@@ -127,6 +130,9 @@ __device__ __forceinline__ Run<T> run_shfl_up(const Run<T> &x, int o) {
 // (aggregate / inclusive prefix), so its look-back needs no fences; the carry-in RUN only ever needs the predecessors'
 // aggregates back to the nearest tile that contains a head (usually the immediate predecessor), which are published
 // (payload, __threadfence, status) before that tile waits for anything.
+constexpr int RD_PAD = RD_TILE + RD_TILE / 8 + 8;
+__device__ __forceinline__ int rd_pad(int e) { return e + (e >> 3); }
+
 enum : uint64_t { RD_AGG = 1ull << 62, RD_PREFIX = 2ull << 62, RD_VALUE = (1ull << 62) - 1 };
 template <typename T>
 struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entries each)
@@ -135,38 +141,23 @@ struct RdDesc {  // per-tile look-back descriptors (device arrays of ntiles entr
     int64_t *run_meta;   // ... and (count << 1) | "the tile contains a head"; valid once heads[] is non-zero
 };
 
-// RD_ITEMS consecutive elements of p[] starting at element `first` (a multiple of RD_ITEMS): 16-byte loads when the
-// array is 16-byte aligned (VEC), element loads otherwise
-template <typename E, bool VEC>
-__device__ __forceinline__ void load_items(const E *__restrict__ p, int64_t first, E (&out)[RD_ITEMS]) {
-    if constexpr (VEC && (RD_ITEMS * sizeof(E)) % 16 == 0) {
-        constexpr int NV = (int)(RD_ITEMS * sizeof(E) / 16);
-        const uint4 *src = reinterpret_cast<const uint4 *>(p + first);
-        uint4 tmp[NV];
-#pragma unroll
-        for (int q = 0; q < NV; ++q) tmp[q] = __ldg(src + q);
-        memcpy(out, tmp, sizeof(out));
-    } else {
-#pragma unroll
-        for (int i = 0; i < RD_ITEMS; ++i) out[i] = p[first + i];
-    }
-}
-
-// OP >= 0: the operator is a compile-time constant (no per-element switch); OP = -1: runtime operator
-template <typename T, int OP, bool VEC>
-__global__ void __launch_bounds__(RD_THREADS, 5)
+// IS_ADD: the operator is known at compile time for sums (the common case): no per-element switch
+template <typename T, bool IS_ADD>
+__global__ void __launch_bounds__(RD_THREADS, 4)
 reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols,
                    FastDiv fcols, int op_rt, RdDesc<T> desc, unsigned int *__restrict__ ticket, T fill, int apply_fix,
                    T result_fill, int64_t *__restrict__ out_gid, T *__restrict__ out_val,
                    unsigned long long *__restrict__ counters /* [0] results equal to result_fill, [1] groups */) {
-    __shared__ int64_t sk[RD_TILE + 1];
-    __shared__ T sv[RD_TILE + 1];
+    __shared__ int64_t sk[RD_PAD];
+    __shared__ T sv[RD_PAD];
+    __shared__ int s_flag[RD_THREADS / 32];
     __shared__ T s_val[RD_THREADS / 32];
     __shared__ int64_t s_cnt[RD_THREADS / 32];
     __shared__ int s_heads[RD_THREADS / 32];
     __shared__ int64_t s_tile, s_hexcl, s_ccnt;
+    __shared__ int s_cflag;
     __shared__ T s_cval;
-    const int op = OP >= 0 ? OP : op_rt;
+    const int op = IS_ADD ? (int)RF_ADD : op_rt;
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ticket, 1u);
     __syncthreads();
     const int64_t tile = s_tile;
@@ -174,51 +165,59 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     const int64_t base = tile_base + (int64_t)threadIdx.x * RD_ITEMS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
+    // coalesced tile load: slot e holds element tile_base + e (group id, value); slot -1 / RD_TILE = neighbours
+#pragma unroll
+    for (int i = 0; i < RD_ITEMS; ++i) {
+        const int e = threadIdx.x + i * RD_THREADS;
+        const int64_t p = tile_base + e;
+        int64_t gk = -1;
+        T vv = T(0);
+        if (p < n) {
+            gk = (int64_t)fcols.div((uint64_t)keys[p]);
+            vv = vals[p];
+        }
+        sk[rd_pad(e)] = gk;
+        sv[rd_pad(e)] = vv;
+    }
+    __shared__ int64_t s_edge[2];
+    if (threadIdx.x == 0) {
+        s_edge[0] = (tile_base > 0) ? (int64_t)fcols.div((uint64_t)keys[tile_base - 1]) : -1;
+        s_edge[1] = (tile_base + RD_TILE < n) ? (int64_t)fcols.div((uint64_t)keys[tile_base + RD_TILE]) : -1;
+    }
+    __syncthreads();
+
     int64_t g[RD_ITEMS];
     T v[RD_ITEMS];
-    unsigned vm = 0xFFu;  // valid items
-    if (base + RD_ITEMS <= n) {
-        load_items<int64_t, VEC>(keys, base, g);
-        load_items<T, VEC>(vals, base, v);
+    bool head[RD_ITEMS];
+    const int e0 = threadIdx.x * RD_ITEMS;
+    const int64_t gprev = (threadIdx.x == 0) ? s_edge[0] : sk[rd_pad(e0 - 1)];
+    const int64_t gnext_thread = (threadIdx.x == RD_THREADS - 1) ? s_edge[1] : sk[rd_pad(e0 + RD_ITEMS)];
 #pragma unroll
-        for (int i = 0; i < RD_ITEMS; ++i) g[i] = (int64_t)fcols.div((uint64_t)g[i]);
-    } else {
-        vm = 0;
+    for (int i = 0; i < RD_ITEMS; ++i) {
+        const int64_t p = base + i;
+        g[i] = sk[rd_pad(e0 + i)];
+        v[i] = sv[rd_pad(e0 + i)];
+        head[i] = (p < n) && ((p == 0) || (g[i] != (i == 0 ? gprev : g[i - 1])));
+    }
+    // thread summary: run still open at the end of the thread's range
+    Run<T> mine;
+    mine.flag = 0;
+    mine.val = T(0);
+    mine.cnt = 0;
+    int nheads = 0;
 #pragma unroll
-        for (int i = 0; i < RD_ITEMS; ++i) {
-            const int64_t p = base + i;
-            g[i] = -1;
-            v[i] = T(0);
-            if (p < n) {
-                g[i] = (int64_t)fcols.div((uint64_t)keys[p]);
-                v[i] = vals[p];
-                vm |= 1u << i;
+    for (int i = 0; i < RD_ITEMS; ++i) {
+        if (base + i < n) {
+            if (head[i]) {
+                mine.flag = 1;
+                mine.val = v[i];
+                mine.cnt = 1;
+                ++nheads;
+            } else {
+                mine.val = mine.cnt == 0 ? v[i] : red_apply<T>(op, mine.val, v[i]);
+                mine.cnt += 1;
             }
         }
-    }
-    // group ids of the neighbours: the previous thread's last element, the next thread's first one
-    int64_t gprev = __shfl_up_sync(0xffffffffu, g[RD_ITEMS - 1], 1);
-    int64_t gnext = __shfl_down_sync(0xffffffffu, g[0], 1);
-    if (lane == 0) gprev = (base > 0 && base - 1 < n) ? (int64_t)fcols.div((uint64_t)keys[base - 1]) : -2;
-    if (lane == 31) gnext = base + RD_ITEMS < n ? (int64_t)fcols.div((uint64_t)keys[base + RD_ITEMS]) : -2;
-    // head mask (an element past the end counts as a head: it closes the last real run and is never emitted) and
-    // "last element of its run" mask
-    unsigned hm = (g[0] != gprev) ? 1u : 0u;
-#pragma unroll
-    for (int i = 1; i < RD_ITEMS; ++i) hm |= (g[i] != g[i - 1]) ? (1u << i) : 0u;
-    hm |= ~vm & 0xFFu;
-    const unsigned lastm = ((hm >> 1) | ((g[RD_ITEMS - 1] != gnext) ? (1u << (RD_ITEMS - 1)) : 0u)) & vm;
-    const int nheads = __popc(hm & vm);
-    // thread summary: the run still open at the end of the thread's range (branch-free)
-    Run<T> mine;
-    mine.val = v[0];
-    mine.hp = (hm & 1u) ? base : -1;
-#pragma unroll
-    for (int i = 1; i < RD_ITEMS; ++i) {
-        const bool h = (hm >> i) & 1u;
-        const T both = red_apply<T>(op, mine.val, v[i]);
-        mine.val = h ? v[i] : both;
-        mine.hp = h ? base + i : mine.hp;
     }
     // block-level inclusive segmented scan of the thread summaries (+ plain scan of head counts)
     Run<T> incl = mine;
@@ -233,46 +232,46 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         }
     }
     if (lane == 31) {
+        s_flag[w] = incl.flag;
         s_val[w] = incl.val;
-        s_cnt[w] = incl.hp;
+        s_cnt[w] = incl.cnt;
         s_heads[w] = hincl;
     }
-    __syncthreads();
-    Run<T> wcarry;  // warps before this one (no tile carry-in yet); warp 0: nothing, replaced by the carry below
+    __syncthreads();  // (also: every thread has copied its inputs out of sk / sv)
+    Run<T> wcarry;  // warps before this one, no carry-in yet
+    wcarry.flag = 0;
     wcarry.val = T(0);
-    wcarry.hp = -1;
+    wcarry.cnt = 0;
     Run<T> tile_agg = wcarry;
     int hbefore_local = 0, tile_heads = 0;
-    bool have_w = false, have_t = false;
 #pragma unroll
     for (int q = 0; q < RD_THREADS / 32; ++q) {
         Run<T> wq;
+        wq.flag = s_flag[q];
         wq.val = s_val[q];
-        wq.hp = s_cnt[q];
+        wq.cnt = s_cnt[q];
         if (q < w) {
-            wcarry = have_w ? run_combine<T>(op, wcarry, wq) : wq;
-            have_w = true;
+            wcarry = run_combine<T>(op, wcarry, wq);
             hbefore_local += s_heads[q];
         }
-        tile_agg = have_t ? run_combine<T>(op, tile_agg, wq) : wq;
-        have_t = true;
+        tile_agg = run_combine<T>(op, tile_agg, wq);
         tile_heads += s_heads[q];
     }
     // publish the aggregate (tile 0: already the inclusive prefix) before waiting for anybody: run payload first,
-    // then the status word that makes it visible.  run_meta = head position + 1 (0: the tile contains no head)
+    // then the status word that makes it visible
     if (threadIdx.x == 0) {
         *(volatile T *)&desc.run_val[tile] = tile_agg.val;
-        *(volatile int64_t *)&desc.run_meta[tile] = tile_agg.hp + 1;
+        *(volatile int64_t *)&desc.run_meta[tile] = (tile_agg.cnt << 1) | (int64_t)tile_agg.flag;
         __threadfence();
         *(volatile uint64_t *)&desc.heads[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | (uint64_t)tile_heads;
     }
-    // output staging: the tile finishes at most tile_heads + 1 runs; mark those slots empty
-    for (int i = threadIdx.x; i < tile_heads + 1; i += RD_THREADS) sk[i] = -1;
+    // the staging buffers alias the input buffers: mark every slot empty
+    for (int i = threadIdx.x; i < RD_TILE + 1; i += RD_THREADS) sk[i] = -1;
     if (w == 0) {
-        Run<T> excl;  // the run open at the first element of the tile
+        Run<T> excl;
+        excl.flag = 0;
         excl.val = T(0);
-        excl.hp = -1;
-        bool have_excl = false;
+        excl.cnt = 0;
         int64_t hexcl = 0;
         if (tile != 0) {
             int64_t p = tile - 1;  // lane 0 looks at the nearest predecessor
@@ -287,34 +286,31 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
                 }
                 __threadfence();
                 const int64_t meta = idx >= 0 ? *(volatile int64_t *)&desc.run_meta[idx] : 1;  // before tile 0: a head
-                const unsigned fm = __ballot_sync(0xffffffffu, meta != 0);
+                const unsigned fm = __ballot_sync(0xffffffffu, (meta & 1) != 0);
                 const int firstf = fm ? __ffs(fm) - 1 : 31;
-                // ordered reduction over lanes 0 .. firstf (lane + o holds an EARLIER tile: it goes on the left);
-                // lanes past firstf and tiles before tile 0 do not take part
-                const bool part = lane <= firstf && idx >= 0;
                 Run<T> x;
-                x.val = part ? *(volatile T *)&desc.run_val[idx] : T(0);
-                x.hp = part ? meta - 1 : -1;
-                int have = part ? 1 : 0;
+                x.flag = 0;
+                x.val = T(0);
+                x.cnt = 0;
+                if (lane <= firstf && idx >= 0) {
+                    x.flag = (int)(meta & 1);
+                    x.cnt = meta >> 1;
+                    x.val = *(volatile T *)&desc.run_val[idx];
+                }
+                // ordered reduction: lane + o holds an EARLIER tile, so it goes on the left
                 const int steps = firstf == 0 ? 0 : 32;
                 for (int o = 1; o < steps; o <<= 1) {
                     Run<T> other;
+                    other.flag = __shfl_down_sync(0xffffffffu, x.flag, o);
                     other.val = __shfl_down_sync(0xffffffffu, x.val, o);
-                    other.hp = __shfl_down_sync(0xffffffffu, x.hp, o);
-                    const int oh = __shfl_down_sync(0xffffffffu, have, o);
-                    if (lane + o < 32 && oh) {
-                        x = have ? run_combine<T>(op, other, x) : other;
-                        have = 1;
-                    }
+                    other.cnt = __shfl_down_sync(0xffffffffu, x.cnt, o);
+                    if (lane + o < 32) x = run_combine<T>(op, other, x);
                 }
                 Run<T> win;
+                win.flag = __shfl_sync(0xffffffffu, x.flag, 0);
                 win.val = __shfl_sync(0xffffffffu, x.val, 0);
-                win.hp = __shfl_sync(0xffffffffu, x.hp, 0);
-                const int winh = __shfl_sync(0xffffffffu, have, 0);
-                if (winh) {  // this window lies before everything gathered so far
-                    excl = have_excl ? run_combine<T>(op, win, excl) : win;
-                    have_excl = true;
-                }
+                win.cnt = __shfl_sync(0xffffffffu, x.cnt, 0);
+                excl = run_combine<T>(op, win, excl);  // this window lies before everything gathered so far
                 if (fm) break;
                 q -= 32;
             }
@@ -352,44 +348,54 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
         }
         if (lane == 0) {
             s_hexcl = hexcl;
+            s_cflag = excl.flag;
             s_cval = excl.val;
-            s_ccnt = excl.hp;
+            s_ccnt = excl.cnt;
             if (tile == (int64_t)gridDim.x - 1) counters[1] = (unsigned long long)(hexcl + tile_heads);
         }
     }
     __syncthreads();
-    // the run open in front of this thread: tile carry-in, then the warps before, then the lanes before.  The first
-    // element of the stream is a head, so an operand that does not exist (tile 0, warp 0, lane 0) is never used.
-    Run<T> st;
-    st.val = s_cval;
-    st.hp = s_ccnt;
-    if (w > 0) st = tile == 0 ? wcarry : run_combine<T>(op, st, wcarry);
-    const Run<T> prev = run_shfl_up(incl, 1);
-    const int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
-    int64_t hcount = s_hexcl + hbefore_local;  // heads strictly before this thread's first element
+    Run<T> carry;
+    carry.flag = s_cflag;
+    carry.val = s_cval;
+    carry.cnt = s_ccnt;
+    carry = run_combine<T>(op, carry, wcarry);
+    const int64_t hbefore = s_hexcl + hbefore_local;
+    const int64_t slot0 = s_hexcl - 1;  // output slot of a run that started before this tile
+    Run<T> prev = run_shfl_up(incl, 1);
+    int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
+    Run<T> st = carry;
+    int64_t hcount = hbefore;  // heads strictly before this thread's first element
     if (lane > 0) {
-        st = (tile == 0 && w == 0) ? prev : run_combine<T>(op, st, prev);
+        st = run_combine<T>(op, carry, prev);
         hcount += hprev;
     }
-    const int64_t slot0 = s_hexcl - 1;  // output slot of a run that started before this tile
     T rv = st.val;
-    int64_t rhp = st.hp;
+    int64_t rc = st.cnt;
 #pragma unroll
     for (int i = 0; i < RD_ITEMS; ++i) {
-        const bool h = (hm >> i) & 1u;
-        const T both = red_apply<T>(op, rv, v[i]);
-        rv = h ? v[i] : both;
-        rhp = h ? base + i : rhp;
-        hcount += (hm & vm) >> i & 1u;
-        if ((lastm >> i) & 1u) {
-            const int loc = (int)(hcount - 1 - slot0);  // 0 .. tile_heads
-            sk[loc] = g[i];
-            sv[loc] = apply_fix ? fill_fix<T>(op, rv, base + i - rhp + 1, ncols, fill) : rv;
+        const int64_t p = base + i;
+        if (p < n) {
+            if (head[i]) {
+                rv = v[i];
+                rc = 1;
+                ++hcount;
+            } else {
+                rv = rc == 0 ? v[i] : red_apply<T>(op, rv, v[i]);
+                rc += 1;
+            }
+            const bool last = (p == n - 1) ||
+                              ((i + 1 < RD_ITEMS) ? (base + i + 1 < n && head[i + 1]) : (g[i] != gnext_thread));
+            if (last) {
+                const int loc = (int)(hcount - 1 - slot0);  // 0 .. RD_TILE
+                sk[loc] = g[i];
+                sv[loc] = apply_fix ? fill_fix<T>(op, rv, rc, ncols, fill) : rv;
+            }
         }
     }
     __syncthreads();
     int eq = 0;
-    for (int l = threadIdx.x; l < tile_heads + 1; l += RD_THREADS) {
+    for (int l = threadIdx.x; l < RD_TILE + 1; l += RD_THREADS) {
         const int64_t gid = sk[l];
         if (gid >= 0) {
             const int64_t idx = slot0 + l;
@@ -434,27 +440,16 @@ static int rd_single_t(const int64_t *keys, const void *vals, int64_t n, int64_t
     T fill, rfill;
     memcpy(&fill, fill_host, sizeof(T));
     memcpy(&rfill, result_fill_host, sizeof(T));
-    const bool vec = (((uintptr_t)keys | (uintptr_t)vals) & 15) == 0;
-    const FastDiv fd = make_fastdiv((uint64_t)ncols);
-#define B2S_RD(OPC)                                                                                                   \
-    do {                                                                                                              \
-        if (vec)                                                                                                      \
-            reduce_tile_kernel<T, OPC, true><<<(unsigned)nt, RD_THREADS, 0, s>>>(                                     \
-                keys, (const T *)vals, n, ncols, fd, op, d, ticket, fill, apply_fix, rfill, gid_out, (T *)vals_out,   \
-                counters);                                                                                            \
-        else                                                                                                          \
-            reduce_tile_kernel<T, OPC, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(                                    \
-                keys, (const T *)vals, n, ncols, fd, op, d, ticket, fill, apply_fix, rfill, gid_out, (T *)vals_out,   \
-                counters);                                                                                            \
-    } while (0)
-    switch (op) {  // the common operators are compile-time constants of their own instantiation
-        case RF_ADD: B2S_RD(RF_ADD); break;
-        case RF_MAX: B2S_RD(RF_MAX); break;
-        case RF_MIN: B2S_RD(RF_MIN); break;
-        case RF_MUL: B2S_RD(RF_MUL); break;
-        default: B2S_RD(-1); break;
-    }
-#undef B2S_RD
+    if (op == RF_ADD)
+        reduce_tile_kernel<T, true><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
+                                                                       make_fastdiv((uint64_t)ncols), op, d, ticket,
+                                                                       fill, apply_fix, rfill, gid_out, (T *)vals_out,
+                                                                       counters);
+    else
+        reduce_tile_kernel<T, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, (const T *)vals, n, ncols,
+                                                                        make_fastdiv((uint64_t)ncols), op, d, ticket,
+                                                                        fill, apply_fix, rfill, gid_out,
+                                                                        (T *)vals_out, counters);
     B2S_CHECK_LAUNCH();
     return B2S_OK;
 }

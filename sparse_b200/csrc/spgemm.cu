@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(WARPS * 32, (OrderedSmem<T, W, I, HMAX, WARPS>
 spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restrict__ a_indices,
                    const T *__restrict__ a_data, const I *__restrict__ b_indptr, const I *__restrict__ b_indices,
                    const T *__restrict__ b_data, const int64_t *__restrict__ Pv, const int64_t *__restrict__ ub_off,
-                   int64_t pmax_short, unsigned int *__restrict__ ticket, int64_t *__restrict__ tmp_idx,
+                   int64_t pmax_short, unsigned int *__restrict__ ticket, I *__restrict__ tmp_idx,
                    T *__restrict__ tmp_val, int64_t *__restrict__ row_nnz, int64_t *__restrict__ row_nz,
                    unsigned long long *__restrict__ totals /* [0] structural entries, [1] entries != +0 */) {
     using L = OrderedSmem<T, W, I, HMAX, WARPS>;
@@ -233,89 +233,97 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
     };
 
     // ---- the products of one A chunk (<= 32 entries; lane l holds entry l: B row start, length, A value) ------------
-    auto multiply_chunk = [&](I bs, int len, T av, unsigned mask) {
+    // exclusive offsets of the entries' product ranges (lanes past the row's entries hold `total`)
+    auto scan_lens = [&](int len, int &excl, int &total) {
         int incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += v;
         }
-        const int total = __shfl_sync(FULL, incl, 31);
-        const int excl = incl - len;  // lanes past the row's entries hold `total`
-        // software pipeline over the chunks of 32 products: the loads of chunk c + 1 are in flight while chunk c is
-        // inserted (two live (column, product) registers -- no register arrays, no unrolled copies of the insert)
-        auto fetch = [&](int c, I &k, T &p) {
-            k = EMPTY;
-            p = T(0);
-            const int t = c * 32 + lane;
-            int lo = 0;
+        total = __shfl_sync(FULL, incl, 31);
+        excl = incl - len;
+    };
+    // issue the loads of product chunk c (column, B value) and pick its A value; NOTHING here waits for the loads: the
+    // product is formed by the consumer one chunk-time (or one row-time) later
+    auto fetch = [&](int c, int excl, int total, I bs, T av, I &k, T &bv, T &a0) {
+        k = EMPTY;
+        bv = T(0);
+        const int t = c * 32 + lane;
+        int lo = 0;
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int e = __shfl_sync(FULL, excl, lo + step);
-                if (e <= t) lo += step;
-            }
-            const I b0 = __shfl_sync(FULL, bs, lo);
-            const T a0 = __shfl_sync(FULL, av, lo);
-            const int e0 = __shfl_sync(FULL, excl, lo);
-            if (t < total) {
-                const int64_t src = (int64_t)b0 + (t - e0);
-                k = b_indices[src];
-                p = mul_rn(a0, b_data[src]);
-            }
-        };
-        I kn;
-        T pn;
-        if (total > 0) fetch(0, kn, pn);
+        for (int step = 16; step > 0; step >>= 1) {
+            const int e = __shfl_sync(FULL, excl, lo + step);
+            if (e <= t) lo += step;
+        }
+        const I b0 = __shfl_sync(FULL, bs, lo);
+        a0 = __shfl_sync(FULL, av, lo);
+        const int e0 = __shfl_sync(FULL, excl, lo);
+        if (t < total) {
+            const int64_t src = (int64_t)b0 + (t - e0);
+            k = b_indices[src];
+            bv = b_data[src];
+        }
+    };
+    // software pipeline over the chunks of 32 products: the loads of chunk c + 1 are in flight while chunk c is
+    // inserted; chunk 0 arrives already fetched (kn, bn, an)
+    auto run_chunks = [&](int excl, int total, I bs, T av, I kn, T bn, T an, unsigned mask) {
 #pragma unroll 1
         for (int c = 0; c * 32 < total; ++c) {
             const I k = kn;
-            const T p = pn;
-            if ((c + 1) * 32 < total) fetch(c + 1, kn, pn);
+            const T p = mul_rn(an, bn);
+            if ((c + 1) * 32 < total) fetch(c + 1, excl, total, bs, av, kn, bn, an);
             insert(k, p, c * 32 + lane < total, mask);
         }
     };
 
     // ---- row pipeline ---------------------------------------------------------------------------------------------
+    // (row numbers fit an int: M < 2^31 is checked on the host; offsets into A are as wide as its index type)
+    using off_t = typename std::conditional<sizeof(I) == 4, int, int64_t>::type;
     constexpr int ROWS_PER_TICKET = 4;
     bool exhausted = false;
-    int64_t gen_next = 0, gen_end = 0;
-    auto next_row = [&]() -> int64_t {
+    int gen_next = 0, gen_end = 0;
+    const int Mi = (int)M;
+    auto next_row = [&]() -> int {
         if (gen_next == gen_end) {
             if (exhausted) return -1;
             unsigned t = 0;
             if (lane == 0) t = atomicAdd(ticket, 1u);
             t = __shfl_sync(FULL, t, 0);
-            gen_next = (int64_t)t * ROWS_PER_TICKET;
-            gen_end = gen_next + ROWS_PER_TICKET < M ? gen_next + ROWS_PER_TICKET : M;
-            if (gen_next >= M) {
+            if (t >= (unsigned)((Mi + ROWS_PER_TICKET - 1) / ROWS_PER_TICKET)) {
                 exhausted = true;
-                gen_next = gen_end = 0;
                 return -1;
             }
+            gen_next = (int)t * ROWS_PER_TICKET;
+            gen_end = gen_next + ROWS_PER_TICKET < Mi ? gen_next + ROWS_PER_TICKET : Mi;
         }
         return gen_next++;
     };
     // stage 3 (ticket + row extent), stage 2 (+ A entries), stage 1 (+ B extents); row < 0 = empty slot
-    int64_t row3 = -1, as3 = 0, ae3 = 0;
-    int64_t row2 = -1, as2 = 0, ae2 = 0;
+    int row3 = -1, row2 = -1, row1 = -1;
+    off_t as3 = 0, ae3 = 0, as2 = 0, ae2 = 0, as1 = 0, ae1 = 0;
     I j2 = 0;
     T av2 = T(0);
-    int64_t row1 = -1, as1 = 0, ae1 = 0;
-    I bs1 = 0;
-    int len1 = 0;
+    I bs1 = 0, be1 = 0;  // B row extent of this lane's A entry (raw loads: nothing is computed from them here)
     T av1 = T(0);
+    // chunk 0 of the NEXT row, fetched before the current row is written out
+    bool pre_ok = false;
+    int pre_excl = 0, pre_total = 0;
+    I pre_k = EMPTY;
+    T pre_b = T(0), pre_a = T(0);
 
     while (true) {
         // rotate the pipeline: the loads issued here are consumed one iteration later
-        const int64_t row = row1, as = as1, ae = ae1;
+        const int row = row1;
+        const off_t as = as1, ae = ae1;
         const I bs = bs1;
-        const int len = len1;
+        const int len = (int)(be1 - bs1);
         const T av = av1;
         row1 = row2, as1 = as2, ae1 = ae2, av1 = av2;
-        bs1 = 0, len1 = 0;
+        bs1 = 0, be1 = 0;
         if (row1 >= 0 && as1 + lane < ae1) {
             bs1 = b_indptr[j2];
-            len1 = (int)(b_indptr[j2 + 1] - bs1);
+            be1 = b_indptr[j2 + 1];
         }
         row2 = row3, as2 = as3, ae2 = ae3;
         j2 = 0, av2 = T(0);
@@ -325,8 +333,8 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
         }
         row3 = next_row();
         if (row3 >= 0) {
-            as3 = (int64_t)a_indptr[row3];
-            ae3 = (int64_t)a_indptr[row3 + 1];
+            as3 = (off_t)a_indptr[row3];
+            ae3 = (off_t)a_indptr[row3 + 1];
         }
         if (row < 0) {
             if (row1 < 0 && row2 < 0 && row3 < 0) break;
@@ -335,31 +343,35 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
 
         // ---- multiply row `row` -------------------------------------------------------------------------------------
         const bool one_chunk = ae - as <= 32;
+        int excl = 0, total = 0;
+        I kn = EMPTY;
+        T bn = T(0), an = T(0);
         int64_t P;
         if (one_chunk) {
-            int tot = len;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-            P = tot;
+            if (pre_ok) {  // scanned and fetched while the previous row was being written
+                excl = pre_excl, total = pre_total, kn = pre_k, bn = pre_b, an = pre_a;
+            } else {
+                scan_lens(len, excl, total);
+                if (total > 0 && total <= pmax_short) fetch(0, excl, total, bs, av, kn, bn, an);
+            }
+            P = total;
         } else {
             P = Pv[row];
         }
-        if (P == 0) {
-            if (lane == 0) row_nnz[row] = 0, row_nz[row] = 0;
-            continue;
-        }
-        if (P > pmax_short) continue;  // long row: the CTA-per-row kernel owns it (and its counts)
+        pre_ok = false;
+        const bool skip_row = P == 0 || P > pmax_short;  // long rows belong to the CTA-per-row kernel (and its counts)
+        if (P == 0 && lane == 0) row_nnz[row] = 0, row_nz[row] = 0;
         distinct = 0;
-        {
+        if (!skip_row) {
             int H = 64;
             while (H < 4 * (int)P && H < HMAX) H <<= 1;  // load <= 1/4 when the table has room, <= 1/2 always
             const unsigned mask = (unsigned)(H - 1);
             for (int s = lane; s < H; s += 32) key[s] = EMPTY;
             __syncwarp();
             if (one_chunk) {
-                multiply_chunk(bs, len, av, mask);
+                run_chunks(excl, total, bs, av, kn, bn, an, mask);
             } else {
-                for (int64_t ab = as; ab < ae; ab += 32) {
+                for (off_t ab = as; ab < ae; ab += 32) {
                     I cbs = 0;
                     int clen = 0;
                     T cav = T(0);
@@ -369,10 +381,22 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
                         cbs = b_indptr[j];
                         clen = (int)(b_indptr[j + 1] - cbs);
                     }
-                    multiply_chunk(cbs, clen, cav, mask);
+                    scan_lens(clen, excl, total);
+                    if (total > 0) {
+                        fetch(0, excl, total, cbs, cav, kn, bn, an);
+                        run_chunks(excl, total, cbs, cav, kn, bn, an, mask);
+                    }
                 }
             }
         }
+        // the next row's first chunk: its B extents landed one row-time ago -- scan them and issue the loads now, so
+        // they are in flight while this row is written out
+        if (row1 >= 0 && ae1 - as1 <= 32) {
+            scan_lens((int)(be1 - bs1), pre_excl, pre_total);
+            if (pre_total > 0 && pre_total <= pmax_short) fetch(0, pre_excl, pre_total, bs1, av1, pre_k, pre_b, pre_a);
+            pre_ok = true;
+        }
+        if (skip_row) continue;
         // ---- write the row at its upper-bound offset, in its final order ---------------------------------------------
         const int64_t ub = ub_off[row];
         int nz = 0;
@@ -380,7 +404,7 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
             for (int i = lane; i < distinct; i += 32) {
                 const int slot = ord[distinct - 1 - i];  // reverse first-touch order
                 const T v = narrow_sum<T, W>(sum[slot]);
-                tmp_idx[ub + i] = (int64_t)key[slot];
+                tmp_idx[ub + i] = key[slot];
                 tmp_val[ub + i] = v;
                 nz += is_pos_zero_bits(v) ? 0 : 1;
             }
@@ -391,7 +415,7 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
                 int rank = 0;
                 for (int f = 0; f < distinct; ++f) rank += (key[ord[f]] < k) ? 1 : 0;
                 const T v = narrow_sum<T, W>(sum[slot]);
-                tmp_idx[ub + rank] = (int64_t)k;
+                tmp_idx[ub + rank] = k;
                 tmp_val[ub + rank] = v;
                 nz += is_pos_zero_bits(v) ? 0 : 1;
             }
@@ -422,7 +446,7 @@ spgemm_block_kernel(const int64_t *__restrict__ rows, int64_t n_rows, int64_t n_
                     const I *__restrict__ a_indptr, const I *__restrict__ a_indices, const T *__restrict__ a_data,
                     const I *__restrict__ b_indptr, const I *__restrict__ b_indices, const T *__restrict__ b_data,
                     const int64_t *__restrict__ Pv, const int64_t *__restrict__ ub_off,
-                    int64_t *__restrict__ tmp_idx, T *__restrict__ tmp_val, int64_t *__restrict__ row_nnz,
+                    I *__restrict__ tmp_idx, T *__restrict__ tmp_val, int64_t *__restrict__ row_nnz,
                     int64_t *__restrict__ row_nz, unsigned char *__restrict__ scratch, size_t per_cta,
                     int64_t Hmax, int64_t Pmax, unsigned long long *__restrict__ totals) {
     constexpr int THREADS = WARPS * 32;
@@ -612,7 +636,7 @@ spgemm_block_kernel(const int64_t *__restrict__ rows, int64_t n_rows, int64_t n_
                 const int64_t wd = t >> 5;
                 const int64_t above = wsuf[wd + 1] + __popc((bits[wd] >> (t & 31)) >> 1);
                 const T v = narrow_sum<T, W>(tb_sum[s]);
-                tmp_idx[ub + above] = (int64_t)k;
+                tmp_idx[ub + above] = k;
                 tmp_val[ub + above] = v;
                 nz += is_pos_zero_bits(v) ? 0 : 1;
             }
@@ -637,10 +661,10 @@ spgemm_block_kernel(const int64_t *__restrict__ rows, int64_t n_rows, int64_t n_
 // ---------------------------------------------------------------------------------------------
 // 4. finish: compaction from the upper-bound layout (+ optional prune, row reversal, COO rows)
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename I>
 __global__ void spgemm_finish_kernel(int64_t M, const int64_t *__restrict__ ub_off,
                                      const int64_t *__restrict__ row_nnz, const int64_t *__restrict__ out_ptr,
-                                     const int64_t *__restrict__ tmp_idx, const T *__restrict__ tmp_val, int prune,
+                                     const I *__restrict__ tmp_idx, const T *__restrict__ tmp_val, int prune,
                                      int reverse, int64_t *__restrict__ out_idx, int64_t *__restrict__ out_rows,
                                      T *__restrict__ out_val) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -658,7 +682,7 @@ __global__ void spgemm_finish_kernel(int64_t M, const int64_t *__restrict__ ub_o
             T v = T(0);
             if (p < n) {
                 const int64_t q = reverse ? (n - 1 - p) : p;
-                k = tmp_idx[src + q];
+                k = (int64_t)tmp_idx[src + q];
                 v = tmp_val[src + q];
                 keep = !prune || !is_pos_zero_bits(v);
             }
@@ -677,17 +701,17 @@ __global__ void spgemm_finish_kernel(int64_t M, const int64_t *__restrict__ ub_o
 // per-row ascending sort of (idx, val) segments for rows that went through the block kernel in SORTED mode
 // (rare, long rows): one CTA per row, odd-even transposition over global memory is too slow, so use a
 // bitonic-free approach: rank by counting inside the CTA (O(n^2 / threads)); rows here have n <= n_col.
-template <typename T>
+template <typename T, typename I>
 __global__ void sort_long_rows_kernel(const int64_t *__restrict__ rows, int64_t n_rows,
                                       const int64_t *__restrict__ ub_off, const int64_t *__restrict__ row_nnz,
-                                      int64_t *__restrict__ tmp_idx, T *__restrict__ tmp_val,
-                                      int64_t *__restrict__ sc_idx, T *__restrict__ sc_val) {
+                                      I *__restrict__ tmp_idx, T *__restrict__ tmp_val,
+                                      I *__restrict__ sc_idx, T *__restrict__ sc_val) {
     for (int64_t ri = blockIdx.x; ri < n_rows; ri += gridDim.x) {
         const int64_t row = rows[ri];
         const int64_t n = row_nnz[row];
         const int64_t off = ub_off[row];
         for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
-            const int64_t k = tmp_idx[off + e];
+            const I k = tmp_idx[off + e];
             int64_t rank = 0;
             for (int64_t f = 0; f < n; ++f) rank += tmp_idx[off + f] < k ? 1 : 0;
             sc_idx[off + rank] = k;
@@ -712,7 +736,8 @@ struct SpgemmPlan {
     int64_t nnz_struct, nnz_pruned, ub_total;
     int64_t *P, *U, *ub_off, *row_nnz, *row_nz, *long_rows;  // [M] (+1 for offsets)
     unsigned long long *counters;                            // [4] products kernel, [4..5] totals, [6] ticket
-    int64_t *tmp_idx;
+    void *tmp_idx;  // column indices of the upper-bound layout, in the operands' index width
+    int idx_bytes;
     void *tmp_val;
     cudaStream_t stream;
 };
@@ -755,7 +780,7 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
     B2S_CUDA(cudaStreamSynchronize(s));
     pl->ub_total = (int64_t)hc[0];
     const int64_t n_long = (int64_t)hc[1];
-    if ((rc = scratch_alloc((void **)&pl->tmp_idx, (size_t)pl->ub_total * 8, s))) return rc;
+    if ((rc = scratch_alloc((void **)&pl->tmp_idx, (size_t)pl->ub_total * sizeof(I), s))) return rc;
     if ((rc = scratch_alloc((void **)&pl->tmp_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
     const int sms = num_sms();
     unsigned long long *totals = pl->counters + 4;
@@ -777,16 +802,16 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
         unsigned char *scratch = nullptr;
         if ((rc = scratch_alloc((void **)&scratch, (size_t)ctas * per_cta, s))) return rc;
         spgemm_block_kernel<T, W, I, WARPS, TILE><<<(unsigned)ctas, WARPS * 32, 0, s>>>(
-            pl->long_rows, n_long, pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off, pl->tmp_idx,
+            pl->long_rows, n_long, pl->n_col, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off, (I *)pl->tmp_idx,
             (T *)pl->tmp_val, pl->row_nnz, pl->row_nz, scratch, per_cta, Hmax, Pmax, totals);
         B2S_CHECK_LAUNCH();
         if (pl->sorted) {
-            int64_t *sc_idx = nullptr;
+            I *sc_idx = nullptr;
             T *sc_val = nullptr;
-            if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->ub_total * 8, s))) return rc;
+            if ((rc = scratch_alloc((void **)&sc_idx, (size_t)pl->ub_total * sizeof(I), s))) return rc;
             if ((rc = scratch_alloc((void **)&sc_val, (size_t)pl->ub_total * sizeof(T), s))) return rc;
-            sort_long_rows_kernel<T><<<(unsigned)ctas, 256, 0, s>>>(pl->long_rows, n_long, pl->ub_off, pl->row_nnz,
-                                                                   pl->tmp_idx, (T *)pl->tmp_val, sc_idx, sc_val);
+            sort_long_rows_kernel<T, I><<<(unsigned)ctas, 256, 0, s>>>(pl->long_rows, n_long, pl->ub_off, pl->row_nnz,
+                                                                      (I *)pl->tmp_idx, (T *)pl->tmp_val, sc_idx, sc_val);
             B2S_CHECK_LAUNCH();
             scratch_free(sc_idx, s);
             scratch_free(sc_val, s);
@@ -809,7 +834,7 @@ static int spgemm_numeric(SpgemmPlan *pl, const void *a_indptr, const void *a_in
         if (blocks > need) blocks = need;
         kern<<<(unsigned)blocks, WARPS * 32, L::total, s>>>(M, ap, ai, ad, bp, bi, bd, pl->P, pl->ub_off,
                                                             g_pmax_short < 256 ? g_pmax_short : (int64_t)256,
-                                                            (unsigned int *)(pl->counters + 6), pl->tmp_idx,
+                                                            (unsigned int *)(pl->counters + 6), (I *)pl->tmp_idx,
                                                             (T *)pl->tmp_val, pl->row_nnz, pl->row_nz, totals);
         B2S_CHECK_LAUNCH();
     }
@@ -840,9 +865,14 @@ static int spgemm_finish_t(SpgemmPlan *pl, int prune, int64_t *indptr_out, int64
     if (pl->nnz_struct > 0) {
         int64_t blocks = (M * 32 + 255) / 256;
         if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
-        spgemm_finish_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(M, pl->ub_off, pl->row_nnz, ptr, pl->tmp_idx,
-                                                                (const T *)pl->tmp_val, prune, reverse, indices_out,
-                                                                rows_out, (T *)data_out);
+        if (pl->idx_bytes == 4)
+            spgemm_finish_kernel<T, int32_t><<<(unsigned)blocks, 256, 0, s>>>(
+                M, pl->ub_off, pl->row_nnz, ptr, (const int32_t *)pl->tmp_idx, (const T *)pl->tmp_val, prune, reverse,
+                indices_out, rows_out, (T *)data_out);
+        else
+            spgemm_finish_kernel<T, int64_t><<<(unsigned)blocks, 256, 0, s>>>(
+                M, pl->ub_off, pl->row_nnz, ptr, (const int64_t *)pl->tmp_idx, (const T *)pl->tmp_val, prune, reverse,
+                indices_out, rows_out, (T *)data_out);
         B2S_CHECK_LAUNCH();
     }
     if (own) scratch_free(own, s);
@@ -889,6 +919,7 @@ int b2s_spgemm_begin(int dtype, int idx_bytes, int64_t M, int64_t K, int64_t n_c
     SpgemmPlan *pl = new SpgemmPlan();
     memset(pl, 0, sizeof(*pl));
     pl->dtype = dtype;
+    pl->idx_bytes = idx_bytes;
     pl->sorted = sorted_order ? 1 : 0;
     const bool wide = wide_accumulate != 0;
     pl->M = M;
