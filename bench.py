@@ -511,6 +511,7 @@ def main():
 
     # ---- e2e through the host-buffer C-ABI call (rank-local; N>1 reports the aggregate) ------------
     e2e = None
+    narrowing = SD.configure_host_staging(int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if not args.no_e2e:
         h_vals = vals.cpu().pin_memory()
         h_cols = cols.cpu().to(torch.int64).pin_memory()
@@ -547,8 +548,24 @@ def main():
                "d2h_bytes_per_step": d2h, "host_input_bytes_per_step": host_in, "ms_per_step": round(e_ms, 3),
                "steps": esteps,
                "api": "sparse_b200.tensordot(GCXS(host arrays, int64 indices), np.ndarray) -> np.ndarray "
-                      "(b2s_spmm_csr_dense_host: host-side int64->int32 index narrowing + 3-stream H2D/K1/D2H "
-                      "pipeline, pinned buffers)"}
+                      "(b2s_spmm_csr_dense_host: int64->int32 index narrowing on the " + narrowing + " + 3-stream "
+                      "H2D/K1/D2H pipeline, pinned buffers)", "index_narrowing": narrowing}
+        if narrowing == "device":  # the raw int64 indices cross the bus
+            e2e["h2d_bytes_per_step"] = host_in
+        if world > 1:  # the other staging mode, for the record
+            _lib.load().b2s_spmm_host_set_threads(_lib.i32(-1 if narrowing == "device" else 0))
+            for _ in range(2):
+                e2e_step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                e2e_step()
+            torch.cuda.synchronize()
+            alt_ms = allmax((time.perf_counter() - t0) * 1e3 / esteps)
+            e2e["other_staging_mode"] = {"index_narrowing": "host" if narrowing == "device" else "device",
+                                         "ms_per_step": round(alt_ms, 3)}
+            SD.configure_host_staging(int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         C_ref = Kn.spmm_csr_dense(vals, cols, indptr, B, M, K, ncols, out=C)
         e2e["matches_device_path"] = bool(allmin(1.0 if torch.equal(h_C.to(dev), C_ref) else 0.0) == 1.0)
         del h_vals, h_cols, h_ptr, h_B, h_C, npv, h_res

@@ -149,10 +149,13 @@ def _einsum_single(lhs, rhs, operand):
             return operand.sum()  # 0-D result per the Array API
         return operand
     if not isinstance(operand, SparseArray):
-        # dense operand: stays dense (the reference calls np.einsum here); the transpose / trace / sum of the dense
-        # side input is done on the device by torch -- plumbing, the sparse data path never goes through it
-        dense = operand if D.is_device_tensor(operand) else D.upload(np.ascontiguousarray(operand))
-        return D.torch().einsum(f"{lhs}->{rhs}", dense).contiguous()
+        # dense operand: stays dense (the reference calls np.einsum here).  It takes the same device path as a sparse
+        # one -- its non-zero entries as a COO through the trace selector / re-keying / reduction kernels -- and is
+        # densified again; no library einsum on the way
+        from ._coo import as_coo
+
+        res = _einsum_single(lhs, rhs, as_coo(operand))
+        return res.todense_device() if isinstance(res, SparseArray) else res
     was_gcxs = isinstance(operand, GCXS)
     operand = operand.tocoo() if was_gcxs else operand
 

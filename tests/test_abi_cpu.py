@@ -73,3 +73,21 @@ def test_host_side_index_narrowing_is_thread_safe():
         assert np.array_equal(d, s.astype(np.int32))
     small = np.arange(5, dtype=np.int64)
     assert np.array_equal(Kn.host_narrow(small, np.empty(5, np.int32)), small.astype(np.int32))
+
+
+def test_host_staging_mode_follows_the_local_world_size():
+    """One rank per GPU with 4+ ranks on a box makes host DRAM the bottleneck of the host-buffer product: the host-side
+    int64 -> int32 narrowing pass is switched off there (raw upload + device narrowing); needs no GPU."""
+    from sparse_b200 import _dist as SD
+
+    assert SD.configure_host_staging(8) == "device" and SD.configure_host_staging(4) == "device"
+    assert SD.configure_host_staging(2) == "host" and SD.configure_host_staging(1) == "host"
+
+
+def test_numa_binding_reports_why_it_could_not_bind():
+    from sparse_b200 import _dist as SD
+
+    got = SD.bind_to_gpu_numa(0, 0, 1)
+    assert got is None or "numa_node" in got
+    if got and got["numa_node"] is None:
+        assert got["note"]
