@@ -62,23 +62,44 @@ def all_gather_rows(shard, group=None):
     return out
 
 
-def all_gather_varlen(x, group=None):
-    """All-gather 1-D tensors of different lengths: returns (list of per-rank tensors)."""
+def all_gather_sizes(values, group=None):
+    """All-gather a short list of host integers (one collective, one host sync): returns a (world, len) int64 array."""
     dist = _dist()
     t = D.torch()
     world = dist.get_world_size(group)
+    dev = D.device()
+    mine = t.tensor([int(v) for v in values], dtype=t.int64, device=dev)
+    out = t.empty((world, len(values)), dtype=t.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine.reshape(1, -1), group=group)
+    return out.cpu().numpy()
+
+
+def all_gather_padded(x, sizes, group=None):
+    """All-gather 1-D tensors whose lengths `sizes` (host, one per rank) are already known: ONE collective into a
+    (world, max) buffer; returns the per-rank views (no copy).  No size exchange, no host sync."""
+    dist = _dist()
+    t = D.torch()
+    world = dist.get_world_size(group)
+    mx = max(int(v) for v in sizes) if len(sizes) else 0
+    mx = max(mx, 1)
+    if int(x.shape[0]) == mx:
+        pad = x.contiguous()
+    else:
+        pad = t.zeros(mx, dtype=x.dtype, device=x.device)
+        pad[: x.shape[0]] = x
+    out = t.empty((world, mx), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, pad.reshape(1, mx), group=group)
+    return [out[r, : int(sizes[r])] for r in range(world)]
+
+
+def all_gather_varlen(x, group=None):
+    """All-gather 1-D tensors of different lengths: returns (list of per-rank tensors)."""
+    dist = _dist()
+    world = dist.get_world_size(group)
     if world == 1:
         return [x]
-    n = t.tensor([x.shape[0]], dtype=t.int64, device=x.device)
-    sizes = [t.zeros(1, dtype=t.int64, device=x.device) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(sizes + [1])
-    pad = t.zeros(mx, dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    bufs = [t.empty(mx, dtype=x.dtype, device=x.device) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return [b[:s] for b, s in zip(bufs, sizes)]
+    sizes = all_gather_sizes([int(x.shape[0])], group)[:, 0]
+    return all_gather_padded(x, sizes, group)
 
 
 class _RawDeviceBuffer:
@@ -297,23 +318,30 @@ def tensordot_rowblock(a_local, b_shard, group=None, out=None):
 
 
 def gather_csr_rows(b_local, group=None):
-    """All-gather a row-sharded CSR operand (each rank owns a block of consecutive rows)."""
+    """All-gather a row-sharded CSR operand (each rank owns a block of consecutive rows): one exchange of the block
+    sizes (the only host sync), then one padded collective per array; the row pointers are rebased with the prefix sums
+    of the exchanged nnz counts (host integers -- no device read-backs)."""
     from ._gcxs import GCXS
 
     t = D.torch()
+    dist = _dist()
+    world = dist.get_world_size(group)
     data, indices, indptr = b_local._dev()
-    datas = all_gather_varlen(data, group)
-    idxs = all_gather_varlen(indices, group)
-    ptrs = all_gather_varlen(indptr, group)
+    if world == 1:
+        return b_local
+    sizes = all_gather_sizes([int(data.shape[0]), int(indptr.shape[0])], group)
+    nnzs, ptr_lens = sizes[:, 0], sizes[:, 1]
+    datas = all_gather_padded(data, nnzs, group)
+    idxs = all_gather_padded(indices.to(t.int64), nnzs, group)
+    ptrs = all_gather_padded(indptr.to(t.int64), ptr_lens, group)
     out_ptr, base = [], 0
-    for r, p in enumerate(ptrs):
-        p = p.to(t.int64)
+    for r in range(world):
+        p = ptrs[r]
         out_ptr.append((p if r == 0 else p[1:]) + base)
-        base += int(p[-1].item())
+        base += int(nnzs[r])
     full_ptr = t.cat(out_ptr)
     rows = int(full_ptr.shape[0]) - 1
-    return GCXS((t.cat(datas), t.cat(idxs).to(t.int64), full_ptr), shape=(rows, b_local.shape[1]),
-                compressed_axes=(0,))
+    return GCXS((t.cat(datas), t.cat(idxs), full_ptr), shape=(rows, b_local.shape[1]), compressed_axes=(0,))
 
 
 def spgemm_rowblock(a_local, b_local, group=None):

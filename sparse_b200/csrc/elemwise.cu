@@ -320,7 +320,7 @@ __device__ __forceinline__ uint64_t lb_load(const uint64_t *p) { return *(const 
 __device__ __forceinline__ void lb_store(uint64_t *p, uint64_t v) { *(volatile uint64_t *)p = v; }
 
 template <typename T, typename O, bool PRED>
-__global__ void __launch_bounds__(EW_THREADS, 6)
+__global__ void __launch_bounds__(EW_THREADS, 1536 / EW_THREADS)
 ew_merge_fused_kernel(Stream A, Stream B, const T *__restrict__ da, const T *__restrict__ db, T fill_a, T fill_b,
                       O out_fill, int op, const int64_t *__restrict__ split_a, O *__restrict__ vals_out,
                       int64_t *__restrict__ keys_out, uint64_t *__restrict__ lb_status,

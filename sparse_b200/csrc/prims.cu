@@ -388,10 +388,9 @@ int b2s_keys_flags(const int64_t *keys_dev, int64_t n, int *unsorted_host, int *
 int b2s_sort_keys(const int64_t *keys_in_dev, int64_t n, int key_bits, int64_t *keys_out_dev, int64_t *perm_out_dev,
                   void *stream) {
     if (n == 0) return B2S_OK;
-    B2S_REQUIRE(n < 2147483647LL, B2S_ERR_OVERFLOW, "sort: n=%lld exceeds the 2^31 limit of the device sort",
-                (long long)n);
     cudaStream_t s = (cudaStream_t)stream;
     if (key_bits <= 0 || key_bits > 64) key_bits = 64;
+    const bool big = n >= 2147483647LL;  // 64-bit offsets inside CUB only when they are needed
     int64_t *iota = nullptr;
     int rc = scratch_alloc((void **)&iota, (size_t)n * 8, s);
     if (rc) return rc;
@@ -399,13 +398,21 @@ int b2s_sort_keys(const int64_t *keys_in_dev, int64_t n, int key_bits, int64_t *
     B2S_CHECK_LAUNCH();
     size_t tmp_bytes = 0;
     // keys are non-negative linear indices: sort them as unsigned over the low key_bits (stable LSD radix)
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint64_t *)keys_in_dev,
-                                             (uint64_t *)keys_out_dev, iota, perm_out_dev, (int)n, 0, key_bits, s));
     void *tmp = nullptr;
-    rc = scratch_alloc(&tmp, tmp_bytes, s);
-    if (rc) return rc;
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t *)keys_in_dev, (uint64_t *)keys_out_dev,
-                                             iota, perm_out_dev, (int)n, 0, key_bits, s));
+    for (int pass = 0; pass < 2; ++pass) {  // size query, then the sort
+        if (big)
+            B2S_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t *)keys_in_dev,
+                                                     (uint64_t *)keys_out_dev, iota, perm_out_dev, (int64_t)n, 0,
+                                                     key_bits, s));
+        else
+            B2S_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t *)keys_in_dev,
+                                                     (uint64_t *)keys_out_dev, iota, perm_out_dev, (int)n, 0, key_bits,
+                                                     s));
+        if (pass == 0) {
+            rc = scratch_alloc(&tmp, tmp_bytes, s);
+            if (rc) return rc;
+        }
+    }
     count_launch(2 + (key_bits + 7) / 8);  // histogram + onesweep passes (CUB kernels inside this .so)
     scratch_free(tmp, s);
     scratch_free(iota, s);
@@ -450,41 +457,46 @@ int b2s_flag_not_fill(int elem_bytes, const void *data_dev, int64_t n, const voi
     return B2S_OK;
 }
 
+}  // extern "C"
+
+// cub::DeviceScan::ExclusiveSum with 32-bit offsets when n fits (the common case), 64-bit ones otherwise
+template <typename InT>
+static int exclusive_sum_any(const InT *in, int64_t *out, int64_t n, cudaStream_t s) {
+    size_t tmp_bytes = 0;
+    void *tmp = nullptr;
+    const bool big = n >= 2147483647LL;
+    for (int pass = 0; pass < 2; ++pass) {  // size query, then the scan
+        if (big) B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int64_t)n, s));
+        else B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, s));
+        if (pass == 0) {
+            const int rc = scratch_alloc(&tmp, tmp_bytes, s);
+            if (rc) return rc;
+        }
+    }
+    count_launch(2);
+    return scratch_free(tmp, s);
+}
+
+extern "C" {
+
 int b2s_scan_flags(const uint8_t *flags_dev, int64_t n, int64_t *pos_out_dev, int64_t *total_host, void *stream) {
     *total_host = 0;
     if (n == 0) return B2S_OK;
-    B2S_REQUIRE(n < 2147483647LL, B2S_ERR_OVERFLOW, "scan: n=%lld exceeds 2^31", (long long)n);
     cudaStream_t s = (cudaStream_t)stream;
-    size_t tmp_bytes = 0;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags_dev, pos_out_dev, (int)n, s));
-    void *tmp = nullptr;
-    int rc = scratch_alloc(&tmp, tmp_bytes, s);
+    const int rc = exclusive_sum_any<uint8_t>(flags_dev, pos_out_dev, n, s);
     if (rc) return rc;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags_dev, pos_out_dev, (int)n, s));
-    count_launch(2);
     int64_t last_pos = 0;
     uint8_t last_flag = 0;
     B2S_CUDA(cudaMemcpyAsync(&last_pos, pos_out_dev + (n - 1), 8, cudaMemcpyDeviceToHost, s));
     B2S_CUDA(cudaMemcpyAsync(&last_flag, flags_dev + (n - 1), 1, cudaMemcpyDeviceToHost, s));
     B2S_CUDA(cudaStreamSynchronize(s));
-    scratch_free(tmp, s);
     *total_host = last_pos + (last_flag ? 1 : 0);
     return B2S_OK;
 }
 
 int b2s_exclusive_scan_i64(const int64_t *in_dev, int64_t n, int64_t *out_dev, void *stream) {
     if (n == 0) return B2S_OK;
-    B2S_REQUIRE(n < 2147483647LL, B2S_ERR_OVERFLOW, "scan: n=%lld exceeds 2^31", (long long)n);
-    cudaStream_t s = (cudaStream_t)stream;
-    size_t tmp_bytes = 0;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in_dev, out_dev, (int)n, s));
-    void *tmp = nullptr;
-    int rc = scratch_alloc(&tmp, tmp_bytes, s);
-    if (rc) return rc;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in_dev, out_dev, (int)n, s));
-    count_launch(2);
-    scratch_free(tmp, s);
-    return B2S_OK;
+    return exclusive_sum_any<int64_t>(in_dev, out_dev, n, (cudaStream_t)stream);
 }
 
 int b2s_compact(int elem_bytes, const void *in_dev, const uint8_t *flags_dev, const int64_t *pos_dev, int64_t n,

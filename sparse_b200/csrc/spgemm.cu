@@ -675,25 +675,38 @@ __global__ void spgemm_finish_kernel(int64_t M, const int64_t *__restrict__ ub_o
         if (n == 0) continue;
         const int64_t src = ub_off[row];
         int64_t dst = out_ptr[row];
-        for (int64_t c = 0; c < n; c += 32) {
-            const int64_t p = c + lane;
-            bool keep = false;
-            int64_t k = 0;
-            T v = T(0);
-            if (p < n) {
-                const int64_t q = reverse ? (n - 1 - p) : p;
-                k = (int64_t)tmp_idx[src + q];
-                v = tmp_val[src + q];
-                keep = !prune || !is_pos_zero_bits(v);
+        // 128 entries at a time: all loads of the group are issued before the first store (4 x the bytes in flight
+        // of a chunk-by-chunk copy; the kernel is a pure stream compaction)
+        for (int64_t c = 0; c < n; c += 128) {
+            int64_t k[4];
+            T v[4];
+            bool keep[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = c + u * 32 + lane;
+                keep[u] = false;
+                k[u] = 0;
+                v[u] = T(0);
+                if (p < n) {
+                    const int64_t q = reverse ? (n - 1 - p) : p;
+                    k[u] = (int64_t)tmp_idx[src + q];
+                    v[u] = tmp_val[src + q];
+                    keep[u] = true;
+                }
             }
-            const unsigned m = __ballot_sync(FULL, keep);
-            if (keep) {
-                const int64_t o = dst + __popc(m & ((1u << lane) - 1));
-                out_idx[o] = k;
-                out_val[o] = v;
-                if (out_rows) out_rows[o] = row;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (c + u * 32 >= n) break;
+                const bool kp = keep[u] && (!prune || !is_pos_zero_bits(v[u]));
+                const unsigned m = __ballot_sync(FULL, kp);
+                if (kp) {
+                    const int64_t o = dst + __popc(m & ((1u << lane) - 1));
+                    out_idx[o] = k[u];
+                    out_val[o] = v[u];
+                    if (out_rows) out_rows[o] = row;
+                }
+                dst += __popc(m);
             }
-            dst += __popc(m);
         }
     }
 }

@@ -156,7 +156,6 @@ int b2s_dense_to_csr_begin(int dtype, int64_t M, int64_t N, const void *x_dev, c
                            int mode, void **plan_out, int64_t *nnz_out, void *stream) {
     B2S_REQUIRE(plan_out && nnz_out, B2S_ERR_INVALID, "dense_to_csr_begin: NULL output");
     const int64_t n = M * N;
-    B2S_REQUIRE(n < 2147483647LL, B2S_ERR_OVERFLOW, "dense_to_csr: M*N=%lld exceeds 2^31", (long long)n);
     cudaStream_t s = (cudaStream_t)stream;
     DensePlan *pl = new DensePlan();
     pl->dtype = dtype;
@@ -189,10 +188,12 @@ int b2s_dense_to_csr_begin(int dtype, int64_t M, int64_t N, const void *x_dev, c
     }
     if ((rc = scratch_alloc((void **)&pl->pos, (size_t)n * 8, s))) return rc;
     size_t tb = 0;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, pl->flags, pl->pos, (int)n, s));
     void *tmp = nullptr;
-    if ((rc = scratch_alloc(&tmp, tb, s))) return rc;
-    B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, pl->flags, pl->pos, (int)n, s));
+    for (int pass = 0; pass < 2; ++pass) {  // size query, then the scan; 64-bit offsets only when M*N needs them
+        if (n >= 2147483647LL) B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, pl->flags, pl->pos, (int64_t)n, s));
+        else B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, pl->flags, pl->pos, (int)n, s));
+        if (pass == 0 && (rc = scratch_alloc(&tmp, tb, s))) return rc;
+    }
     count_launch(2);
     int64_t lp = 0;
     uint8_t lf = 0;

@@ -250,3 +250,23 @@ def test_elemwise_union_over_thousands_of_tiles_int_exact():
         want = f(a.todense(), b.todense())
         assert np.array_equal(got.todense(), want), f.__name__
         assert got.nnz == np.count_nonzero(want), f.__name__
+
+
+def test_flag_scan_beyond_2_31_elements():
+    """The scan / compaction primitives switch to 64-bit offsets when an array has 2^31 or more elements (round 1
+    refused them): positions of the set flags of a 2^31 + 4099 element array, set every 2^20 elements."""
+    import torch
+
+    from sparse_b200 import _kernels as Kn
+
+    _sp()
+    n = 2**31 + 4099
+    flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    flags[:: 2**20] = 1
+    flags[n - 1] = 1
+    pos, total = Kn.scan_flags(flags)
+    want = (n + 2**20 - 1) // 2**20 + 1
+    assert total == want
+    assert int(pos[n - 1].item()) == want - 1 and int(pos[2**31].item()) == 2**11 and int(pos[2**31 + 1].item()) == 2**11 + 1
+    del flags, pos
+    torch.cuda.empty_cache()

@@ -231,9 +231,11 @@ def main():
             g = torch.Generator(device=dev).manual_seed(5 + rank)
             sel = torch.randint(0, int(od.shape[0]), (4096,), generator=g, device=dev)
             sc_, sd_ = s_local._dev()
-            same_coords = bool(torch.equal(oc, sc_))
+            live = sd_ != 0  # float32 uniform[0,1) draws hit exactly 0.0 a few times in 1e8: those products are pruned
+            same_coords = bool(torch.equal(oc, sc_[:, live]))
+            sel = torch.randint(0, int(od.shape[0]), (4096,), generator=g, device=dev)
             dots = (a_local[oc[0, sel]].double() * Bt[oc[1, sel]].double()).sum(dim=1)
-            want = sd_[sel].double() * dots
+            want = sd_[live][sel].double() * dots
             ok = same_coords and bool(torch.allclose(od[sel].double(), want, rtol=2e-5, atol=0))
             results["C4"]["row_block_matches_fp64_restatement_on_samples"] = all_true(ok)
             del Bt
