@@ -353,6 +353,74 @@ def spgemm_rowblock(a_local, b_local, group=None):
     return _dot(a_local, B)
 
 
+def all_to_all_varlen(chunks, group=None):
+    """Send chunks[q] (1-D, same dtype) to rank q; returns the list of chunks received (one per source rank).  One
+    exchange of the chunk lengths (host sync), then `all_to_all_single` with uneven splits (NCCL); backends without it
+    (gloo on CPU, used by the tests) gather every chunk and keep their own."""
+    dist = _dist()
+    t = D.torch()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return [chunks[0]]
+    send_sizes = [int(c.shape[0]) for c in chunks]
+    table = all_gather_sizes(send_sizes, group)  # table[src, dst]
+    recv_sizes = [int(table[src, rank]) for src in range(world)]
+    send = t.cat(chunks) if sum(send_sizes) else chunks[0][:0]
+    recv = t.empty(sum(recv_sizes), dtype=send.dtype, device=send.device)
+    try:
+        if dist.get_backend(group) != "nccl":
+            raise RuntimeError("no all_to_all_single")
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes, group=group)
+    except RuntimeError:
+        everything = all_gather_padded(send, [int(table[r].sum()) for r in range(world)], group)
+        pieces = []
+        for src in range(world):
+            lo = int(table[src, :rank].sum())
+            pieces.append(everything[src][lo:lo + recv_sizes[src]])
+        recv = t.cat(pieces) if pieces else recv
+    out, at = [], 0
+    for n in recv_sizes:
+        out.append(recv[at:at + n])
+        at += n
+    return out
+
+
+def spgemm_ksplit(a_colblock, b_rowblock, group=None):
+    """``A @ B`` with the CONTRACTION axis split (the alternative to row blocking): rank r holds the
+    column block A[:, K_r] (all M rows) and the matching row block B[K_r, :]; every rank multiplies its pair into a
+    sparse partial over ALL rows, the partials' row blocks are exchanged (all-to-all of (key, value) fragments -- the
+    "reduce-scatter of output rows": NCCL has no sparse reduce-scatter) and each rank sums the `world` fragments of its
+    row block (device sort + duplicate summation).  Returns this rank's block of consecutive output rows as a canonical
+    COO (columns ascending; partial sums are added across K blocks, so values equal the row-blocked product to
+    rounding, not bit for bit -- which is one reason row blocking is the production form; the other is traffic: the
+    partials hold up to `world` x the output entries)."""
+    from ._coo import COO
+    from ._dot import _dot
+
+    dist = _dist()
+    t = D.torch()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    M, N = int(a_colblock.shape[0]), int(b_rowblock.shape[1])
+    part = _dot(a_colblock, b_rowblock)  # GCXS (compressed rows), M x N
+    data, indices, indptr = part._dev()
+    nnz = int(data.shape[0])
+    rows = Kn.rows_from_indptr(indptr, nnz, np.int64)
+    keys = Kn.linearize(t.stack([rows, indices.to(t.int64)]), [N, 1])
+    bounds = [M * q // world for q in range(world + 1)]
+    cut = D.download(indptr[t.as_tensor(bounds, device=indptr.device)]).astype(np.int64)  # entries before each block
+    k_in = all_to_all_varlen([keys[int(cut[q]):int(cut[q + 1])] for q in range(world)], group)
+    v_in = all_to_all_varlen([data[int(cut[q]):int(cut[q + 1])] for q in range(world)], group)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    allk = t.cat(k_in) - r0 * N
+    allv = t.cat(v_in)
+    shape = (r1 - r0, N)
+    if int(allk.shape[0]) == 0:
+        return COO(np.zeros((2, 0), dtype=np.intp), np.empty(0, dtype=part.dtype), shape=shape)
+    return COO(Kn.unravel(allk, shape, np.int64), allv, shape=shape, has_duplicates=True, sorted=False, prune=True)
+
+
 def sddmm_rowblock(s_local, a_local, b_cols_shard, group=None):
     """Local row block of ``s * (a @ b)``: `b` arrives column-sharded (K x N/world) and is gathered as b^T rows."""
     from ._fused import sddmm

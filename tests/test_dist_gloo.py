@@ -67,7 +67,20 @@ def _worker(rank, world, port, q):
         out = DD.sddmm_rowblock(s_local, torch.from_numpy(A[t0:t1].copy()),
                                 torch.from_numpy(np.ascontiguousarray(Bm[:, rank * cs:(rank + 1) * cs])))
         ok3 = np.allclose(out.todense(), full[t0:t1], rtol=1e-12, atol=1e-12)
-        q.put((rank, bool(ok1), bool(ok2), bool(ok3), bounds))
+
+        # contraction split: A[:, K_r] @ B[K_r, :], all-to-all of the partials' row blocks, local merge
+        kb = [K * r // world for r in range(world + 1)]
+        a_full = sp.GCXS((ad, indices, indptr), shape=(M, K), compressed_axes=(0,))
+        b_full = sp.GCXS((bd, bi, bp), shape=(K, 40), compressed_axes=(0,))
+        a_cols = a_full[:, kb[rank]:kb[rank + 1]]
+        b_rows = b_full[kb[rank]:kb[rank + 1], :]
+        a_cols = a_cols if isinstance(a_cols, sp.GCXS) else a_cols.asformat("gcxs", compressed_axes=(0,))
+        b_rows = b_rows if isinstance(b_rows, sp.GCXS) else b_rows.asformat("gcxs", compressed_axes=(0,))
+        blk = DD.spgemm_ksplit(a_cols, b_rows)
+        m0, m1 = M * rank // world, M * (rank + 1) // world
+        want_k = (a_full.todense() @ b_full.todense())[m0:m1]
+        ok4 = blk.shape == (m1 - m0, 40) and np.allclose(blk.todense(), want_k, rtol=1e-12, atol=1e-13)
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3) and bool(ok4), bounds))
     finally:
         dist.destroy_process_group()
 
@@ -87,7 +100,7 @@ def test_rowblock_paths_world2():
     for rank, ok1, ok2, ok3, bounds in res:
         assert ok1, f"rank {rank}: tensordot_rowblock differs from the single-process product"
         assert ok2, f"rank {rank}: spgemm_rowblock differs"
-        assert ok3, f"rank {rank}: sddmm_rowblock differs"
+        assert ok3, f"rank {rank}: sddmm_rowblock / spgemm_ksplit differs"
         assert bounds[0] == 0 and bounds[-1] == 60 and bounds == sorted(bounds)
 
 

@@ -16,5 +16,6 @@ def test_bench_multi_cpu_smoke_world2():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
     got = {k: v for d in lines for k, v in d.items()}
-    assert set(got) == {"C4", "C5"}
+    assert set(got) == {"C4", "C5", "C5 contraction-split"}
+    assert got["C5 contraction-split"]["matches_row_blocked_result_rtol_1e-5"] is True
     assert got["C5"]["n_gpus"] == 2 and got["C5"]["out_nnz"] > 0 and got["C4"]["mask_nnz"] > 0

@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 def parse():
     p = argparse.ArgumentParser()
-    p.add_argument("which", nargs="*", default=["c5", "c3", "c4"])
+    p.add_argument("which", nargs="*", default=["c5", "c5k", "c3", "c4"])
     p.add_argument("--scale", type=float, default=1.0, help="shrinks M (and nnz with it) for quick runs")
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--cpu-smoke", action="store_true")
@@ -192,6 +192,27 @@ def main():
             want = (full @ full).todense()
             lo = sum(rows_per for b in range(blocks) if b * world // blocks < rank)
             assert np.allclose(out.todense(), want[lo:lo + out.shape[0]]), "C5 row block differs"
+        # the CONTRACTION-split form of the same product (BASELINE config 5's "reduce-scatter of output rows"): rank r
+        # holds A[:, K_r] and B[K_r, :] = its own row panels; partial products over all rows, all-to-all of the row
+        # blocks, local merge.  Measured next to the row-blocked form, not instead of it.
+        if world > 1 and "c5k" in args.which:
+            full = SD.gather_csr_rows(a_local)
+            lo = sum(rows_per for b in range(blocks) if b * world // blocks < rank)
+            a_cols = full[:, lo:lo + a_local.shape[0]]
+            a_cols = a_cols if isinstance(a_cols, sp.GCXS) else a_cols.asformat("gcxs", compressed_axes=(0,))
+            if a_cols.compressed_axes != (0,):
+                a_cols = a_cols.change_compressed_axes((0,))
+            a_cols.to_device()
+            del full
+            ms_k, blk = timed(lambda: SD.spgemm_ksplit(a_cols, a_local))
+            oc = out.tocoo()
+            same = bool(torch.equal(blk.sorted_keys(), oc.sorted_keys())) and bool(
+                torch.allclose(blk._data_dev(), oc._data_dev(), rtol=1e-5, atol=0))
+            results["C5 contraction-split"] = {
+                "config": f"same product, A column blocks x B row blocks, all-to-all of the partials' row blocks + merge",
+                "n_gpus": world, "ms_per_step": round(ms_k, 4), "Gnnz_out_s": round(nnz_out / ms_k / 1e6, 4),
+                "scaling": "strong", "matches_row_blocked_result_rtol_1e-5": all_true(same)}
+            del a_cols, blk, oc
         del a_local, out
 
     # ---- C4: mask row blocks x local rows of a; b arrives column-sharded and is gathered as b^T ------------------------

@@ -15,5 +15,5 @@ if [ "$N" != "1" ]; then
   echo "bench nccl rc=$?"; tail -c 1500 gpurun_out/bench_n${N}_nccl.json; tail -3 gpurun_out/bench_n${N}_nccl.err
 fi
 if [ "$N" = "1" ]; then RUN3="python"; else RUN3="$RUN --master-port 29503"; fi
-timeout 900 $RUN3 tools/bench_multi.py c5 c3 c4 > gpurun_out/multi_${N}.log 2>&1
+timeout 900 $RUN3 tools/bench_multi.py c5 c5k c3 c4 > gpurun_out/multi_${N}.log 2>&1
 echo "bench_multi rc=$?"; tail -12 gpurun_out/multi_${N}.log | cut -c1-900
