@@ -97,6 +97,8 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index = index
         self.samples = []
+        self.stamps = []
+        self.window = None  # (t0, t1) wall-clock bounds of the timed region, set by the caller
         self._stop = threading.Event()
         self._t = None
 
@@ -110,6 +112,7 @@ class ClockSampler:
                 line = line.strip()
                 if line:
                     self.samples.append([x.strip() for x in line.split(",")])
+                    self.stamps.append(time.time())
                 if self._stop.is_set():
                     break
         except Exception:
@@ -133,6 +136,14 @@ class ClockSampler:
         self._t.join(timeout=3)
 
     def summary(self):
+        if self.window is not None and self.samples:
+            t0, t1 = self.window
+            inside = [s for s, t in zip(self.samples, self.stamps) if t0 - 0.02 <= t <= t1 + 0.02]
+            # a region shorter than the sampling period: take the samples nearest to it
+            if not inside:
+                order = sorted(range(len(self.samples)), key=lambda i: abs(self.stamps[i] - 0.5 * (t0 + t1)))
+                inside = [self.samples[i] for i in order[:3]]
+            self.samples = inside
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
@@ -417,19 +428,19 @@ def main():
     def timed(run, steps, clock_index=None):
         """K steps between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        clk = ClockSampler(clock_index) if clock_index is not None else None
-        if clk:
-            clk.__enter__()
+        clk = clock_index  # a ClockSampler that is already running (started before the warm-up), or None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
         t0.record()
         run(steps, kev)
         t1.record()
         torch.cuda.synchronize()
         if clk:
+            clk.window = (w0, time.time())
             clk.__exit__()
         total = allmax(t0.elapsed_time(t1))
         kern = sum(a.elapsed_time(b) for a, b in kev) / steps
@@ -438,6 +449,13 @@ def main():
         return total / steps, kern, clk
 
     run_steps = make_steps((vals, cols, indptr), C, M, gatherer, B)
+    # clocks / throttle reasons DURING the timed region: one nvidia-smi in loop mode on rank 0 only (eight of them slow
+    # each other down), started before the warm-up so that it is up when the region starts; samples are time-stamped
+    # and only those inside the region are summarised
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(local_rank)
+        sampler.__enter__()
     run_steps(max(args.warmup, 3))
     torch.cuda.synchronize()
 
@@ -455,7 +473,7 @@ def main():
         torch.cuda.synchronize()
 
     launches0 = _lib.launch_count()
-    ms_per_step, kern_ms, clk = timed(run_steps, args.steps, clock_index=local_rank)
+    ms_per_step, kern_ms, clk = timed(run_steps, args.steps, clock_index=sampler)
     launches = _lib.launch_count() - launches0
     nnz_all = allsum(nnz)
     value = nnz_all / (ms_per_step * 1e-3) / 1e9

@@ -271,6 +271,10 @@ int b2s_reduce_single(int dtype, int op, const int64_t *keys_dev, const void *va
                       int64_t *gid_out_dev, void *vals_out_dev, int64_t *n_groups_out, int64_t *n_equal_fill_out,
                       void *stream);
 
+/* test hook: 0 = choose the form of b2s_reduce_single by ncols (count / scan / emit without inter-tile communication
+ * when a run cannot be longer than one tile, single-pass look-back otherwise), 1 / 2 = force one of them */
+int b2s_reduce_set_form(int form);
+
 /* ---- fused example paths (K8 / K9, fused.cu) ---------------------------------------------- */
 /* examples/sddmm_example.py:51-52  s * (a @ b): out_vals[p] = s_vals[p] * dot(A[i_p,:], Bt[j_p,:]). */
 int b2s_sddmm(int dtype, int idx_bytes, int64_t M, int64_t N, int64_t K, const void *indptr_dev,

@@ -603,6 +603,11 @@ def reduce_fused(op, keys, vals, ncols, fill_value, result_fill, kept_shape, wan
     return coords, gids, out, int(neq.value)
 
 
+def reduce_set_form(form: int = 0):
+    """Test hook: 0 = choose the reduction kernel by ncols, 1 = single-pass look-back, 2 = count / scan / emit."""
+    _lib.check(_lib.load().b2s_reduce_set_form(i32(form)))
+
+
 # ------------------------------------------------------------------------------------------------
 # K8 / K9 fused example paths
 # ------------------------------------------------------------------------------------------------

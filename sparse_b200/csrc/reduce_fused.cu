@@ -13,6 +13,7 @@
 //
 // Traffic: n x (8 + sizeof(T)) bytes read, n_groups x (8 + sizeof(T)) written.
 // Association order differs from NumPy's reduceat (itself unspecified) -> tolerance parity for float add/multiply.
+#include <cub/cub.cuh>
 #include <type_traits>
 
 #include "common.cuh"
@@ -422,6 +423,319 @@ reduce_tile_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals,
     if (lane == 0 && eq) atomicAdd(&counters[0], (unsigned long long)eq);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Communication-free form for SHORT runs (ncols <= RD_TILE, i.e. a run never spans more than two tile boundaries):
+//   pass 1  rd_count_kernel   reads the keys only and counts the run heads of every tile;
+//   scan    exclusive sum of the 2048-entry tiles' head counts = the tiles' output offsets (+ the group count);
+//   pass 2  rd_emit_kernel    every tile reduces the runs that START in it.  The run that is still open at the tile's end
+//           is finished by one warp reading AHEAD (at most ncols - 1 elements of the following tiles); the elements in
+//           front of the tile's first head belong to a run the previous tile finishes the same way and are skipped.
+// No tile ever waits for another one: no look-back, no descriptors, no polling -- the single-pass kernel above spends
+// most of its time at the barrier behind warp 0's look-back (ncu: 10.9 barrier-stall cycles per issued instruction).
+// The price is one extra pass over the keys (8 of the 16 input bytes per entry).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename E, bool VEC>
+__device__ __forceinline__ void rd_load_items(const E *__restrict__ p, int64_t first, E (&out)[RD_ITEMS]) {
+    if constexpr (VEC && (RD_ITEMS * sizeof(E)) % 16 == 0) {
+        constexpr int NV = (int)(RD_ITEMS * sizeof(E) / 16);
+        const uint4 *src = reinterpret_cast<const uint4 *>(p + first);
+        uint4 tmp[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tmp[q] = __ldg(src + q);
+        memcpy(out, tmp, sizeof(out));
+    } else {
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) out[i] = p[first + i];
+    }
+}
+
+// group ids of a thread's RD_ITEMS consecutive elements, the valid mask, the head mask (an element past the end counts
+// as a head) and the group ids of the two neighbours outside the thread's range (-2: none)
+template <bool VEC>
+__device__ __forceinline__ void rd_thread_keys(const int64_t *__restrict__ keys, int64_t n, int64_t base,
+                                               const FastDiv &fcols, int lane, int64_t (&g)[RD_ITEMS], unsigned &vm,
+                                               unsigned &hm, int64_t &gnext) {
+    vm = 0xFFu;
+    if (base + RD_ITEMS <= n) {
+        rd_load_items<int64_t, VEC>(keys, base, g);
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) g[i] = (int64_t)fcols.div((uint64_t)g[i]);
+    } else {
+        vm = 0;
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) {
+            const int64_t p = base + i;
+            g[i] = -1;
+            if (p < n) {
+                g[i] = (int64_t)fcols.div((uint64_t)keys[p]);
+                vm |= 1u << i;
+            }
+        }
+    }
+    int64_t gprev = __shfl_up_sync(0xffffffffu, g[RD_ITEMS - 1], 1);
+    gnext = __shfl_down_sync(0xffffffffu, g[0], 1);
+    if (lane == 0) gprev = (base > 0 && base - 1 < n) ? (int64_t)fcols.div((uint64_t)keys[base - 1]) : -2;
+    if (lane == 31) gnext = base + RD_ITEMS < n ? (int64_t)fcols.div((uint64_t)keys[base + RD_ITEMS]) : -2;
+    hm = (g[0] != gprev) ? 1u : 0u;
+#pragma unroll
+    for (int i = 1; i < RD_ITEMS; ++i) hm |= (g[i] != g[i - 1]) ? (1u << i) : 0u;
+    hm |= ~vm & 0xFFu;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(RD_THREADS)
+rd_count_kernel(const int64_t *__restrict__ keys, int64_t n, FastDiv fcols, int64_t *__restrict__ tile_heads) {
+    __shared__ int s_h[RD_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * RD_TILE + (int64_t)threadIdx.x * RD_ITEMS;
+    int64_t g[RD_ITEMS], gnext;
+    unsigned vm, hm;
+    rd_thread_keys<VEC>(keys, n, base, fcols, lane, g, vm, hm, gnext);
+    int c = __popc(hm & vm);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_h[w] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int q = 0; q < RD_THREADS / 32; ++q) t += s_h[q];
+        tile_heads[blockIdx.x] = t;
+    }
+}
+
+// value of the run that is open at some position + the GLOBAL position of its head (-1: the head lies before the range)
+template <typename T>
+struct RunP {
+    T val;
+    int64_t hp;
+};
+template <typename T>
+__device__ __forceinline__ RunP<T> runp_combine(int op, const RunP<T> &a, const RunP<T> &b) {  // b comes after a
+    RunP<T> r;
+    r.hp = a.hp > b.hp ? a.hp : b.hp;
+    const T both = red_apply<T>(op, a.val, b.val);
+    r.val = b.hp >= 0 ? b.val : both;
+    return r;
+}
+
+template <typename T, int OP, bool VEC>
+__global__ void __launch_bounds__(RD_THREADS, 4)
+rd_emit_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int64_t n, int64_t ncols, FastDiv fcols,
+               int op_rt, const int64_t *__restrict__ tile_off, T fill, int apply_fix, T result_fill,
+               int64_t *__restrict__ out_gid, T *__restrict__ out_val, unsigned long long *__restrict__ counters) {
+    __shared__ int64_t sk[RD_TILE + 1];
+    __shared__ T sv[RD_TILE + 1];
+    __shared__ T s_val[RD_THREADS / 32];
+    __shared__ int64_t s_hp[RD_THREADS / 32];
+    __shared__ int s_heads[RD_THREADS / 32];
+    const int op = OP >= 0 ? OP : op_rt;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_base = tile * RD_TILE;
+    const int64_t base = tile_base + (int64_t)threadIdx.x * RD_ITEMS;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t g[RD_ITEMS], gnext;
+    T v[RD_ITEMS];
+    unsigned vm, hm;
+    rd_thread_keys<VEC>(keys, n, base, fcols, lane, g, vm, hm, gnext);
+    if (base + RD_ITEMS <= n) {
+        rd_load_items<T, VEC>(vals, base, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < RD_ITEMS; ++i) v[i] = (base + i < n) ? vals[base + i] : T(0);
+    }
+    const unsigned lastm = ((hm >> 1) | ((g[RD_ITEMS - 1] != gnext) ? (1u << (RD_ITEMS - 1)) : 0u)) & vm;
+    const int nheads = __popc(hm & vm);
+    // thread summary: the run still open at the end of the thread's range
+    RunP<T> mine;
+    mine.val = v[0];
+    mine.hp = (hm & 1u) ? base : -1;
+#pragma unroll
+    for (int i = 1; i < RD_ITEMS; ++i) {
+        const bool h = (hm >> i) & 1u;
+        const T both = red_apply<T>(op, mine.val, v[i]);
+        mine.val = h ? v[i] : both;
+        mine.hp = h ? base + i : mine.hp;
+    }
+    // inclusive segmented scan over the warp, warp aggregates through shared memory
+    RunP<T> incl = mine;
+    int hincl = nheads;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        RunP<T> up;
+        up.val = __shfl_up_sync(0xffffffffu, incl.val, o);
+        up.hp = __shfl_up_sync(0xffffffffu, incl.hp, o);
+        const int hu = __shfl_up_sync(0xffffffffu, hincl, o);
+        if (lane >= o) {
+            incl = runp_combine<T>(op, up, incl);
+            hincl += hu;
+        }
+    }
+    if (lane == 31) {
+        s_val[w] = incl.val;
+        s_hp[w] = incl.hp;
+        s_heads[w] = hincl;
+    }
+    __syncthreads();
+    RunP<T> wcarry;  // the run open in front of this warp, as far as it lies inside the tile
+    wcarry.val = T(0);
+    wcarry.hp = -1;
+    RunP<T> tile_agg = wcarry;
+    int hbefore = 0, tile_heads = 0;
+    bool have_w = false, have_t = false;
+#pragma unroll
+    for (int q = 0; q < RD_THREADS / 32; ++q) {
+        RunP<T> wq;
+        wq.val = s_val[q];
+        wq.hp = s_hp[q];
+        if (q < w) {
+            wcarry = have_w ? runp_combine<T>(op, wcarry, wq) : wq;
+            have_w = true;
+            hbefore += s_heads[q];
+        }
+        tile_agg = have_t ? runp_combine<T>(op, tile_agg, wq) : wq;
+        have_t = true;
+        tile_heads += s_heads[q];
+    }
+    for (int i = threadIdx.x; i < tile_heads; i += RD_THREADS) sk[i] = -1;
+    __syncthreads();
+    // second walk over the thread's elements with the carry-in.  A run whose head lies before the tile (hp < 0 after
+    // the combination) is not ours: the previous tile finishes it by reading ahead.
+    RunP<T> st = wcarry;
+    RunP<T> prev;
+    prev.val = (T)__shfl_up_sync(0xffffffffu, incl.val, 1);
+    prev.hp = __shfl_up_sync(0xffffffffu, incl.hp, 1);
+    const int hprev = __shfl_up_sync(0xffffffffu, hincl, 1);
+    int hcount = hbefore;  // heads of the tile strictly before this thread's first element
+    if (lane > 0) {
+        st = have_w ? runp_combine<T>(op, st, prev) : prev;
+        hcount += hprev;
+    }
+    T rv = st.val;
+    int64_t rhp = (lane > 0 || have_w) ? st.hp : -1;
+#pragma unroll
+    for (int i = 0; i < RD_ITEMS; ++i) {
+        const bool h = (hm >> i) & 1u;
+        const T both = red_apply<T>(op, rv, v[i]);
+        rv = h ? v[i] : both;
+        rhp = h ? base + i : rhp;
+        hcount += (hm & vm) >> i & 1u;
+        if (((lastm >> i) & 1u) && rhp >= tile_base) {
+            sk[hcount - 1] = g[i];
+            sv[hcount - 1] = apply_fix ? fill_fix<T>(op, rv, base + i - rhp + 1, ncols, fill) : rv;
+        }
+    }
+    // the run that is still open at the end of the tile (and started in it): warp 0 reads ahead until the group changes
+    if (w == 0 && tile_heads > 0) {
+        const int64_t tile_end = tile_base + RD_TILE;
+        const int64_t last_g = tile_end - 1 < n ? (int64_t)fcols.div((uint64_t)keys[tile_end - 1]) : -3;
+        if (tile_end < n && tile_agg.hp >= tile_base &&
+            (int64_t)fcols.div((uint64_t)keys[tile_end]) == last_g) {
+            T acc = tile_agg.val;
+            int64_t p = tile_end;
+            for (;;) {
+                const int64_t q = p + lane;
+                bool same = false;
+                T x = T(0);
+                if (q < n) {
+                    same = (int64_t)fcols.div((uint64_t)keys[q]) == last_g;
+                    x = vals[q];
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, same);
+                const int take = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;  // leading lanes that still belong to the run
+                // ordered fold of the `take` leading values into acc (lane order = stored order)
+                for (int j = 0; j < take; ++j) {
+                    const T xv = __shfl_sync(0xffffffffu, x, j);
+                    acc = red_apply<T>(op, acc, xv);
+                }
+                p += take;
+                if (take < 32) break;
+            }
+            if (lane == 0) {
+                sk[tile_heads - 1] = last_g;
+                sv[tile_heads - 1] = apply_fix ? fill_fix<T>(op, acc, p - tile_agg.hp, ncols, fill) : acc;
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t off = tile_off[tile];
+    int eq = 0;
+    for (int l = threadIdx.x; l < tile_heads; l += RD_THREADS) {
+        const int64_t gid = sk[l];
+        if (gid >= 0) {
+            const T outv = sv[l];
+            out_val[off + l] = outv;
+            out_gid[off + l] = gid;
+            bool same;
+            if constexpr (sizeof(T) == 1) same = (*(const uint8_t *)&outv) == (*(const uint8_t *)&result_fill);
+            else if constexpr (sizeof(T) == 4) {
+                uint32_t x, y;
+                memcpy(&x, &outv, 4);
+                memcpy(&y, &result_fill, 4);
+                same = x == y;
+            } else {
+                uint64_t x, y;
+                memcpy(&x, &outv, 8);
+                memcpy(&y, &result_fill, 8);
+                same = x == y;
+            }
+            eq += same ? 1 : 0;
+        }
+    }
+    eq = __reduce_add_sync(0xffffffffu, eq);
+    if (lane == 0 && eq) atomicAdd(&counters[0], (unsigned long long)eq);
+}
+
+// host side of the communication-free form; scratch: counters[2] | tile_heads i64[nt + 1] | tile_off i64[nt + 1]
+template <typename T>
+static int rd_twopass_t(const int64_t *keys, const void *vals, int64_t n, int64_t ncols, int op, const void *fill_host,
+                        int apply_fix, const void *result_fill_host, int64_t *gid_out, void *vals_out, int64_t nt,
+                        void *scratch, cudaStream_t s) {
+    char *b = (char *)scratch;
+    unsigned long long *counters = (unsigned long long *)b;
+    int64_t *tile_heads = (int64_t *)(b + 16);
+    int64_t *tile_off = tile_heads + (nt + 1);
+    T fill, rfill;
+    memcpy(&fill, fill_host, sizeof(T));
+    memcpy(&rfill, result_fill_host, sizeof(T));
+    const bool vec = (((uintptr_t)keys | (uintptr_t)vals) & 15) == 0;
+    const FastDiv fd = make_fastdiv((uint64_t)ncols);
+    if (vec) rd_count_kernel<true><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, n, fd, tile_heads);
+    else rd_count_kernel<false><<<(unsigned)nt, RD_THREADS, 0, s>>>(keys, n, fd, tile_heads);
+    B2S_CHECK_LAUNCH();
+    {
+        size_t tb = 0;
+        void *tmp = nullptr;
+        B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, tile_heads, tile_off, (int)(nt + 1), s));
+        int rc = scratch_alloc(&tmp, tb, s);
+        if (rc) return rc;
+        B2S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, tile_heads, tile_off, (int)(nt + 1), s));
+        count_launch(2);
+        scratch_free(tmp, s);
+        // the group count travels with the other counter: counters[1] = tile_off[nt]
+        B2S_CUDA(cudaMemcpyAsync(counters + 1, tile_off + nt, 8, cudaMemcpyDeviceToDevice, s));
+    }
+#define B2S_RE(OPC)                                                                                                   \
+    do {                                                                                                              \
+        if (vec)                                                                                                      \
+            rd_emit_kernel<T, OPC, true><<<(unsigned)nt, RD_THREADS, 0, s>>>(                                         \
+                keys, (const T *)vals, n, ncols, fd, op, tile_off, fill, apply_fix, rfill, gid_out, (T *)vals_out,    \
+                counters);                                                                                            \
+        else                                                                                                          \
+            rd_emit_kernel<T, OPC, false><<<(unsigned)nt, RD_THREADS, 0, s>>>(                                        \
+                keys, (const T *)vals, n, ncols, fd, op, tile_off, fill, apply_fix, rfill, gid_out, (T *)vals_out,    \
+                counters);                                                                                            \
+    } while (0)
+    switch (op) {  // the common operators are compile-time constants of their own instantiation
+        case RF_ADD: B2S_RE(RF_ADD); break;
+        case RF_MAX: B2S_RE(RF_MAX); break;
+        case RF_MIN: B2S_RE(RF_MIN); break;
+        default: B2S_RE(-1); break;
+    }
+#undef B2S_RE
+    B2S_CHECK_LAUNCH();
+    return B2S_OK;
+}
+
 template <typename T>
 static int rd_single_t(const int64_t *keys, const void *vals, int64_t n, int64_t ncols, int op, const void *fill_host,
                        int apply_fix, const void *result_fill_host, int64_t *gid_out, void *vals_out, int64_t nt,
@@ -454,11 +768,19 @@ static int rd_single_t(const int64_t *keys, const void *vals, int64_t n, int64_t
     return B2S_OK;
 }
 
+static int g_reduce_form = 0;  // 0 = by ncols, 1 = always the single-pass look-back kernel, 2 = always count / scan / emit
+
 }  // namespace b2s
 
 using namespace b2s;
 
 extern "C" {
+
+/* test hook: force one of the two forms of b2s_reduce_single (0 = choose by ncols) */
+int b2s_reduce_set_form(int form) {
+    g_reduce_form = (form == 1 || form == 2) ? form : 0;
+    return B2S_OK;
+}
 
 /*
  * Segmented reduction of `vals` over runs of equal group id (= key / ncols) of the sorted `keys`, in ONE pass:
@@ -481,10 +803,24 @@ int b2s_reduce_single(int dtype, int op, const int64_t *keys_dev, const void *va
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t nt = (n + RD_TILE - 1) / RD_TILE;
     B2S_REQUIRE(nt < 2147483647LL, B2S_ERR_OVERFLOW, "reduce: too many tiles");
-    const size_t bytes = 24 + (size_t)nt * 3 * 8;
+    const size_t bytes = 24 + (size_t)(nt + 1) * 3 * 8;
     void *scratch = nullptr;
     int rc = scratch_alloc(&scratch, bytes, s);
     if (rc) return rc;
+    // short runs (a group holds at most ncols entries): the communication-free count / scan / emit form; long runs: the
+    // single-pass kernel with the decoupled look-back
+    const bool two_pass = g_reduce_form == 0 ? (ncols <= RD_TILE) : (g_reduce_form == 2);
+    if (two_pass) {
+        B2S_CUDA(cudaMemsetAsync(scratch, 0, 16 + (size_t)(nt + 1) * 8, s));  // counters, head counts (+ sentinel)
+        switch (dtype) {
+            case B2S_F32: rc = rd_twopass_t<float>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+            case B2S_F64: rc = rd_twopass_t<double>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+            case B2S_I32: rc = rd_twopass_t<int32_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+            case B2S_I64: rc = rd_twopass_t<int64_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+            case B2S_BOOL: rc = rd_twopass_t<uint8_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
+            default: set_error("reduce_single: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
+        }
+    } else {
     B2S_CUDA(cudaMemsetAsync(scratch, 0, 24 + (size_t)nt * 8, s));  // counters, ticket and every status word start at 0
     switch (dtype) {
         case B2S_F32: rc = rd_single_t<float>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
@@ -493,6 +829,7 @@ int b2s_reduce_single(int dtype, int op, const int64_t *keys_dev, const void *va
         case B2S_I64: rc = rd_single_t<int64_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
         case B2S_BOOL: rc = rd_single_t<uint8_t>(keys_dev, vals_dev, n, ncols, op, fill_host, apply_fill_fix, result_fill_host, gid_out_dev, vals_out_dev, nt, scratch, s); break;
         default: set_error("reduce_single: dtype %d", dtype); rc = B2S_ERR_UNSUPPORTED;
+    }
     }
     unsigned long long h[2] = {0, 0};
     if (rc == B2S_OK) {

@@ -270,3 +270,54 @@ def test_flag_scan_beyond_2_31_elements():
     assert int(pos[n - 1].item()) == want - 1 and int(pos[2**31].item()) == 2**11 and int(pos[2**31 + 1].item()) == 2**11 + 1
     del flags, pos
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
+@pytest.mark.parametrize("ncols", [1, 7, 64, 2048])
+def test_both_reduction_kernels_agree(dtype, ncols):
+    """b2s_reduce_single has two forms: count / scan / emit without inter-tile communication (runs no longer than a
+    tile) and the single-pass look-back kernel.  Same group ids, values equal (integers) or to rounding, on streams
+    whose runs start and end on every position relative to the 2048-element tiles (incl. completely filled groups of
+    exactly one tile)."""
+    import torch
+
+    from sparse_b200 import _device as D
+    from sparse_b200 import _kernels as Kn
+
+    _sp()
+    rng = np.random.default_rng(ncols)
+    groups = 40_000 if ncols <= 64 else 600
+    keep = rng.random(groups * ncols) < (0.6 if ncols > 1 else 0.8)
+    if ncols == 2048:
+        keep[: 5 * ncols] = True  # five groups that fill whole tiles
+    keys = np.nonzero(keep)[0].astype(np.int64)
+    vals = rng.integers(-4, 5, len(keys)).astype(dtype) if dtype == np.int64 else (rng.random(len(keys)) - 0.3).astype(dtype)
+    kd, vd = D.upload(keys), D.upload(vals)
+    fill = dtype(0.5) if dtype != np.int64 else dtype(2)
+    res = {}
+    for op in (0, 2, 3):  # add, max, min
+        for form in (1, 2):
+            Kn.reduce_set_form(form)
+            try:
+                _, gids, out, neq = Kn.reduce_fused(op, kd, vd, ncols, fill, fill, (groups,), want_coords=False)
+            finally:
+                Kn.reduce_set_form(0)
+            res[form] = (D.download(gids), D.download(out), neq)
+        assert np.array_equal(res[1][0], res[2][0]) and np.array_equal(res[1][0], np.unique(keys // ncols))
+        if dtype == np.int64 or op != 0:
+            assert np.array_equal(res[1][1], res[2][1]), (op, ncols)
+        else:
+            assert np.allclose(res[1][1], res[2][1], rtol=1e-5 if dtype == np.float32 else 1e-12, atol=1e-6 if dtype == np.float32 else 1e-13)
+        assert res[1][2] == res[2][2]
+        # against NumPy (fill-value contribution of the reference: op(v, fill) where the group is incomplete)
+        gk = keys // ncols
+        uk, start = np.unique(gk, return_index=True)
+        cnt = np.diff(np.r_[start, len(gk)])
+        f = {0: np.add, 2: np.maximum, 3: np.minimum}[op]
+        want = f.reduceat(vals.astype(np.float64 if dtype != np.int64 else np.int64), start)
+        if op == 0:
+            want = want + (ncols - cnt) * (np.float64(fill) if dtype != np.int64 else np.int64(fill))
+        else:
+            want = np.where(cnt < ncols, f(want, fill), want)
+        got = res[2][1].astype(np.float64 if dtype != np.int64 else np.int64)
+        assert np.allclose(got, want, rtol=2e-5 if dtype == np.float32 else 1e-11, atol=1e-5 if dtype == np.float32 else 1e-12)

@@ -314,7 +314,8 @@ def main():
         for k, v in results.items():
             print(json.dumps({k: v}), flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"multi_{world}.json"), "w") as f:
+        name = f"multi_cpu_smoke_{world}.json" if args.cpu_smoke else f"multi_{world}.json"
+        with open(os.path.join(ROOT, "gpurun_out", name), "w") as f:
             json.dump(results, f, indent=1)
     if world > 1:
         dist.destroy_process_group()
