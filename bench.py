@@ -219,7 +219,14 @@ def dump_sample(vals, cols, indptr, B, rows_sample, K):
     """Write the first `rows_sample` rows of A (int64 indices, the reference's own layout) and the full B as .npy."""
     import tempfile
 
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    need = int(B.numel()) * 4 * 2 + (64 << 20)  # B + the sample of A + the results, with slack
+    base = None
+    try:
+        st = os.statvfs("/dev/shm")
+        if os.access("/dev/shm", os.W_OK) and st.f_bavail * st.f_frsize > need + int(indptr[rows_sample].item()) * 24:
+            base = "/dev/shm"
+    except OSError:
+        pass
     d = tempfile.mkdtemp(prefix="b2s_ref_", dir=base)
     ip = indptr[: rows_sample + 1].cpu().numpy().astype(np.int64)
     n = int(ip[-1])

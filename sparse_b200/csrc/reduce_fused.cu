@@ -536,13 +536,14 @@ rd_emit_kernel(const int64_t *__restrict__ keys, const T *__restrict__ vals, int
     int64_t g[RD_ITEMS], gnext;
     T v[RD_ITEMS];
     unsigned vm, hm;
-    rd_thread_keys<VEC>(keys, n, base, fcols, lane, g, vm, hm, gnext);
+    // the value loads are issued BEFORE the keys are consumed: one round trip to memory for both arrays
     if (base + RD_ITEMS <= n) {
         rd_load_items<T, VEC>(vals, base, v);
     } else {
 #pragma unroll
         for (int i = 0; i < RD_ITEMS; ++i) v[i] = (base + i < n) ? vals[base + i] : T(0);
     }
+    rd_thread_keys<VEC>(keys, n, base, fcols, lane, g, vm, hm, gnext);
     const unsigned lastm = ((hm >> 1) | ((g[RD_ITEMS - 1] != gnext) ? (1u << (RD_ITEMS - 1)) : 0u)) & vm;
     const int nheads = __popc(hm & vm);
     // thread summary: the run still open at the end of the thread's range
