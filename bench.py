@@ -52,7 +52,7 @@ def parse():
     p.add_argument("--rows", type=int, default=1_000_000, help="M (= K) of the C2 workload")
     p.add_argument("--nnz", type=int, default=100_000_000)
     p.add_argument("--ncols", type=int, default=128)
-    p.add_argument("--variant", type=int, default=0, help="K1 variant override (1 LDG, 2 bulk-TMA)")
+    p.add_argument("--variant", type=int, default=0, help="K1 variant override (1 LDG dynamic rows = default, 2 bulk-TMA, 3 LDG static grid)")
     p.add_argument("--unroll", type=int, default=0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
@@ -490,8 +490,9 @@ def main():
     achieved = alg / (kern_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": known_traffic(ncols),
-            "kernel": "spmm_csr_dense_kernel<f32,i32,VEC4,G32>" if not args.variant or args.variant == 1
-            else "spmm_csr_dense_tma_kernel<f32,i32>",
+            "kernel": {0: "spmm_csr_dense_dyn_kernel<f32,i32,VEC4,G32,U8>", 1: "spmm_csr_dense_dyn_kernel<f32,i32,VEC4,G32,U8>",
+                       2: "spmm_csr_dense_tma_kernel<f32,i32>", 3: "spmm_csr_dense_kernel<f32,i32,VEC4,G32,U8>"}.get(
+                           args.variant, "spmm_csr_dense_dyn_kernel<f32,i32,VEC4,G32,U8>"),
             "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_launch": alg,
             "bytes_per_nnz_model": round(alg / nnz, 2), "peak_source": peak_src,
             "compulsory_bytes_per_launch": nnz * 8 + (M + 1) * 4 + K * ncols * 4 + M * ncols * 4,

@@ -115,11 +115,13 @@ int b2s_spmm_csr_dense_ex(int dtype, int idx_bytes, int64_t M, int64_t K, int64_
                           const void *a_data_dev, const void *a_indices_dev, const void *a_indptr_dev,
                           const void *b_dev, int64_t ldb, void *out_dev, int64_t ldc, int n_panels, int rows_sorted,
                           int long_rows, void *stream);
-/* Largest number of stored entries in a row: callers enable `long_rows` (the nnz-balanced column-split kernel for rows
- * with more than 4096 entries, run concurrently on a side stream) only for matrices that have such rows. */
+/* Largest number of stored entries in a row: callers enable `long_rows` (nnz-balanced mode: rows longer than
+ * max(512, 4 x mean) go to the column-split shared-memory-ring kernel, run concurrently on a side stream) only for
+ * matrices whose longest row exceeds max(512, 8 x mean). */
 int b2s_csr_max_row_nnz(int idx_bytes, int64_t M, const void *indptr_dev, int64_t *max_host, void *stream);
 
-/* Tuning knob for K1 (0 = default).  variant: 1 = register-staged LDG gather,
+/* Tuning knob for K1 (0 = default).  variant: 1 = register-staged LDG gather with DYNAMIC row assignment (persistent
+ * warps draw rows from a counter; the default), 3 = the same gather on the static one-row-per-warp grid,
  * 2 = 1-D bulk-TMA (cp.async.bulk) gather through a shared-memory ring. */
 int b2s_spmm_set_variant(int variant, int unroll);
 /* process-wide default of the nnz-balanced long-row path used by b2s_spmm_csr_dense (default off; b2s_spmm_csr_dense_ex

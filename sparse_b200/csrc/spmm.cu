@@ -126,8 +126,8 @@ spmm_csr_dense_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const 
     if (row_ok && col_ok && !skipped) store_c<T, VEC>(C + row * ldc + col0, acc);
 }
 
-template <typename T, typename I, int VEC, int G, int U>
-__global__ void __launch_bounds__(256)
+template <typename T, typename I, int VEC, int G, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 spmm_csr_dense_dyn_kernel(int64_t M, int64_t N, const T *__restrict__ a_data, const I *__restrict__ a_indices,
                       const I *__restrict__ a_indptr, const T *__restrict__ B, int64_t ldb, T *__restrict__ C,
                       int64_t ldc, const uint8_t *__restrict__ skip, unsigned int *__restrict__ row_counter) {
@@ -338,6 +338,8 @@ spmm_csr_dense_tma_kernel(int64_t M, int N, const T *__restrict__ a_data, const 
 static int g_variant = 1;
 static int g_unroll = 8;
 static int g_skew = 0;  // process-wide default of the long-row (nnz-balanced) path; per-call override below
+static int g_dyn_form = 0;     // tuning of the dynamic-row kernel (see dispatch_g)
+static int g_static_rows = 0;  // 1 = the static one-row-per-warp grid instead of the dynamic-row default (A/B, tests)
 static thread_local int t_skew = -1;
 void set_call_skew(int v) { t_skew = v; }
 
@@ -370,33 +372,49 @@ static int dispatch_g(int64_t M, int64_t N, const void *ad, const void *ai, cons
     const int64_t packs = (N + VEC - 1) / VEC;  // column packs per row
 #define B2S_GO(G, U) return launch_v1<T, I, VEC, G, U>(M, N, ad, ai, ap, b, ldb, out, ldc, s)
     if (packs >= 32) {
-        if ((t_skew >= 0 ? t_skew : g_skew) && g_variant == 1 && M >= 4096) {
-            // nnz-balanced mode: rows longer than kLongRow go to the column-split kernel on a side stream (they start
-            // first and run concurrently with the row-split kernel, which skips them)
+        // Default for wide B rows: PERSISTENT warps that draw rows two at a time from a global counter
+        // (spmm_csr_dense_dyn_kernel).  Written for skewed matrices, it also wins on the uniform C2 matrix: 6.43 ms
+        // vs 7.84 ms for the static one-row-per-warp grid (56 instead of 79 registers -> 4 instead of 3 CTAs per SM in
+        // flight, no tail of partially idle CTAs); bit-identical, since the per-row loop is the same code.
+        const bool skew = (t_skew >= 0 ? t_skew : g_skew) && g_variant == 1 && M >= 4096;
+        const int64_t gy = (N + (int64_t)32 * VEC - 1) / ((int64_t)32 * VEC);
+        if (g_variant == 1 && g_unroll == 8 && g_static_rows == 0 && gy <= 64) {
+            // nnz-balanced mode on top: rows longer than max(512, 4 x mean) go to the column-split kernel on a side
+            // stream (they start first and run concurrently with the row kernel, which skips them)
             uint8_t *skip = nullptr;
-            int rc = skew_begin<T, I>(M, N, ad, ai, ap, b, ldb, out, ldc, s, &skip, VEC > 1);
-            if (rc) return rc;
-            {
-                // the rows that stay row-split are drawn dynamically by persistent warps
-                unsigned int *counter = skew_row_counter();
-                const int64_t gy = (N + (int64_t)32 * VEC - 1) / ((int64_t)32 * VEC);
-                if (counter != nullptr && gy <= 64) {
-                    B2S_CUDA(cudaMemsetAsync(counter, 0, 64 * sizeof(unsigned int), s));
-                    auto kern = spmm_csr_dense_dyn_kernel<T, I, VEC, 32, 8>;
-                    int occ = 1;
-                    B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-                    if (occ < 1) occ = 1;
-                    dim3 grid((unsigned)(num_sms() * occ), (unsigned)gy);
-                    kern<<<grid, 256, 0, s>>>(M, N, (const T *)ad, (const I *)ai, (const I *)ap, (const T *)b, ldb,
-                                              (T *)out, ldc, skip, counter);
-                    B2S_CHECK_LAUNCH();
-                    rc = B2S_OK;
-                } else {
-                    rc = launch_v1<T, I, VEC, 32, 8>(M, N, ad, ai, ap, b, ldb, out, ldc, s, skip);
-                }
+            int rc = B2S_OK;
+            unsigned int *counter = nullptr;
+            if (skew) {
+                rc = skew_begin<T, I>(M, N, ad, ai, ap, b, ldb, out, ldc, s, &skip, VEC > 1);
+                if (rc) return rc;
+                counter = skew_row_counter();
             }
-            const int rc2 = skew_end(s, skip);
-            return rc ? rc : rc2;
+            unsigned int *own = nullptr;
+            if (counter == nullptr) {
+                if ((rc = scratch_alloc((void **)&own, 64 * sizeof(unsigned int), s))) return rc;
+                counter = own;
+            }
+            B2S_CUDA(cudaMemsetAsync(counter, 0, 64 * sizeof(unsigned int), s));
+            // g_dyn_form (tuning): 0 = 8 gathers in flight per lane, 4 CTAs per SM (the default); 1 = 16 in flight, 4 CTAs;
+            // 2 = 8 in flight, 5 CTAs per SM; 3 = 16 in flight, 3 CTAs per SM
+            using KernT = void (*)(int64_t, int64_t, const T *, const I *, const I *, const T *, int64_t, T *, int64_t,
+                                   const uint8_t *, unsigned int *);
+            KernT kern = spmm_csr_dense_dyn_kernel<T, I, VEC, 32, 8, 4>;
+            if (g_dyn_form == 1) kern = spmm_csr_dense_dyn_kernel<T, I, VEC, 32, 16, 4>;
+            else if (g_dyn_form == 2) kern = spmm_csr_dense_dyn_kernel<T, I, VEC, 32, 8, 5>;
+            else if (g_dyn_form == 3) kern = spmm_csr_dense_dyn_kernel<T, I, VEC, 32, 16, 3>;
+            int occ = 1;
+            B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+            const int occ_cached = occ < 1 ? 1 : occ;
+            int64_t blocks = (int64_t)num_sms() * occ_cached;
+            const int64_t need = (M + 15) / 16;  // 8 warps x 2 rows per ticket
+            if (blocks > need) blocks = need > 0 ? need : 1;
+            dim3 grid((unsigned)blocks, (unsigned)gy);
+            kern<<<grid, 256, 0, s>>>(M, N, (const T *)ad, (const I *)ai, (const I *)ap, (const T *)b, ldb, (T *)out, ldc,
+                                      skip, counter);
+            B2S_CHECK_LAUNCH();
+            if (own) scratch_free(own, s);
+            return skew ? skew_end(s, skip) : B2S_OK;
         }
         if (g_unroll == 4) B2S_GO(32, 4);
         if (g_unroll == 16) B2S_GO(32, 16);
@@ -488,6 +506,8 @@ int b2s_spmm_set_skew(int enabled) {
 
 int b2s_spmm_set_variant(int variant, int unroll) {
     g_variant = (variant == 2) ? 2 : 1;
+    g_static_rows = (variant == 3) ? 1 : 0;
+    g_dyn_form = (variant >= 10 && variant <= 13) ? variant - 10 : 0;  // 10..13: forms of the dynamic-row kernel
     g_unroll = (unroll == 4 || unroll == 16 || unroll == 32) ? unroll : 8;
     return B2S_OK;
 }
