@@ -197,6 +197,13 @@ spgemm_rows_kernel(int64_t M, const I *__restrict__ a_indptr, const I *__restric
             if (pending) cur = key[h];
             const bool empty = pending && cur == EMPTY;
             __syncwarp();
+            // Every lane that found this slot empty stores its key with ONE warp-wide store instruction.  When several
+            // lanes target the same slot, the hardware serialises their stores and exactly one key ends up there (CUDA
+            // programming guide, "if a non-atomic instruction executed by a warp writes to the same location ... for more
+            // than one of the threads of the warp, ... one of the writes is guaranteed to succeed"); the re-read below
+            // tells every lane whether it was the one.  compute-sanitizer racecheck reports this store as a WAW hazard
+            // (profiles/r02_compute_sanitizer_racecheck.log): it is the election itself.  Electing the writer with
+            // __match_any_sync instead costs 25 % of the whole product (2.13 -> 2.66 ms at C5, measured).
             if (empty) key[h] = k;
             __syncwarp();
             if (empty) {
