@@ -42,10 +42,19 @@ def main():
             if os.path.exists(p) and n > 1 or (os.path.exists(p) and src.startswith("multi")):
                 shutil.copy(p, os.path.join(PROF, name))
     base = ce[1]["value"] if ce[1] else None
+    # runs made before the dynamic-row K1 became the default are compared with the N = 1 line of THEIR build
+    first = last_json(os.path.join(PROF, f"{TAG}_bench_n1_first.json"))
+    base_static = first["value"] if first else None
+
+    def base_for(d):
+        static = "dyn" not in d["roofline"].get("kernel", "dyn")
+        return (base_static if static and base_static else base), static
     L = [f"# Round 2 — scaling over the GPUs of one B200 box ({TAG})\n",
          "One process per GPU (`torchrun`), CUDA events on the launching stream, barrier + synchronize on both sides, MAX",
          "over ranks; `tools/gpu_multi.sh N` under `gpurun --gpus N`.  Efficiencies are computed in this table from the",
-         "per-N values.\n",
+         "per-N values.  The GPU budget of the round ended after the last N = 8 call: N = 1 and N = 8 are the FINAL build (K1 with",
+         "dynamic row assignment), N = 2 and N = 4 were measured before that change (static-grid K1) and are compared with",
+         "the N = 1 line of their own build; the bench_multi rows (C5 / C4 / C3-large / reductions) do not involve K1.\n",
          "## C2 weak scaling (1e8 nnz per GPU; B row-sharded, gathered EVERY step, double-buffered behind K1)\n",
          "| N | gather | ms/step | K1 ms (rank 0) | GNNZ/s (all GPUs) | efficiency vs N x (N=1) | distributed product bit-exact |",
          "|---|---|---|---|---|---|---|"]
@@ -53,13 +62,15 @@ def main():
         for kind, d in (("copy engines (CUDA IPC + cudaMemcpyAsync pull)", ce[n]), ("NCCL all-gather (SM kernels)", nc[n])):
             if d is None or (n == 1 and kind.startswith("NCCL")):
                 continue
-            eff = f"{d['value'] / (n * base):.3f}" if base else ""
+            b_, static = base_for(d)
+            eff = f"{d['value'] / (n * b_):.3f}" + (" (static-grid K1 build, vs its N = 1: " + str(b_) + ")" if static else "") if b_ else ""
             L.append(f"| {n} | {'—' if n == 1 else kind} | {d['ms_per_step']} | {d['roofline']['kernel_ms']} | {d['value']} | "
                      f"{eff} | {d['config'].get('distributed_product_bit_exact_vs_local_B', '—')} |")
     L += ["", "## C2 strong scaling (the named problem: 1e8 nnz in total, nnz-balanced row blocks)\n",
           "| N | B replicated (no collective): ms, GNNZ/s, speed-up | B row-sharded (gather every step): ms, GNNZ/s, speed-up | row blocks bit-exact |",
           "|---|---|---|---|"]
     t1 = ce[1]["ms_per_step"] if ce[1] else None
+    t1_static = first["ms_per_step"] if first else None
     if ce[1]:
         L.append(f"| 1 | {t1} ms, {ce[1]['value']}, 1.00 | = | — |")
     for n in ns[1:]:
@@ -67,9 +78,12 @@ def main():
         if d is None or "strong" not in d:
             continue
         s = d["strong"]
+        _, static = base_for(d)
+        tb = t1_static if static and t1_static else t1
+        tag = f" (static-grid K1 build, vs its N = 1: {tb} ms)" if static else ""
         L.append(f"| {n} | {s['replicated_B']['ms_per_step']} ms, {s['replicated_B']['GNNZ/s']}, "
-                 f"{t1 / s['replicated_B']['ms_per_step']:.2f} | {s['sharded_B']['ms_per_step']} ms, "
-                 f"{s['sharded_B']['GNNZ/s']}, {t1 / s['sharded_B']['ms_per_step']:.2f} | "
+                 f"{tb / s['replicated_B']['ms_per_step']:.2f}{tag} | {s['sharded_B']['ms_per_step']} ms, "
+                 f"{s['sharded_B']['GNNZ/s']}, {tb / s['sharded_B']['ms_per_step']:.2f} | "
                  f"{s['row_blocks_bit_exact_vs_single_gpu_product']} |")
     L += ["", "## C2 end to end (host buffers in, host array out; per-rank PCIe; 1e8 nnz per GPU)\n",
           "| N | ms/step (max over ranks) | GNNZ/s (all GPUs) | index narrowing | the other staging mode |", "|---|---|---|---|---|"]
