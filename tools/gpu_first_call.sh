@@ -1,16 +1,11 @@
 #!/bin/bash
-# What to run with the first GPU call of a round (everything the last round-1 session could not measure):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
-# 1. the full GPU test-suite (the tests/test_widen_zz_*.py files have only run on the NumPy mock),
-# 2. the headline bench line, 3. the per-config timings.  Multi-GPU (C4 / C5 over row blocks) is a second call:
-#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
-#       --master-addr 127.0.0.1 --master-port 29511 tools/bench_multi.py > gpurun_out/multi_2.log 2>&1'
-set -u
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/gpu_tests.log
-tail -5 gpurun_out/gpu_tests.log
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-tail -c 600 gpurun_out/bench_n1.json
-timeout 900 python tools/bench_configs.py > gpurun_out/configs.log 2>&1
-tail -20 gpurun_out/configs.log
+# What to run with the first GPU call of a round (one B200, ~5 GPU-minutes):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_first_call.sh'
+# = tools/gpu_call.sh: the GPU test-suite as the driver runs it (-x), the reference arm, the bench line with the configs
+# block, smoke(), the static-vs-dynamic-rows A/B of K1 and the ncu evidence for profiles/.
+# Multi-GPU (bench weak / strong / e2e with both gather transports + bench_multi over row blocks) is one call per N:
+#   /usr/local/graft/bin/gpurun --gpus N --timeout 1800 -- 'bash tools/gpu_multi.sh N'      (N = 2, 4, 8; charged N x)
+# then `python tools/make_scaling_table.py r0X` collects gpurun_out/ into profiles/.
+# Kernel iteration: tools/gpu_kernels.sh (targeted tests + tools/bench_configs.py, optional ncu / skew probe);
+# compute-sanitizer: tools/gpu_sanitizer.sh.
+exec bash "$(dirname "$0")/gpu_call.sh"
