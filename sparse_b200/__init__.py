@@ -56,7 +56,7 @@ __version__ = "0.1.0"
 
 def clip(a, min=None, max=None, out=None):
     """_coo/common.py:1028-1071."""
-    return (a if isinstance(a, SparseArray) else as_coo(a)).clip(min, max, out=out)
+    return asCOO(a, name="clip").clip(min, max, out=out)
 
 
 concat = concatenate

@@ -199,10 +199,17 @@ def _transpose_reshape(x, axes, newshape):
             return x
         if x.ndim == 2 and tuple(axes) == (1, 0) and shape == tuple(x.shape[::-1]):
             return x._2d_transpose()
+        identity = tuple(axes) == tuple(range(x.ndim))
         c = x.tocoo()
-        c = c.reshape(shape) if tuple(axes) == tuple(range(x.ndim)) else c._permute_reshape(tuple(axes), shape)
-        # the reference keeps GCXS here; the compressed axis of the 2-D view follows reshape's default
-        return GCXS.from_coo(c, (int(np.argmin(shape)),) if len(shape) == 2 else None)
+        c = c.reshape(shape) if identity else c._permute_reshape(tuple(axes), shape)
+        # the reference keeps GCXS here.  Compressed axis of the 2-D view: a 2-D operand keeps the axis its (O(1))
+        # transpose has (compressed.py:728-729,761; reshape to the same ndim keeps it: :665-667); any other operand
+        # gets reshape's default, the shorter axis (:671)
+        if x.ndim == 2:
+            ca = (int(x.compressed_axes[0]) if identity else (int(x.compressed_axes[0]) + 1) % 2,)
+        else:
+            ca = (int(np.argmin(shape)),)
+        return GCXS.from_coo(c, ca)
     if isinstance(x, np.ndarray):
         return x.transpose(axes).reshape(newshape)
     # device tensor

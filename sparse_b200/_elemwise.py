@@ -19,7 +19,7 @@ from . import _device as D
 from . import _kernels as Kn
 from ._coo import COO, _is_scipy_sparse
 from ._sparse_array import SparseArray
-from ._utils import c_strides, isscalar, key_bits, prod
+from ._utils import _zero_of_dtype, c_strides, isscalar, key_bits, prod
 
 def nan_replace(a, b):
     """where(isnan(a), b, a): NumPy meaning of device op 14 (`_replace_nan`, _coo/common.py:674-693); type resolution
@@ -62,7 +62,10 @@ _UNARY = {
     np.invert: 23, np.arcsinh: 24, np.arctanh: 25, np.deg2rad: 26, np.rad2deg: 27, np.exp2: 28, np.log2: 29,
     np.log10: 30, np.cbrt: 31, np.isnan: 64, np.isinf: 65, np.isfinite: 66, np.logical_not: 67, np.signbit: 68,
 }
-_BOOL_BITWISE = {np.bitwise_and: np.logical_and, np.bitwise_or: np.logical_or, np.bitwise_xor: np.logical_xor}
+# on two boolean operands these ufuncs ARE the logical ones (NumPy keeps bool: True + True is True)
+_BOOL_BITWISE = {np.bitwise_and: np.logical_and, np.bitwise_or: np.logical_or, np.bitwise_xor: np.logical_xor,
+                 np.add: np.logical_or, np.maximum: np.logical_or, np.fmax: np.logical_or,
+                 np.multiply: np.logical_and, np.minimum: np.logical_and, np.fmin: np.logical_and}
 _COMPUTE_DTYPES = (np.dtype("float32"), np.dtype("float64"), np.dtype("int32"), np.dtype("int64"))
 
 
@@ -262,12 +265,39 @@ class _Elemwise:
         if not any(isinstance(a, COO) for a in self.args):
             # every sparse operand was 0-D and became a scalar (_umath.py:438-439): the result is the 0-D array
             # whose fill value is func(scalars) -- host scalar arithmetic, no data path involved
-            host = [D.download(a) if D.is_device_tensor(a) else np.asarray(a) for a in self.args]
+            # Python scalars stay Python scalars (weak promotion: clip(float32, -1, 2) is float32); NumPy values go
+            # through the ARRAY loop as in the reference (np.atleast_1d, _umath.py:516-527 -- for float16 results it
+            # is not the scalar loop bit for bit)
+            host = [D.download(a) if D.is_device_tensor(a) else a for a in self.args]
             with np.errstate(all="ignore"):
-                res = np.asarray(self.func(*host))
+                if all(np.ndim(h) == 0 for h in host):
+                    res = np.asarray(self.func(*[np.atleast_1d(h) if isinstance(h, (np.generic, np.ndarray)) else h
+                                                 for h in host])).reshape(())
+                else:
+                    res = np.asarray(self.func(*host))
             if self.dtype is not None:
                 res = res.astype(self.dtype)
-            return COO.from_numpy(res) if res.ndim == 0 else res
+            if res.ndim:
+                # 0-D sparse operands next to a dense array: dense, unless func(fills, ndarray) is one constant --
+                # then that constant is the fill value of an array without stored entries (_umath.py:536-546); with
+                # a zero-length axis the constant is func(fills, zero of the ndarray's dtype) (:529-534)
+                from ._utils import equivalent
+
+                if res.size == 0:
+                    with np.errstate(all="ignore"):
+                        const = np.asarray(self.func(*[h if np.ndim(h) == 0 else _zero_of_dtype(h.dtype)
+                                                       for h in host])).astype(res.dtype)[()]
+                elif equivalent(res.reshape(-1)[0], res, loose=True).all():
+                    const = res.reshape(-1)[0]
+                else:
+                    return res
+                return COO(np.empty((res.ndim, 0), dtype=np.intp), np.empty(0, dtype=res.dtype), shape=res.shape,
+                           has_duplicates=False, sorted=True, fill_value=const) if res.size == 0 else COO(
+                    np.empty((res.ndim, 0), dtype=np.intp), np.empty(0, dtype=res.dtype), shape=res.shape,
+                    has_duplicates=False, sorted=True, fill_value=const).asformat(self.out_type, **self.out_kwargs)
+            # no stored entry, the value is the fill value, and the operands' format is kept (_umath.py:480-503)
+            return COO(np.empty((0, 0), dtype=np.intp), np.empty(0, dtype=res.dtype), shape=(), has_duplicates=False,
+                       sorted=True, fill_value=res[()]).asformat(self.out_type, **self.out_kwargs)
         from . import _complex as C
 
         if isinstance(self.func, np.ufunc) and builtins_any(C.is_complex(a) for a in self.args) \
@@ -302,6 +332,8 @@ class _Elemwise:
         if isinstance(out, COO):
             if self.dtype is not None and np.dtype(self.dtype) != out.dtype:
                 out = out.astype(self.dtype)
+            if any(s == 0 for s in self.shape):
+                return out  # a zero-length axis: the reference returns the empty COO as it is (_umath.py:467-477)
             return out.asformat(self.out_type, **self.out_kwargs)
         return out
 
@@ -333,6 +365,10 @@ class _Elemwise:
         func = self.func
         if func is np.conjugate and a.dtype.kind in "fiu":
             func = np.positive  # conj of a real array is the array itself
+        if a.dtype == np.bool_ and func in (np.invert, np.absolute):
+            if func is np.absolute:
+                return a.copy()  # |bool| is the array itself (NumPy keeps bool)
+            func = np.logical_not  # ~bool
         op = _op_code(func, _UNARY, "unary")
         out_dt, T = _resolve(func, _stand_in(a))
         if T in _WIDE_FOR and func not in _NOT_VIA_WIDE:
@@ -432,7 +468,11 @@ class _Elemwise:
         # _get_fill_value (:505-555): func(fill, ndarray) must be constant, else the result is dense
         g, _ = Kn.ew_map(op, 1 if not swap else 0, flat, T.type(sp.fill_value), 0, out_dt)
         if flat.shape[0] == 0:
-            return self._empty(out_dt, out_dt.type(0))
+            # nothing to test for constancy: func(fill, zero of the dense dtype) (_umath.py:529-534)
+            z = _zero_of_dtype(np.dtype(dn.dtype) if isinstance(dn, np.ndarray) else D.np_dtype(dn.dtype))
+            with np.errstate(all="ignore"):
+                f0 = func(z, sp.fill_value) if swap else func(sp.fill_value, z)
+            return self._empty(out_dt, np.asarray(f0).astype(out_dt)[()])
         fill = D.download(g[:1])[0]
         if fill != fill:
             _, nflags = Kn.ew_map(_UNARY[np.isnan], 2, Kn.cast(g, T) if out_dt != T else g, None, True, np.bool_)
@@ -534,6 +574,9 @@ def broadcast_to(x, shape):
     if shape == x.shape:
         return x
     result_shape = _get_broadcast_shape(x.shape, shape, is_result=True)
+    if any(s == 0 for s in result_shape):  # a length-1 axis stretched to length 0: nothing is left
+        return COO(np.empty((len(result_shape), 0), dtype=np.intp), np.empty(0, dtype=x.dtype), shape=result_shape,
+                   has_duplicates=False, sorted=True, fill_value=x.fill_value)
     keys, data, R = _stream(x, result_shape)
     if R > 1:
         # materialise the virtual trailing expansion: key = k*R + r

@@ -391,6 +391,9 @@ class GCXS(SparseArray):
             return self
         if not np.can_cast(self.dtype, dtype, casting=casting):
             raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
+        if any(s == 0 for s in self.shape):
+            # upstream's astype is an elemwise call, and elemwise hands back the empty COO as it is (_umath.py:467-477)
+            return self.tocoo().astype(dtype, casting=casting, copy=copy)
         data, indices, indptr = self._dev()
         if dtype != self.dtype and (self.dtype.kind == "c" or dtype.kind == "c"):
             from ._complex import cast_values

@@ -54,9 +54,9 @@ def reduce_impl(x, method, axis=(0,), keepdims=False, **kwargs):
     if out.ndim == 0:
         # 0-D result per the Array API: a COO whose single element is its fill value (nnz = 0), for GCXS input too
         return COO.from_numpy(out.todense())
-    if was_gcxs:
+    if was_gcxs and len(set(axis)) < x.ndim:
         return GCXS.from_coo(out, None if out.ndim == 1 else (int(np.argmin(out.shape)),))
-    return out
+    return out  # a reduction over EVERY axis of a GCXS array goes through COO and stays COO (compressed.py:355-360)
 
 
 _SIGN64 = np.int64(-(2**63))

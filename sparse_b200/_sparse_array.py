@@ -6,6 +6,7 @@ np.tensordot / np.matmul / np.dot / np.sum ... to this package's functions.
 """
 from __future__ import annotations
 
+import builtins
 import operator
 import warnings
 from functools import reduce as _functools_reduce
@@ -284,6 +285,12 @@ class SparseArray(NDArrayOperatorsMixin):
         if out is not None and not isinstance(out, tuple):
             out = (out,)
         kw = {"out": out} if out is not None else {}
+        if self.dtype.kind in "iu":
+            # numpy.clip accepts Python integers outside the dtype's range (a bound below the type's minimum clips
+            # nothing); minimum / maximum do not (NEP 50: OverflowError), so such bounds are brought into range first
+            info = np.iinfo(self.dtype)
+            min, max = (builtins.min(builtins.max(int(b), info.min), info.max)
+                        if type(b) is int else b for b in (min, max))
         if max is None:
             return np.maximum(self, min, **kw)
         if min is None:

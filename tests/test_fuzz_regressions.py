@@ -1,0 +1,131 @@
+"""Regression tests for the differences `tools/fuzz_vs_reference.py` found between this package's host layer and the
+reference itself (differential fuzzing over formats, dtypes, fill values, shapes with zero-length axes, 0-D operands).
+Expected values are what the reference returns (cited file:line); the host layer is what is under test, so the bodies
+run on the NumPy mock of the kernel layer (no GPU needed, `-m "not gpu"`)."""
+import numpy as np
+import pytest
+import torch
+
+import _mock_kernels
+
+pytestmark = pytest.mark.skipif(torch.cuda.is_available(), reason="host-layer tests on the mock backend")
+
+
+@pytest.fixture
+def sp():
+    import sparse_b200
+
+    _mock_kernels.install()
+    yield sparse_b200
+    _mock_kernels.uninstall()
+
+
+def _gcxs(sp, d, ca=None, fill=0):
+    c = sp.COO.from_numpy(d, fill_value=np.asarray(fill, dtype=d.dtype)[()])
+    return c.asformat("gcxs", **({"compressed_axes": ca} if ca is not None else {}))
+
+
+def test_tensordot_2d_gcxs_operand_keeps_its_transposed_compressed_axis(sp):
+    """_common.py:212-214 + compressed.py:665-667,728-729: a 2-D GCXS operand is transposed in O(1) (compressed axis
+    flips) and a reshape to another 2-D shape keeps that axis -- it decides which CSR/CSC kernel runs and therefore
+    the compressed axis of the product."""
+    a = _gcxs(sp, np.arange(1.0, 5.0, dtype=np.float32).reshape(1, 4), ca=(0,))
+    b = sp.COO.from_numpy(np.arange(16, dtype=np.int32).reshape(2, 4, 2, 1) % 3)
+    r = sp.tensordot(a, b, ([1, 0], [1, 3]))
+    assert isinstance(r, sp.GCXS) and tuple(r.compressed_axes) == (1,)
+    assert np.array_equal(r.todense(), np.tensordot(a.todense(), b.todense(), ([1, 0], [1, 3])))
+
+
+def test_elemwise_of_0d_gcxs_stays_gcxs_and_stores_nothing(sp):
+    """_umath.py:438-439,480-503: 0-D sparse operands become scalars, the result has no stored entry, its value is the
+    fill value, and `asformat(out_type)` keeps GCXS."""
+    x = _gcxs(sp, np.array(3, dtype=np.int64))
+    r = np.add(np.float64(-1.0), x)
+    assert isinstance(r, sp.GCXS) and r.shape == () and r.nnz == 0 and r.fill_value == 2.0 and r.dtype == np.float64
+    y = sp.COO.from_numpy(np.array(3.0, dtype=np.float32))
+    r = y.clip(-1, 2)  # Python bounds are weak scalars: float32 stays float32
+    assert isinstance(r, sp.COO) and r.dtype == np.float32 and r.fill_value == np.float32(2)
+
+
+def test_elemwise_with_a_zero_length_axis_returns_coo_whatever_the_operands(sp):
+    """_umath.py:467-477: the empty result is returned before `asformat`."""
+    x = _gcxs(sp, np.zeros((0, 3), dtype=np.float32), fill=2)
+    r = np.negative(x)
+    assert isinstance(r, sp.COO) and r.shape == (0, 3) and r.fill_value == np.float32(-2)
+    # next to an empty ndarray the fill value is func(fill, zero of the ndarray's dtype) (:529-534)
+    s = sp.COO.from_numpy(np.ones((2, 0, 3), dtype=bool), fill_value=True)
+    r = np.logical_or(s, np.zeros((2, 0, 3), dtype=np.int32))
+    assert isinstance(r, sp.COO) and r.fill_value == np.True_ and r.dtype == np.bool_
+
+
+def test_0d_sparse_next_to_a_dense_array(sp):
+    """_umath.py:536-546: func(fill, ndarray) constant -> an array without stored entries whose fill value is that
+    constant; otherwise the dense result."""
+    x = sp.COO.from_numpy(np.array(2.0))
+    r = np.logical_and(np.zeros(3, dtype=np.float32), x)
+    assert isinstance(r, sp.COO) and r.shape == (3,) and r.nnz == 0 and r.fill_value == np.False_
+    r = np.add(np.arange(3.0), x)
+    assert isinstance(r, np.ndarray) and np.array_equal(r, np.arange(3.0) + 2)
+
+
+@pytest.mark.parametrize("name,want", [("add", np.logical_or), ("multiply", np.logical_and),
+                                       ("maximum", np.logical_or), ("minimum", np.logical_and),
+                                       ("fmax", np.logical_or), ("fmin", np.logical_and)])
+def test_arithmetic_on_two_boolean_operands_is_the_logical_op(sp, name, want):
+    rng = np.random.default_rng(5)
+    da, db = rng.random((3, 4)) < 0.5, rng.random((3, 4)) < 0.5
+    a, b = sp.COO.from_numpy(da), sp.COO.from_numpy(db)
+    r = getattr(np, name)(a, b)
+    assert r.dtype == np.bool_ and np.array_equal(r.todense(), getattr(np, name)(da, db))
+    assert np.array_equal(r.todense(), want(da, db))
+    r = getattr(np, name)(a, True)
+    assert r.dtype == np.bool_ and np.array_equal(r.todense(), getattr(np, name)(da, True))
+
+
+def test_invert_and_abs_of_bool(sp):
+    d = np.array([[True, False, True], [False, False, True]])
+    x = sp.COO.from_numpy(d, fill_value=True)
+    r = np.invert(x)
+    assert r.dtype == np.bool_ and r.fill_value == np.False_ and np.array_equal(r.todense(), ~d)
+    r = np.abs(x)
+    assert r.dtype == np.bool_ and np.array_equal(r.todense(), d)
+
+
+def test_clip(sp):
+    """`sparse.clip` converts to COO first (_coo/common.py:1070-1071), the method keeps the format; numpy.clip takes
+    Python integers outside the dtype's range."""
+    d = np.array([[5, 0, 1], [0, 3, 0]], dtype=np.uint32)
+    g = _gcxs(sp, d)
+    assert isinstance(sp.clip(g, 1, 2), sp.COO) and isinstance(g.clip(1, 2), sp.GCXS)
+    r = sp.clip(g, -1, 2)
+    assert r.dtype == np.uint32 and np.array_equal(r.todense(), np.clip(d, -1, 2))
+    with pytest.raises(ValueError, match="dense result"):
+        sp.clip(d, 0, 1)
+
+
+@pytest.mark.parametrize("axis", [None, (0, 1, 2)])
+def test_reduction_over_every_axis_of_gcxs_goes_through_coo(sp, axis):
+    """compressed.py:355-360: `flatten().tocoo().reduce(...)`; with keepdims the reshaped COO is returned."""
+    d = (np.arange(24).reshape(2, 3, 4) % 5 == 0).astype(np.float64)
+    g = _gcxs(sp, d)
+    r = g.sum(axis=axis, keepdims=True)
+    assert isinstance(r, sp.COO) and r.shape == (1, 1, 1) and r.todense().item() == d.sum()
+    r = g.sum(axis=(0, 2), keepdims=True)
+    assert isinstance(r, sp.GCXS) and np.array_equal(r.todense(), d.sum(axis=(0, 2), keepdims=True))
+
+
+def test_broadcast_to_a_zero_length_axis_is_empty(sp):
+    """A length-1 axis stretched to length 0 (numpy.broadcast_to allows it): no entry survives."""
+    x = sp.COO.from_numpy(np.array([[1.0, 0.0, 2.0]]))
+    r = sp.broadcast_to(x, (2, 0, 3))
+    assert isinstance(r, sp.COO) and r.shape == (2, 0, 3) and r.nnz == 0 and r.coords.shape == (3, 0)
+    assert r.todense().shape == (2, 0, 3)
+
+
+def test_astype_of_an_empty_gcxs_is_the_empty_coo(sp):
+    """astype is an elemwise call upstream (_sparse_array.py:626-658) and elemwise returns the empty COO as it is."""
+    g = _gcxs(sp, np.zeros((0, 2)), ca=(0,))
+    assert isinstance(g.astype("float32"), sp.COO)
+    g = _gcxs(sp, np.ones((3, 2)), ca=(0,))
+    r = g.astype("float32")
+    assert isinstance(r, sp.GCXS) and tuple(r.compressed_axes) == (0,)

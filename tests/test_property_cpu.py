@@ -1,6 +1,8 @@
 """Property tests of the host logic (broadcast rules, fill values, axis bookkeeping, index normalisation) against dense
 NumPy, with the NumPy mock of the kernel layer: random shapes / densities / fill values / operators drawn by
 hypothesis.  CPU only -- the kernels themselves are covered by the golden-vector tests on the GPU."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -11,7 +13,11 @@ import _mock_kernels
 
 pytestmark = pytest.mark.skipif(torch.cuda.is_available(), reason="mock backend is only used on boxes without a GPU")
 
-SET = settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+# The gate run (driver: `pytest -m "not gpu"`) is DERANDOMISED so that it cannot flake; the exploratory campaign is
+#   B2S_HYP_EXAMPLES=3000 python -m pytest tests/test_property_cpu.py   (random seeds; failures become regular tests)
+_N = int(os.environ.get("B2S_HYP_EXAMPLES", "0"))
+SET = settings(max_examples=_N or 60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=not _N,
+               database=None)
 
 
 @pytest.fixture(autouse=True)

@@ -1,0 +1,639 @@
+#!/usr/bin/env python
+"""Differential fuzzing of the host layer against the REFERENCE itself (authoring container only).
+
+    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family dot|elemwise|reduce|all] [-v]
+
+Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
+upstream package, numba kernels), this package runs on the NumPy mock of the kernel layer (tests/_mock_kernels.py) --
+there is no GPU here, so what is fuzzed is everything ABOVE the C ABI: axis bookkeeping, broadcasting, dtype promotion,
+fill values, result formats, error classes.  The kernels are compared with the oracle / golden vectors on the GPU
+(tests/, -m gpu).  Random shapes (0-4 dims, zero-length axes included), densities, dtypes, fill values, formats,
+operators; every result is compared field by field: class, shape, dtype, fill value, and the stored entries EXACTLY
+(COO: coords + data; GCXS: compressed axes, indptr, indices -- including the reference's unsorted column order after a
+CSR x CSR product -- and data).  Inputs are small integers stored in the drawn dtype, so every sum is exact in any order.
+An exception on one side must be the same class on the other.  Every mismatch prints a reproducer line.
+
+Nothing here is imported by the product, the tests, or bench.py.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import traceback
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+import sparse as R  # noqa: E402  (the reference)
+
+import _mock_kernels  # noqa: E402
+
+_mock_kernels.install()
+import sparse_b200 as S  # noqa: E402
+
+assert "baseline/_ref" in R.__file__, R.__file__
+
+FLOATS = ["float64", "float32"]
+INTS = ["int64", "int32", "int16", "int8", "uint8", "uint32"]
+DTYPES = FLOATS * 3 + INTS + ["bool"]
+
+
+def eq_scalar(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype != b.dtype:
+        return False
+    return bool(np.array_equal(a, b, equal_nan=a.dtype.kind in "fc"))
+
+
+def arr_eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return False
+    if a.dtype.kind in "fc" or b.dtype.kind in "fc":
+        return bool(np.array_equal(a, b, equal_nan=True))
+    return bool(np.array_equal(a, b))
+
+
+def compare(got, want, exact_layout=True):
+    """None when equal, else a description."""
+    if isinstance(want, R.COO):
+        if not isinstance(got, S.COO):
+            return f"class {type(got).__name__} != COO"
+        if tuple(got.shape) != tuple(want.shape):
+            return f"shape {got.shape} != {want.shape}"
+        if got.dtype != want.dtype:
+            return f"dtype {got.dtype} != {want.dtype}"
+        if not eq_scalar(got.fill_value, want.fill_value):
+            return f"fill {got.fill_value!r} ({np.asarray(got.fill_value).dtype}) != {want.fill_value!r} ({np.asarray(want.fill_value).dtype})"
+        if exact_layout:
+            if not arr_eq(np.asarray(got.coords), want.coords):
+                if arr_eq(got.todense(), want.todense()):
+                    return f"coords differ (dense equal): nnz {got.nnz} vs {want.nnz}"
+                return "coords differ and dense differs"
+            if not arr_eq(np.asarray(got.data), want.data):
+                return "data differ"
+        elif not arr_eq(got.todense(), want.todense()):
+            return "dense differs"
+        return None
+    if isinstance(want, R.GCXS):
+        if not isinstance(got, S.GCXS):
+            return f"class {type(got).__name__} != GCXS"
+        if tuple(got.shape) != tuple(want.shape):
+            return f"shape {got.shape} != {want.shape}"
+        if got.dtype != want.dtype:
+            return f"dtype {got.dtype} != {want.dtype}"
+        if not eq_scalar(got.fill_value, want.fill_value):
+            return f"fill {got.fill_value!r} != {want.fill_value!r}"
+        ca_g = tuple(got.compressed_axes) if got.compressed_axes is not None else None
+        ca_w = tuple(want.compressed_axes) if want.compressed_axes is not None else None
+        if ca_g != ca_w:
+            return f"compressed_axes {ca_g} != {ca_w}"
+        if exact_layout:
+            if not arr_eq(np.asarray(got.indptr), np.asarray(want.indptr)):
+                return "indptr differ" + (" (dense equal)" if arr_eq(got.todense(), want.todense()) else "")
+            if not arr_eq(np.asarray(got.indices), want.indices):
+                return "indices differ" + (" (dense equal)" if arr_eq(got.todense(), want.todense()) else "")
+            if not arr_eq(np.asarray(got.data), want.data):
+                return "data differ"
+        elif not arr_eq(got.todense(), want.todense()):
+            return "dense differs"
+        return None
+    if isinstance(want, R.DOK):
+        if not isinstance(got, S.DOK):
+            return f"class {type(got).__name__} != DOK"
+        return None if arr_eq(got.todense(), want.todense()) else "dense differs"
+    if isinstance(got, S.SparseArray):
+        return f"class {type(got).__name__} != {type(want).__name__}"
+    g, w = np.asarray(got), np.asarray(want)
+    if g.shape != w.shape:
+        return f"dense shape {g.shape} != {w.shape}"
+    if g.dtype != w.dtype:
+        return f"dense dtype {g.dtype} != {w.dtype}"
+    if not arr_eq(g, w):
+        return "dense values differ"
+    if isinstance(want, np.ndarray) != isinstance(got, np.ndarray) and not (np.isscalar(want) or np.isscalar(got)):
+        return f"container {type(got).__name__} != {type(want).__name__}"
+    return None
+
+
+def draw_shape(rng, lo=0, hi=4, zero_ok=True):
+    nd = int(rng.integers(lo, hi + 1))
+    return tuple(int(rng.integers(0 if (zero_ok and rng.random() < 0.07) else 1, 6)) for _ in range(nd))
+
+
+def draw_dense(rng, shape, dtype, density=None, fill=0):
+    density = rng.choice([0.0, 0.15, 0.5, 1.0]) if density is None else density
+    dt = np.dtype(dtype)
+    if dt.kind == "b":
+        vals = rng.random(shape) < 0.5
+        d = np.full(shape, bool(fill), dtype=dt)
+    else:
+        lo = 0 if dt.kind == "u" else -4
+        vals = rng.integers(lo, 5, size=shape).astype(dt)
+        d = np.full(shape, fill, dtype=dt)
+    mask = rng.random(shape) < density
+    d[mask] = vals[mask]
+    return d
+
+
+def both(d, fmt, fill=0, rng=None):
+    """The same array in both packages (fmt: coo | gcxs | dense)."""
+    if fmt == "dense":
+        return d, d
+    fv = np.asarray(fill, dtype=d.dtype)[()]
+    r = R.COO.from_numpy(d, fill_value=fv)
+    s = S.COO.from_numpy(d, fill_value=fv)
+    if fmt == "gcxs":
+        kw = {}
+        if d.ndim >= 2 and rng is not None and rng.random() < 0.5:
+            k = int(rng.integers(1, d.ndim))
+            kw["compressed_axes"] = tuple(sorted(int(x) for x in rng.choice(d.ndim, size=k, replace=False)))
+        r = r.asformat("gcxs", **kw)
+        s = s.asformat("gcxs", **kw)
+    return s, r
+
+
+def run_pair(f_s, f_r):
+    """Run both sides; returns (got, want, err_s, err_r)."""
+    got = want = es = er = None
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            want = f_r()
+        except Exception as e:  # noqa: BLE001
+            er = e
+        try:
+            got = f_s()
+        except Exception as e:  # noqa: BLE001
+            es = e
+    return got, want, es, er
+
+
+def ref_crash(er):
+    """Crashes INSIDE the reference on degenerate input -- a zero-length contraction (ZeroDivisionError), all axes of a
+    GCXS array given as a permuted tuple (min() of an empty list), the fill value's contribution computed in a narrow
+    dtype (OverflowError).  A result here (NumPy's) is not a parity failure."""
+    return (isinstance(er, ZeroDivisionError) or "min() iterable argument is empty" in str(er)
+            or (isinstance(er, OverflowError) and "out of bounds for" in str(er)))
+
+
+class Stats:
+    def __init__(self, verbose):
+        self.n = self.bad = self.errs_both = self.ref_crashes = self.ref_wrong = 0
+        self.kinds = {}
+        self.verbose = verbose
+
+    def report(self, family, desc, msg):
+        self.bad += 1
+        key = (family, msg.split(":")[0][:60])
+        self.kinds[key] = self.kinds.get(key, 0) + 1
+        if self.kinds[key] <= 3 or self.verbose:
+            print(f"MISMATCH [{family}] {desc}\n    -> {msg}", flush=True)
+
+    def check(self, family, desc, f_s, f_r, exact_layout=True, truth=None):
+        """`truth`: NumPy's dense answer where one exists -- a reference result that disagrees with it while this
+        package agrees (the uninitialised tail `_dot_csc_ndarray_sparse` reads, DESIGN s4) is counted, not reported."""
+        self.n += 1
+        got, want, es, er = run_pair(f_s, f_r)
+        if truth is not None and es is None and er is None:
+            try:
+                t = truth()
+                dense = lambda v: v.todense() if hasattr(v, "todense") else np.asarray(v)  # noqa: E731
+                if not arr_eq(dense(want), t) and arr_eq(dense(got), t):
+                    self.ref_wrong += 1
+                    return
+            except Exception:  # noqa: BLE001
+                pass
+        if er is not None or es is not None:
+            if er is not None and es is not None:
+                self.errs_both += 1
+                if type(es).__name__ != type(er).__name__ and not isinstance(es, type(er)):
+                    self.report(family, desc, f"error class: {type(es).__name__}({es}) != {type(er).__name__}({er})")
+                return
+            if er is not None and ref_crash(er):
+                self.ref_crashes += 1
+                return
+            if er is not None:
+                self.report(family, desc, f"reference raised {type(er).__name__}({er}); here: result")
+            else:
+                tb = traceback.format_exception(type(es), es, es.__traceback__)[-3:]
+                self.report(family, desc, f"here raised {type(es).__name__}({es}); reference: result\n      " +
+                            "      ".join(tb))
+            return
+        msg = compare(got, want, exact_layout)
+        if msg:
+            self.report(family, desc, msg)
+
+
+# ------------------------------------------------------------------------------------------------------------ families
+def fam_dot(rng, st, i):
+    kind = rng.choice(["tensordot", "matmul", "dot"])
+    dt_a, dt_b = rng.choice(DTYPES[:-1]), rng.choice(DTYPES[:-1])
+    fa, fb = rng.choice(["coo", "gcxs", "dense"]), rng.choice(["coo", "gcxs", "dense"])
+    if fa == "dense" and fb == "dense":
+        fa = "coo"
+    if kind == "tensordot":
+        nd_a, nd_b = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        k = int(rng.integers(0, min(nd_a, nd_b) + 1))
+        ax_a = [int(x) for x in rng.choice(nd_a, size=k, replace=False)]
+        ax_b = [int(x) for x in rng.choice(nd_b, size=k, replace=False)]
+        sa = [int(rng.integers(1, 5)) for _ in range(nd_a)]
+        sb = [int(rng.integers(1, 5)) for _ in range(nd_b)]
+        for x, y in zip(ax_a, ax_b):
+            sb[y] = sa[x]
+        if rng.random() < 0.05 and k:
+            sb[ax_b[0]] += 1  # shape mismatch -> error parity
+        if rng.random() < 0.06:
+            sa[int(rng.integers(nd_a))] = 0
+            for x, y in zip(ax_a, ax_b):
+                sb[y] = sa[x]
+        form = rng.random()
+        if form < 0.25 and k and ax_a == list(range(nd_a - k, nd_a)) and ax_b == list(range(k)):
+            axes = k
+        elif form < 0.4 and k == 1:
+            axes = (ax_a[0] - (nd_a if rng.random() < 0.5 else 0), ax_b[0])
+        else:
+            axes = (ax_a, ax_b)
+        rt_name = rng.choice(["none", "none", "coo", "gcxs", "dense"])
+    else:
+        K = int(rng.integers(1, 5))
+        if kind == "matmul":
+            batch = draw_shape(rng, 0, 2, zero_ok=False)
+            ba = tuple(1 if rng.random() < 0.3 else b for b in batch)[int(rng.integers(0, len(batch) + 1)):]
+            bb = tuple(1 if rng.random() < 0.3 else b for b in batch)[int(rng.integers(0, len(batch) + 1)):]
+            sa = list(ba) + ([int(rng.integers(1, 5))] if rng.random() < 0.85 or ba else []) + [K]
+            sb = list(bb) + [K] + ([int(rng.integers(1, 5))] if rng.random() < 0.85 or bb else [])
+        else:
+            sa = list(draw_shape(rng, 0, 2, zero_ok=False)) + [K]
+            sb = list(draw_shape(rng, 0, 1, zero_ok=False)) + [K] + ([int(rng.integers(1, 5))] if rng.random() < 0.8 else [])
+            if len(sb) == 1:
+                pass
+        axes, rt_name = None, "none"
+    da = draw_dense(rng, tuple(sa), dt_a)
+    db = draw_dense(rng, tuple(sb), dt_b)
+    a_s, a_r = both(da, fa, rng=rng)
+    b_s, b_r = both(db, fb, rng=rng)
+    rts_s = {"none": None, "coo": S.COO, "gcxs": S.GCXS, "dense": np.ndarray}
+    rts_r = {"none": None, "coo": R.COO, "gcxs": R.GCXS, "dense": np.ndarray}
+    ca = lambda x: getattr(x, "compressed_axes", None)  # noqa: E731
+    desc = (f"#{i} {kind} a={fa}{tuple(sa)}:{dt_a} ca={ca(a_r)} b={fb}{tuple(sb)}:{dt_b} ca={ca(b_r)} axes={axes} "
+            f"rt={rt_name}")
+    if kind == "tensordot":
+        st.check("dot", desc, lambda: S.tensordot(a_s, b_s, axes, return_type=rts_s[rt_name]),
+                 lambda: R.tensordot(a_r, b_r, axes, return_type=rts_r[rt_name]),
+                 truth=lambda: np.tensordot(da, db, axes))
+    elif kind == "matmul":
+        st.check("dot", desc, lambda: S.matmul(a_s, b_s), lambda: R.matmul(a_r, b_r), truth=lambda: np.matmul(da, db))
+    else:
+        st.check("dot", desc, lambda: S.dot(a_s, b_s), lambda: R.dot(a_r, b_r), truth=lambda: np.dot(da, db))
+
+
+BINARY = ["add", "subtract", "multiply", "maximum", "minimum", "greater", "less", "greater_equal", "less_equal",
+          "equal", "not_equal", "true_divide", "floor_divide", "power", "logical_and", "logical_or", "logical_xor",
+          "bitwise_and", "bitwise_or", "bitwise_xor", "remainder", "fmax", "fmin"]  # hypot, arctan2, copysign: outside the CUDA op set (TypeError by design)
+UNARY = ["negative", "abs", "sign", "square", "sqrt", "sin", "expm1", "log1p", "tanh", "isnan", "isfinite", "floor",
+         "ceil", "rint", "logical_not", "exp", "cos", "positive", "conj", "invert", "signbit", "trunc", "deg2rad"]
+
+
+F16_FROM_8BIT = {"sqrt", "sin", "expm1", "log1p", "tanh", "exp", "cos", "deg2rad", "floor", "ceil", "rint", "trunc"}
+
+
+def fam_elemwise(rng, st, i):
+    mode = rng.choice(["binary", "binary", "binary", "unary", "scalar", "nary"])
+    base = draw_shape(rng, 0, 4)
+    dt_a = rng.choice(DTYPES)
+    fill_a = rng.choice([0, 0, 0, 1, 2]) if dt_a != "bool" else rng.choice([0, 0, 1])
+    fa = rng.choice(["coo", "coo", "gcxs"])
+    da = draw_dense(rng, base, dt_a, fill=fill_a)
+    a_s, a_r = both(da, fa, fill=fill_a, rng=rng)
+    if mode == "unary":
+        name = rng.choice(UNARY)
+        if np.dtype(dt_a).itemsize == 1 and name in F16_FROM_8BIT:
+            name = "negative" if dt_a != "bool" else "logical_not"  # float16 loops: outside the CUDA dtype matrix
+        f = getattr(np, name)
+        st.check("elemwise", f"#{i} np.{name}({fa}{base}:{dt_a} fill={fill_a})", lambda: f(a_s), lambda: f(a_r))
+        return
+    if mode == "scalar":
+        name = rng.choice(BINARY)
+        f = getattr(np, name)
+        sc = rng.choice([0, 1, 2, -1, 2.5, True, np.float32(3), np.int8(2), np.float64("nan")])
+        left = rng.random() < 0.5
+        st.check("elemwise", f"#{i} np.{name}({'scalar,' if left else ''}{fa}{base}:{dt_a} fill={fill_a}"
+                             f"{'' if left else ',scalar'}) scalar={sc!r}",
+                 (lambda: f(sc, a_s)) if left else (lambda: f(a_s, sc)),
+                 (lambda: f(sc, a_r)) if left else (lambda: f(a_r, sc)))
+        return
+    # second operand: a broadcast-compatible shape
+    other = tuple(s if rng.random() < 0.65 else 1 for s in base)
+    other = other[int(rng.integers(0, len(other) + 1)):]
+    if rng.random() < 0.2:
+        other = tuple(int(rng.integers(1, 4)) for _ in range(int(rng.integers(0, 2)))) + other
+    if rng.random() < 0.04 and other:
+        other = other[:-1] + (other[-1] + 1,)  # incompatible -> error parity
+    dt_b = rng.choice(DTYPES)
+    fill_b = rng.choice([0, 0, 0, 1, 3]) if dt_b != "bool" else rng.choice([0, 0, 1])
+    fb = rng.choice(["coo", "coo", "gcxs", "dense"])
+    db = draw_dense(rng, other, dt_b, fill=fill_b)
+    b_s, b_r = both(db, fb, fill=fill_b, rng=rng)
+    if mode == "nary":
+        dc = draw_dense(rng, base, rng.choice(FLOATS + ["int64"]))
+        c_s, c_r = both(dc, "coo")
+        which = rng.choice(["where", "fma", "clip"])
+        if which == "where":
+            st.check("elemwise", f"#{i} where(a{base}:{dt_a}!=0, b{other}:{dt_b} {fb}, c)",
+                     lambda: S.where(a_s != 0, b_s, c_s), lambda: R.where(a_r != 0, b_r, c_r))
+        elif which == "fma":
+            st.check("elemwise", f"#{i} elemwise(lambda x,y,z: x*y+z) a{base}:{dt_a} f={fill_a} b{other}:{dt_b} {fb} f={fill_b}",
+                     lambda: S.elemwise(lambda x, y, z: x * y + z, a_s, b_s, c_s),
+                     lambda: R.elemwise(lambda x, y, z: x * y + z, a_r, b_r, c_r))
+        else:
+            st.check("elemwise", f"#{i} clip a{base}:{dt_a} f={fill_a}",
+                     lambda: S.clip(a_s, -1, 2), lambda: R.clip(a_r, -1, 2))
+        return
+    name = rng.choice(BINARY)
+    if name == "power" and (np.dtype(dt_a).itemsize < 4 or np.dtype(dt_b).itemsize < 4 or "uint32" in (dt_a, dt_b)):
+        name = "multiply"  # integer power in a narrow / unsigned type: outside the CUDA dtype matrix (TypeError)
+    f = getattr(np, name)
+    swap = rng.random() < 0.5
+    desc = (f"#{i} np.{name}({fa}{base}:{dt_a} fill={fill_a}, {fb}{other}:{dt_b} fill={fill_b})"
+            f"{' swapped' if swap else ''}")
+    if swap:
+        st.check("elemwise", desc, lambda: f(b_s, a_s), lambda: f(b_r, a_r))
+    else:
+        st.check("elemwise", desc, lambda: f(a_s, b_s), lambda: f(a_r, b_r))
+
+
+REDUCE = ["sum", "prod", "max", "min", "any", "all", "mean", "var", "std", "nansum", "nanmax",
+          "nanmin", "nanprod", "nanmean"]
+
+
+def fam_reduce(rng, st, i):
+    shape = draw_shape(rng, 1, 4)
+    dt = rng.choice(DTYPES)
+    fill = rng.choice([0, 0, 0, 1, 2]) if dt != "bool" else rng.choice([0, 0, 1])
+    fmt = rng.choice(["coo", "coo", "gcxs"])
+    name = rng.choice(REDUCE)
+    if np.dtype(dt).itemsize < 4 and name in ("sum", "prod", "nansum", "nanprod"):
+        fill = 0  # the reference multiplies / exponentiates the fill value IN the narrow dtype (wraps; NumPy does not)
+    d = draw_dense(rng, shape, dt, fill=fill)
+    if name.startswith("nan") and np.dtype(dt).kind == "f" and d.size and rng.random() < 0.7:
+        d = d.copy()
+        d[rng.random(shape) < 0.2] = np.nan
+    x_s, x_r = both(d, fmt, fill=fill, rng=rng)
+    nd = len(shape)
+    r = rng.random()
+    if r < 0.3:
+        axis = None
+    elif r < 0.7:
+        axis = int(rng.integers(-nd, nd))
+    else:
+        k = int(rng.integers(1, nd + 1))
+        axis = tuple(int(x) for x in rng.choice(nd, size=k, replace=False))
+    kw = {"axis": axis}
+    if name in ("argmax", "argmin"):
+        if isinstance(axis, tuple):
+            kw["axis"] = axis[0]
+    if rng.random() < 0.4:
+        kw["keepdims"] = True
+    if name in ("sum", "prod", "mean", "var", "std", "nansum", "nanmean") and rng.random() < 0.3:
+        kw["dtype"] = rng.choice(["float64", "float32"] + ([] if name in ("mean", "var", "std", "nanmean") else ["int64"]))
+    if name in ("var", "std") and rng.random() < 0.4:
+        kw["ddof"] = 1
+    via = rng.choice(["func", "method", "numpy"])
+    desc = f"#{i} {name}[{via}]({fmt}{shape}:{dt} fill={fill}, {kw})"
+    exact = name not in ("mean", "var", "std", "nanmean")  # compositions: values to rounding, compared densely below
+
+    def call(mod, x):
+        if via == "method" and hasattr(x, name):
+            return getattr(x, name)(**kw)
+        if via == "numpy" and hasattr(np, name):
+            return getattr(np, name)(x, **kw)
+        return getattr(mod, name)(x, **kw)
+
+    if exact:
+        st.check("reduce", desc, lambda: call(S, x_s), lambda: call(R, x_r))
+    else:
+        st.n += 1
+        got, want, es, er = run_pair(lambda: call(S, x_s), lambda: call(R, x_r))
+        if es is not None or er is not None:
+            if es is None and ref_crash(er):
+                st.ref_crashes += 1
+            elif (es is None) != (er is None):
+                st.report("reduce", desc, f"error on one side only: here={es!r} reference={er!r}")
+            elif type(es).__name__ != type(er).__name__ and not isinstance(es, type(er)):
+                st.report("reduce", desc, f"error class: {type(es).__name__}({es}) != {type(er).__name__}({er})")
+            return
+        g = got.todense() if hasattr(got, "todense") else np.asarray(got)
+        w = want.todense() if hasattr(want, "todense") else np.asarray(want)
+        if type(got).__name__ != type(want).__name__ and (hasattr(got, "todense") or hasattr(want, "todense")):
+            st.report("reduce", desc, f"class {type(got).__name__} != {type(want).__name__}")
+        elif g.shape != w.shape or g.dtype != w.dtype:
+            st.report("reduce", desc, f"shape/dtype {g.shape}:{g.dtype} != {w.shape}:{w.dtype}")
+        elif not np.allclose(g, w, rtol=1e-5 if g.dtype == np.float32 else 1e-12, atol=1e-6 if g.dtype == np.float32 else 1e-12, equal_nan=True):
+            st.report("reduce", desc, "values differ beyond rounding")
+
+
+def fam_formats(rng, st, i):
+    """Construction and format changes: COO from raw coords with duplicates / unsorted
+    coords / explicit fill entries, GCXS with drawn compressed axes, transpose / reshape / change_compressed_axes /
+    asformat round trips, broadcast_to."""
+    shape = draw_shape(rng, 1, 4)
+    dt = rng.choice(DTYPES)
+    fill = rng.choice([0, 0, 1]) if dt != "bool" else rng.choice([0, 0, 1])
+    nd = len(shape)
+    what = rng.choice(["ctor", "gcxs_chain", "coo_chain", "broadcast_to", "getitem"])
+    if what == "ctor":
+        n = int(rng.integers(0, 12)) if all(shape) else 0
+        coords = np.stack([rng.integers(0, max(s, 1), size=n) for s in shape]) if n else np.zeros((nd, 0), dtype=np.int64)
+        data = (rng.integers(0 if np.dtype(dt).kind in "ub" else -3, 4, size=n)).astype(dt)
+        kw = {}
+        if rng.random() < 0.3:
+            kw["prune"] = True
+        if rng.random() < 0.3:
+            kw["fill_value"] = np.asarray(fill, dtype=dt)[()]
+        desc = f"#{i} COO(coords[{nd}x{n}], data:{dt}, shape={shape}, {kw})"
+        st.check("formats", desc, lambda: S.COO(coords, data, shape=shape, **kw),
+                 lambda: R.COO(coords, data, shape=shape, **kw))
+        return
+    d = draw_dense(rng, shape, dt, fill=fill)
+    if what == "broadcast_to":
+        lead = tuple(int(rng.integers(1, 4)) for _ in range(int(rng.integers(0, 3))))
+        src = tuple(1 if rng.random() < 0.4 else s for s in shape)
+        d2 = draw_dense(rng, src, dt, fill=fill)
+        x_s, x_r = both(d2, "coo", fill=fill)
+        target = lead + shape
+        st.check("formats", f"#{i} broadcast_to(coo{src}:{dt} fill={fill}, {target})",
+                 lambda: S.broadcast_to(x_s, target), lambda: R.broadcast_to(x_r, target))
+        return
+    # GCXS indexing is left out: upstream's result for None / negative-step indices is not NumPy's (axes land in
+    # other positions), and indexing is not a row of SURVEY s8
+    fmt = "gcxs" if what == "gcxs_chain" else ("coo" if what == "getitem" else rng.choice(["coo", "gcxs"]))
+    x_s, x_r = both(d, fmt, fill=fill, rng=rng)
+    if what == "getitem":
+        idx = []
+        for s in shape[: int(rng.integers(1, nd + 1))]:
+            r = rng.random()
+            if r < 0.35 and s:
+                idx.append(int(rng.integers(-s, s)))
+            elif r < 0.75:
+                lo, hi = sorted(int(v) for v in rng.integers(-s - 1, s + 2, size=2))
+                idx.append(slice(lo if rng.random() < 0.8 else None, hi if rng.random() < 0.8 else None,
+                                 int(rng.choice([1, 1, 2, -1])) if rng.random() < 0.4 else None))
+            elif r < 0.85:
+                idx.append(None)
+            elif r < 0.93 and Ellipsis not in idx:
+                idx.append(Ellipsis)
+            else:
+                idx.append(slice(None))
+        idx = tuple(idx)
+        st.check("formats", f"#{i} {fmt}{shape}:{dt} fill={fill} ca={getattr(x_r, 'compressed_axes', None)} [{idx}]",
+                 lambda: x_s[idx], lambda: x_r[idx])
+        return
+    steps = []
+    for _ in range(int(rng.integers(1, 4))):
+        op = rng.choice(["transpose", "reshape", "cca", "asformat", "T", "astype", "tocoo", "flatten"])
+        if op == "transpose":
+            steps.append(("transpose", tuple(int(v) for v in rng.permutation(nd))))
+        elif op == "reshape":
+            steps.append(("reshape", None))
+        elif op == "cca":
+            steps.append(("cca", None))
+        elif op == "asformat":
+            steps.append(("asformat", rng.choice(["coo", "gcxs"])))
+        elif op == "astype":
+            steps.append(("astype", rng.choice(["float64", "float32", "int64", "int32", "bool"])))
+        else:
+            steps.append((op, None))
+    seed = int(rng.integers(1 << 30))
+
+    def run(x, mod):
+        r2 = np.random.default_rng(seed)
+        for op, arg in steps:
+            is_g = type(x).__name__ == "GCXS"
+            if op == "transpose":
+                if len(arg) == x.ndim:
+                    x = x.transpose(arg)
+            elif op == "reshape":
+                n = int(np.prod(x.shape))
+                cands = [(n,), (-1,)] + [(k, n // k) for k in (1, 2, 3, 4, 5, 6) if n and n % k == 0] + \
+                        [(k, -1) for k in (2, 3) if n and n % k == 0] + [(1, n, 1)]
+                x = x.reshape(cands[int(r2.integers(len(cands)))])
+            elif op == "cca":
+                if is_g and x.ndim >= 2:
+                    k = int(r2.integers(1, x.ndim))
+                    x = x.change_compressed_axes(tuple(sorted(int(v) for v in r2.choice(x.ndim, size=k, replace=False))))
+            elif op == "asformat":
+                x = x.asformat(arg)
+            elif op == "T":
+                x = x.T
+            elif op == "astype":
+                x = x.astype(arg)
+            elif op == "tocoo":
+                x = x.tocoo() if is_g else x
+            elif op == "flatten":
+                x = x.flatten()
+        return x
+
+    st.check("formats", f"#{i} {fmt}{shape}:{dt} fill={fill} ca={getattr(x_r, 'compressed_axes', None)} -> {steps} seed={seed}",
+             lambda: run(x_s, S), lambda: run(x_r, R))
+
+
+def fam_protocol(rng, st, i):
+    """`__array_ufunc__` beyond the plain call (row a-17): ufunc.reduce, ufunc.outer, out=, in-place operators."""
+    shape = draw_shape(rng, 1, 3, zero_ok=False)
+    dt = rng.choice(FLOATS + ["int64", "int32"])
+    fill = rng.choice([0, 0, 2])
+    fmt = rng.choice(["coo", "gcxs"])
+    d = draw_dense(rng, shape, dt, fill=fill)
+    x_s, x_r = both(d, fmt, fill=fill, rng=rng)
+    what = rng.choice(["reduce", "outer", "out", "inplace"])
+    if what in ("out", "inplace") and fmt == "gcxs":
+        # upstream's `out=` / in-place update of a GCXS array leaves a broken object behind (`_make_shallow_copy_of`
+        # copies the COO result's attributes: no `_compressed_axes`), so there is nothing to compare with
+        fmt = "coo"
+        x_s, x_r = both(d, fmt, fill=fill)
+    if what == "reduce":
+        uf = getattr(np, rng.choice(["add", "multiply", "maximum", "minimum", "logical_and", "logical_or", "bitwise_or"]))
+        if uf is np.bitwise_or and np.dtype(dt).kind == "f":
+            uf = np.add
+        axis = int(rng.integers(-len(shape), len(shape))) if rng.random() < 0.7 else None
+        kw = {"axis": axis}
+        if rng.random() < 0.3:
+            kw["keepdims"] = True
+        st.check("protocol", f"#{i} np.{uf.__name__}.reduce({fmt}{shape}:{dt} fill={fill}, {kw})",
+                 lambda: uf.reduce(x_s, **kw), lambda: uf.reduce(x_r, **kw))
+    elif what == "outer":
+        d2 = draw_dense(rng, draw_shape(rng, 1, 2, zero_ok=False), dt)
+        y_s, y_r = both(d2, "coo")
+        uf = getattr(np, rng.choice(["multiply", "add", "maximum"]))
+        st.check("protocol", f"#{i} np.{uf.__name__}.outer({fmt}{shape}:{dt} fill={fill}, coo{d2.shape})",
+                 lambda: uf.outer(x_s, y_s), lambda: uf.outer(x_r, y_r))
+    elif what == "out":
+        d2 = draw_dense(rng, shape, dt, fill=0)
+        y_s, y_r = both(d2, fmt, rng=None)
+        odt = rng.choice([dt, "float64", "float32"])
+        o_s, o_r = both(np.zeros(shape, dtype=odt), fmt)
+        uf = getattr(np, rng.choice(["add", "multiply", "subtract"]))
+
+        def go(a, b, o):
+            r = uf(a, b, out=o)
+            assert r is o
+            return r
+
+        st.check("protocol", f"#{i} np.{uf.__name__}({fmt}{shape}:{dt} fill={fill}, {fmt}, out={fmt}:{odt})",
+                 lambda: go(x_s, y_s, o_s), lambda: go(x_r, y_r, o_r))
+    else:
+        d2 = draw_dense(rng, tuple(s if rng.random() < 0.7 else 1 for s in shape), dt)
+        y_s, y_r = both(d2, rng.choice(["coo", "dense"]))
+        opn = rng.choice(["iadd", "imul", "isub"])
+        import operator
+
+        def go(a, b):
+            a = a.copy() if hasattr(a, "copy") else a
+            return getattr(operator, opn)(a, b)
+
+        st.check("protocol", f"#{i} {opn}({fmt}{shape}:{dt} fill={fill}, {type(y_r).__name__}{d2.shape})",
+                 lambda: go(x_s, y_s), lambda: go(x_r, y_r))
+
+
+FAMILIES = {"dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+            "protocol": fam_protocol}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=3000)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--family", default="all")
+    ap.add_argument("--only", type=int, default=-1, help="re-run one case index")
+    ap.add_argument("-v", action="store_true")
+    args = ap.parse_args()
+    fams = list(FAMILIES) if args.family == "all" else args.family.split(",")
+    st = Stats(args.v)
+    for fam in fams:
+        for i in range(args.cases):
+            if args.only >= 0 and i != args.only:
+                continue
+            rng = np.random.default_rng([args.seed, i, sum(map(ord, fam))])
+            try:
+                FAMILIES[fam](rng, st, i)
+            except Exception as e:  # noqa: BLE001  (a bug of the fuzzer itself or of input construction)
+                st.report(fam, f"#{i}", f"fuzzer/construct error {type(e).__name__}: {e}\n" +
+                          "".join(traceback.format_exception(type(e), e, e.__traceback__)[-4:]))
+        print(f"== {fam}: {st.n} comparisons so far, {st.bad} mismatches, {st.errs_both} raised on both sides", flush=True)
+    print("\nmismatch classes:")
+    for (fam, k), v in sorted(st.kinds.items(), key=lambda kv: -kv[1]):
+        print(f"  {v:5d}  [{fam}] {k}")
+    print(f"TOTAL {st.n} comparisons, {st.bad} mismatches ({st.errs_both} raised the same error class on both sides, "
+          f"{st.ref_crashes} crashed inside the reference only, {st.ref_wrong} reference results contradicted by NumPy)")
+    return 1 if st.bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
