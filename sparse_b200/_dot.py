@@ -351,12 +351,14 @@ def _dot(a, b, return_type=None):
 
         def widen(x):
             if isinstance(x, SparseArray):
-                return x.astype(W) if x.dtype != W else x
+                if x.dtype == W:
+                    return x
+                return x.astype(W, _keep_format=True) if isinstance(x, GCXS) else x.astype(W)
             return Kn.cast(D.upload(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x, W)
 
         out = _dot(widen(a), widen(b), return_type)
         if isinstance(out, SparseArray):
-            return out.astype(dtr)
+            return out.astype(dtr, _keep_format=True) if isinstance(out, GCXS) else out.astype(dtr)
         out = Kn.cast(out if D.is_device_tensor(out) else D.upload(np.ascontiguousarray(out)), dtr)
         return D.download(out) if host_in else out
     out_shape = (a.shape[0], b.shape[1])

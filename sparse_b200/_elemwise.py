@@ -365,9 +365,9 @@ class _Elemwise:
         func = self.func
         if func is np.conjugate and a.dtype.kind in "fiu":
             func = np.positive  # conj of a real array is the array itself
-        if a.dtype == np.bool_ and func in (np.invert, np.absolute):
-            if func is np.absolute:
-                return a.copy()  # |bool| is the array itself (NumPy keeps bool)
+        if a.dtype == np.bool_ and func in (np.invert, np.absolute, np.conjugate):
+            if func is not np.invert:
+                return a.copy()  # |bool| and conj(bool) are the array itself (NumPy keeps bool)
             func = np.logical_not  # ~bool
         op = _op_code(func, _UNARY, "unary")
         out_dt, T = _resolve(func, _stand_in(a))

@@ -384,14 +384,15 @@ class GCXS(SparseArray):
             return self.todense()
         raise NotImplementedError(f"The given format is not supported: {format}")
 
-    def astype(self, dtype, casting="unsafe", copy=True):
-        """Cast; entries that become equal to the fill value are pruned, as upstream's elemwise-based astype does."""
+    def astype(self, dtype, casting="unsafe", copy=True, _keep_format=False):
+        """Cast; entries that become equal to the fill value are pruned, as upstream's elemwise-based astype does.
+        (`_keep_format`: internal casts of intermediate results stay GCXS also when the array is empty.)"""
         dtype = np.dtype(dtype)
         if self.dtype == dtype and not copy:
             return self
         if not np.can_cast(self.dtype, dtype, casting=casting):
             raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
-        if any(s == 0 for s in self.shape):
+        if any(s == 0 for s in self.shape) and not _keep_format:
             # upstream's astype is an elemwise call, and elemwise hands back the empty COO as it is (_umath.py:467-477)
             return self.tocoo().astype(dtype, casting=casting, copy=copy)
         data, indices, indptr = self._dev()

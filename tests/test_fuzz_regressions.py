@@ -129,3 +129,9 @@ def test_astype_of_an_empty_gcxs_is_the_empty_coo(sp):
     g = _gcxs(sp, np.ones((3, 2)), ca=(0,))
     r = g.astype("float32")
     assert isinstance(r, sp.GCXS) and tuple(r.compressed_axes) == (0,)
+
+
+def test_conj_of_bool_is_the_array(sp):
+    d = np.array([[True, False], [False, True]])
+    r = np.conj(sp.COO.from_numpy(d))
+    assert r.dtype == np.bool_ and np.array_equal(r.todense(), d)
