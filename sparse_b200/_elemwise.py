@@ -366,8 +366,10 @@ class _Elemwise:
         if func is np.conjugate and a.dtype.kind in "fiu":
             func = np.positive  # conj of a real array is the array itself
         if a.dtype == np.bool_ and func in (np.invert, np.absolute, np.conjugate):
-            if func is not np.invert:
-                return a.copy()  # |bool| and conj(bool) are the array itself (NumPy keeps bool)
+            if func is np.absolute:
+                return a.copy()  # |bool| is the array itself (NumPy keeps bool)
+            if func is np.conjugate:
+                return a.astype(np.int8)  # NumPy has no bool loop for conjugate: the int8 one runs
             func = np.logical_not  # ~bool
         op = _op_code(func, _UNARY, "unary")
         out_dt, T = _resolve(func, _stand_in(a))

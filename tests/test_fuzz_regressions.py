@@ -131,7 +131,7 @@ def test_astype_of_an_empty_gcxs_is_the_empty_coo(sp):
     assert isinstance(r, sp.GCXS) and tuple(r.compressed_axes) == (0,)
 
 
-def test_conj_of_bool_is_the_array(sp):
+def test_conj_of_bool_is_int8_as_in_numpy(sp):
     d = np.array([[True, False], [False, True]])
-    r = np.conj(sp.COO.from_numpy(d))
-    assert r.dtype == np.bool_ and np.array_equal(r.todense(), d)
+    r = np.conj(sp.COO.from_numpy(d, fill_value=True))
+    assert r.dtype == np.conj(d).dtype == np.int8 and np.array_equal(r.todense(), np.conj(d)) and r.fill_value == 1

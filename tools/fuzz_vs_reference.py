@@ -185,6 +185,11 @@ def ref_crash(er):
             or (isinstance(er, OverflowError) and "out of bounds for" in str(er)))
 
 
+def _has_duplicate_indices(g):
+    ip, ix = np.asarray(g.indptr).astype(np.int64), np.asarray(g.indices)
+    return any(len(np.unique(ix[ip[r]:ip[r + 1]])) < ip[r + 1] - ip[r] for r in range(len(ip) - 1))
+
+
 class Stats:
     def __init__(self, verbose):
         self.n = self.bad = self.errs_both = self.ref_crashes = self.ref_wrong = self.unmockable = 0
@@ -232,6 +237,9 @@ class Stats:
                             "      ".join(tb))
             return
         msg = compare(got, want, exact_layout)
+        if msg and isinstance(want, R.GCXS) and want.ndim >= 2 and _has_duplicate_indices(want):
+            self.ref_wrong += 1  # entries of the uninitialised tail (same column twice in one row, denormal values)
+            return
         if msg:
             self.report(family, desc, msg)
 
@@ -688,7 +696,94 @@ def fam_scipy(rng, st, i):
                  lambda: R.COO(coords, data, shape=(M, K), **kw) @ b_r, truth=None)
 
 
-FAMILIES = {"scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+def fam_einsum(rng, st, i):
+    """`einsum` (the MTTKRP example's call, examples/mttkrp_example.py upstream): random subscripts over 1-3 operands,
+    repeated indices inside an operand included, explicit and implicit outputs, COO / GCXS / dense operands."""
+    letters = "ijkl"
+    sizes = {c: int(rng.integers(1, 5)) for c in letters}
+    n_ops = int(rng.integers(1, 4))
+    subs, ops_s, ops_r, descs = [], [], [], []
+    dt = rng.choice(FLOATS + ["int64"])
+    for k in range(n_ops):
+        nd = int(rng.integers(1, 4))
+        sub = "".join(rng.choice(list(letters), size=nd, replace=rng.random() < 0.15))
+        shape = tuple(sizes[c] for c in sub)
+        fmt = rng.choice(["coo", "coo", "gcxs", "dense"]) if (k or n_ops > 1) else rng.choice(["coo", "gcxs"])
+        d = draw_dense(rng, shape, dt)
+        a_s, a_r = both(d, fmt, rng=rng)
+        subs.append(sub), ops_s.append(a_s), ops_r.append(a_r), descs.append(f"{fmt}{shape}")
+    if not any(isinstance(o, R.SparseArray) for o in ops_r):
+        ops_s[0], ops_r[0] = both(np.asarray(ops_r[0]), "coo")
+    used = sorted(set("".join(subs)))
+    expr = ",".join(subs)
+    if rng.random() < 0.7:
+        k = int(rng.integers(0, len(used) + 1))
+        out = "".join(rng.permutation(used)[:k])
+        expr += "->" + out
+    kw = {}
+    if rng.random() < 0.15:
+        kw["dtype"] = rng.choice(["float64", "float32"])
+    st.check("einsum", f"#{i} einsum('{expr}', {', '.join(descs)}) :{dt} {kw}",
+             lambda: S.einsum(expr, *ops_s, **kw), lambda: R.einsum(expr, *ops_r, **kw))
+
+
+def fam_helpers(rng, st, i):
+    """Row a-22: `equivalent` (bit-pattern equality with NaN == NaN, +0.0 != -0.0), `check_zero_fill_value`,
+    `normalize_axis`, `_dot_dtype` -- called directly on both sides."""
+    from sparse.numba_backend import _utils as RU
+    from sparse_b200 import _utils as SU
+
+    pool = [0.0, -0.0, 1.0, np.nan, -np.nan, np.inf, -np.inf, 2, 0, True, False, np.float32("nan"), np.float32(-0.0),
+            np.int8(0), np.uint8(3), np.float32(1.5), 1.5]
+    what = rng.choice(["equivalent", "czfv", "normalize_axis"])
+    if what == "equivalent":
+        def pick():
+            if rng.random() < 0.5:
+                return pool[int(rng.integers(len(pool)))]
+            dt = rng.choice(["float64", "float32", "int64", "bool"])
+            vals = [pool[int(rng.integers(len(pool)))] for _ in range(int(rng.integers(1, 5)))]
+            with np.errstate(all="ignore"):
+                return np.array([0 if (isinstance(v, float) and v != v and dt in ("int64", "bool")) or
+                                 (isinstance(v, (float, np.floating)) and np.isinf(v) and dt in ("int64", "bool")) else v
+                                 for v in vals]).astype(dt)
+        x, y = pick(), pick()
+        if np.ndim(x) and np.ndim(y) and np.shape(x) != np.shape(y):
+            y = np.resize(y, np.shape(x))
+        loose = bool(rng.random() < 0.5)
+        st.check("helpers", f"#{i} equivalent({x!r}, {y!r}, loose={loose})",
+                 lambda: np.asarray(SU.equivalent(x, y, loose=loose)), lambda: np.asarray(RU.equivalent(x, y, loose=loose)))
+    elif what == "czfv":
+        fills = [pool[int(rng.integers(len(pool)))] for _ in range(int(rng.integers(1, 3)))]
+        dts = [rng.choice(["float64", "float32", "int64"]) for _ in fills]
+        def mk(mod):
+            out = []
+            for f, dt in zip(fills, dts):
+                with np.errstate(all="ignore"):
+                    fv = np.asarray(f).astype(dt)[()] if not (np.asarray(f).dtype.kind == "f" and not np.isfinite(f) and dt == "int64") else np.int64(1)
+                out.append(mod.COO.from_numpy(np.full((2, 2), fv, dtype=dt), fill_value=fv))
+            return out
+        loose = bool(rng.random() < 0.7)
+        st.check("helpers", f"#{i} check_zero_fill_value(fills={fills} as {dts}, loose={loose})",
+                 lambda: SU.check_zero_fill_value(*mk(S), loose=loose), lambda: RU.check_zero_fill_value(*mk(R), loose=loose))
+    else:
+        nd = int(rng.integers(1, 5))
+        r = rng.random()
+        if r < 0.3:
+            axis = int(rng.integers(-nd - 1, nd + 1))
+        elif r < 0.7:
+            axis = tuple(int(v) for v in rng.integers(-nd - 1, nd + 1, size=int(rng.integers(0, 4))))
+        elif r < 0.8:
+            axis = None
+        elif r < 0.9:
+            axis = [int(v) for v in rng.integers(-nd, nd, size=2)]
+        else:
+            axis = rng.choice([1.5, "x"])
+            axis = float(axis) if axis == "1.5" else str(axis)
+        st.check("helpers", f"#{i} normalize_axis({axis!r}, {nd})",
+                 lambda: np.asarray(SU.normalize_axis(axis, nd), dtype=object), lambda: np.asarray(RU.normalize_axis(axis, nd), dtype=object))
+
+
+FAMILIES = {"helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
             "protocol": fam_protocol}
 
 
