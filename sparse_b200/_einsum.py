@@ -243,7 +243,12 @@ def einsum(*operands, **kwargs):
             array = _einsum_single(term, pterm, array)
         shape = tuple(array.shape[pterm.index(ch)] if ch in pterm else 1 for ch in aligned)
         parts.append(array.reshape(shape) if tuple(array.shape) != shape else array)
-    return _einsum_single(aligned, rhs, _product(parts))
+    out = _einsum_single(aligned, rhs, _product(parts))
+    if D.is_device_tensor(out) and not any(D.is_device_tensor(o) for o in operands):
+        # every sparse operand collapsed to a scalar factor: the result is dense, and host operands get a host array
+        # back (the reference returns an ndarray here)
+        out = D.download(out)
+    return out
 
 
 def _product(parts):

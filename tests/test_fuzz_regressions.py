@@ -135,3 +135,11 @@ def test_conj_of_bool_is_int8_as_in_numpy(sp):
     d = np.array([[True, False], [False, True]])
     r = np.conj(sp.COO.from_numpy(d, fill_value=True))
     assert r.dtype == np.conj(d).dtype == np.int8 and np.array_equal(r.todense(), np.conj(d)) and r.fill_value == 1
+
+
+def test_einsum_with_a_fully_summed_sparse_operand_returns_a_host_array(sp):
+    """The sparse operand collapses to a scalar factor, the product is dense: an ndarray for host operands, as upstream."""
+    a = np.array([2, -1], dtype=np.int64)
+    b = (np.arange(48).reshape(4, 4, 3) % 5 - 2).astype(np.int64)
+    r = sp.einsum("k,jil->ij", sp.COO.from_numpy(a), b)
+    assert isinstance(r, np.ndarray) and np.array_equal(r, np.einsum("k,jil->ij", a, b))
