@@ -154,7 +154,13 @@ def _einsum_single(lhs, rhs, operand):
         # densified again; no library einsum on the way
         from ._coo import as_coo
 
-        res = _einsum_single(lhs, rhs, as_coo(operand))
+        if D.is_device_tensor(operand):  # the product of two dense operands computed on the device
+            if operand.ndim == 0:
+                operand = D.download(operand)
+            else:
+                dt = D.np_dtype(operand)
+                operand = COO._from_dense_device(operand.contiguous(), tuple(operand.shape), dt.type(0))
+        res = _einsum_single(lhs, rhs, as_coo(operand) if not isinstance(operand, SparseArray) else operand)
         return res.todense_device() if isinstance(res, SparseArray) else res
     was_gcxs = isinstance(operand, GCXS)
     operand = operand.tocoo() if was_gcxs else operand

@@ -143,3 +143,16 @@ def test_einsum_with_a_fully_summed_sparse_operand_returns_a_host_array(sp):
     b = (np.arange(48).reshape(4, 4, 3) % 5 - 2).astype(np.int64)
     r = sp.einsum("k,jil->ij", sp.COO.from_numpy(a), b)
     assert isinstance(r, np.ndarray) and np.array_equal(r, np.einsum("k,jil->ij", a, b))
+
+
+def test_einsum_reduces_a_device_side_product_of_two_dense_operands(sp):
+    """'j,ik,lj->...': the two dense operands are multiplied first (on the device); the single-term step that follows
+    must accept that intermediate."""
+    a = np.array([1.0, -2.0])
+    c = np.array([[3.0, 1.0], [0.0, 2.0]])
+    g = np.array([[1.0, 0, 0, 2], [0, 0, 3, 0], [0, 0, 0, 0], [4, 0, 0, 5]])
+    for expr in ("j,ik,lj->", "j,ik,lj->il", "j,lj,ik->k"):
+        ops = (a, _gcxs(sp, g), c) if expr.startswith("j,ik") else (a, c, _gcxs(sp, g))
+        dense = tuple(np.asarray(o.todense()) if hasattr(o, "todense") else o for o in ops)
+        r = sp.einsum(expr, *ops)
+        assert np.array_equal(r.todense() if hasattr(r, "todense") else r, np.einsum(expr, *dense))
