@@ -48,7 +48,17 @@ def sddmm(s, a, b, *, b_transposed=False):
     ad = _dense_dev(a, T)
     bt = _dense_dev(b, T) if b_transposed else Kn.transpose_dense(_dense_dev(b, T))  # (N, K): contiguous gathers
     out = Kn.sddmm(indptr, cols, vals, ad, bt, M, N, K)
-    res = COO._from_device(c._coords, out, s.shape, T.type(0), keys=c.sorted_keys())
+    fill = T.type(0)
+    if isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and M and N and K:
+        # the unfused expression's fill value is `0 * (a @ b)[0, 0]` (_umath.py:520-527: the first element of
+        # func(fill, ndarray)), i.e. -0.0 when that corner is negative -- and the prune test below is by bit pattern,
+        # so the sign decides WHICH zeros stay stored.  K multiply-adds on the host; device operands keep +0.0
+        # (no read-back on the asynchronous path)
+        with np.errstate(all="ignore"):
+            corner = np.dot(a[0].astype(T, copy=False), (b[0] if b_transposed else b[:, 0]).astype(T, copy=False))
+            if np.isfinite(corner):
+                fill = T.type(T.type(0) * (corner + T.type(0)))  # a sum that starts at +0.0 is never -0.0
+    res = COO._from_device(c._coords, out, s.shape, fill, keys=c.sorted_keys())
     res._canonicalise(check_sort=False, sum_dups=False, prune=True)  # s * dense drops exact zeros (_umath.py:627-633)
     return res.asformat("gcxs", compressed_axes=s.compressed_axes) if was_gcxs else res
 

@@ -156,3 +156,23 @@ def test_einsum_reduces_a_device_side_product_of_two_dense_operands(sp):
         dense = tuple(np.asarray(o.todense()) if hasattr(o, "todense") else o for o in ops)
         r = sp.einsum(expr, *ops)
         assert np.array_equal(r.todense() if hasattr(r, "todense") else r, np.einsum(expr, *dense))
+
+
+def test_sddmm_keeps_the_zero_sign_of_the_unfused_expression(sp):
+    """`s * (a @ b)` upstream: the result's fill value is `0 * (a @ b)[0, 0]` (_umath.py:520-527) -- -0.0 under a
+    negative corner -- and pruning is by bit pattern, so that sign decides which zero products stay stored.  The
+    fused entry point gives the same arrays as the expression."""
+    s = sp.COO.from_numpy(np.array([[0.0, -3.0, 0.0], [-1.0, 2.0, 0.0]], dtype=np.float32))
+    a = np.array([[-3.0], [2.0]], dtype=np.float32)
+    b = np.array([[1.0, 0.0, -1.0]], dtype=np.float32)  # a @ b = [[-3, +0, 3], [2, +0, -2]]: negative corner
+    fused, plain = sp.sddmm(s, a, b), s * (a @ b)
+    for r in (fused, plain):
+        # -3 * +0.0 = -0.0 equals the -0.0 fill: pruned; 2 * +0.0 = +0.0 does not: stored
+        assert np.signbit(r.fill_value) and r.nnz == 2
+        assert np.array_equal(r.coords, [[1, 1], [0, 1]]) and np.array_equal(r.data, np.float32([-2.0, 0.0]))
+        assert not np.signbit(r.data[1])
+    b2 = np.array([[-1.0, 0.0, 1.0]], dtype=np.float32)  # corner +3: +0.0 fill, now the -0.0 product stays stored
+    fused, plain = sp.sddmm(s, a, b2), s * (a @ b2)
+    for r in (fused, plain):
+        assert not np.signbit(r.fill_value) and r.nnz == 2
+        assert np.array_equal(r.coords, [[0, 1], [1, 0]]) and r.data[0] == 0 and np.signbit(r.data[0]) and r.data[1] == 2

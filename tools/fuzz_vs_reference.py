@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the host layer against the REFERENCE itself (authoring container only).
 
-    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
+    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
                                       [--only CASE] [-v]
 
 Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
@@ -819,7 +819,51 @@ def fam_io(rng, st, i):
                  lambda: x_s, lambda: R.load_npz(f2))
 
 
-FAMILIES = {"io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+def fam_fused(rng, st, i):
+    """Rows a-20 / a-21: the fused SDDMM / MTTKRP entry points AND the unfused example expressions
+    (`s * (a @ b)`, examples/sddmm_example.py:52; `sum(B[..., None] * D[None, None] * C[None, :, None], axis=(1, 2))`,
+    examples/mttkrp_example.py:52) against the reference evaluating the example expression.  Integer-valued floats:
+    every order of summation gives the same bits, so the comparison is exact."""
+    dt = rng.choice(FLOATS)
+    if rng.random() < 0.5:
+        M, K, N = (int(v) for v in rng.integers(1, 7, size=3))
+        fmt = rng.choice(["coo", "gcxs"])
+        ds = draw_dense(rng, (M, N), dt)
+        a, b = draw_dense(rng, (M, K), dt, density=1.0), draw_dense(rng, (K, N), dt, density=1.0)
+        s_s, s_r = both(ds, fmt, rng=rng)
+        fused = rng.random() < 0.5
+        st.check("fused", f"#{i} {'sddmm(s,a,b)' if fused else 's * (a @ b)'} s={fmt}({M},{N}) K={K} :{dt}",
+                 (lambda: S.sddmm(s_s, a, b)) if fused else (lambda: s_s * (a @ b)), lambda: s_r * (a @ b))
+    else:
+        I, Kk, L, J = (int(v) for v in rng.integers(1, 6, size=4))
+        fmt = rng.choice(["coo", "gcxs"])
+        dB = draw_dense(rng, (I, Kk, L), dt)
+        Dm, Cm = draw_dense(rng, (L, J), dt, density=1.0), draw_dense(rng, (Kk, J), dt, density=1.0)
+        B_s, B_r = both(dB, fmt, rng=rng)
+        fused = rng.random() < 0.5
+
+        def expr(mod, B):
+            return mod.sum(B[:, :, :, None] * Dm[None, None, :, :] * Cm[None, :, None, :], axis=(1, 2))
+
+        if fmt == "gcxs":  # upstream's GCXS indexing with None is not NumPy's (DESIGN s4): give both sides COO there
+            B_r = B_r.tocoo()
+            B_s2 = B_s.tocoo()
+        else:
+            B_s2 = B_s
+        want = lambda: expr(R, B_r)  # noqa: E731
+        if fused:
+            # the fused kernel returns the format of B; the expression's result is compared densely
+            st.n += 1
+            got, w, es, er = run_pair(lambda: S.mttkrp(B_s, Dm, Cm), want)
+            if es is not None or er is not None:
+                st.report("fused", f"#{i} mttkrp", f"raised: here={es!r} reference={er!r}")
+            elif not arr_eq(got.todense(), w.todense()) or got.dtype != w.dtype:
+                st.report("fused", f"#{i} mttkrp(B={fmt}({I},{Kk},{L}), J={J}) :{dt}", "values / dtype differ")
+        else:
+            st.check("fused", f"#{i} mttkrp expression B={fmt}({I},{Kk},{L}) J={J} :{dt}", lambda: expr(S, B_s2), want)
+
+
+FAMILIES = {"fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
             "protocol": fam_protocol}
 
 
