@@ -214,6 +214,16 @@ def dense_binary(func, x, y):
     return vals.reshape(shape)
 
 
+def _fill_of(func, *fills):
+    """func(fill values) the way the reference evaluates it (_umath.py:516-527): NumPy values go through the ARRAY
+    loop as 1-element arrays, Python scalars stay weak scalars.  NumPy's scalar and array loops are not bit-identical
+    everywhere (float16 transcendental results, fmin / fmax of +0.0 and -0.0), and the fill value decides what is
+    pruned, so the same loop has to run."""
+    with np.errstate(all="ignore"):
+        res = func(*[np.atleast_1d(f) if isinstance(f, (np.generic, np.ndarray)) else f for f in fills])
+    return np.asarray(res).reshape(-1)[0]
+
+
 class _Elemwise:
     def __init__(self, func, *args, **kwargs):
         from ._gcxs import GCXS
@@ -376,8 +386,7 @@ class _Elemwise:
         if T in _WIDE_FOR and func not in _NOT_VIA_WIDE:
             return self._via_wide(func, T, out_dt)
         _check_compute_dtype(T, func)
-        with np.errstate(all="ignore"):
-            fill = np.asarray(func(a.fill_value)).astype(out_dt)[()]
+        fill = np.asarray(_fill_of(func, a.fill_value)).astype(out_dt)[()]
         data = a._data_dev()
         if any(s == 0 for s in self.shape):
             return COO(np.empty((len(self.shape), 0), dtype=np.intp), np.empty(0, dtype=out_dt), shape=self.shape,
@@ -439,8 +448,7 @@ class _Elemwise:
             return x.fill_value if isinstance(x, COO) else x
 
         if a_sp and b_sp:
-            with np.errstate(all="ignore"):
-                fill = np.asarray(func(a.fill_value, b.fill_value)).astype(out_dt)[()]
+            fill = np.asarray(_fill_of(func, a.fill_value, b.fill_value)).astype(out_dt)[()]
             if empty:
                 return self._empty(out_dt, fill)
             ka, da, Ra = _stream(a, shape)
@@ -452,9 +460,10 @@ class _Elemwise:
 
         if (a_sp and not b_dn) or (b_sp and not a_dn):  # sparse (x) scalar
             sp, sc, mode = (a, b, 0) if a_sp else (b, a, 1)
+            weak = sc if type(sc) in (bool, int, float) else np.asarray(sc)[()]  # a Python scalar promotes weakly
             sc = np.asarray(sc)[()]
-            with np.errstate(all="ignore"):
-                fill = np.asarray(func(a.fill_value, sc) if a_sp else func(sc, b.fill_value)).astype(out_dt)[()]
+            fill = np.asarray(_fill_of(func, a.fill_value, weak) if a_sp else _fill_of(func, weak, b.fill_value)
+                              ).astype(out_dt)[()]
             if empty:
                 return self._empty(out_dt, fill)
             data = sp._data_dev()
