@@ -5,8 +5,8 @@
                                       [--only CASE] [-v]
 
 Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
-upstream package, numba kernels), this package runs on the NumPy mock of the kernel layer (tests/_mock_kernels.py) --
-there is no GPU here, so what is fuzzed is everything ABOVE the C ABI: axis bookkeeping, broadcasting, dtype promotion,
+upstream package, numba kernels), this package runs on the NumPy mock of the kernel layer (tests/_mock_kernels.py) when
+there is no GPU -- then what is fuzzed is everything ABOVE the C ABI (on a GPU box the CUDA kernels run instead): axis bookkeeping, broadcasting, dtype promotion,
 fill values, result formats, error classes.  The kernels are compared with the oracle / golden vectors on the GPU
 (tests/, -m gpu).  Random shapes (0-4 dims, zero-length axes included), densities, dtypes, fill values, formats,
 operators; every result is compared field by field: class, shape, dtype, fill value, and the stored entries EXACTLY
@@ -40,9 +40,12 @@ sys.path.insert(0, ROOT)
 
 import sparse as R  # noqa: E402  (the reference)
 
-import _mock_kernels  # noqa: E402
+import torch  # noqa: E402
 
-_mock_kernels.install()
+if not torch.cuda.is_available():  # authoring container: the NumPy mock of the kernel layer; on a GPU box
+    import _mock_kernels  # noqa: E402   (baseline/_ref travels with gpurun) the real CUDA kernels are fuzzed
+
+    _mock_kernels.install()
 import sparse_b200 as S  # noqa: E402
 
 assert "baseline/_ref" in R.__file__, R.__file__
