@@ -308,14 +308,29 @@ def fam_dot(rng, st, i):
     ca = lambda x: getattr(x, "compressed_axes", None)  # noqa: E731
     desc = (f"#{i} {kind} a={fa}{tuple(sa)}:{dt_a} ca={ca(a_r)} b={fb}{tuple(sb)}:{dt_b} ca={ca(b_r)} axes={axes} "
             f"rt={rt_name}")
-    if kind == "tensordot":
+    if kind == "tensordot" and rt_name == "none" and rng.random() < 0.3:
+        st.check("dot", desc + " via=numpy", lambda: np.tensordot(a_s, b_s, axes), lambda: np.tensordot(a_r, b_r, axes),
+                 truth=lambda: np.tensordot(da, db, axes))
+    elif kind == "tensordot":
         st.check("dot", desc, lambda: S.tensordot(a_s, b_s, axes, return_type=rts_s[rt_name]),
                  lambda: R.tensordot(a_r, b_r, axes, return_type=rts_r[rt_name]),
                  truth=lambda: np.tensordot(da, db, axes))
     elif kind == "matmul":
-        st.check("dot", desc, lambda: S.matmul(a_s, b_s), lambda: R.matmul(a_r, b_r), truth=lambda: np.matmul(da, db))
+        # the module function, the operator (also with the ndarray on the left: __rmatmul__ / __array_ufunc__) and
+        # NumPy's own entry point (__array_function__)
+        via = rng.choice(["func", "operator", "numpy"])
+        call = {"func": lambda m, x, y: m.matmul(x, y), "operator": lambda m, x, y: x @ y,
+                "numpy": lambda m, x, y: np.matmul(x, y)}[via]
+        st.check("dot", desc + f" via={via}", lambda: call(S, a_s, b_s), lambda: call(R, a_r, b_r),
+                 truth=lambda: np.matmul(da, db))
     else:
-        st.check("dot", desc, lambda: S.dot(a_s, b_s), lambda: R.dot(a_r, b_r), truth=lambda: np.dot(da, db))
+        via = rng.choice(["func", "method", "numpy"])
+        if via == "method" and fa == "dense":
+            via = "func"
+        call = {"func": lambda m, x, y: m.dot(x, y), "method": lambda m, x, y: x.dot(y),
+                "numpy": lambda m, x, y: np.dot(x, y)}[via]
+        st.check("dot", desc + f" via={via}", lambda: call(S, a_s, b_s), lambda: call(R, a_r, b_r),
+                 truth=lambda: np.dot(da, db))
 
 
 BINARY = ["add", "subtract", "multiply", "maximum", "minimum", "greater", "less", "greater_equal", "less_equal",
@@ -480,7 +495,40 @@ def fam_formats(rng, st, i):
     dt = rng.choice(DTYPES)
     fill = rng.choice([0, 0, 1]) if dt != "bool" else rng.choice([0, 0, 1])
     nd = len(shape)
-    what = rng.choice(["ctor", "gcxs_chain", "coo_chain", "broadcast_to", "getitem"])
+    what = rng.choice(["ctor", "gcxs_chain", "coo_chain", "broadcast_to", "getitem", "gcxs_raw"])
+    if what == "gcxs_raw" and nd >= 2 and all(shape):
+        # GCXS from raw (data, indices, indptr) with drawn compressed axes (the arrays come from the reference's own
+        # conversion), then one consumer: tocoo / todense / transpose / a reduction / a product with a vector
+        d = draw_dense(rng, shape, dt, fill=fill)
+        k = int(rng.integers(1, nd))
+        ca = tuple(sorted(int(x) for x in rng.choice(nd, size=k, replace=False)))
+        g0 = R.COO.from_numpy(d, fill_value=np.asarray(fill, dtype=dt)[()]).asformat("gcxs", compressed_axes=ca)
+        arrays = (g0.data.copy(), g0.indices.copy(), np.asarray(g0.indptr).copy())
+        use = rng.choice(["tocoo", "todense", "T", "sum", "vec", "scipy"])
+
+        def go(mod):
+            g = mod.GCXS(arrays, shape=shape, compressed_axes=ca, fill_value=g0.fill_value)
+            if use == "tocoo":
+                return g.tocoo()
+            if use == "todense":
+                return g.todense()
+            if use == "T":
+                return g.T
+            if use == "sum":
+                return g.sum(axis=0)
+            if use == "vec":
+                if fill != 0:
+                    return g.tocoo()
+                return mod.tensordot(g, np.ones(shape[-1], dtype=np.float64), axes=1)
+            if len(shape) == 2 and fill == 0 and np.dtype(dt).kind != "b":
+                return mod.GCXS.from_scipy_sparse(g.to_scipy_sparse())
+            return g
+
+        st.check("formats", f"#{i} GCXS(raw arrays, shape={shape}, ca={ca}):{dt} fill={fill} -> {use}",
+                 lambda: go(S), lambda: go(R))
+        return
+    if what == "gcxs_raw":
+        what = "ctor"
     if what == "ctor":
         n = int(rng.integers(0, 12)) if all(shape) else 0
         coords = np.stack([rng.integers(0, max(s, 1), size=n) for s in shape]) if n else np.zeros((nd, 0), dtype=np.int64)
