@@ -541,6 +541,8 @@ def where(condition, x=None, y=None):
         return tuple(c.coords)
     if x_given != y_given:
         raise ValueError("either both or neither of x and y should be given")
+    # one three-way broadcast check up front: the error names all three shapes, as upstream's single elemwise call does
+    _get_nary_broadcast_shape(*[tuple(v.shape) if hasattr(v, "shape") else np.shape(v) for v in (condition, x, y)])
     with np.errstate(all="ignore"):
         T = np.result_type(_stand_in(x), _stand_in(y))
     work = np.dtype("int32") if T == np.bool_ else T

@@ -54,8 +54,10 @@ def _normalize(index, shape):
                 i = operator.index(ind)
             except TypeError:
                 raise IndexError("only integers, slices (`:`), ellipsis (`...`) and None are valid indices") from None
-            if not -extent <= i < extent:
-                raise IndexError(f"index {i} is out of bounds for axis {d} with size {extent}")
+            if i >= extent:  # upstream's wording (_slicing.py:127-132)
+                raise IndexError(f"Index is not smaller than dimension {i:d} >= {extent:d}")
+            if i < -extent:
+                raise IndexError(f"Negative index is not greater than negative dimension {i:d} <= -{extent:d}")
             items.append(("int", i + extent if i < 0 else i))
         d += 1
     return items

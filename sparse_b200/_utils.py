@@ -68,7 +68,8 @@ def normalize_axis(axis, ndim):
     except TypeError:
         raise ValueError(f"axis {axis} not understood") from None
     if not -ndim <= a < ndim:
-        raise ValueError(f"Invalid axis index {a} for ndim={ndim}")
+        # upstream's message shows the index after its `+= ndim` (_utils.py:389-393): -5 with ndim 4 reads -1
+        raise ValueError(f"Invalid axis index {a + ndim if a < 0 else a} for ndim={ndim}")
     return a + ndim if a < 0 else a
 
 
