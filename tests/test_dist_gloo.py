@@ -1,4 +1,4 @@
-"""N>1 host logic on CPU: world_size-2 `gloo` run of the row-block partition + all-gather paths
+"""N>1 host logic on CPU: world_size 2 and 3 `gloo` runs of the row-block partition + all-gather paths
 (sparse_b200/_dist.py) with the NumPy mock of the kernel layer; results must equal the single-process product."""
 import os
 import sys
@@ -54,16 +54,17 @@ def _worker(rank, world, port, q):
                and np.array_equal(g.data.view(np.uint64), wd.view(np.uint64)))
 
         # sddmm row block with b column-sharded
-        S = sp.random((M, 32), density=0.2, random_state=np.random.default_rng(5)).astype(np.float64)
+        NS = 36  # divisible by every world size the tests use (equal column shards of b)
+        S = sp.random((M, NS), density=0.2, random_state=np.random.default_rng(5)).astype(np.float64)
         A = rand_dense(rng, (M, 8), np.float64)
-        Bm = rand_dense(rng, (8, 32), np.float64)
+        Bm = rand_dense(rng, (8, NS), np.float64)
         full = (S.todense() * (A @ Bm))
         sd, si, sptr = (S.asformat("gcxs", compressed_axes=(0,)).data, S.asformat("gcxs", compressed_axes=(0,)).indices,
                         S.asformat("gcxs", compressed_axes=(0,)).indptr)
         sb = DD.nnz_balanced_splits(sptr, world)
         t0, t1 = sb[rank], sb[rank + 1]
-        s_local = sp.GCXS(DD.row_block(sd, si, sptr, t0, t1), shape=(t1 - t0, 32), compressed_axes=(0,))
-        cs = 32 // world
+        s_local = sp.GCXS(DD.row_block(sd, si, sptr, t0, t1), shape=(t1 - t0, NS), compressed_axes=(0,))
+        cs = NS // world
         out = DD.sddmm_rowblock(s_local, torch.from_numpy(A[t0:t1].copy()),
                                 torch.from_numpy(np.ascontiguousarray(Bm[:, rank * cs:(rank + 1) * cs])))
         ok3 = np.allclose(out.todense(), full[t0:t1], rtol=1e-12, atol=1e-12)
@@ -85,11 +86,11 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_rowblock_paths_world2():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_rowblock_paths(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + 2000 * (world - 2)
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
