@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """Where does the time go on power-law matrices?  Sweep the row-length clamp with the long-row path on / off."""
-import ctypes, os, sys
+import os
+import sys
+
 import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
-from sparse_b200 import _kernels as Kn, _lib
-from tools.tune_k1 import timeit
+from sparse_b200 import _kernels as Kn  # noqa: E402
+from sparse_b200 import _lib  # noqa: E402
+from tools.tune_k1 import timeit  # noqa: E402
 
 dev = torch.device("cuda", 0)
 M = K = 1_000_000
