@@ -73,6 +73,20 @@ def spmm_csr_dense(a_data, a_indices, a_indptr, b, M, K, N, out=None, n_panels=1
     return r
 
 
+def spmm_csr_dense_host(a_data, a_indices, a_indptr, b, out=None):
+    """Host-buffer form of K1 (the real one uploads, launches and downloads inside one C call): same product, host
+    arrays in and out, the dtype matrix of the real wrapper."""
+    D.dtype_code(a_data.dtype)
+    assert b.dtype == a_data.dtype
+    M, (K, N) = len(a_indptr) - 1, b.shape
+    r = oracle.dot_csr_ndarray((M, N), np.asarray(a_data), np.asarray(a_indices), np.asarray(a_indptr),
+                               np.ascontiguousarray(b))
+    if out is not None:
+        out[...] = r
+        return out
+    return r
+
+
 def linearize(coords, strides):
     c = n(coords).astype(np.int64)
     k = np.zeros(c.shape[1], dtype=np.int64)

@@ -17,7 +17,7 @@ An exception on one side must be the same class on the other.  Every mismatch pr
 
 Counted but not reported (each with the reason next to the code that recognises it): crashes INSIDE the reference on
 degenerate input, reference results that NumPy contradicts while this package agrees with NumPy, garbage entries from
-the uninitialised tail of `_dot_csc_ndarray_sparse`, and the host-buffer product, which has no mock.  Left out of the
+the uninitialised tail of `_dot_csc_ndarray_sparse`.  Left out of the
 draws because the answer is a documented `TypeError` here (DESIGN s4): ops outside the CUDA op set (hypot, arctan2,
 copysign), integer power in narrow dtypes, float16 results.
 
@@ -235,7 +235,7 @@ class Stats:
                     self.report(family, desc, f"error class: {type(es).__name__}({es}) != {type(er).__name__}({er})")
                 return
             if es is not None and "no CUDA device visible" in str(es):
-                self.unmockable += 1  # the host-buffer product (b2s_spmm_host) has no mock: it IS the CUDA path
+                self.unmockable += 1  # a path without a mock (none left: the host-buffer product has one now)
                 return
             if er is not None and ref_crash(er):
                 self.ref_crashes += 1
