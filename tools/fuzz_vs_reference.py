@@ -654,6 +654,14 @@ def fam_protocol(rng, st, i):
         kw = {"axis": axis}
         if rng.random() < 0.3:
             kw["keepdims"] = True
+        if rng.random() < 0.4:  # the method form, with the rest of the reduction op set
+            uf2 = getattr(np, rng.choice(["fmax", "fmin", "maximum", "add", "logical_and", "logical_or"] +
+                                         ([] if np.dtype(dt).kind == "f" else ["bitwise_and", "bitwise_xor"])))
+            if uf2 is np.add and fill > 1:
+                uf2 = np.maximum
+            st.check("protocol", f"#{i} x.reduce(np.{uf2.__name__}, {kw}) x={fmt}{shape}:{dt} fill={fill}",
+                     lambda: x_s.reduce(uf2, **kw), lambda: x_r.reduce(uf2, **kw))
+            return
         st.check("protocol", f"#{i} np.{uf.__name__}.reduce({fmt}{shape}:{dt} fill={fill}, {kw})",
                  lambda: uf.reduce(x_s, **kw), lambda: uf.reduce(x_r, **kw))
     elif what == "outer":
