@@ -270,8 +270,8 @@ def fam_dot(rng, st, i):
         k = int(rng.integers(0, min(nd_a, nd_b) + 1))
         ax_a = [int(x) for x in rng.choice(nd_a, size=k, replace=False)]
         ax_b = [int(x) for x in rng.choice(nd_b, size=k, replace=False)]
-        sa = [int(rng.integers(1, 5)) for _ in range(nd_a)]
-        sb = [int(rng.integers(1, 5)) for _ in range(nd_b)]
+        sa = [int(rng.integers(1, max(5, MAX_EXTENT[0] - 1))) for _ in range(nd_a)]
+        sb = [int(rng.integers(1, max(5, MAX_EXTENT[0] - 1))) for _ in range(nd_b)]
         for x, y in zip(ax_a, ax_b):
             sb[y] = sa[x]
         if rng.random() < 0.05 and k:
@@ -289,16 +289,16 @@ def fam_dot(rng, st, i):
             axes = (ax_a, ax_b)
         rt_name = rng.choice(["none", "none", "coo", "gcxs", "dense"])
     else:
-        K = int(rng.integers(1, 5))
+        K = int(rng.integers(1, max(5, MAX_EXTENT[0] - 1)))
         if kind == "matmul":
             batch = draw_shape(rng, 0, 2, zero_ok=False)
             ba = tuple(1 if rng.random() < 0.3 else b for b in batch)[int(rng.integers(0, len(batch) + 1)):]
             bb = tuple(1 if rng.random() < 0.3 else b for b in batch)[int(rng.integers(0, len(batch) + 1)):]
-            sa = list(ba) + ([int(rng.integers(1, 5))] if rng.random() < 0.85 or ba else []) + [K]
-            sb = list(bb) + [K] + ([int(rng.integers(1, 5))] if rng.random() < 0.85 or bb else [])
+            sa = list(ba) + ([int(rng.integers(1, max(5, MAX_EXTENT[0] - 1)))] if rng.random() < 0.85 or ba else []) + [K]
+            sb = list(bb) + [K] + ([int(rng.integers(1, max(5, MAX_EXTENT[0] - 1)))] if rng.random() < 0.85 or bb else [])
         else:
             sa = list(draw_shape(rng, 0, 2, zero_ok=False)) + [K]
-            sb = list(draw_shape(rng, 0, 1, zero_ok=False)) + [K] + ([int(rng.integers(1, 5))] if rng.random() < 0.8 else [])
+            sb = list(draw_shape(rng, 0, 1, zero_ok=False)) + [K] + ([int(rng.integers(1, max(5, MAX_EXTENT[0] - 1)))] if rng.random() < 0.8 else [])
             if len(sb) == 1:
                 pass
         axes, rt_name = None, "none"
@@ -775,7 +775,7 @@ def fam_einsum(rng, st, i):
     """`einsum` (the MTTKRP example's call, examples/mttkrp_example.py upstream): random subscripts over 1-3 operands,
     repeated indices inside an operand included, explicit and implicit outputs, COO / GCXS / dense operands."""
     letters = "ijkl"
-    sizes = {c: int(rng.integers(1, 5)) for c in letters}
+    sizes = {c: int(rng.integers(1, max(5, MAX_EXTENT[0] - 1))) for c in letters}
     n_ops = int(rng.integers(1, 4))
     subs, ops_s, ops_r, descs = [], [], [], []
     dt = rng.choice(FLOATS + ["int64"])
