@@ -214,6 +214,21 @@ def dense_binary(func, x, y):
     return vals.reshape(shape)
 
 
+def _out_format(sparse_args):
+    """Result format of an element-wise call (_umath.py:414-425): DOK when every sparse operand is DOK, GCXS when
+    every one is GCXS (with their compressed axes when they all agree), COO otherwise."""
+    from ._dok import DOK
+    from ._gcxs import GCXS
+
+    if all(isinstance(arg, DOK) for arg in sparse_args):
+        return DOK, {}
+    if all(isinstance(arg, GCXS) for arg in sparse_args):
+        if len({arg.compressed_axes for arg in sparse_args}) == 1:
+            return GCXS, {"compressed_axes": sparse_args[0].compressed_axes}
+        return GCXS, {}
+    return COO, {}
+
+
 def _fill_of(func, *fills):
     """func(fill values) the way the reference evaluates it (_umath.py:516-527): NumPy values go through the ARRAY
     loop as 1-element arrays, Python scalars stay weak scalars.  NumPy's scalar and array loops are not bit-identical
@@ -232,17 +247,7 @@ class _Elemwise:
         sparse_args = [arg for arg in args if isinstance(arg, SparseArray)]
         if len(sparse_args) == 0:
             raise ValueError(f"None of the args is sparse: {args}")
-        out_kwargs = {}
-        from ._dok import DOK
-
-        if all(isinstance(arg, DOK) for arg in sparse_args):
-            out_type = DOK  # _umath.py:417-418: DOK operands only -> DOK result
-        elif all(isinstance(arg, GCXS) for arg in sparse_args):
-            out_type = GCXS
-            if len({arg.compressed_axes for arg in sparse_args}) == 1:
-                out_kwargs["compressed_axes"] = sparse_args[0].compressed_axes
-        else:
-            out_type = COO
+        out_type, out_kwargs = _out_format(sparse_args)
         self.args = None
         for arg in args:
             if _is_scipy_sparse(arg):
@@ -295,8 +300,10 @@ class _Elemwise:
 
                 if res.size == 0:
                     with np.errstate(all="ignore"):
-                        const = np.asarray(self.func(*[h if np.ndim(h) == 0 else _zero_of_dtype(h.dtype)
-                                                       for h in host])).astype(res.dtype)[()]
+                        # upstream substitutes the zero of the dtype for EVERY ndarray here, the densified 0-D
+                        # sparse operands included (:531-533)
+                        const = np.asarray(self.func(*[_zero_of_dtype(h.dtype) if isinstance(h, (np.ndarray, np.generic))
+                                                       else h for h in host])).astype(res.dtype)[()]
                 elif equivalent(res.reshape(-1)[0], res, loose=True).all():
                     const = res.reshape(-1)[0]
                 else:
@@ -480,7 +487,7 @@ class _Elemwise:
         g, _ = Kn.ew_map(op, 1 if not swap else 0, flat, T.type(sp.fill_value), 0, out_dt)
         if flat.shape[0] == 0:
             # nothing to test for constancy: func(fill, zero of the dense dtype) (_umath.py:529-534)
-            z = _zero_of_dtype(np.dtype(dn.dtype) if isinstance(dn, np.ndarray) else D.np_dtype(dn.dtype))
+            z = _zero_of_dtype(np.dtype(dn.dtype) if isinstance(dn, np.ndarray) else D.np_dtype(dn))
             with np.errstate(all="ignore"):
                 f0 = func(z, sp.fill_value) if swap else func(sp.fill_value, z)
             return self._empty(out_dt, np.asarray(f0).astype(out_dt)[()])
@@ -543,6 +550,10 @@ def where(condition, x=None, y=None):
         raise ValueError("either both or neither of x and y should be given")
     # one three-way broadcast check up front: the error names all three shapes, as upstream's single elemwise call does
     _get_nary_broadcast_shape(*[tuple(v.shape) if hasattr(v, "shape") else np.shape(v) for v in (condition, x, y)])
+    sparse_ops = [v for v in (condition, x, y) if isinstance(v, SparseArray)]
+    if sparse_ops and all(v.ndim == 0 for v in sparse_ops):
+        # every sparse operand is 0-D: they are scalars to upstream (_umath.py:438-439) and the call is host arithmetic
+        return _Elemwise(np.where, condition, x, y).get_result()
     with np.errstate(all="ignore"):
         T = np.result_type(_stand_in(x), _stand_in(y))
     work = np.dtype("int32") if T == np.bool_ else T
@@ -575,10 +586,81 @@ def where(condition, x=None, y=None):
 
         return dense_binary(func, dev(a), dev(b))
 
-    out = step(_bitor_raw, step(_sel_x, c, as_t(x)), step(_sel_y, c, as_t(y)))
+    # sparse or dense?  Upstream decides on the INPUTS of its one elemwise call (_umath.py:536-546):
+    # where(fill_c, fill_x | ndarray, fill_y | ndarray) must be one constant for the result to stay sparse; otherwise
+    # it is dense (or an error when the sparse operands would have to be broadcast up).  Deciding pass by pass would
+    # differ (an intermediate that happens to be constant, two ndarrays of different shapes).  The decision is host
+    # arithmetic on the fill values and the ndarrays, as upstream's; the values come from the device passes below.
+    ops = (condition, x, y)
+    dense_ops = [v for v in ops if (isinstance(v, np.ndarray) and v.ndim > 0) or D.is_device_tensor(v)]
+    full = _get_nary_broadcast_shape(*[tuple(v.shape) if hasattr(v, "shape") else np.shape(v) for v in ops])
+
+    def densified(v):
+        return Kn.cast(v.asformat("coo").todense_device(), work) if isinstance(v, SparseArray) else v
+
+    def dense_passes():
+        """The three passes on densified operands (device kernels throughout); host array of the full shape."""
+        cd, xd, yd = densified(c), densified(as_t(x)), densified(as_t(y))
+        res = D.download(step(_bitor_raw, step(_sel_x, cd, xd), step(_sel_y, cd, yd)))
+        res = np.broadcast_to(res, full) if tuple(res.shape) != tuple(full) else res
+        return res.astype(np.bool_) if T == np.bool_ else res
+
+    fv = None
+    if dense_ops or any(s == 0 for s in full):
+        from ._utils import equivalent
+
+        def stand_in(v, zeros=False):
+            """What upstream feeds its fill-value probe (_umath.py:516-534): the fill value of a sparse operand, the
+            whole array for an ndarray (a 0-D sparse operand IS an ndarray by then); `zeros`: the zero of the dtype
+            instead of the array, the fallback when the probe comes out empty."""
+            if isinstance(v, SparseArray) and v.ndim:
+                return np.atleast_1d(v.fill_value)
+            if isinstance(v, SparseArray):
+                v = v.todense()
+            elif D.is_device_tensor(v):
+                v = D.download(v)
+            if isinstance(v, (np.ndarray, np.generic)):
+                return _zero_of_dtype(v.dtype) if zeros else np.atleast_1d(v)
+            return v
+
+        def probe(zeros=False):
+            h = [stand_in(v, zeros) for v in ops]
+            with np.errstate(all="ignore"):
+                return np.asarray(np.where(np.asarray(h[0]) != 0, h[1], h[2]))
+
+        fva = probe()
+        fv = fva.reshape(-1)[0] if fva.size else probe(zeros=True).reshape(-1)[0]
+        if fva.size and not equivalent(fv, fva, loose=True).all():
+            nd_shape = _get_nary_broadcast_shape(*[tuple(v.shape) for v in dense_ops])
+            if tuple(full) != tuple(nd_shape):
+                raise ValueError("Performing a mixed sparse-dense operation that would result in a dense array. "
+                                 "Please make sure that func(sparse_fill_values, ndarrays) is a constant array.")
+            return dense_passes()
+        if any(s == 0 for s in full):  # nothing to compute: the empty COO (_umath.py:467-477)
+            return COO(np.empty((len(full), 0), dtype=np.intp), np.empty(0, dtype=T), shape=tuple(full),
+                       has_duplicates=False, sorted=True, fill_value=np.asarray(fv).astype(T)[()])
+    cast_back = T == np.bool_
+    try:
+        out = step(_bitor_raw, step(_sel_x, c, as_t(x)), step(_sel_y, c, as_t(y)))
+    except ValueError:
+        # a single pass can need a dense intermediate that the whole expression does not (the probe above said
+        # "sparse"): compute the passes on densified operands instead -- only when the result is small enough to hold
+        if fv is None or prod(full) > (1 << 27):
+            raise
+        out, cast_back = dense_passes(), False
     if D.is_device_tensor(out):  # every step was dense (only reachable through the np.where dispatch)
         out = D.download(out)
-    return out.astype(np.bool_) if T == np.bool_ else out
+    out = out.astype(np.bool_) if cast_back else out
+    if sparse_ops and fv is not None and not isinstance(out, SparseArray):
+        # the probe said "sparse" (constant fill) but the passes went through a dense intermediate (a 0-D sparse
+        # operand next to an ndarray): same values, stored relative to the probed fill value
+        out = np.asarray(out)
+        out = COO.from_numpy(np.broadcast_to(out, full) if tuple(out.shape) != tuple(full) else out,
+                             fill_value=np.asarray(fv).astype(out.dtype)[()])
+    if isinstance(out, SparseArray) and sparse_ops and not any(s == 0 for s in out.shape):
+        fmt, kw = _out_format(sparse_ops)  # the format of ONE elemwise call over the three operands
+        out = out.asformat("coo").asformat(fmt, **kw)
+    return out
 
 
 def broadcast_to(x, shape):

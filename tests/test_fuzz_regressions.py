@@ -176,3 +176,37 @@ def test_sddmm_keeps_the_zero_sign_of_the_unfused_expression(sp):
     for r in (fused, plain):
         assert not np.signbit(r.fill_value) and r.nnz == 2
         assert np.array_equal(r.coords, [[0, 1], [1, 0]]) and r.data[0] == 0 and np.signbit(r.data[0]) and r.data[1] == 2
+
+
+def test_where_decides_sparse_or_dense_on_its_inputs(sp):
+    """Upstream's three-argument where is ONE elemwise call: the result is sparse iff where(fills | ndarrays) is one
+    constant (_umath.py:536-546), whatever a pass-by-pass evaluation would see on the way."""
+    a = sp.COO.from_numpy(np.array([-4.0, 0.0, 2.0, 0.0], dtype=np.float32), fill_value=np.float32(2))
+    b = np.array([0.0, 2.0, 0.0, 0.0], dtype=np.float32)
+    c = sp.COO.from_numpy(np.array([0, 0, 0, -4], dtype=np.int64))
+    r = sp.where(a != 0, b, c)  # fill of the condition is True -> where(True, b, 0) = b: not constant -> dense
+    assert isinstance(r, np.ndarray) and np.array_equal(r, np.where(a.todense() != 0, b, c.todense()))
+    # constant probe, but a single pass would need a dense intermediate: still sparse, fill value from the probe
+    cond = np.array([-1, -2, 0, -4])
+    x0 = sp.COO.from_numpy(np.array(3))  # 0-D, value 3
+    y = _gcxs(sp, np.array([[-3]]), fill=3)
+    r = sp.where(cond, x0, y)
+    assert isinstance(r, sp.COO) and r.shape == (1, 4) and r.fill_value == 3 and r.nnz == 1
+    assert np.array_equal(r.todense(), np.where(cond, 3, np.array([[-3]])))
+    # the sparse operands would have to be broadcast up to a non-constant dense result: the reference's error
+    with pytest.raises(ValueError, match="mixed sparse-dense"):
+        sp.where(np.array([1, 0, 1]), sp.COO.from_numpy(np.ones((2, 3))), np.array([5.0, 6.0, 7.0]))
+
+
+def test_where_result_format_and_degenerate_operands(sp):
+    g1 = _gcxs(sp, np.array([[1.0, 0.0], [0.0, 2.0]]), ca=(1,))
+    g2 = _gcxs(sp, np.array([[0.0, 5.0], [6.0, 0.0]]), ca=(1,))
+    r = sp.where(g1 != 0, g1, g2)  # every sparse operand GCXS with the same compressed axis: kept (_umath.py:419-422)
+    assert isinstance(r, sp.GCXS) and tuple(r.compressed_axes) == (1,)
+    assert isinstance(sp.where(g1 != 0, g1, g2.tocoo()), sp.COO)
+    # all operands 0-D: host arithmetic, a 0-D array without stored entries in the operands' format
+    z = sp.where(_gcxs(sp, np.array(True)), _gcxs(sp, np.array(2.0)), np.float64(5.0))
+    assert isinstance(z, sp.GCXS) and z.shape == () and z.nnz == 0 and z.fill_value == 2.0
+    # a zero-length axis: the empty COO; its fill value comes from the probe on fills and ndarrays (:516-534)
+    e = sp.where(sp.COO.from_numpy(np.zeros((0,), dtype=bool)), _gcxs(sp, np.zeros(1, dtype=np.float32)), np.int64(3))
+    assert isinstance(e, sp.COO) and e.shape == (0,) and e.fill_value == 3.0 and e.dtype == np.float64

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the host layer against the REFERENCE itself (authoring container only).
 
-    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
+    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
                                       [--only CASE] [-v]
 
 Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
@@ -994,7 +994,28 @@ def fam_special(rng, st, i):
                  exact_layout=name not in ("sum", "prod", "nansum", "nanprod"))
 
 
-FAMILIES = {"special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+def fam_where(rng, st, i):
+    """Three-argument `where` with every operand drawn independently: COO / GCXS / ndarray in each slot, 0-D and
+    zero-length operands, broadcasting between all three, non-zero fill values.  Upstream's one elemwise call decides
+    sparse-vs-dense (and the error) on where(fills | ndarrays); the result format follows the sparse operands."""
+    base = draw_shape(rng, 0, 3)
+
+    def operand(kinds, dts, fills):
+        shape = tuple(s if rng.random() < 0.7 else 1 for s in base)
+        shape = shape[int(rng.integers(0, len(shape) + 1)):]
+        dt, fill, fmt = rng.choice(dts), rng.choice(fills), rng.choice(kinds)
+        d = draw_dense(rng, shape, dt, fill=fill)
+        return both(d, fmt, fill=fill, rng=rng) + (f"{fmt}{shape}:{dt} f={fill}",)
+
+    c_s, c_r, dc = operand(["coo", "coo", "gcxs", "dense"], ["bool", "float32", "int64"], [0, 0, 1])
+    x_s, x_r, dx = operand(["coo", "gcxs", "dense"], ["float64", "float32", "int64"], [0, 0, 2])
+    y_s, y_r, dy = operand(["coo", "gcxs", "dense"], ["float64", "float32", "int64"], [0, 0, 3])
+    if not any(isinstance(v, R.SparseArray) for v in (c_r, x_r, y_r)):
+        c_s, c_r = both(np.asarray(c_r), "coo")
+    st.check("where", f"#{i} where({dc}, {dx}, {dy})", lambda: S.where(c_s, x_s, y_s), lambda: R.where(c_r, x_r, y_r))
+
+
+FAMILIES = {"where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
             "protocol": fam_protocol}
 
 
