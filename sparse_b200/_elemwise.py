@@ -367,15 +367,88 @@ class _Elemwise:
         if isinstance(self.func, np.ufunc):
             raise TypeError(f"sparse_b200: {self.func.__name__} with {len(self.args)} operands is not in the CUDA op "
                             "set; there is no CPU fallback.")
-        out = self.func(*self.args)
-        if out is NotImplemented or not (isinstance(out, (SparseArray, np.ndarray)) or isscalar(out)):
+        from ._utils import equivalent
+
+        def is_dense(a):
+            return (isinstance(a, np.ndarray) and a.ndim > 0) or D.is_device_tensor(a)
+
+        # Next to ndarrays (or with a zero-length axis) upstream decides sparse-or-dense, the error and the fill value
+        # on ONE probe of func(fill values | ndarrays) (_umath.py:505-546); evaluating `func` operator by operator
+        # decides per operator, which differs (an intermediate that happens to be constant, ndarrays of different
+        # shapes, 0-D operands).  The probe is host arithmetic on fill values and the ndarrays, as upstream's.
+        probe = None
+        dense_args = [a for a in self.args if is_dense(a)]
+        shape = tuple(self.shape)
+        if dense_args or any(s == 0 for s in shape):
+            def stand_in(a, zeros=False):
+                if isinstance(a, COO):
+                    return a.fill_value if zeros else np.atleast_1d(a.fill_value)
+                if D.is_device_tensor(a):
+                    a = D.download(a)
+                if isinstance(a, (np.ndarray, np.generic)):
+                    return _zero_of_dtype(a.dtype) if zeros else np.atleast_1d(a)
+                return a
+
+            with np.errstate(all="ignore"):
+                fva = np.asarray(self.func(*[stand_in(a) for a in self.args]))
+                fv = fva.reshape(-1)[0] if fva.size else np.asarray(
+                    self.func(*[stand_in(a, zeros=True) for a in self.args])).reshape(-1)[0]
+            const = bool(equivalent(fv, fva, loose=True).all()) if fva.size else True
+            if not const:
+                nd_shape = _get_nary_broadcast_shape(*[tuple(a.shape) for a in dense_args])
+                if shape != tuple(nd_shape):
+                    raise ValueError("Performing a mixed sparse-dense operation that would result in a dense array. "
+                                     "Please make sure that func(sparse_fill_values, ndarrays) is a constant array.")
+            probe = (fv, const)
+        if probe is None:
+            out = self.func(*self.args)
+        else:
+            # next to ndarrays every operator would take its own sparse-or-dense decision (and a sparse (x) dense
+            # product keeps ONE zero for +0.0 and -0.0): evaluate with every ndarray as a COO of its non-zero entries
+            # instead -- the sparse kernels then compute the exact value at every position, the probe above decides
+            # what the result looks like
+            from ._coo import as_coo
+
+            out = self.func(*[as_coo(D.download(a) if D.is_device_tensor(a) else a) if is_dense(a) else a
+                              for a in self.args])
+        if out is NotImplemented or not (isinstance(out, (SparseArray, np.ndarray)) or isscalar(out)
+                                         or D.is_device_tensor(out)):
             raise TypeError("sparse_b200.elemwise: the function did not evaluate to an array through the NumPy ufunc "
                             "protocol; only compositions of the supported ufuncs run on the CUDA path")
         if isscalar(out):
             out = COO.from_numpy(np.asarray(out))
-        if isinstance(out, SparseArray) and tuple(out.shape) != tuple(self.shape):
-            out = broadcast_to(out.asformat("coo"), self.shape)
-        return out.asformat("coo") if isinstance(out, SparseArray) else out
+        if isinstance(out, SparseArray) and tuple(out.shape) != shape:
+            out = broadcast_to(out.asformat("coo"), shape)
+        if probe is None:
+            return out.asformat("coo") if isinstance(out, SparseArray) else out
+        fv, const = probe
+        host = out.todense() if isinstance(out, SparseArray) and (not const or not any(s == 0 for s in shape)) else out
+        if not const:  # dense result (_umath.py:463-465)
+            host = D.download(host) if D.is_device_tensor(host) else np.asarray(host)
+            return np.broadcast_to(host, shape).copy() if tuple(host.shape) != shape else host
+        dt = np.dtype(out.dtype) if isinstance(out, (SparseArray, np.ndarray)) else D.np_dtype(out)
+        fv = np.asarray(fv).astype(dt)[()]
+        if any(s == 0 for s in shape):
+            return self._empty(dt, fv)
+        if prod(shape) > (1 << 27):  # too large to reconcile through a dense copy: the operator-by-operator result
+            return out.asformat("coo") if isinstance(out, SparseArray) else out
+        # Sparse by the probe.  Upstream stores, among the positions some sparse operand has an entry at (the only
+        # ones it visits), those whose value differs from the fill value by bit pattern (_umath.py:627-633); the
+        # operator-by-operator evaluation can store more (positions only an ndarray is non-zero at, -0.0 there) or be
+        # relative to another fill value.  Rebuild exactly that set: visited positions = union of the operands'
+        # stored coordinates, broadcast to the result.
+        host = D.download(host) if D.is_device_tensor(host) else np.asarray(host)
+        host = np.broadcast_to(host, shape) if tuple(host.shape) != shape else host
+        visited = None
+        for a in self.args:
+            if isinstance(a, COO):
+                m = COO(a.coords, np.ones(a.nnz, dtype=np.bool_), shape=a.shape, has_duplicates=False, sorted=True)
+                m = broadcast_to(m, shape) if tuple(m.shape) != shape else m
+                visited = m if visited is None else np.logical_or(visited, m)
+        coords = np.asarray(visited.coords)
+        vals = host[tuple(coords)].astype(dt, copy=False)
+        keep = ~np.asarray(equivalent(vals, fv), dtype=bool).reshape(-1) if vals.size else np.zeros(0, dtype=bool)
+        return COO(coords[:, keep], vals[keep], shape=shape, has_duplicates=False, sorted=True, fill_value=fv)
 
     def _unary(self):
         (a,) = self.args

@@ -210,3 +210,26 @@ def test_where_result_format_and_degenerate_operands(sp):
     # a zero-length axis: the empty COO; its fill value comes from the probe on fills and ndarrays (:516-534)
     e = sp.where(sp.COO.from_numpy(np.zeros((0,), dtype=bool)), _gcxs(sp, np.zeros(1, dtype=np.float32)), np.int64(3))
     assert isinstance(e, sp.COO) and e.shape == (0,) and e.fill_value == 3.0 and e.dtype == np.float64
+
+
+def test_nary_elemwise_next_to_ndarrays_follows_upstreams_probe(sp):
+    """A user-defined function with ndarray operands: upstream probes func(fill values | ndarrays) once
+    (_umath.py:505-546) -- constant: sparse with that fill value, the stored set being the visited positions whose
+    value differs from it BY BIT PATTERN; not constant: dense, or the error when the sparse operands would have to be
+    broadcast up.  Signed zeros survive ((x + y) * 0 is -0.0 where x + y < 0)."""
+    x = np.array([[0.0, 0.0, 0.0, 4.0], [0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 2.0, 0.0]])
+    yd = np.array([[-3.0, 3.0, 3.0, 0.0], [-3.0, 4.0, -4.0, -2.0], [3.0, 0.0, -3.0, 1.0]])
+    y = sp.COO.from_numpy(yd, fill_value=2.0)
+    z = _gcxs(sp, np.zeros((3, 4), dtype=np.float32))
+    r = sp.elemwise(lambda a, b, c: (a + b) * c, x, y, z)
+    want = (x + yd) * np.zeros((3, 4), dtype=np.float32)
+    assert isinstance(r, sp.COO) and not np.signbit(r.fill_value) and r.nnz == int(np.signbit(want).sum()) == 5
+    assert np.array_equal(np.signbit(r.todense()), np.signbit(want)) and np.array_equal(r.todense(), want)
+    # not constant and nothing to broadcast up: the dense result
+    d = sp.elemwise(lambda a, b, c: a + b * c, sp.COO.from_numpy(yd), x + 1.0, np.full((3, 4), 0.5))
+    assert isinstance(d, np.ndarray) and np.array_equal(d, yd + (x + 1.0) * 0.5)
+    # constant probe (0 * b + 0.5): sparse, fill value 0.5
+    s5 = sp.elemwise(lambda a, b, c: a * b + c, sp.COO.from_numpy(yd), x + 1.0, np.full((3, 4), 0.5))
+    assert isinstance(s5, sp.COO) and s5.fill_value == 0.5 and np.array_equal(s5.todense(), yd * (x + 1.0) + 0.5)
+    with pytest.raises(ValueError, match="mixed sparse-dense"):
+        sp.elemwise(lambda a, b, c: a + b * c, sp.COO.from_numpy(yd), np.array([1.0, 2.0, 3.0, 4.0]), np.float64(1.0))

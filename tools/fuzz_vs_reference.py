@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the host layer against the REFERENCE itself (authoring container only).
 
-    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
+    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|nary,where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
                                       [--only CASE] [-v]
 
 Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
@@ -1015,7 +1015,33 @@ def fam_where(rng, st, i):
     st.check("where", f"#{i} where({dc}, {dx}, {dy})", lambda: S.where(c_s, x_s, y_s), lambda: R.where(c_r, x_r, y_r))
 
 
-FAMILIES = {"where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+NARY = {"x*y+z": lambda x, y, z: x * y + z, "(x+y)*z": lambda x, y, z: (x + y) * z,
+        "max(x,y)-z": lambda x, y, z: np.maximum(x, y) - z, "x*y": lambda x, y: x * y, "x+y": lambda x, y: x + y,
+        "x*(y>z)": lambda x, y, z: x * (y > z)}
+
+
+def fam_nary(rng, st, i):
+    """User-defined functions through `elemwise` with every operand drawn independently (COO / GCXS / ndarray, 0-D and
+    zero-length operands, non-zero fill values, broadcasting between all of them): upstream evaluates the function on
+    matched data and decides sparse-or-dense on one probe; the operator-by-operator evaluation here has to agree in
+    class, fill value and the exact stored set (signed zeros included)."""
+    base = draw_shape(rng, 0, 3)
+    name = rng.choice(list(NARY))
+    f = NARY[name]
+    ops_s, ops_r, descs = [], [], []
+    for _ in range(f.__code__.co_argcount):
+        shape = tuple(s if rng.random() < 0.7 else 1 for s in base)
+        shape = shape[int(rng.integers(0, len(shape) + 1)):]
+        dt, fill, fmt = rng.choice(["float64", "float32", "int64"]), rng.choice([0, 0, 2]), rng.choice(["coo", "gcxs", "dense"])
+        a, b = both(draw_dense(rng, shape, dt, fill=fill), fmt, fill=fill, rng=rng)
+        ops_s.append(a), ops_r.append(b), descs.append(f"{fmt}{shape}:{dt} f={fill}")
+    if not any(isinstance(v, R.SparseArray) for v in ops_r):
+        ops_s[0], ops_r[0] = both(np.asarray(ops_r[0]), "coo")
+    st.check("nary", f"#{i} elemwise({name}; {', '.join(descs)})", lambda: S.elemwise(f, *ops_s),
+             lambda: R.elemwise(f, *ops_r))
+
+
+FAMILIES = {"nary": fam_nary, "where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
             "protocol": fam_protocol}
 
 
