@@ -284,12 +284,23 @@ class _Elemwise:
             # through the ARRAY loop as in the reference (np.atleast_1d, _umath.py:516-527 -- for float16 results it
             # is not the scalar loop bit for bit)
             host = [D.download(a) if D.is_device_tensor(a) else a for a in self.args]
+
+            def call(*args):
+                # `dtype=` selects the loop (operands are cast BEFORE the operation); functions that do not take it
+                # are called without and the result is cast (_umath.py:521-524, 612-620)
+                if self.dtype is not None:
+                    try:
+                        return self.func(*args, dtype=self.dtype)
+                    except TypeError:
+                        pass
+                return self.func(*args)
+
             with np.errstate(all="ignore"):
                 if all(np.ndim(h) == 0 for h in host):
-                    res = np.asarray(self.func(*[np.atleast_1d(h) if isinstance(h, (np.generic, np.ndarray)) else h
-                                                 for h in host])).reshape(())
+                    res = np.asarray(call(*[np.atleast_1d(h) if isinstance(h, (np.generic, np.ndarray)) else h
+                                            for h in host])).reshape(())
                 else:
-                    res = np.asarray(self.func(*host))
+                    res = np.asarray(call(*host))
             if self.dtype is not None:
                 res = res.astype(self.dtype)
             if res.ndim:

@@ -364,12 +364,19 @@ def fam_elemwise(rng, st, i):
     if mode == "scalar":
         name = rng.choice(BINARY)
         f = getattr(np, name)
+        if name == "power" and (np.dtype(dt_a).itemsize < 4 or dt_a == "uint32"):
+            name, f = "multiply", np.multiply  # integer power in a narrow / unsigned type: documented TypeError
         sc = rng.choice([0, 1, 2, -1, 2.5, True, np.float32(3), np.int8(2), np.float64("nan")])
+        if rng.random() < 0.3:  # a 0-D ndarray operand (strongly typed, unlike a Python scalar)
+            sc = np.array(rng.integers(0, 4)).astype(rng.choice(["float64", "float32", "int64", "int8", "bool"]))
+        kw = {}
+        if rng.random() < 0.2 and name in ("add", "multiply", "subtract", "maximum", "minimum", "true_divide"):
+            kw["dtype"] = rng.choice(["float64", "float32"])  # selects the loop: operands are cast first
         left = rng.random() < 0.5
         st.check("elemwise", f"#{i} np.{name}({'scalar,' if left else ''}{fa}{base}:{dt_a} fill={fill_a}"
-                             f"{'' if left else ',scalar'}) scalar={sc!r}",
-                 (lambda: f(sc, a_s)) if left else (lambda: f(a_s, sc)),
-                 (lambda: f(sc, a_r)) if left else (lambda: f(a_r, sc)))
+                             f"{'' if left else ',scalar'}, {kw}) scalar={sc!r}",
+                 (lambda: f(sc, a_s, **kw)) if left else (lambda: f(a_s, sc, **kw)),
+                 (lambda: f(sc, a_r, **kw)) if left else (lambda: f(a_r, sc, **kw)))
         return
     # second operand: a broadcast-compatible shape
     other = tuple(s if rng.random() < 0.65 else 1 for s in base)
