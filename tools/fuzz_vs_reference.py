@@ -1019,7 +1019,9 @@ def fam_where(rng, st, i):
     y_s, y_r, dy = operand(["coo", "gcxs", "dense"], ["float64", "float32", "int64"], [0, 0, 3])
     if not any(isinstance(v, R.SparseArray) for v in (c_r, x_r, y_r)):
         c_s, c_r = both(np.asarray(c_r), "coo")
-    st.check("where", f"#{i} where({dc}, {dx}, {dy})", lambda: S.where(c_s, x_s, y_s), lambda: R.where(c_r, x_r, y_r))
+    via = "numpy" if rng.random() < 0.3 and isinstance(c_r, R.SparseArray) else "func"  # np.where: __array_function__
+    st.check("where", f"#{i} where({dc}, {dx}, {dy}) via={via}", (lambda: S.where(c_s, x_s, y_s)) if via == "func" else (lambda: np.where(c_s, x_s, y_s)),
+             (lambda: R.where(c_r, x_r, y_r)) if via == "func" else (lambda: np.where(c_r, x_r, y_r)))
 
 
 NARY = {"x*y+z": lambda x, y, z: x * y + z, "(x+y)*z": lambda x, y, z: (x + y) * z,
