@@ -805,6 +805,10 @@ def fam_einsum(rng, st, i):
     kw = {}
     if rng.random() < 0.15:
         kw["dtype"] = rng.choice(["float64", "float32"])
+    if rng.random() < 0.25 and isinstance(ops_r[0], R.SparseArray) and not kw:
+        st.check("einsum", f"#{i} np.einsum('{expr}', {', '.join(descs)}) :{dt}",
+                 lambda: np.einsum(expr, *ops_s), lambda: np.einsum(expr, *ops_r))
+        return
     st.check("einsum", f"#{i} einsum('{expr}', {', '.join(descs)}) :{dt} {kw}",
              lambda: S.einsum(expr, *ops_s, **kw), lambda: R.einsum(expr, *ops_r, **kw))
 
