@@ -75,6 +75,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=400)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--max-extent", type=int, default=49, help="M, K, N are drawn below this (default 49)")
     args = ap.parse_args()
     O.build()
     bad, n = 0, 0
@@ -91,7 +92,7 @@ def main():
     warnings.simplefilter("ignore")
     for i in range(args.cases):
         rng = np.random.default_rng([args.seed, i])
-        M, K, N = (int(v) for v in rng.integers(1, 49, size=3))
+        M, K, N = (int(v) for v in rng.integers(1, args.max_extent, size=3))
         if rng.random() < 0.1:
             M, K, N = (int(v) for v in rng.integers(1, 5, size=3))
         da_t, db_t = rng.choice(DTS), rng.choice(DTS)
