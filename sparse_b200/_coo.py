@@ -508,8 +508,9 @@ class COO(SparseArray):
 
         return self._cached("tocsc", (), build)
 
-    def astype(self, dtype, casting="unsafe", copy=True):
-        """Cast of the stored values and the fill value.  Upstream routes this through `elemwise`
+    def astype(self, dtype, casting="unsafe", copy=True, _raw=False):
+        """Cast of the stored values and the fill value (`_raw`: internal casts of intermediate results keep a 0-D
+        array's stored entry / fill value structure).  Upstream routes this through `elemwise`
         (_sparse_array.py:626-643), so values that BECOME equal to the fill value under the cast (0.4 -> int 0, a
         double that underflows to float32 0) are dropped from the result; same here (flag, scan, compact)."""
         dtype = np.dtype(dtype)
@@ -517,6 +518,11 @@ class COO(SparseArray):
             return self
         if not np.can_cast(self.dtype, dtype, casting=casting):
             raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
+        if self.ndim == 0 and not _raw:
+            # a 0-D operand is a scalar to upstream's elemwise (_umath.py:438-439): the cast VALUE comes back as the
+            # fill value of an array without stored entries, whatever was stored before
+            return COO(np.empty((0, 0), dtype=np.intp), np.empty(0, dtype=dtype), shape=(), has_duplicates=False,
+                       sorted=True, fill_value=np.asarray(self.todense()).astype(dtype)[()])
         data = self._data_dev()
         fill = np.asarray(self.fill_value).astype(dtype)[()]
         if self.dtype == dtype:

@@ -353,12 +353,12 @@ def _dot(a, b, return_type=None):
             if isinstance(x, SparseArray):
                 if x.dtype == W:
                     return x
-                return x.astype(W, _keep_format=True) if isinstance(x, GCXS) else x.astype(W)
+                return x.astype(W, _keep_format=True) if isinstance(x, GCXS) else x.astype(W, _raw=True)
             return Kn.cast(D.upload(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x, W)
 
         out = _dot(widen(a), widen(b), return_type)
         if isinstance(out, SparseArray):
-            return out.astype(dtr, _keep_format=True) if isinstance(out, GCXS) else out.astype(dtr)
+            return out.astype(dtr, _keep_format=True) if isinstance(out, GCXS) else out.astype(dtr, _raw=True)
         out = Kn.cast(out if D.is_device_tensor(out) else D.upload(np.ascontiguousarray(out)), dtr)
         return D.download(out) if host_in else out
     out_shape = (a.shape[0], b.shape[1])

@@ -504,7 +504,7 @@ class _Elemwise:
             return out
         if isinstance(out, np.ndarray):
             return out.astype(out_dt)
-        return out.asformat("coo").astype(out_dt)
+        return out.asformat("coo").astype(out_dt, _raw=True)
 
     def _keep(self, a, vals, flags, fill):
         pos, total = Kn.scan_flags(flags)

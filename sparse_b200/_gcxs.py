@@ -392,6 +392,8 @@ class GCXS(SparseArray):
             return self
         if not np.can_cast(self.dtype, dtype, casting=casting):
             raise TypeError(f"Cannot cast array data from {self.dtype!r} to {dtype!r} according to the rule {casting!r}")
+        if self.ndim == 0 and not _keep_format:
+            return self.tocoo().astype(dtype, casting=casting, copy=copy).asformat("gcxs")  # value-as-fill, see COO
         if any(s == 0 for s in self.shape) and not _keep_format:
             # upstream's astype is an elemwise call, and elemwise hands back the empty COO as it is (_umath.py:467-477)
             return self.tocoo().astype(dtype, casting=casting, copy=copy)

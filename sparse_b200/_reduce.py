@@ -119,4 +119,4 @@ def _reduce_coo(x, method, axis, super_ufunc, kwargs):
         vals, _ = Kn.ew_map(_BINARY[np.bitwise_xor], 0, vals, _SIGN64, 0, np.int64)
         result_fill = np.int64(result_fill) ^ _SIGN64
     out = COO._from_device(None, vals, kept_shape, result_fill, keys=gids)  # coordinates are derived lazily
-    return out.astype(narrow_back) if narrow_back is not None else out
+    return out.astype(narrow_back, _raw=True) if narrow_back is not None else out

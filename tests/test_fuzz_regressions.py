@@ -233,3 +233,18 @@ def test_nary_elemwise_next_to_ndarrays_follows_upstreams_probe(sp):
     assert isinstance(s5, sp.COO) and s5.fill_value == 0.5 and np.array_equal(s5.todense(), yd * (x + 1.0) + 0.5)
     with pytest.raises(ValueError, match="mixed sparse-dense"):
         sp.elemwise(lambda a, b, c: a + b * c, sp.COO.from_numpy(yd), np.array([1.0, 2.0, 3.0, 4.0]), np.float64(1.0))
+
+
+def test_astype_of_a_0d_array_returns_the_value_as_fill_value(sp):
+    """astype is an elemwise call upstream and a 0-D operand is a scalar to it (_umath.py:438-439): the cast value
+    comes back as the fill value of an array without stored entries."""
+    x = sp.COO(np.empty((0, 1), dtype=np.intp), np.array([0], dtype=np.uint32), shape=(), fill_value=np.uint32(1))
+    assert x.nnz == 1 and x.todense() == 0
+    r = x.astype(np.int32)
+    assert isinstance(r, sp.COO) and r.nnz == 0 and r.fill_value == 0 and r.dtype == np.int32
+    g = x.asformat("gcxs").astype(np.float64)
+    assert isinstance(g, sp.GCXS) and g.nnz == 0 and g.fill_value == 0.0
+    # full reductions of narrow integers go through an internal cast that must NOT do this (fill value preserved)
+    y = sp.COO.from_numpy(np.array([[1, 4, 1]], dtype=np.uint8), fill_value=np.uint8(1))
+    m = y.max(axis=None, keepdims=True)
+    assert m.shape == (1, 1) and m.fill_value == 1 and m.todense().item() == 4 and m.dtype == np.uint8
