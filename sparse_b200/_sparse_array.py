@@ -361,6 +361,12 @@ class SparseArray(NDArrayOperatorsMixin):
     def real(self):
         """numpy.real: the array itself for real dtypes, the pruned real plane for complex ones."""
         if self.dtype.kind != "c":
+            # upstream: elemwise(np.real, x) -- the same array, in elemwise's clothes: a 0-D array comes back as its
+            # value-as-fill-value form, an array with a zero-length axis as the empty COO (_umath.py:438-439, 467-477)
+            if self.ndim == 0:
+                return self.astype(self.dtype)
+            if any(s == 0 for s in self.shape):
+                return self.asformat("coo")
             return self
         from ._complex import planes
 
@@ -370,7 +376,15 @@ class SparseArray(NDArrayOperatorsMixin):
     def imag(self):
         """numpy.imag: all zeros (same dtype) for real dtypes, the pruned imaginary plane for complex ones."""
         if self.dtype.kind != "c":
-            return np.multiply(self, self.dtype.type(0)) if self._zero_fill() else np.subtract(self, self)
+            # every element is +0 (x * 0 would leave -0.0 behind negative entries): no stored entry, same format
+            from ._coo import COO
+
+            out = COO(np.empty((self.ndim, 0), dtype=np.intp), np.empty(0, dtype=self.dtype), shape=self.shape,
+                      has_duplicates=False, sorted=True, fill_value=self.dtype.type(0))
+            if any(s == 0 for s in self.shape) or isinstance(self, COO):
+                return out
+            ca = getattr(self, "compressed_axes", None)
+            return out.asformat(self.format, **({"compressed_axes": ca} if self.format == "gcxs" else {}))
         from ._complex import planes
 
         return np.positive(planes(self)[1])

@@ -248,3 +248,16 @@ def test_astype_of_a_0d_array_returns_the_value_as_fill_value(sp):
     y = sp.COO.from_numpy(np.array([[1, 4, 1]], dtype=np.uint8), fill_value=np.uint8(1))
     m = y.max(axis=None, keepdims=True)
     assert m.shape == (1, 1) and m.fill_value == 1 and m.todense().item() == 4 and m.dtype == np.uint8
+
+
+def test_imag_of_a_real_array_is_all_positive_zero(sp):
+    """numpy.imag of a real array is +0 everywhere: no stored entry (x * 0 would leave -0.0 behind negative values)."""
+    d = np.array([[0.0, 3.0, 0.0], [0.0, -2.0, 0.0]])
+    for x in (sp.COO.from_numpy(d), _gcxs(sp, d, ca=(1,))):
+        r = x.imag
+        assert type(r) is type(x) and r.nnz == 0 and r.dtype == d.dtype and not np.signbit(r.todense()).any()
+    g = _gcxs(sp, d, ca=(1,)).imag
+    assert tuple(g.compressed_axes) == (1,)
+    z = sp.COO.from_numpy(np.array(-3, dtype=np.int32), fill_value=np.int32(1))  # 0-D: value -3 stored, fill 1
+    r = z.real
+    assert r.nnz == 0 and r.fill_value == -3  # elemwise form of a 0-D array (_umath.py:438-439)
