@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the host layer against the REFERENCE itself (authoring container only).
 
-    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|nary,where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
+    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|methods,nary,where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
                                       [--only CASE] [-v]
 
 Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
@@ -1054,7 +1054,112 @@ def fam_nary(rng, st, i):
              lambda: R.elemwise(f, *ops_r))
 
 
-FAMILIES = {"nary": fam_nary, "where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+def fam_methods(rng, st, i):
+    """Methods and properties next to the path: astype (casting / copy, values that collapse onto the fill value,
+    0-D arrays), real / imag / conj / T, COO and GCXS constructors in their argument forms, linear_loc / nonzero /
+    flatten / squeeze / swapaxes."""
+    shape = draw_shape(rng, 0, 3)
+    dt = rng.choice(DTYPES)
+    fill = int(rng.choice([0, 0, 1, 2])) if dt != "bool" else int(rng.choice([0, 1]))
+    d = draw_dense(rng, shape, dt, fill=fill)
+    what = rng.choice(["astype", "attr", "coo_ctor", "gcxs_ctor", "helper"])
+    if what == "astype":
+        if np.dtype(dt).kind == "f" and d.size and rng.random() < 0.3:
+            d = d.copy()
+            d[rng.random(shape) < 0.3] = rng.choice([0.4, -0.6, 1e-50, 3e9, np.nan])
+        fmt = rng.choice(["coo", "gcxs"])
+        x_s, x_r = both(d, fmt, fill=fill, rng=rng)
+        to, kw = rng.choice(DTYPES), {}
+        if rng.random() < 0.3:
+            kw["casting"] = rng.choice(["safe", "same_kind", "unsafe", "no", "equiv"])
+        if rng.random() < 0.3:
+            kw["copy"] = bool(rng.random() < 0.5)
+        st.check("methods", f"#{i} {fmt}{shape}:{dt} f={fill} .astype({to}, {kw})",
+                 lambda: x_s.astype(to, **kw), lambda: x_r.astype(to, **kw))
+    elif what == "attr":
+        fmt = rng.choice(["coo", "gcxs"])
+        x_s, x_r = both(d, fmt, fill=fill, rng=rng)
+        attr = rng.choice(["real", "imag", "conj()", "T", "mT" if len(shape) >= 2 else "T", "nbytes", "density", "nnz"])
+        if attr == "nbytes" and (fmt == "gcxs" and len(shape) < 2):
+            attr = "nnz"  # upstream's nbytes of a 0-D / 1-D GCXS array raises (indptr is a tuple there)
+
+        def get(x):
+            v = x.conj() if attr == "conj()" else getattr(x, attr)
+            return np.asarray(v) if attr in ("nbytes", "density", "nnz") else v
+
+        st.check("methods", f"#{i} {fmt}{shape}:{dt} f={fill} .{attr}", lambda: get(x_s), lambda: get(x_r))
+    elif what == "coo_ctor":
+        nd = max(1, len(shape))
+        shp = tuple(max(1, s) for s in (shape or (3,)))[:nd]
+        n = int(rng.integers(0, 8))
+        coords = np.stack([rng.integers(0, s, size=n) for s in shp])
+        data = rng.integers(0 if dt == "bool" else -3, 4, size=n).astype(dt)
+        mode = rng.choice(["list", "noshape", "scalar_data", "1d", "copy_of", "fill", "prune_false", "dups", "idx_dtype"])
+        kw = {"shape": shp}
+        args = (coords, data)
+        if mode == "list":
+            args = (coords.tolist(), data.tolist())
+        elif mode == "noshape":
+            kw = {}
+        elif mode == "scalar_data":
+            args = (coords, np.dtype(dt).type(2))
+        elif mode == "1d":
+            kw, args = {"shape": (shp[0],)}, (coords[0], data)
+        elif mode == "fill":
+            kw["fill_value"] = np.dtype(dt).type(1)
+        elif mode == "prune_false":
+            kw["prune"] = False
+        elif mode == "dups":
+            kw["has_duplicates"] = True
+        elif mode == "idx_dtype":
+            kw["idx_dtype"] = rng.choice([np.int32, np.uint8, np.int64])
+        if mode == "copy_of":
+            st.check("methods", f"#{i} COO(COO) {shp}:{dt}", lambda: S.COO(S.COO(coords, data, shape=shp)),
+                     lambda: R.COO(R.COO(coords, data, shape=shp)))
+        else:
+            st.check("methods", f"#{i} COO[{mode}] n={n} {shp}:{dt}", lambda: S.COO(*args, **kw), lambda: R.COO(*args, **kw))
+    elif what == "gcxs_ctor":
+        if not shape:
+            shape, d = (3,), draw_dense(rng, (3,), dt, fill=fill)
+        nd, kw = len(shape), {}
+        if nd >= 2 and rng.random() < 0.6:
+            k = int(rng.integers(1, nd))
+            kw["compressed_axes"] = tuple(sorted(int(x) for x in rng.choice(nd, size=k, replace=False)))
+        fv = np.asarray(fill, dtype=dt)[()]
+        mode = rng.choice(["from_numpy", "from_coo", "ctor_coo", "ctor_nd", "ctor_gcxs"])
+        if mode == "from_numpy":
+            st.check("methods", f"#{i} GCXS.from_numpy({shape}:{dt}, {kw})", lambda: S.GCXS.from_numpy(d, **kw),
+                     lambda: R.GCXS.from_numpy(d, **kw))
+        elif mode == "from_coo":
+            st.check("methods", f"#{i} GCXS.from_coo({shape}:{dt} f={fill}, {kw})",
+                     lambda: S.GCXS.from_coo(S.COO.from_numpy(d, fill_value=fv), **kw),
+                     lambda: R.GCXS.from_coo(R.COO.from_numpy(d, fill_value=fv), **kw))
+        elif mode == "ctor_coo":
+            st.check("methods", f"#{i} GCXS(coo {shape}:{dt} f={fill}, {kw})",
+                     lambda: S.GCXS(S.COO.from_numpy(d, fill_value=fv), **kw),
+                     lambda: R.GCXS(R.COO.from_numpy(d, fill_value=fv), **kw))
+        elif mode == "ctor_nd":
+            st.check("methods", f"#{i} GCXS(ndarray {shape}:{dt}, {kw})", lambda: S.GCXS(d, **kw), lambda: R.GCXS(d, **kw))
+        else:
+            st.check("methods", f"#{i} GCXS(GCXS {shape}:{dt}, {kw})", lambda: S.GCXS(S.GCXS.from_numpy(d), **kw),
+                     lambda: R.GCXS(R.GCXS.from_numpy(d), **kw))
+    else:
+        if not shape:
+            shape, d = (4,), draw_dense(rng, (4,), dt, fill=0)
+        x_s, x_r = both(draw_dense(rng, shape, dt), "coo")
+        m = rng.choice(["linear_loc", "nonzero", "flatten", "squeeze", "swapaxes"])
+
+        def call(x):
+            if m == "linear_loc":
+                return np.asarray(x.linear_loc())
+            if m == "nonzero":
+                return np.stack([np.asarray(v) for v in x.nonzero()])
+            return x.flatten() if m == "flatten" else x.squeeze() if m == "squeeze" else x.swapaxes(0, -1)
+
+        st.check("methods", f"#{i} coo{shape}:{dt} .{m}()", lambda: call(x_s), lambda: call(x_r))
+
+
+FAMILIES = {"methods": fam_methods, "nary": fam_nary, "where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
             "protocol": fam_protocol}
 
 
