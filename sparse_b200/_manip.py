@@ -98,6 +98,8 @@ def _wrap_like(arrays, out, axis, compressed_axes=None):
         out._idx_vis = v if np.can_cast(np.min_scalar_type(max(out.shape)), v) else np.dtype(
             np.min_scalar_type(max(out.shape)))
     if builtins.all(isinstance(a, GCXS) for a in arrays):
+        if arrays[0].ndim == 1:
+            return out  # 1-D GCXS inputs are joined as COO upstream (_compressed/common.py:18-22)
         if out.ndim < 2:
             return GCXS.from_coo(out)
         return GCXS.from_coo(out, tuple(compressed_axes) if compressed_axes is not None else (axis,))
@@ -522,8 +524,15 @@ def kron(a, b):
     ka = Kn.gather(_rekey(a, [sb * st for sb, st in zip(b.shape, c_strides(out_shape))]), ia)
     kb = Kn.gather(_rekey(b, c_strides(out_shape)), ib)
     keys = dense_binary(np.add, ka, kb)
-    data = dense_binary(np.multiply, Kn.cast(Kn.gather(a._data_dev(), ia), dtr),
-                        Kn.cast(Kn.gather(b._data_dev(), ib), dtr))
+    # narrow / unsigned integers and bool are storage-only on the device: the product runs in the wider signed type and
+    # the cast back wraps exactly like NumPy's arithmetic in the narrow type (bool: any non-zero product is True)
+    from ._elemwise import _WIDE_FOR
+
+    wide = np.dtype("int32") if dtr == np.bool_ else _WIDE_FOR.get(dtr, dtr)
+    data = dense_binary(np.multiply, Kn.cast(Kn.gather(a._data_dev(), ia), wide),
+                        Kn.cast(Kn.gather(b._data_dev(), ib), wide))
+    if wide != dtr:
+        data = Kn.cast(data, dtr)
     del t
     return _sorted_result(keys, data, out_shape, dtr.type(0))
 

@@ -261,3 +261,17 @@ def test_imag_of_a_real_array_is_all_positive_zero(sp):
     z = sp.COO.from_numpy(np.array(-3, dtype=np.int32), fill_value=np.int32(1))  # 0-D: value -3 stored, fill 1
     r = z.real
     assert r.nnz == 0 and r.fill_value == -3  # elemwise form of a 0-D array (_umath.py:438-439)
+
+
+def test_kron_of_narrow_integers_and_join_of_1d_gcxs(sp):
+    a = np.array([[16, 0], [-3, 2]], dtype=np.int8)
+    b = np.array([[16, 1]], dtype=np.int8)
+    k = sp.kron(sp.COO.from_numpy(a), sp.COO.from_numpy(b))
+    want = np.kron(a, b)  # 16 * 16 wraps to 0 in int8
+    assert k.dtype == np.int8 and np.array_equal(k.todense(), want) and k.nnz == np.count_nonzero(want)
+    kb = sp.kron(sp.COO.from_numpy(a != 0), sp.COO.from_numpy(b != 0))
+    assert kb.dtype == np.bool_ and np.array_equal(kb.todense(), np.kron(a != 0, b != 0))
+    g = _gcxs(sp, np.array([0.0, 1.0, 0.0]))
+    assert isinstance(sp.concatenate([g, g]), sp.COO) and isinstance(sp.stack([g, g]), sp.COO)  # 1-D GCXS joins as COO
+    g2 = _gcxs(sp, np.array([[0.0, 1.0], [2.0, 0.0]]))
+    assert isinstance(sp.concatenate([g2, g2]), sp.GCXS) and isinstance(sp.stack([g2, g2]), sp.GCXS)

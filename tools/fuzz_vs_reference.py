@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the host layer against the REFERENCE itself (authoring container only).
 
-    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|methods,nary,where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
+    python tools/fuzz_vs_reference.py [--cases 3000] [--seed 0] [--family all|join,methods,nary,where,special,fused,io,helpers,einsum,scipy,dot,elemwise,reduce,formats,protocol]
                                       [--only CASE] [-v]
 
 Both packages live in one process: the reference is imported from baseline/_ref (tools/make_ref.sh: the unmodified
@@ -1159,7 +1159,38 @@ def fam_methods(rng, st, i):
         st.check("methods", f"#{i} coo{shape}:{dt} .{m}()", lambda: call(x_s), lambda: call(x_r))
 
 
-FAMILIES = {"methods": fam_methods, "nary": fam_nary, "where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
+def fam_join(rng, st, i):
+    """kron (row 7 / the round-1 advisor item: stored x stored only), concatenate and stack (the N-D matmul is built on
+    stack): formats, fill values, zero-length pieces, narrow integer dtypes."""
+    what = rng.choice(["kron", "concatenate", "stack"])
+    dt = rng.choice(["float64", "float32", "int64", "int8", "bool"])
+    if what == "kron":
+        sa, sb = draw_shape(rng, 1, 3, zero_ok=False), draw_shape(rng, 1, 3, zero_ok=False)
+        da, db = draw_dense(rng, sa, dt), draw_dense(rng, sb, rng.choice(["float64", "int64", dt]))
+        fa, fb = rng.choice(["coo", "gcxs", "dense"]), rng.choice(["coo", "gcxs", "dense"])
+        if fa == "dense" and fb == "dense":
+            fa = "coo"
+        a_s, a_r = both(da, fa, rng=rng)
+        b_s, b_r = both(db, fb, rng=rng)
+        st.check("join", f"#{i} kron({fa}{sa}:{da.dtype}, {fb}{sb}:{db.dtype})", lambda: S.kron(a_s, b_s),
+                 lambda: R.kron(a_r, b_r))
+        return
+    base = draw_shape(rng, 1, 3)
+    k, axis = int(rng.integers(1, 4)), int(rng.integers(-len(base), len(base)))
+    fill = int(rng.choice([0, 0, 2])) if dt != "bool" else 0
+    fmt = rng.choice(["coo", "gcxs"])
+    arrs_s, arrs_r = [], []
+    for _ in range(k):
+        shp = list(base)
+        if what == "concatenate":
+            shp[axis] = int(rng.integers(0, 4))
+        a, b = both(draw_dense(rng, tuple(shp), dt, fill=fill), fmt, fill=fill, rng=rng)
+        arrs_s.append(a), arrs_r.append(b)
+    st.check("join", f"#{i} {what}({k} x {fmt}{base}:{dt} f={fill}, axis={axis})",
+             lambda: getattr(S, what)(arrs_s, axis=axis), lambda: getattr(R, what)(arrs_r, axis=axis))
+
+
+FAMILIES = {"join": fam_join, "methods": fam_methods, "nary": fam_nary, "where": fam_where, "special": fam_special, "fused": fam_fused, "io": fam_io, "helpers": fam_helpers, "einsum": fam_einsum, "scipy": fam_scipy, "dot": fam_dot, "elemwise": fam_elemwise, "reduce": fam_reduce, "formats": fam_formats,
             "protocol": fam_protocol}
 
 
